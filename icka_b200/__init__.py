@@ -1,0 +1,18 @@
+"""icka_b200 -- B200 (sm_100a) drop-in for ICKA's cross-modal fusion + CRF hot path.
+
+Public surface (mirrors /root/reference/Cross_Modal_Interaction_Module.py and torchcrf):
+    modules.BertCrossEncoder, BertCrossAttentionLayer, BertCrossAttention, BertCoAttention,
+    BertSelfOutput, BertIntermediate, BertOutput, BertLayerNorm, cls_layer_both, CrossModalFusion
+    crf.CRF
+    set_precision('bf16' | 'fp32')
+Everything computes through libicka_b200.so (include/icka_b200.h); there is no CPU fallback.
+"""
+from .config import FusionConfig  # noqa: F401
+from .modules import (BertCoAttention, BertCrossAttention, BertCrossAttentionLayer, BertCrossEncoder,  # noqa: F401
+                      BertIntermediate, BertLayerNorm, BertOutput, BertSelfOutput, CrossModalFusion,
+                      cls_layer_both, get_precision, set_precision)
+from .crf import CRF  # noqa: F401
+
+__all__ = ['FusionConfig', 'BertCoAttention', 'BertCrossAttention', 'BertCrossAttentionLayer', 'BertCrossEncoder',
+           'BertIntermediate', 'BertLayerNorm', 'BertOutput', 'BertSelfOutput', 'CrossModalFusion', 'cls_layer_both',
+           'CRF', 'get_precision', 'set_precision']

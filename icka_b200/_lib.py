@@ -1,0 +1,90 @@
+"""ctypes binding of libicka_b200.so (the C ABI declared in include/icka_b200.h).
+
+The library has no CPU fallback: importing works anywhere (so CPU-only tests can check that every
+symbol is exported), but ``handle()`` -- needed by every compute call -- raises unless a sm_100 GPU is
+present, and every non-zero status becomes a ``RuntimeError`` carrying ``icka_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libicka_b200.so')
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU_ERF = 0, 1
+
+# name -> (restype, argtypes); must list every symbol of include/icka_b200.h
+SIGNATURES = {
+    'icka_version': (c_int, []),
+    'icka_last_error': (c_char_p, []),
+    'icka_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    'icka_destroy': (c_int, [c_void_p]),
+    'icka_launch_count': (c_int64, [c_void_p]),
+    'icka_cast_f32_to_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'icka_region_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_linear_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                   c_int, c_void_p]),
+    'icka_cross_attn_core_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                         c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_gate_fold': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_void_p]),
+    'icka_gate_blend_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'icka_viterbi_decode': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_int, c_int, c_void_p]),
+    'icka_crf_llh_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_void_p]),
+}
+
+_lib = None
+_handles = {}
+_lock = threading.Lock()
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and attach prototypes.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m icka_b200.build` '
+                '(icka_b200 has no CPU or PyTorch fallback)')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return (load().icka_last_error() or b'').decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f'{what} failed ({rc}): {last_error()}')
+
+
+def handle(device_index: int) -> c_void_p:
+    """Per-device library handle (created on first use, kept for the life of the process)."""
+    with _lock:
+        h = _handles.get(device_index)
+        if h is None:
+            lib = load()
+            out = c_void_p()
+            check(lib.icka_create(int(device_index), ctypes.byref(out)), 'icka_create')
+            h = _handles[device_index] = out
+        return h
+
+
+def launch_count(device_index: int = 0) -> int:
+    h = _handles.get(device_index)
+    return int(load().icka_launch_count(h)) if h is not None else 0

@@ -1,0 +1,56 @@
+// Handle lifecycle, error channel, version.  Part of libicka_b200.so (see include/icka_b200.h).
+#include "common.cuh"
+
+#include <string.h>
+
+static thread_local char g_last_error[512] = "";
+
+void icka_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int icka_version(void) { return 100; }
+
+extern "C" const char* icka_last_error(void) { return g_last_error; }
+
+extern "C" int icka_create(int device, icka_handle** out) {
+  ICKA_REQUIRE(out != nullptr, "icka_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  ICKA_CUDA(cudaGetDeviceCount(&count));
+  ICKA_REQUIRE(device >= 0 && device < count, "icka_create: device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  ICKA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    ICKA_FAIL(ICKA_ERR_UNSUPPORTED,
+              "icka_create: device %d is sm_%d%d; libicka_b200 is built for sm_100a only and has no fallback",
+              device, prop.major, prop.minor);
+  icka_handle* h = new icka_handle();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major;
+  h->cc_minor = prop.minor;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  h->launches.store(0);
+  h->encode_tiled = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete h;
+    ICKA_FAIL(ICKA_ERR_CUDA, "icka_create: cuTensorMapEncodeTiled not available from the driver");
+  }
+  h->encode_tiled = fn;
+  *out = h;
+  return ICKA_OK;
+}
+
+extern "C" int icka_destroy(icka_handle* h) {
+  delete h;
+  return ICKA_OK;
+}
+
+extern "C" int64_t icka_launch_count(const icka_handle* h) { return h ? (int64_t)h->launches.load() : 0; }

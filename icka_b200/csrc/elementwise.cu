@@ -1,0 +1,293 @@
+// HBM-bound helpers of the fusion path: operand casts, region-grid relayout, LayerNorm, gate + blend.
+// All loops are 128-bit vectorised and coalesced; none of these kernels has data reuse beyond a row.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (GEMM A operand copy; the fp32 residual stream is kept as is)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x,
+                                                            __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t nvec = n / 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const float4 a = reinterpret_cast<const float4*>(x)[2 * v];
+    const float4 b = reinterpret_cast<const float4*>(x)[2 * v + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y);
+    o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y);
+    o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(y)[v] = o;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Region relayout: grid [B, C, R] fp32 (R contiguous)  ->  rows [B*R, C] (C contiguous), CMIM:956.
+// One block moves a [64 channels x R] slab through shared memory (coalesced on both sides).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRegC = 64;
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) region_rows_kernel(const float* __restrict__ grid, OutT* __restrict__ rows,
+                                                          int C, int R) {
+  extern __shared__ float tile[];   // [kRegC][Rp]
+  const int Rp = R | 1;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kRegC;
+  const int nc = min(kRegC, C - c0);
+  const float* src = grid + ((size_t)b * C + c0) * R;
+  const int total = nc * R;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c = i / R, r = i - c * R;
+    tile[c * Rp + r] = src[i];
+  }
+  __syncthreads();
+  OutT* dst = rows + (size_t)b * R * C + c0;
+  // each thread writes two adjacent channels of one region row
+  const int pairs = kRegC / 2;
+  for (int i = threadIdx.x; i < R * pairs; i += blockDim.x) {
+    const int r = i / pairs, c = (i - r * pairs) * 2;
+    if (c + 1 < nc) {
+      const float v0 = tile[c * Rp + r], v1 = tile[(c + 1) * Rp + r];
+      if constexpr (sizeof(OutT) == 2) {
+        *reinterpret_cast<uint32_t*>(dst + (size_t)r * C + c) = pack_bf16x2(v0, v1);
+      } else {
+        *reinterpret_cast<float2*>(dst + (size_t)r * C + c) = make_float2(v0, v1);
+      }
+    } else if (c < nc) {
+      dst[(size_t)r * C + c] = from_f32<OutT>(tile[c * Rp + r]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BertLayerNorm (CMIM:518-522): u = mean(x); s = mean((x-u)^2); y = w * (x-u)/sqrt(s+eps) + b
+// One warp per row, the row lives in registers (N <= 32*4*kMaxVec), two-pass statistics like the
+// reference.  Emits the fp32 residual stream and/or the bf16 operand copy for the next GEMM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxVec = 8;   // N <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        float* __restrict__ y32, __nv_bfloat16* __restrict__ y16,
+                                                        int M, int N) {
+  const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= M) return;
+  const int nvec = N / 4;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * N);
+  float4 v[kMaxVec];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      v[i] = xr[c];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)N;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)N + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+      const float4 bt = reinterpret_cast<const float4*>(beta)[c];
+      float4 o;
+      o.x = g.x * ((v[i].x - mean) * rstd) + bt.x;
+      o.y = g.y * ((v[i].y - mean) * rstd) + bt.y;
+      o.z = g.z * ((v[i].z - mean) * rstd) + bt.z;
+      o.w = g.w * ((v[i].w - mean) * rstd) + bt.w;
+      if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * N)[c] = o;
+      if (y16) {
+        uint2 p;
+        p.x = pack_bf16x2(o.x, o.y);
+        p.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(y16 + (size_t)row * N)[c] = p;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate fold: w_fold[k] = sum_j wa[j] * Wp[j][k];  c_fold = sum_j wa[j] * bp[j] + ba
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gate_fold_kernel(const float* __restrict__ Wp, const float* __restrict__ bp,
+                                                        const float* __restrict__ wa, const float* __restrict__ ba,
+                                                        float* __restrict__ w_fold, float* __restrict__ c_fold, int H) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < H) {
+    float acc = 0.0f;
+    for (int j = 0; j < H; ++j) acc = fmaf(wa[j], Wp[(size_t)j * H + k], acc);
+    w_fold[k] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    float acc = 0.0f;
+    for (int j = threadIdx.x; j < H; j += 32) acc = fmaf(wa[j], bp[j], acc);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) c_fold[0] = acc + ba[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gate + blend (CMIM:1029-1036).  One block per sentence: LayerNorm of the [CLS] rows, dot with the
+// folded gate vector, sigmoid, then a streaming blend of the sentence's S*H elements.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGateThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (l < kGateThreads / 32) ? red[l] : 0.0f;
+  return warp_sum(t);
+}
+
+__global__ void __launch_bounds__(kGateThreads) gate_blend_kernel(
+    const float* __restrict__ fused, const float* __restrict__ tok, const float* __restrict__ ln_w,
+    const float* __restrict__ ln_b, float ln_eps, const float* __restrict__ w_fold, const float* __restrict__ c_fold,
+    float* __restrict__ out, float* __restrict__ gate_out, int S, int H) {
+  __shared__ float red[kGateThreads / 32];
+  const int b = blockIdx.x;
+  const float* f = fused + (size_t)b * S * H;
+  const float* t = tok + (size_t)b * S * H;
+  float* o = out + (size_t)b * S * H;
+
+  float sum = 0.0f;
+  for (int k = threadIdx.x; k < H; k += kGateThreads) sum += f[k] + t[k];
+  const float mean = block_sum(sum, red) / (float)H;
+  float sq = 0.0f;
+  for (int k = threadIdx.x; k < H; k += kGateThreads) {
+    const float d = (f[k] + t[k]) - mean;
+    sq += d * d;
+  }
+  const float rstd = 1.0f / sqrtf(block_sum(sq, red) / (float)H + ln_eps);
+  float dot = 0.0f;
+  for (int k = threadIdx.x; k < H; k += kGateThreads) {
+    const float n = ((f[k] + t[k]) - mean) * rstd * ln_w[k] + ln_b[k];
+    dot = fmaf(n, w_fold[k], dot);
+  }
+  const float logit = block_sum(dot, red) + c_fold[0];
+  const float g = 1.0f / (1.0f + expf(-logit));
+  const float og = 1.0f - g;
+  if (threadIdx.x == 0 && gate_out) gate_out[b] = g;
+
+  const int nvec = S * H / 4;
+  const float4* f4 = reinterpret_cast<const float4*>(f);
+  const float4* t4 = reinterpret_cast<const float4*>(t);
+  float4* o4 = reinterpret_cast<float4*>(o);
+  for (int v = threadIdx.x; v < nvec; v += kGateThreads) {
+    const float4 a = __ldcs(t4 + v), c = __ldcs(f4 + v);
+    float4 r;
+    r.x = g * a.x + og * c.x;
+    r.y = g * a.y + og * c.y;
+    r.z = g * a.z + og * c.z;
+    r.w = g * a.w + og * c.w;
+    __stcs(o4 + v, r);
+  }
+}
+
+}  // namespace
+
+extern "C" int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y, int64_t n, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(n >= 0 && x && y, "cast: bad arguments");
+  ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(y, 16), "cast: pointers must be 16-byte aligned");
+  if (n == 0) return ICKA_OK;
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_region_rows(icka_handle* h, const float* grid, void* rows, int out_dtype, int B, int C, int R,
+                                void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && C >= 1 && R >= 1 && grid && rows, "region_rows: bad arguments");
+  ICKA_REQUIRE(C % 2 == 0, "region_rows: channel count %d must be even", C);
+  ICKA_REQUIRE(B <= 65535, "region_rows: B=%d exceeds the grid.y limit; shard the batch", B);
+  ICKA_REQUIRE(out_dtype == ICKA_F32 || out_dtype == ICKA_BF16, "region_rows: bad dtype %d", out_dtype);
+  if (B == 0) return ICKA_OK;
+  const size_t smem = (size_t)kRegC * (R | 1) * sizeof(float);
+  ICKA_REQUIRE(smem <= h->smem_optin, "region_rows: R=%d too large", R);
+  dim3 g((C + kRegC - 1) / kRegC, B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == ICKA_BF16) {
+    ICKA_CUDA(cudaFuncSetAttribute(region_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    region_rows_kernel<__nv_bfloat16><<<g, 256, smem, st>>>(grid, static_cast<__nv_bfloat16*>(rows), C, R);
+  } else {
+    ICKA_CUDA(cudaFuncSetAttribute(region_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    region_rows_kernel<float><<<g, 256, smem, st>>>(grid, static_cast<float*>(rows), C, R);
+  }
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_layernorm_fwd(icka_handle* h, const float* x, const float* gamma, const float* beta, float eps,
+                                  float* y_f32, void* y_bf16, int M, int N, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(M >= 0 && N >= 4 && x && gamma && beta, "layernorm: bad arguments");
+  ICKA_REQUIRE(N % 4 == 0 && N <= 128 * kMaxVec, "layernorm: N=%d must be a multiple of 4 and <= %d", N, 128 * kMaxVec);
+  ICKA_REQUIRE(y_f32 || y_bf16, "layernorm: no output");
+  ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(gamma, 16) && icka_aligned(beta, 16) &&
+                   icka_aligned(y_f32, 16) && icka_aligned(y_bf16, 8),
+               "layernorm: pointers must be 16-byte aligned");
+  if (M == 0) return ICKA_OK;
+  const int rows_per_block = 8;
+  layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, gamma, beta, eps, y_f32, static_cast<__nv_bfloat16*>(y_bf16), M, N);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_gate_fold(icka_handle* h, const float* Wp, const float* bp, const float* wa, const float* ba,
+                              float* w_fold, float* c_fold, int H, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(H >= 1 && Wp && bp && wa && ba && w_fold && c_fold, "gate_fold: bad arguments");
+  gate_fold_kernel<<<(H + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(Wp, bp, wa, ba, w_fold, c_fold, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_gate_blend_fwd(icka_handle* h, const float* fused, const float* tok, const float* ln_w,
+                                   const float* ln_b, float ln_eps, const float* w_fold, const float* c_fold,
+                                   float* out, float* gate_out, int B, int S, int H, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && H >= 1 && fused && tok && ln_w && ln_b && w_fold && c_fold && out,
+               "gate_blend: bad arguments");
+  ICKA_REQUIRE(((size_t)S * H) % 4 == 0, "gate_blend: S*H must be a multiple of 4");
+  ICKA_REQUIRE(icka_aligned(fused, 16) && icka_aligned(tok, 16) && icka_aligned(out, 16),
+               "gate_blend: pointers must be 16-byte aligned");
+  if (B == 0) return ICKA_OK;
+  gate_blend_kernel<<<B, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(fused, tok, ln_w, ln_b, ln_eps, w_fold,
+                                                                            c_fold, out, gate_out, S, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}

@@ -1,0 +1,283 @@
+// bf16 tensor-core path of icka_linear_fwd: a persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N])       A, W bf16 (K-major), fp32 accumulate
+//
+// This is the kernel behind every dense contraction of the fusion path (>99 % of its FLOPs):
+// region projection (CMIM:958), Q and K|V projections (CMIM:592-594), attention out-proj (CMIM:562),
+// FFN up + erf-GELU (CMIM:549-550) and FFN down (CMIM:533).  nn.Linear weights are [out, in] row-major,
+// i.e. already the K-major B operand; activations are [rows, in] row-major = K-major A.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2-D boxes {64 x 128} of A and {64 x BN} of W into a
+//              kStages-deep shared-memory ring, 128-byte swizzle, completion on "full" mbarriers
+//   warp 1     allocates TMEM, then one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per
+//              k-block; tcgen05.commit releases the smem slot ("empty") and, after the last k-block,
+//              publishes the accumulator ("tmem_full")
+//   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (lane = row), add bias, erf-GELU,
+//              add the fp32 residual, convert, store; then hand the accumulator back ("tmem_empty")
+// Two accumulators (2 x BN TMEM columns) let the epilogue of tile i overlap the mainloop of tile i+1.
+// Tiles are walked n-fastest so the CTAs that share an A row-block run together and A is read from
+// HBM once (weights are a few MB and stay in the 126 MB L2).
+// Ragged edges: TMA zero-fills out-of-bounds rows/columns (M, N and K tails), the epilogue masks
+// rows >= M and columns >= N.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  const float* bias;
+  const float* residual;   // [M, N] fp32 or null
+  void* out;
+  int64_t ldo;
+  int M, N, K;
+};
+
+template <int BN, int ACT, bool OUT_BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmArgs args) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const int M = args.M, N = args.N, K = args.K;
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+          tma_load_2d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            const uint64_t da = make_kmajor_sw128_desc(a_addr + k * (kUmmaK * 2));
+            const uint64_t db = make_kmajor_sw128_desc(b_addr + k * (kUmmaK * 2));
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);                 // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, 128 rows) =====================
+    const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBM + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      const float* res_row = args.residual ? args.residual + (size_t)row * N : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= N) break;                               // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {                   // 8 columns per group
+            const int n = n0 + g * 8;
+            if (n < N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = __uint_as_float(r[g * 8 + j]);
+                if (args.bias) x += __ldg(args.bias + n + j);
+                if (ACT == ICKA_ACT_GELU_ERF) x = gelu_erf(x);
+                v[j] = x;
+              }
+              if (res_row) {
+                const float4 r0 = *reinterpret_cast<const float4*>(res_row + n);
+                const float4 r1 = *reinterpret_cast<const float4*>(res_row + n + 4);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+              if (OUT_BF16) {
+                uint4 o;
+                o.x = pack_bf16x2(v[0], v[1]);
+                o.y = pack_bf16x2(v[2], v[3]);
+                o.z = pack_bf16x2(v[4], v[5]);
+                o.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)row * args.ldo + n) = o;
+              } else {
+                float* op = static_cast<float*>(args.out) + (size_t)row * args.ldo + n;
+                *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = {64 cols, box_rows}, 128-byte swizzle.
+int make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                   int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    ICKA_FAIL(ICKA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, box_rows);
+  return ICKA_OK;
+}
+
+template <int BN, int ACT, bool OUT_BF16>
+int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16>;
+  ICKA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+  const int m_tiles = (args.M + kBM - 1) / kBM, n_tiles = (args.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, args);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+}  // namespace
+
+int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                          const float* residual, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
+                          cudaStream_t st) {
+  ICKA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "linear(bf16): lda=%lld, ldw=%lld must be multiples of 8",
+               (long long)lda, (long long)ldw);
+  ICKA_REQUIRE(icka_aligned(A, 16) && icka_aligned(W, 16) && icka_aligned(out, 16),
+               "linear(bf16): A, W, out must be 16-byte aligned");
+  ICKA_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "linear(bf16): N=%d and ldo=%lld must be multiples of 8", N, (long long)ldo);
+  ICKA_REQUIRE(!residual || icka_aligned(residual, 16), "linear(bf16): residual must be 16-byte aligned");
+  ICKA_REQUIRE(h->smem_optin >= GemmCfg<256>::kSmemBytes, "linear(bf16): device offers too little shared memory");
+  const int BN = (N > 128) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(h, &tb, W, N, K, ldw, BN);
+  if (rc) return rc;
+  GemmArgs args{bias, residual, out, ldo, M, N, K};
+  const bool bf = out_dtype == ICKA_BF16;
+  const bool gelu = act == ICKA_ACT_GELU_ERF;
+#define ICKA_GEMM(BN_, ACT_, BF_) return launch_gemm<BN_, ACT_, BF_>(h, ta, tb, args, st)
+  if (BN == 256) {
+    if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false); }
+    else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true);     else ICKA_GEMM(256, ICKA_ACT_NONE, false); }
+  } else {
+    if (gelu) { if (bf) ICKA_GEMM(128, ICKA_ACT_GELU_ERF, true); else ICKA_GEMM(128, ICKA_ACT_GELU_ERF, false); }
+    else      { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true);     else ICKA_GEMM(128, ICKA_ACT_NONE, false); }
+  }
+#undef ICKA_GEMM
+}

@@ -1,0 +1,376 @@
+"""Drop-in mirrors of the reference's cross-modal modules, running on libicka_b200.so.
+
+Same class names, constructor arguments, ``forward`` signatures, parameter names (state_dict keys) and
+error behaviour as /root/reference/Cross_Modal_Interaction_Module.py ("CMIM"):
+
+    BertLayerNorm (509)  BertOutput (525)  BertIntermediate (539)  BertSelfOutput (554)
+    BertCoAttention (568)  BertCrossAttention (627)  BertCrossAttentionLayer (639)
+    BertCrossEncoder (653)  cls_layer_both (873)
+
+plus ``CrossModalFusion``: the hot-path slice of ``MTCCMBertForMMTokenClassificationCRF.forward``
+(CMIM:954-989, 1029-1036) under the reference's own attribute names (vismap2text, vismapping,
+txt2img_attention, cls_layer_Y, cls_layer, aux_head), so a reference checkpoint loads with
+``load_state_dict(..., strict=False)`` exactly as My_cross_attention.py:997-998 does.
+
+Parameters are ordinary fp32 ``nn.Parameter``s.  Arithmetic never runs in PyTorch: every forward is a
+sequence of C-ABI kernel launches (icka_b200.ops).  Two precision modes (``set_precision``):
+
+  'bf16'  bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate; the residual stream, LayerNorm
+          and softmax statistics stay fp32 (SURVEY 7.3 #3b) -- the fast path (max-abs 2e-2 gate)
+  'fp32'  everything fp32 on CUDA cores -- the parity path (max-rel 1e-5 gate)
+
+This round is forward-only: dropout must be inactive (eval mode or p = 0), like the reference's
+dev/test calls (My_cross_attention.py:872, 1047).
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ACT_GELU_ERF, ACT_NONE
+
+_PRECISION = 'bf16'
+
+
+def set_precision(mode: str) -> None:
+    global _PRECISION
+    if mode not in ('bf16', 'fp32'):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+def _cdt() -> torch.dtype:
+    return torch.bfloat16 if _PRECISION == 'bf16' else torch.float32
+
+
+class _OperandCache:
+    """Compute-dtype copies of fp32 parameters, refreshed when the parameter is modified in place."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key: str, params, build):
+        sig = (_PRECISION,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        hit = self._store.get(key)
+        if hit is None or hit[0] != sig:
+            with torch.no_grad():
+                hit = (sig, build())
+            self._store[key] = hit
+        return hit[1]
+
+
+def _operand(cache: _OperandCache, key: str, w: torch.Tensor) -> torch.Tensor:
+    if _PRECISION == 'fp32':
+        return w.detach()
+    return cache.get(key, (w,), lambda: ops.cast_bf16(w.detach().contiguous()))
+
+
+def _to_lp(x32: torch.Tensor) -> torch.Tensor:
+    return ops.cast_bf16(x32) if _PRECISION == 'bf16' else x32
+
+
+def _rows(x: torch.Tensor) -> torch.Tensor:
+    """[B, S, H] (any float dtype / strides) -> contiguous fp32 [B*S, H] view."""
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous().view(-1, x.shape[-1])
+
+
+def _mask2d(mask: Optional[torch.Tensor], B: int, Skv: int) -> Optional[torch.Tensor]:
+    """The reference passes an additive mask broadcastable as [B,1,1,Skv] (CMIM:962-965, 976-982)."""
+    if mask is None:
+        return None
+    if mask.numel() != B * Skv:
+        raise RuntimeError(f'attention mask of shape {tuple(mask.shape)} is not [B,1,1,Skv]=[{B},1,1,{Skv}]')
+    return mask.reshape(B, Skv).float().contiguous()
+
+
+def _check_inference(module: nn.Module, *ps: float) -> None:
+    if module.training and any(p > 0 for p in ps):
+        raise NotImplementedError('icka_b200 is forward-only in this round: call .eval() (dropout must be off)')
+
+
+class BertLayerNorm(nn.Module):
+    """CMIM:509-522."""
+
+    def __init__(self, hidden_size, eps=1e-12):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.bias = nn.Parameter(torch.zeros(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        shape = x.shape
+        y, _ = ops.layernorm(_rows(x), self.weight.detach(), self.bias.detach(), self.variance_epsilon)
+        return y.view(shape)
+
+
+class _DenseResidualNorm(nn.Module):
+    """Shared body of BertSelfOutput (CMIM:554-565) and BertOutput (CMIM:525-536)."""
+
+    def __init__(self, in_features, config):
+        super().__init__()
+        self.dense = nn.Linear(in_features, config.hidden_size)
+        self.LayerNorm = BertLayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self._cache = _OperandCache()
+
+    def _run(self, h_lp: torch.Tensor, res32: torch.Tensor):
+        w = _operand(self._cache, 'w', self.dense.weight)
+        pre = ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32)
+        return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
+                             self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=_PRECISION == 'bf16')
+
+    def forward(self, hidden_states, input_tensor):
+        _check_inference(self, self.dropout.p)
+        shape = input_tensor.shape
+        y32, _ = self._run(_to_lp(_rows(hidden_states)), _rows(input_tensor))
+        return y32.view(shape)
+
+
+class BertSelfOutput(_DenseResidualNorm):
+    def __init__(self, config):
+        super().__init__(config.hidden_size, config)
+
+
+class BertOutput(_DenseResidualNorm):
+    def __init__(self, config):
+        super().__init__(config.intermediate_size, config)
+
+
+class BertIntermediate(nn.Module):
+    """CMIM:539-551; only the reference's default activation 'gelu' (erf form, CMIM:31-37) is built."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        if config.hidden_act != 'gelu':
+            raise NotImplementedError(f"hidden_act={config.hidden_act!r}: only 'gelu' (erf) is implemented")
+        self._cache = _OperandCache()
+
+    def _run(self, x_lp: torch.Tensor) -> torch.Tensor:
+        w = _operand(self._cache, 'w', self.dense.weight)
+        return ops.linear(x_lp, w, self.dense.bias.detach(), act=ACT_GELU_ERF, out_dtype=_cdt())
+
+    def forward(self, hidden_states):
+        shape = hidden_states.shape[:-1]
+        return self._run(_to_lp(_rows(hidden_states))).float().view(*shape, -1)
+
+
+class BertCoAttention(nn.Module):
+    """CMIM:568-624."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.hidden_size % config.num_attention_heads != 0:
+            raise ValueError(
+                "The hidden size (%d) is not a multiple of the number of attention "
+                "heads (%d)" % (config.hidden_size, config.num_attention_heads))
+        self.num_attention_heads = config.num_attention_heads
+        self.attention_head_size = int(config.hidden_size / config.num_attention_heads)
+        self.all_head_size = self.num_attention_heads * self.attention_head_size
+        self.query = nn.Linear(config.hidden_size, self.all_head_size)
+        self.key = nn.Linear(config.hidden_size, self.all_head_size)
+        self.value = nn.Linear(config.hidden_size, self.all_head_size)
+        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+        self._cache = _OperandCache()
+
+    def _kv_operands(self):
+        """One [K|V] projection: weights [2H, H] in the compute dtype, bias [2H] fp32."""
+        ps = (self.key.weight, self.value.weight, self.key.bias, self.value.bias)
+
+        def build():
+            w = torch.cat([self.key.weight.detach(), self.value.weight.detach()], dim=0).contiguous()
+            b = torch.cat([self.key.bias.detach(), self.value.bias.detach()], dim=0).contiguous()
+            return (ops.cast_bf16(w) if _PRECISION == 'bf16' else w), b
+
+        return self._cache.get('kv', ps, build)
+
+    def _run(self, x_lp, y_lp, mask2d, B, Sq, Skv):
+        H = self.all_head_size
+        wq = _operand(self._cache, 'q', self.query.weight)
+        wkv, bkv = self._kv_operands()
+        q = ops.linear(x_lp, wq, self.query.bias.detach(), out_dtype=_cdt())
+        kv = ops.linear(y_lp, wkv, bkv, out_dtype=_cdt())
+        return ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask2d, B, Sq, Skv, self.num_attention_heads,
+                                   self.attention_head_size)
+
+    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask):
+        _check_inference(self, self.dropout.p)
+        B, Sq, H = s1_hidden_states.shape
+        Skv = s2_hidden_states.shape[1]
+        ctx = self._run(_to_lp(_rows(s1_hidden_states)), _to_lp(_rows(s2_hidden_states)),
+                        _mask2d(s2_attention_mask, B, Skv), B, Sq, Skv)
+        return ctx.float().view(B, Sq, H)
+
+
+class BertCrossAttention(nn.Module):
+    """CMIM:627-636."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.self = BertCoAttention(config)
+        self.output = BertSelfOutput(config)
+
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv):
+        ctx = self.self._run(x_lp, y_lp, mask2d, B, Sq, Skv)
+        return self.output._run(ctx, x32)
+
+    def forward(self, s1_input_tensor, s2_input_tensor, s2_attention_mask):
+        _check_inference(self, self.self.dropout.p, self.output.dropout.p)
+        B, Sq, H = s1_input_tensor.shape
+        Skv = s2_input_tensor.shape[1]
+        x32 = _rows(s1_input_tensor)
+        y32, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_input_tensor)), _mask2d(s2_attention_mask, B, Skv),
+                           B, Sq, Skv)
+        return y32.view(B, Sq, H)
+
+
+class BertCrossAttentionLayer(nn.Module):
+    """CMIM:639-650: attention block, then FFN block."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.attention = BertCrossAttention(config)
+        self.intermediate = BertIntermediate(config)
+        self.output = BertOutput(config)
+
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv):
+        a32, a_lp = self.attention._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
+        f = self.intermediate._run(a_lp if a_lp is not None else a32)
+        o32, o_lp = self.output._run(f, a32)
+        return o32, (o_lp if o_lp is not None else o32)
+
+    def _dropouts(self):
+        return (self.attention.self.dropout.p, self.attention.output.dropout.p, self.output.dropout.p)
+
+    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask):
+        _check_inference(self, *self._dropouts())
+        B, Sq, H = s1_hidden_states.shape
+        Skv = s2_hidden_states.shape[1]
+        x32 = _rows(s1_hidden_states)
+        o32, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_hidden_states)), _mask2d(s2_attention_mask, B, Skv),
+                           B, Sq, Skv)
+        return o32.view(B, Sq, H)
+
+
+class BertCrossEncoder(nn.Module):
+    """CMIM:653-667.  All layers start as deep copies of one layer, as in the reference (656-657)."""
+
+    def __init__(self, config, layer_num):
+        super().__init__()
+        layer = BertCrossAttentionLayer(config)
+        self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(layer_num)])
+
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True):
+        outs = []
+        for layer_module in self.layer:
+            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
+            if keep_all:
+                outs.append(x32)
+        if not keep_all:
+            outs.append(x32)
+        return outs, x_lp
+
+    def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask, output_all_encoded_layers=True):
+        for l in self.layer:
+            _check_inference(l, *l._dropouts())
+        B, Sq, H = s1_hidden_states.shape
+        Skv = s2_hidden_states.shape[1]
+        x32 = _rows(s1_hidden_states)
+        outs, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_hidden_states)), _mask2d(s2_attention_mask, B, Skv),
+                            B, Sq, Skv, keep_all=output_all_encoded_layers)
+        return [o.view(B, Sq, H) for o in outs]
+
+
+class cls_layer_both(nn.Module):  # noqa: N801  (reference class name, CMIM:873)
+    """CMIM:873-884; ``proj_norm`` and ``LayerNorm`` are the same module under two names (876)."""
+
+    def __init__(self, input_dim, output_dim):
+        super().__init__()
+        self.proj_norm = self.LayerNorm = nn.LayerNorm(input_dim)
+        self.proj = nn.Linear(input_dim, output_dim)
+
+    def forward(self, lang_feat, img_feat):
+        saved = get_precision()
+        set_precision('fp32')          # a [B, H] x [H, H] product: run it on the fp32 kernel
+        try:
+            x = (lang_feat + img_feat).float().contiguous()
+            n, _ = ops.layernorm(x, self.proj_norm.weight.detach(), self.proj_norm.bias.detach(), self.proj_norm.eps)
+            return ops.linear(n, self.proj.weight.detach(), self.proj.bias.detach())
+        finally:
+            set_precision(saved)
+
+
+class CrossModalFusion(nn.Module):
+    """Hot-path slice of MTCCMBertForMMTokenClassificationCRF (CMIM:887-1057).
+
+    Constructor mirrors the reference's use of ``config`` and ``layer_num1`` (CMIM:888-901, 933-934);
+    ``num_i2t_encoders`` is 2 in the live model and 5 in the ``_bert`` clone (CMIM:1075).
+    """
+
+    def __init__(self, config, layer_num1=1, region_dim=2048, clip_dim=512, num_i2t_encoders=2):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.vismap2text = nn.Linear(region_dim, config.hidden_size)                 # CMIM:897
+        self.vismapping = nn.Linear(clip_dim, config.hidden_size)                    # CMIM:899
+        self.txt2img_attention = BertCrossEncoder(config, layer_num1)                # CMIM:900
+        self.cls_layer_Y = nn.ModuleList([BertCrossEncoder(config, layer_num1)       # CMIM:901
+                                          for _ in range(num_i2t_encoders)])
+        self.cls_layer = cls_layer_both(config.hidden_size, config.hidden_size)      # CMIM:933
+        self.aux_head = nn.Linear(config.hidden_size, 1)                             # CMIM:934
+        self._cache = _OperandCache()
+
+    def forward(self, sequence_output, visual_embeds_att, clip_features, token_embedding, added_attention_mask,
+                ori_input_mask, return_dict=False):
+        """sequence_output [B,S,H] (CMIM:953), visual_embeds_att [B,2048,g,g], clip_features [B,1,512],
+        token_embedding [B,S,H] (CMIM:1024), added_attention_mask [B,>=R], ori_input_mask [B,S].
+        Returns (result [B,S,H], clip_features [B,1,H]) -- CMIM:1036 and the loop result of CMIM:984-989."""
+        for enc in (self.txt2img_attention, *self.cls_layer_Y):
+            for l in enc.layer:
+                _check_inference(l, *l._dropouts())
+        B, S, H = sequence_output.shape
+        grid = visual_embeds_att.float().contiguous()
+        R = grid.numel() // (B * grid.shape[1])
+
+        # region projection, CMIM:956-958
+        rows = ops.region_rows(grid, _cdt())
+        regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
+                                self.vismap2text.bias.detach(), out_dtype=_cdt())
+        # masks, CMIM:962-965 and 976-982
+        img_mask = (1.0 - added_attention_mask[:, :R].float()) * -10000.0
+        txt_mask = (1.0 - ori_input_mask.float()) * -10000.0
+
+        # text -> image, CMIM:968-969
+        x32 = _rows(sequence_output)
+        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask.contiguous(), B, S, R,
+                                                     keep_all=False)
+        fused32 = outs[-1]
+
+        # image -> text, CMIM:954, 981-989 (single CLIP token as the query)
+        clip_in = _to_lp(clip_features.float().reshape(B, -1).contiguous())
+        z32 = ops.linear(clip_in, _operand(self._cache, 'vmap', self.vismapping.weight), self.vismapping.bias.detach(),
+                         out_dtype=torch.float32)
+        z_lp = _to_lp(z32)
+        for enc in self.cls_layer_Y:
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask.contiguous(), B, 1, S, keep_all=False)
+            z32 = zs[-1]
+
+        # gated fusion, CMIM:1029-1036
+        w_fold, c_fold = ops.gate_fold(self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+                                       self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach())
+        ln = self.cls_layer.proj_norm
+        result, gate = ops.gate_blend(fused32.view(B, S, H), _rows(token_embedding).view(B, S, H), ln.weight.detach(),
+                                      ln.bias.detach(), ln.eps, w_fold, c_fold)
+        if return_dict:
+            return dict(regions=regions_lp.view(B, R, H), fused=fused32.view(B, S, H), clip=z32.view(B, 1, H),
+                        result=result, gate=gate)
+        return result, z32.view(B, 1, H)

@@ -1,0 +1,120 @@
+/* icka_b200.h -- C ABI of libicka_b200.so: the B200 (sm_100a) drop-in for ICKA's cross-modal
+ * fusion + CRF hot path.
+ *
+ * The reference (buctcurry/ICKA) is pure Python/PyTorch and has no FFI of its own: the boundary it
+ * exposes for this path is nn.Module composition inside Cross_Modal_Interaction_Module.py ("CMIM").
+ * Each entry point below replaces the ATen call chain of the cited reference statement(s); the Python
+ * mirror of the reference modules (icka_b200/modules.py, icka_b200/crf.py) binds them with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; every pointer is a DEVICE pointer on the handle's
+ *     device unless stated otherwise; tensors are dense row-major.
+ *   - return 0 on success, <0 on error; icka_last_error() returns a thread-local message.
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *     no entry point synchronises with the host or allocates device memory.
+ *   - re-entrant: one handle per device; no global mutable state (CMIM is driven by one thread per GPU
+ *     under nn.DataParallel, My_cross_attention.py:777-779).
+ *   - there is NO CPU fallback: every entry point fails if the device is not sm_100.
+ */
+#ifndef ICKA_B200_H_
+#define ICKA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct icka_handle icka_handle;
+
+enum icka_status {
+  ICKA_OK = 0,
+  ICKA_ERR_INVALID = -1,      /* bad argument (shape, alignment, dtype) */
+  ICKA_ERR_CUDA = -2,         /* a CUDA runtime/driver call failed       */
+  ICKA_ERR_UNSUPPORTED = -3   /* device is not sm_100 / shape outside the kernels' envelope */
+};
+
+enum icka_dtype { ICKA_F32 = 0, ICKA_BF16 = 1 };
+enum icka_act { ICKA_ACT_NONE = 0, ICKA_ACT_GELU_ERF = 1 };  /* CMIM:31-37 */
+
+int icka_version(void);
+const char* icka_last_error(void);
+int icka_create(int device, icka_handle** out);
+int icka_destroy(icka_handle* h);
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t icka_launch_count(const icka_handle* h);
+
+/* ---- ingest ---------------------------------------------------------------------------------- */
+
+/* fp32 -> bf16 copy of a GEMM operand (the residual stream itself stays fp32). */
+int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y_bf16, int64_t n, void* stream);
+
+/* CMIM:956  `visual_embeds_att.view(-1, 2048, 49).permute(0, 2, 1)`:
+ * grid [B, C, R] fp32 (R contiguous) -> rows [B*R, C] in `out_dtype` (C contiguous, the K-major GEMM
+ * operand the region projection wants). */
+int icka_region_rows(icka_handle* h, const float* grid, void* rows, int out_dtype,
+                     int B, int C, int R, void* stream);
+
+/* ---- dense layers ---------------------------------------------------------------------------- */
+
+/* nn.Linear with fused epilogue:  out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N]).
+ * Replaces CMIM:958 (vismap2text), :954 (vismapping), :592-594 (query/key/value), :562 (+ the `+ input`
+ * of :564 via `residual`), :549-550 (dense + erf-GELU), :533 (+ :535 residual).
+ *   in_dtype  ICKA_BF16: A and W are bf16 -> tcgen05/TMEM tensor-core kernel fed by TMA, fp32 accumulate.
+ *             ICKA_F32 : A and W are fp32 -> CUDA-core FFMA kernel (the 1e-5 parity path).
+ *   bias fp32 (may be NULL); residual fp32 [M,N] (may be NULL); out_dtype ICKA_F32 or ICKA_BF16.
+ *   lda / ldw / ldo are row pitches in ELEMENTS (lda >= K, ldw >= K, ldo >= N); residual has pitch N.
+ *   bf16 path needs 16-byte aligned pointers and lda, ldw multiples of 8. */
+int icka_linear_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
+                    const float* bias, const float* residual, void* out, int64_t ldo,
+                    int in_dtype, int out_dtype, int M, int N, int K, int act, void* stream);
+
+/* BertLayerNorm CMIM:518-522 (TF style: biased variance, eps inside the sqrt) over rows of x[M,N]
+ * (x already holds dense(...) + input).  Writes y_f32 and/or y_bf16 (either may be NULL). */
+int icka_layernorm_fwd(icka_handle* h, const float* x, const float* gamma, const float* beta, float eps,
+                       float* y_f32, void* y_bf16, int M, int N, void* stream);
+
+/* ---- attention core -------------------------------------------------------------------------- */
+
+/* BertCoAttention CMIM:598-623 after the three projections: per sentence b and head h
+ *   P = softmax( Q_h K_h^T / sqrt(d) + mask_add[b] ),  ctx_h = P V_h,  heads merged in place.
+ * q [B*Sq, >=nh*d] (pitch ldq), k/v [B*Skv, ...] (pitch ldkv; k and v may alias one [K|V] buffer),
+ * mask_add [B, Skv] fp32 additive (0 / -10000, CMIM:965, :977) or NULL, ctx [B*Sq, nh*d] (pitch ldc).
+ * `dtype` applies to q, k, v and ctx.  d must be 64. */
+int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                             int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
+                             int B, int Sq, int Skv, int nh, int d, void* stream);
+
+/* ---- gated fusion ---------------------------------------------------------------------------- */
+
+/* Folds cls_layer_both.proj (CMIM:877, :882) and aux_head (CMIM:934, :1034) into one H-vector:
+ *   w_fold = Wp^T wa,  c_fold = wa . bp + ba   so that  logit = w_fold . LN(feat) + c_fold. */
+int icka_gate_fold(icka_handle* h, const float* Wp, const float* bp, const float* wa, const float* ba,
+                   float* w_fold, float* c_fold, int H, void* stream);
+
+/* CMIM:1029-1036: feat = LN_{eps}(fused[:,0] + tok[:,0]); g = sigmoid(w_fold.feat + c_fold);
+ * out = g*tok + (1-g)*fused.  fused/tok/out [B,S,H] fp32, gate_out [B] fp32 (may be NULL). */
+int icka_gate_blend_fwd(icka_handle* h, const float* fused, const float* tok, const float* ln_w,
+                        const float* ln_b, float ln_eps, const float* w_fold, const float* c_fold,
+                        float* out, float* gate_out, int B, int S, int H, void* stream);
+
+/* ---- CRF ------------------------------------------------------------------------------------- */
+
+/* torchcrf.CRF.decode (call sites CMIM:1051, :1056): Viterbi best path per sentence.
+ * emissions [B,S,T] fp32, mask [B,S] u8 (NULL = all on), start/end [T], trans [T,T] (from i to j),
+ * tags_out [B,S] i32 (positions >= len hold -1), lens_out [B] i32.  T <= 32.  Bit-exact with the
+ * reference's fp32 op order ((score+trans)+emission, first index wins ties).  Inputs must be NaN-free. */
+int icka_viterbi_decode(icka_handle* h, const float* emissions, const uint8_t* mask, const float* start,
+                        const float* end, const float* trans, int32_t* tags_out, int32_t* lens_out,
+                        int B, int S, int T, void* stream);
+
+/* torchcrf.CRF.forward with reduction='none' (call sites CMIM:1047-1048, :1052-1053): per-sentence
+ * log-likelihood  llh[b] = score(gold path) - log Z.  tags [B,S] i64. */
+int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const int64_t* tags, const uint8_t* mask,
+                     const float* start, const float* end, const float* trans, float* llh_out,
+                     int B, int S, int T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICKA_B200_H_ */

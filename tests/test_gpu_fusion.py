@@ -1,0 +1,113 @@
+"""GPU parity of the full fusion segment (region proj -> t2i -> i2t -> gate) through the drop-in modules.
+
+Gates (BASELINE.json north_star / SURVEY 8d):
+  fp32 path: max |a-b| / max(|b|, 1) <= 1e-5 on every post-LayerNorm tensor
+  bf16 path: max |a-b| <= 2e-2 on post-LayerNorm activations (vs the fp32 oracle)
+Checked against oracle/fusion_ref.py on the same seeded inputs AND against the committed golden vectors
+(outputs of the reference's own classes, oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import icka_b200
+from oracle import fusion_ref
+from oracle.make_golden import CASES, build_case
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def rel(a, b):
+    return float(((a - b).abs() / b.abs().clamp(min=1.0)).max())
+
+
+def run_ours(name, precision):
+    B, shape, params, inp, stride = build_case(name)
+    cfg = icka_b200.FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads,
+                                 intermediate_size=shape.inter, layer_norm_eps=shape.eps)
+    model = icka_b200.CrossModalFusion(cfg, layer_num1=shape.L, region_dim=shape.region_dim,
+                                       clip_dim=shape.clip_dim).to(DEV).eval()
+    model.load_state_dict(params, strict=True)
+    icka_b200.set_precision(precision)
+    try:
+        with torch.no_grad():
+            out = model(inp['text_states'].to(DEV), inp['visual_embeds_att'].to(DEV), inp['clip_features'].to(DEV),
+                        inp['token_embedding'].to(DEV), inp['img_mask'].to(DEV), inp['text_mask'].to(DEV),
+                        return_dict=True)
+        torch.cuda.synchronize()
+    finally:
+        icka_b200.set_precision('bf16')
+    out = {k: v.float().cpu() for k, v in out.items()}
+    return B, shape, params, inp, stride, out
+
+
+def oracle(shape, params, inp):
+    return fusion_ref.fusion_segment(inp['text_states'], inp['visual_embeds_att'], inp['clip_features'],
+                                     inp['token_embedding'], inp['img_mask'], inp['text_mask'], params,
+                                     num_layers=shape.L, num_heads=shape.heads, layer_norm_eps=shape.eps)
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_fusion_fp32_parity(name):
+    B, shape, params, inp, stride, out = run_ours(name, 'fp32')
+    want = oracle(shape, params, inp)
+    for k in ('regions', 'fused', 'clip', 'result', 'gate'):
+        assert rel(out[k].reshape(want[k].shape), want[k]) <= 1e-5, k
+    g = np.load(os.path.join(GOLDEN, f'fusion_{name}.npz'))
+    assert rel(out['fused'][:, ::stride], torch.from_numpy(g['fused'])) <= 1e-5
+    assert rel(out['result'][:, ::stride], torch.from_numpy(g['result'])) <= 1e-5
+    assert rel(out['clip'], torch.from_numpy(g['clip'])) <= 1e-5
+    assert rel(out['gate'], torch.from_numpy(g['gate'])) <= 1e-5
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_fusion_bf16_parity(name):
+    B, shape, params, inp, stride, out = run_ours(name, 'bf16')
+    g = np.load(os.path.join(GOLDEN, f'fusion_{name}.npz'))
+    for k, ref in (('fused', g['fused']), ('result', g['result'])):
+        err = float((out[k][:, ::stride] - torch.from_numpy(ref)).abs().max())
+        assert err <= 2e-2, (k, err)
+    assert float((out['clip'] - torch.from_numpy(g['clip'])).abs().max()) <= 2e-2
+    assert float((out['gate'] - torch.from_numpy(g['gate'])).abs().max()) <= 2e-2
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('bf16', 2e-2)])
+def test_cross_encoder_dropin_signature(precision, tol):
+    """BertCrossEncoder(config, layer_num).forward(s1, s2, mask[B,1,1,R]) -> list of per-layer outputs (CMIM:659-667)."""
+    B, shape, params, inp, stride = build_case('std_L2_eps5')
+    cfg = icka_b200.FusionConfig(layer_norm_eps=shape.eps)
+    enc = icka_b200.BertCrossEncoder(cfg, shape.L).to(DEV).eval()
+    sub = {k[len('txt2img_attention.'):]: v for k, v in params.items() if k.startswith('txt2img_attention.')}
+    enc.load_state_dict(sub, strict=True)
+    g = torch.Generator().manual_seed(5)
+    s2 = torch.randn(B, shape.R, shape.H, generator=g)
+    m01 = (torch.rand(B, shape.R, generator=g) > 0.3).long()
+    ext = fusion_ref.additive_mask(m01, torch.float32)
+    want = fusion_ref.cross_encoder(inp['text_states'], s2, ext, params, 'txt2img_attention', shape.L, shape.heads, shape.eps)
+    icka_b200.set_precision(precision)
+    try:
+        with torch.no_grad():
+            got = enc(inp['text_states'].to(DEV), s2.to(DEV), ext.to(DEV))
+            last_only = enc(inp['text_states'].to(DEV), s2.to(DEV), ext.to(DEV), output_all_encoded_layers=False)
+    finally:
+        icka_b200.set_precision('bf16')
+    assert isinstance(got, list) and len(got) == shape.L and len(last_only) == 1
+    for a, b in zip(got, want):
+        err = rel(a.cpu(), b) if precision == 'fp32' else float((a.cpu() - b).abs().max())
+        assert err <= tol, err
+    assert torch.equal(last_only[0], got[-1])
+
+
+def test_weight_update_refreshes_operand_cache():
+    cfg = icka_b200.FusionConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256)
+    enc = icka_b200.BertCrossEncoder(cfg, 1).to(DEV).eval()
+    x, y = torch.randn(2, 8, 128, device=DEV), torch.randn(2, 5, 128, device=DEV)
+    m = torch.zeros(2, 1, 1, 5, device=DEV)
+    with torch.no_grad():
+        a = enc(x, y, m)[-1].clone()
+        enc.layer[0].output.dense.weight.mul_(0.5)
+        b = enc(x, y, m)[-1]
+    assert (a - b).abs().max() > 1e-3

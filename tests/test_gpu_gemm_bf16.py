@@ -1,0 +1,58 @@
+"""GPU parity of the tcgen05 bf16 GEMM (icka_linear_fwd, in_dtype=bf16) vs torch fp32 matmul on the same
+bf16-rounded operands.  fp32 accumulation => errors are at the fp32 reassociation level for fp32 outputs
+and half a bf16 ulp for bf16 outputs."""
+import math
+
+import pytest
+import torch
+
+from icka_b200 import ops
+from icka_b200._lib import ACT_GELU_ERF, ACT_NONE
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def gelu(x):
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+SHAPES = [(128, 256, 64), (128, 256, 16), (128, 128, 64), (128, 256, 768), (256, 768, 768), (49 * 5, 768, 2048),
+          (1024, 3072, 768), (1000, 768, 3072), (7, 768, 512), (130, 1536, 768), (300, 136, 40), (128 * 40, 768, 768)]
+
+
+@pytest.mark.parametrize('M,N,K', SHAPES)
+def test_linear_bf16_fp32_out(M, N, K):
+    a = rnd(M, K, seed=1).bfloat16()
+    w = (rnd(N, K, seed=2) / math.sqrt(K)).bfloat16()
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
+    got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), out_dtype=torch.float32).cpu()
+    want = a.double() @ w.double().t() + bias.double() + res.double()
+    err = float((got.double() - want).abs().max())
+    assert err <= 2e-5, err
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 3072, 768), (77, 256, 128), (128, 768, 768)])
+def test_linear_bf16_gelu_bf16_out(M, N, K):
+    a = rnd(M, K, seed=5).bfloat16()
+    w = (rnd(N, K, seed=6) / math.sqrt(K)).bfloat16()
+    bias = rnd(N, seed=7)
+    got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), act=ACT_GELU_ERF, out_dtype=torch.bfloat16).cpu()
+    want = gelu(a.double() @ w.double().t() + bias.double())
+    err = float(((got.double() - want).abs() / want.abs().clamp(min=1.0)).max())
+    assert err <= 2 ** -8, err
+
+
+def test_linear_bf16_pitched_kv_views():
+    """Consumers read K and V as column halves of one [K|V] buffer; A may be a pitched view too."""
+    M, H = 200, 768
+    a_full = rnd(M, 2 * H, seed=8).bfloat16().to(DEV)
+    w = (rnd(H, H, seed=9) / math.sqrt(H)).bfloat16().to(DEV)
+    got = ops.linear(a_full[:, H:], w, None, out_dtype=torch.float32).cpu()
+    want = a_full[:, H:].cpu().double() @ w.cpu().double().t()
+    assert float((got.double() - want).abs().max()) <= 2e-5

@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference interface: names, state_dict keys, error behaviour (no GPU needed)."""
+import pytest
+import torch
+
+import icka_b200
+from oracle import fusion_ref
+
+# state_dict keys of the reference's BertCrossEncoder(config, 1) (verified against the reference class in
+# tests/test_oracle_fusion.py::test_reference_state_dict_keys)
+LAYER_KEYS = [
+    'attention.self.query.weight', 'attention.self.query.bias', 'attention.self.key.weight',
+    'attention.self.key.bias', 'attention.self.value.weight', 'attention.self.value.bias',
+    'attention.output.dense.weight', 'attention.output.dense.bias', 'attention.output.LayerNorm.weight',
+    'attention.output.LayerNorm.bias', 'intermediate.dense.weight', 'intermediate.dense.bias',
+    'output.dense.weight', 'output.dense.bias', 'output.LayerNorm.weight', 'output.LayerNorm.bias']
+
+
+def cfg(**kw):
+    return icka_b200.FusionConfig(hidden_size=128, num_attention_heads=2, intermediate_size=256, **kw)
+
+
+def test_cross_encoder_state_dict_keys():
+    enc = icka_b200.BertCrossEncoder(cfg(), 2)
+    assert sorted(enc.state_dict()) == sorted(f'layer.{i}.{k}' for i in range(2) for k in LAYER_KEYS)
+    assert sum(p.numel() for p in icka_b200.BertCrossEncoder(icka_b200.FusionConfig(), 1).parameters()) == 7087872
+
+
+def test_layers_start_identical_like_the_reference():
+    enc = icka_b200.BertCrossEncoder(cfg(), 3)
+    sd = enc.state_dict()
+    assert torch.equal(sd['layer.0.output.dense.weight'], sd['layer.2.output.dense.weight'])
+
+
+def test_fusion_loads_oracle_params_and_aliases_layernorm():
+    m = icka_b200.CrossModalFusion(cfg(), layer_num1=2, region_dim=64, clip_dim=32)
+    p = fusion_ref.make_params(128, 2, 256, 2, region_dim=64, clip_dim=32)
+    res = m.load_state_dict(p, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert m.cls_layer.proj_norm is m.cls_layer.LayerNorm                     # CMIM:876
+    assert {'cls_layer.proj_norm.weight', 'cls_layer.LayerNorm.weight'} <= set(m.state_dict())
+    n = sum(p.numel() for p in icka_b200.CrossModalFusion(icka_b200.FusionConfig(), 1).parameters())
+    assert n == 1573632 + 393984 + 3 * 7087872 + 592128 + 769                 # SURVEY 8e, minus the CRF's 255
+
+
+def test_hidden_size_not_multiple_of_heads():
+    with pytest.raises(ValueError, match='not a multiple of the number of attention'):
+        icka_b200.BertCoAttention(icka_b200.FusionConfig(hidden_size=100, num_attention_heads=12))
+
+
+def test_training_mode_is_refused():
+    enc = icka_b200.BertCrossEncoder(cfg(), 1).train()
+    with pytest.raises(NotImplementedError):
+        enc(torch.zeros(1, 4, 128), torch.zeros(1, 3, 128), torch.zeros(1, 1, 1, 3))
+
+
+def test_precision_switch():
+    icka_b200.set_precision('fp32')
+    assert icka_b200.get_precision() == 'fp32'
+    icka_b200.set_precision('bf16')
+    with pytest.raises(ValueError):
+        icka_b200.set_precision('fp8')
+
+
+def test_crf_constructor_and_validation():
+    with pytest.raises(ValueError, match='invalid number of tags'):
+        icka_b200.CRF(0)
+    crf = icka_b200.CRF(4, batch_first=True)
+    assert sorted(crf.state_dict()) == ['end_transitions', 'start_transitions', 'transitions']
+    assert crf.transitions.abs().max() <= 0.1
+    e = torch.zeros(2, 3, 4)
+    with pytest.raises(ValueError, match='dimension of 3'):
+        crf.decode(torch.zeros(2, 3))
+    with pytest.raises(ValueError, match='expected last dimension'):
+        crf.decode(torch.zeros(2, 3, 5))
+    with pytest.raises(ValueError, match='emissions and mask must match'):
+        crf.decode(e, mask=torch.ones(3, 3, dtype=torch.bool))
+    m = torch.ones(2, 3, dtype=torch.bool); m[1, 0] = False
+    with pytest.raises(ValueError, match='first timestep'):
+        crf.decode(e, mask=m)
+    with pytest.raises(ValueError, match='emissions and tags must match'):
+        crf(e, torch.zeros(2, 4, dtype=torch.long))
+    with pytest.raises(ValueError, match='invalid reduction'):
+        crf(e, torch.zeros(2, 3, dtype=torch.long), reduction='bogus')
