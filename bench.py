@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- sentences/s of the ICKA fusion + Viterbi hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W                  (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W (reference arm: CPU oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic sentences per GPU: region relayout +
+projection, text->image cross encoder, image->text cross encoders, gated fusion, and CRF Viterbi decode
+of that batch's emission scores.  Workload = BASELINE.json configs[2] (Twitter-2017-shaped inference
+sweep, batch-sharded, no communication): --batch sentences per GPU (default 1024, inside the 256-4096
+sweep), S=128, R=49, H=768, 12 heads, I=3072, T=15, --layers cross layers per encoder (default 1 = the
+reference constructor default, CMIM:888).
+
+`value`  : whole-job sentences/s with the inputs already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : same metric through FusionViterbiPipeline.infer_host: pinned HOST inputs -> H2D -> kernels ->
+           D2H of tags/lengths/gates, all inside the timed region.
+`roofline`: the dominant kernel (tcgen05 bf16 GEMM): algorithmic 2*M*N*K FLOPs per launch / mean launch
+           duration from CUDA events on the launch stream, against MEASURED_PEAKS.json (sustained bf16).
+`cpu_baseline`: the oracle port (torch-CPU restatement of the reference modules + C Viterbi) timed on this
+           box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'sentences/sec fusion+Viterbi'
+UNIT = 'sentences/s'
+FALLBACK_PEAKS = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='icka', choices=['icka', 'reference'])
+    ap.add_argument('--batch', type=int, default=1024, help='sentences per GPU per step')
+    ap.add_argument('--layers', type=int, default=1, help='cross layers per encoder (layer_num1)')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--hires', action='store_true', help='S=256, R=196 variant (BASELINE configs[3])')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='sentences in the CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        d['_source'] = 'measured (MEASURED_PEAKS.json)'
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d['_source'] = 'fallback (B200_PROFILING.md)'
+    return d
+
+
+def workload_name(args, shape):
+    return (f'twitter2017_inference_B{args.batch}_per_gpu_S{shape.S}_R{shape.R}_H{shape.H}_nh{shape.heads}'
+            f'_I{shape.inter}_T{shape.T}_L{shape.L}')
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the only place bench.py executes oracle/
+# --------------------------------------------------------------------------------------------------
+class CpuBaseline:
+    """The reference's modules restated on torch-CPU (oracle/fusion_ref.py; the reference itself is Python
+    and /root/reference does not exist on the GPU box) + the C restatement of pytorch-crf's Viterbi."""
+
+    def __init__(self, shape, sample, seed):
+        import torch
+        from icka_b200 import synth
+        from oracle import fusion_ref, viterbi_c
+        self.torch, self.fusion_ref, self.viterbi_c = torch, fusion_ref, viterbi_c
+        self.shape, self.sample = shape, sample
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.params = fusion_ref.make_params(shape.H, shape.heads, shape.inter, shape.L, seed=seed,
+                                             distinct_layers=True, perturb_ln=False)
+        self.inp = synth.fusion_inputs(sample, shape, seed=seed)
+        self.crf = synth.crf_batch(sample, shape, seed=seed)
+        self.cp = synth.crf_params(shape.T, seed)
+        viterbi_c.lib()
+
+    def step(self):
+        torch, sh = self.torch, self.shape
+        with torch.no_grad():
+            self.fusion_ref.fusion_segment(
+                self.inp['text_states'], self.inp['visual_embeds_att'], self.inp['clip_features'],
+                self.inp['token_embedding'], self.inp['img_mask'], self.inp['text_mask'], self.params,
+                num_layers=sh.L, num_heads=sh.heads, layer_norm_eps=sh.eps)
+        self.viterbi_c.viterbi(self.crf['emissions'].numpy(), self.crf['mask'].numpy(),
+                               self.cp['start_transitions'].numpy(), self.cp['end_transitions'].numpy(),
+                               self.cp['transitions'].numpy())
+
+    def run(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        dt = time.perf_counter() - t0
+        return self.sample * steps / dt, dt / steps
+
+
+def run_reference_arm(args, shape):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base = CpuBaseline(shape, args.cpu_sample, seed=19260817)
+    value, sec = base.run(args.steps, max(1, min(args.warmup, 3)))
+    sample = (f'{args.cpu_sample} sentences per step (fusion fwd fp32 + Viterbi) of workload {workload_name(args, shape)}; '
+              f'oracle port: torch-CPU restatement of CMIM:509-667,873-884,954-989,1029-1036 + C Viterbi')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args, shape), 'batch_per_gpu': args.batch, 'layers': shape.L,
+                   'l2_policy': 'n/a (CPU)'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': base.cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs during the timed region
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b and name != 'gpu_idle':
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return False
+
+    def report(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml unavailable']}
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu_arm(args, shape):
+    import torch
+    import torch.distributed as dist
+    from icka_b200 import _lib
+    from icka_b200.pipeline import FusionViterbiPipeline
+    from icka_b200.profiler import KernelTimer
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...')
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    seed = 19260817 + rank
+    pipe = FusionViterbiPipeline(shape, dev, args.precision, seed=seed)
+    host = pipe.make_host_batch(args.batch, shape, seed)
+    d = pipe.to_device(host)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        pipe.step_device(d)
+    barrier()
+    launches0 = _lib.launch_count(local_rank)
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        s_ev.record()
+        for _ in range(args.steps):
+            pipe.step_device(d)
+        e_ev.record()
+        barrier()
+    ms_total = s_ev.elapsed_time(e_ev)
+    launches = _lib.launch_count(local_rank) - launches0
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = args.batch * world * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel roofline pass (same step, CUDA events around every C-ABI launch) ----
+    with KernelTimer() as kt:
+        for _ in range(args.steps):
+            pipe.step_device(d)
+        kernels = kt.summary()
+    gemm = kernels.get('linear_bf16_tcgen05') or kernels.get('linear_fp32_ffma')
+    peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
+    roofline = {
+        'kernel': 'gemm_bf16_tcgen05_kernel (icka_linear_fwd)' if 'linear_bf16_tcgen05' in kernels else 'sgemm_tn_kernel',
+        'bound': 'tensor', 'achieved': gemm['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'frac': gemm['tflops'] / peak_tf, 'traffic': None,
+        'peak_source': peaks['_source'] + ', bf16_tflops_sustained (kernel timed inside a long step)',
+        'launches_per_step': gemm['launches'] // args.steps, 'ms_per_launch': gemm['ms_per_launch'],
+        'flops_per_launch': gemm['flops_per_launch'],
+    }
+    hbm = peaks.get('hbm_gbs', FALLBACK_PEAKS['hbm_gbs'])
+    kernel_table = {}
+    for name, k in kernels.items():
+        kernel_table[name] = {'launches_per_step': k['launches'] // args.steps, 'ms_per_step': k['ms_total'] / args.steps,
+                              'tflops': round(k['tflops'], 2), 'gbs': round(k['gbs'], 1),
+                              'frac_tensor': round(k['tflops'] / peak_tf, 4), 'frac_hbm': round(k['gbs'] / hbm, 4)}
+
+    # ---- end to end from pinned host memory ----
+    e2e = None
+    if not args.no_e2e:
+        hosts = [host, pipe.make_host_batch(args.batch, shape, seed + 1000)]
+        n_e2e = max(4, min(args.steps, 10))
+        seq = [hosts[i & 1] for i in range(n_e2e)]
+        pipe.infer_host(seq[:2])
+        barrier()
+        results, (s2, e2) = pipe.infer_host(seq)
+        barrier()
+        ms_e2e = s2.elapsed_time(e2)
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+        d2h = sum(x.numel() * x.element_size() for x in results[0])
+        e2e = {'value': args.batch * world * n_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': pipe.h2d_bytes(host), 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
+               'api': 'icka_b200.pipeline.FusionViterbiPipeline.infer_host (pinned host fp32 inputs; H2D of batch i+1 '
+                      'overlaps kernels of batch i; D2H of tags, lengths, gates)'}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = CpuBaseline(shape, args.cpu_sample, seed=19260817)
+        reps = 3 if shape.L == 1 else 2
+        v, sec = base.run(reps, 1)
+        cpu = {'value': v, 'unit': UNIT, 'cores': base.cores, 'kind': 'port',
+               'sample': f'{args.cpu_sample} sentences x {reps} passes (fusion fwd fp32 + Viterbi), oracle port on host CPU, '
+                         f'{sec * 1e3:.0f} ms per pass'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(args, shape), 'batch_per_gpu': args.batch, 'global_batch': args.batch * world,
+                       'layers': shape.L, 'parallelism': f'batch-sharded x{world}, no collectives',
+                       'precision': 'bf16 GEMM operands, fp32 accumulate/residual/LayerNorm/softmax' if args.precision == 'bf16' else 'fp32',
+                       'weights': 'random init (nn.Linear default)',
+                       'l2_policy': 'inputs larger than L2 (>= 1.2 GB of inputs per step vs 126 MB L2); no flush needed'},
+            'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+            'cpu_baseline': cpu, 'kernels': kernel_table,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from icka_b200 import synth
+    shape = synth.Shape(L=args.layers, S=256 if args.hires else 128, R=196 if args.hires else 49)
+    if args.impl == 'reference':
+        run_reference_arm(args, shape)
+    else:
+        run_gpu_arm(args, shape)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,107 @@
+"""Fusion + Viterbi inference pipeline: the call a user of the drop-in makes for a batch of sentences.
+
+Mirrors what ``MTCCMBertForMMTokenClassificationCRF.forward(mode='test')`` does on the hot path
+(CMIM:954-989, 1029-1036, 1045, 1056): cross-modal fusion of the text states with the image regions,
+then CRF Viterbi decode of the emission scores.  The encoders and the BiLSTM between the two stages are
+outside the hot path; their outputs (`token_embedding`, `emissions`) are inputs here.
+
+``infer_host`` is the end-to-end entry: pinned host buffers in, host tags out, with the host->device
+copies of batch i+1 overlapped with the kernels of batch i on a second stream.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import synth
+from .config import FusionConfig
+from .crf import CRF
+from .modules import CrossModalFusion, set_precision
+
+FUSION_KEYS = ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask', 'text_mask')
+CRF_KEYS = ('emissions', 'crf_mask')
+
+
+class FusionViterbiPipeline:
+    def __init__(self, shape: synth.Shape = synth.STD, device: str = 'cuda:0', precision: str = 'bf16', seed: int = 0):
+        self.shape = shape
+        self.device = torch.device(device)
+        self.precision = precision
+        torch.manual_seed(seed)
+        cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
+                           layer_norm_eps=shape.eps)
+        self.fusion = CrossModalFusion(cfg, layer_num1=shape.L, region_dim=shape.region_dim,
+                                       clip_dim=shape.clip_dim).to(self.device).eval()
+        self.crf = CRF(shape.T, batch_first=True).to(self.device)
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+
+    # ---- device-resident step -------------------------------------------------------------------
+    @torch.no_grad()
+    def step_device(self, d: Dict[str, torch.Tensor]):
+        """One pass of the hot path over a device-resident batch; returns (result, clip, tags, lens, gate)."""
+        set_precision(self.precision)
+        out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                          d['img_mask'], d['text_mask'], return_dict=True)
+        tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
+        return out['result'], out['clip'], tags, lens, out['gate']
+
+    # ---- host batches ---------------------------------------------------------------------------
+    @staticmethod
+    def make_host_batch(B: int, shape: synth.Shape, seed: int, pin: bool = True) -> Dict[str, torch.Tensor]:
+        f = synth.fusion_inputs(B, shape, seed=seed)
+        c = synth.crf_batch(B, shape, seed=seed)
+        host = {k: f[k] for k in FUSION_KEYS}
+        host['emissions'] = c['emissions']
+        host['crf_mask'] = c['mask'].to(torch.uint8)
+        if pin:
+            host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+        return host
+
+    def to_device(self, host: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        return {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
+
+    @staticmethod
+    def h2d_bytes(host: Dict[str, torch.Tensor]) -> int:
+        return sum(v.numel() * v.element_size() for v in host.values())
+
+    @torch.no_grad()
+    def infer_host(self, batches: List[Dict[str, torch.Tensor]]):
+        """End-to-end over pinned host batches: H2D copy of every input, fusion + Viterbi, D2H of tags,
+        lengths and gate values.  Copies of batch i+1 overlap the kernels of batch i (two device buffer
+        sets).  Returns per-batch (tags [B,S] int32, lens [B] int32, gate [B] fp32) pinned host tensors
+        and the (start, end) CUDA events that bracket all the work."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        main = torch.cuda.current_stream(self.device)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dev_bufs = [None, None]
+        compute_done = [None, None]
+        results = []
+        cs.wait_stream(main)
+        start.record(cs)
+        for i, host in enumerate(batches):
+            slot = i & 1
+            if dev_bufs[slot] is None:
+                dev_bufs[slot] = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
+            with torch.cuda.stream(cs):
+                if compute_done[slot] is not None:
+                    cs.wait_event(compute_done[slot])          # buffer set is free again
+                for k, v in host.items():
+                    dev_bufs[slot][k].copy_(v, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(cs)
+            main.wait_event(copied)
+            _, _, tags, lens, gate = self.step_device(dev_bufs[slot])
+            out = (torch.empty(tags.shape, dtype=tags.dtype, pin_memory=True),
+                   torch.empty(lens.shape, dtype=lens.dtype, pin_memory=True),
+                   torch.empty(gate.shape, dtype=gate.dtype, pin_memory=True))
+            out[0].copy_(tags, non_blocking=True)
+            out[1].copy_(lens, non_blocking=True)
+            out[2].copy_(gate, non_blocking=True)
+            compute_done[slot] = torch.cuda.Event()
+            compute_done[slot].record(main)
+            results.append(out)
+        end.record(main)
+        return results, (start, end)

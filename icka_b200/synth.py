@@ -101,5 +101,6 @@ def crf_batch(B: int, shape: Shape = STD, seed: int = BASE_SEED, kind: str = 'no
     lens = lengths(B, shape.S, g, median_len)
     mask = prefix_mask(lens, shape.S).bool()
     e = emissions(B, shape.S, shape.T, seed, kind)
-    tags = torch.randint(1, shape.T, (B, shape.S), generator=g) * mask.long()
+    tags = (torch.randint(1, shape.T, (B, shape.S), generator=g) if shape.T > 1
+            else torch.zeros(B, shape.S, dtype=torch.long)) * mask.long()
     return dict(emissions=e, mask=mask, tags=tags, lens=lens)

@@ -34,7 +34,7 @@ def test_linear_bf16_fp32_out(M, N, K):
     got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), out_dtype=torch.float32).cpu()
     want = a.double() @ w.double().t() + bias.double() + res.double()
     err = float((got.double() - want).abs().max())
-    assert err <= 2e-5, err
+    assert err <= 1e-6 * math.sqrt(K) + 2e-6, err     # fp32 accumulation over K exact bf16 products
 
 
 @pytest.mark.parametrize('M,N,K', [(256, 3072, 768), (77, 256, 128), (128, 768, 768)])

@@ -62,7 +62,8 @@ def test_linear_fp32(M, N, K, act):
     got = ops.linear(a.to(DEV), w.to(DEV), bias.to(DEV), residual=res.to(DEV), act=act).cpu()
     want = (a.double() @ w.double().t() + bias.double())
     want = (gelu(want) if act else want) + res.double()
-    assert rel(got.double(), want) <= 3e-6
+    # fp32 accumulation over K terms vs an fp64 reference: sqrt(K)-growth of the rounding error
+    assert rel(got.double(), want) <= 4e-7 * math.sqrt(K) + 1e-6
 
 
 def test_linear_fp32_pitched_views():
