@@ -136,6 +136,204 @@ __global__ void __launch_bounds__(kRows) cross_attn_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bf16 path: same contract, scores and P.V on the tensor cores (mma.sync m16n8k16, fp32 accumulate).
+// The attention core is 1.2 % of the layer's FLOPs and is bound by the HBM traffic of Q, K|V and ctx, so
+// the legacy warp-level MMA is enough to take the arithmetic off the critical path; the tcgen05 budget
+// goes to the projections around it.  One block = one (sentence, head, 128-query tile): 8 warps x 16
+// query rows.  Q (128x64), and K / V in 64-key blocks, are staged in shared memory with 16-byte cp.async
+// (row pitch 144 B -> conflict-free ldmatrix); softmax runs online over key blocks in registers (quad
+// shuffles), P is rounded to bf16 for the second MMA, and the context tile is written back through the
+// Q buffer so that global stores are 16 bytes per lane and row-contiguous.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMmaThreads = 256;
+constexpr int kPitch = 72;        // bf16 elements per smem row (64 + 8 pad)
+constexpr int kKeyBlk = 64;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(sa));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(sa));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// grid = (ceil(Sq / 128), nh, B)
+__global__ void __launch_bounds__(kMmaThreads) cross_attn_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
+    const __nv_bfloat16* __restrict__ v, int64_t ldkv, const float* __restrict__ mask_add,
+    __nv_bfloat16* __restrict__ ctx, int64_t ldc, int Sq, int Skv) {
+  __shared__ __align__(16) __nv_bfloat16 Qs[kRows * kPitch];
+  __shared__ __align__(16) __nv_bfloat16 Ks[kKeyBlk * kPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vs[kKeyBlk * kPitch];
+  __shared__ float Ms[kKeyBlk];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int row0 = blockIdx.x * kRows;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  // ---- stage the Q tile (rows beyond Sq are zero-filled) ----
+  const __nv_bfloat16* qb = q + ((size_t)b * Sq + row0) * ldq + (size_t)h * kD;
+  for (int i = tid; i < kRows * 8; i += kMmaThreads) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    if (row0 + r < Sq) cp_async16(Qs + r * kPitch + c, qb + (size_t)r * ldq + c);
+    else *reinterpret_cast<uint4*>(Qs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+  }
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;   // rows g and g+8 of this warp's 16
+  uint32_t qf[4][4];
+  const bool warp_active = row0 + warp * 16 < Sq;
+
+  const __nv_bfloat16* kb = k + (size_t)b * Skv * ldkv + (size_t)h * kD;
+  const __nv_bfloat16* vb = v + (size_t)b * Skv * ldkv + (size_t)h * kD;
+  for (int key0 = 0; key0 < Skv; key0 += kKeyBlk) {
+    if (key0 > 0) __syncthreads();   // previous block fully consumed
+    for (int i = tid; i < kKeyBlk * 8; i += kMmaThreads) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      if (key0 + r < Skv) {
+        cp_async16(Ks + r * kPitch + c, kb + (size_t)(key0 + r) * ldkv + c);
+        cp_async16(Vs + r * kPitch + c, vb + (size_t)(key0 + r) * ldkv + c);
+      } else {
+        *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (tid < kKeyBlk) {
+      const int key = key0 + tid;
+      Ms[tid] = (key < Skv) ? (mask_add ? mask_add[(size_t)b * Skv + key] * kLog2e : 0.0f) : -INFINITY;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    if (!warp_active) continue;
+
+    if (key0 == 0) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        ldmatrix_x4(qf[kk], Qs + (warp * 16 + (lane & 15)) * kPitch + kk * 16 + (lane >> 4) * 8);
+    }
+    const int nkt = min(8, (Skv - key0 + 7) / 8);   // 8-key tiles that hold at least one real key
+
+    // ---- S = Q K^T for this key block ----
+    float sacc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+      if (j < nkt) {
+        uint32_t kf[4];
+        ldmatrix_x4(kf, Ks + (j * 8 + (lane & 7)) * kPitch + (lane >> 3) * 8);          // d = 0..31
+        mma_bf16_16816(sacc[j], qf[0], kf[0], kf[1]);
+        mma_bf16_16816(sacc[j], qf[1], kf[2], kf[3]);
+        ldmatrix_x4(kf, Ks + (j * 8 + (lane & 7)) * kPitch + 32 + (lane >> 3) * 8);     // d = 32..63
+        mma_bf16_16816(sacc[j], qf[2], kf[0], kf[1]);
+        mma_bf16_16816(sacc[j], qf[3], kf[2], kf[3]);
+      }
+    }
+    // ---- scale, mask, online softmax (log2 domain) ----
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+    constexpr float kScale = 0.125f * kLog2e;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mk0 = Ms[j * 8 + 2 * t], mk1 = Ms[j * 8 + 2 * t + 1];
+      sacc[j][0] = fmaf(sacc[j][0], kScale, mk0);
+      sacc[j][1] = fmaf(sacc[j][1], kScale, mk1);
+      sacc[j][2] = fmaf(sacc[j][2], kScale, mk0);
+      sacc[j][3] = fmaf(sacc[j][3], kScale, mk1);
+      bm0 = fmaxf(bm0, fmaxf(sacc[j][0], sacc[j][1]));
+      bm1 = fmaxf(bm1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    const float sc0 = fast_exp2(m0 - mn0), sc1 = fast_exp2(m1 - mn1);   // first block: exp2(-inf) = 0
+    m0 = mn0;
+    m1 = mn1;
+    float ps0 = 0.0f, ps1 = 0.0f;
+    uint32_t pf[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = fast_exp2(sacc[j][0] - mn0), p1 = fast_exp2(sacc[j][1] - mn0);
+      const float p2 = fast_exp2(sacc[j][2] - mn1), p3 = fast_exp2(sacc[j][3] - mn1);
+      ps0 += p0 + p1;
+      ps1 += p2 + p3;
+      pf[j][0] = pack_bf16x2(p0, p1);
+      pf[j][1] = pack_bf16x2(p2, p3);
+    }
+    l0 = l0 * sc0 + ps0;
+    l1 = l1 * sc1 + ps1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= sc0; o[j][1] *= sc0; o[j][2] *= sc1; o[j][3] *= sc1;
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks * 2 < nkt) {
+        const uint32_t a[4] = {pf[2 * ks][0], pf[2 * ks][1], pf[2 * ks + 1][0], pf[2 * ks + 1][1]};
+#pragma unroll
+        for (int jn = 0; jn < 8; jn += 2) {
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, Vs + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + jn * 8 + (lane >> 4) * 8);
+          mma_bf16_16816(o[jn], a, vf[0], vf[1]);
+          mma_bf16_16816(o[jn + 1], a, vf[2], vf[3]);
+        }
+      }
+    }
+  }
+
+  // ---- normalise, stage through the Q buffer (each warp owns its 16 rows), coalesced write-out ----
+  if (warp_active) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    __nv_bfloat16* ow = Qs + (warp * 16) * kPitch;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(ow + g * kPitch + j * 8 + 2 * t) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+      *reinterpret_cast<uint32_t*>(ow + (g + 8) * kPitch + j * 8 + 2 * t) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+    }
+    __syncwarp();
+    __nv_bfloat16* ob = ctx + ((size_t)b * Sq + row0 + warp * 16) * ldc + (size_t)h * kD;
+#pragma unroll
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      if (row0 + warp * 16 + r < Sq)
+        *reinterpret_cast<uint4*>(ob + (size_t)r * ldc + c) = *reinterpret_cast<const uint4*>(ow + r * kPitch + c);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
@@ -157,8 +355,7 @@ extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t l
   dim3 grid((Sq + kRows - 1) / kRows, nh, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == ICKA_BF16) {
-    ICKA_CUDA(cudaFuncSetAttribute(cross_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cross_attn_kernel<__nv_bfloat16><<<grid, kRows, smem, st>>>(
+    cross_attn_mma_kernel<<<grid, kMmaThreads, 0, st>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
         static_cast<const __nv_bfloat16*>(v), ldkv, mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, Sq, Skv);
   } else {

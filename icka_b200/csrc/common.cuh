@@ -73,3 +73,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // erf-GELU exactly as the reference writes it (CMIM:31-37): x * 0.5 * (1 + erf(x / sqrt(2)))
 __device__ __forceinline__ float gelu_erf(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Same function through the Abramowitz-Stegun 7.1.26 rational form of erf (|error| <= 1.5e-7 before
+// rounding): 2 MUFU + ~12 FMA-pipe instructions instead of erff's ~30.  Used where the result is rounded
+// to bf16 (2^-9 relative) straight away, so the epilogue of the FFN-up GEMM keeps pace with the MMA.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(erf_abs, z), hx);
+}

@@ -13,8 +13,11 @@
 //   warp 1     allocates TMEM, then one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per
 //              k-block; tcgen05.commit releases the smem slot ("empty") and, after the last k-block,
 //              publishes the accumulator ("tmem_full")
-//   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (lane = row), add bias, erf-GELU,
-//              add the fp32 residual, convert, store; then hand the accumulator back ("tmem_empty")
+//   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (lane = row) 32 columns at a time,
+//              transpose each 32x32 block through a swizzled shared-memory tile so that global traffic is
+//              row-contiguous (lane = column pair): coalesced bias / fp32-residual loads and stores, with
+//              erf-GELU and the bf16 conversion applied on the way; the accumulator is handed back
+//              ("tmem_empty") as soon as its last column block has been read
 // Two accumulators (2 x BN TMEM columns) let the epilogue of tile i overlap the mainloop of tile i+1.
 // Tiles are walked n-fastest so the CTAs that share an A row-block run together and A is read from
 // HBM once (weights are a few MB and stay in the 126 MB L2).
@@ -40,7 +43,9 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
+  static constexpr size_t kSmemBytes =
+      (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -61,7 +66,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
@@ -148,62 +154,91 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue (4 warps, 128 rows) =====================
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
+    uint8_t* stage_tile = smem_stage + (size_t)(warp - 2) * (32 * 128);
+    const uint32_t stage_u32 = smem_u32(stage_tile);
+    const int sub = lane >> 4;                            // row parity handled in the transposed phase
+    const int cp = lane & 15;                             // column pair handled in the transposed phase
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int n_tile0 = n_blk * BN;
+      const int nchunks = min(BN / 32, (N - n_tile0 + 31) / 32);
+      const int row_base = m_blk * kBM + quad * 32;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * kBM + quad * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      const float* res_row = args.residual ? args.residual + (size_t)row * N : nullptr;
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr0, r);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= N) break;                               // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+      for (int c = 0; c < nchunks; ++c) {
         tmem_ld_wait();
-        if (row_ok) {
+        // row-per-lane -> swizzled staging tile (16-byte slot s of row l lives at slot s ^ (l & 7))
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {                   // 8 columns per group
-            const int n = n0 + g * 8;
-            if (n < N) {
-              float v[8];
+        for (int sl = 0; sl < 8; ++sl) {
+          const uint32_t addr = stage_u32 + (uint32_t)lane * 128u + (uint32_t)((sl ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(r[4 * sl]), "r"(r[4 * sl + 1]),
+                       "r"(r[4 * sl + 2]), "r"(r[4 * sl + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        if (c + 1 < nchunks) {
+          tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * 32), r);   // overlaps the transposed phase below
+        } else {
+          // accumulator fully read: give it back to the MMA warp before doing the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int col = n_tile0 + c * 32 + 2 * cp;
+        const bool col_ok = col < N;
+        float b0 = 0.0f, b1 = 0.0f;
+        if (args.bias && col_ok) {
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
+          b0 = bb.x;
+          b1 = bb.y;
+        }
+        float2 res[16];
+        if (args.residual) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float x = __uint_as_float(r[g * 8 + j]);
-                if (args.bias) x += __ldg(args.bias + n + j);
-                if (ACT == ICKA_ACT_GELU_ERF) x = gelu_erf(x);
-                v[j] = x;
-              }
-              if (res_row) {
-                const float4 r0 = *reinterpret_cast<const float4*>(res_row + n);
-                const float4 r1 = *reinterpret_cast<const float4*>(res_row + n + 4);
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-              }
-              if (OUT_BF16) {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)row * args.ldo + n) = o;
-              } else {
-                float* op = static_cast<float*>(args.out) + (size_t)row * args.ldo + n;
-                *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              }
+          for (int i = 0; i < 16; ++i) {
+            const int row = row_base + 2 * i + sub;
+            res[i] = (col_ok && row < M)
+                         ? __ldg(reinterpret_cast<const float2*>(args.residual + (size_t)row * N + col))
+                         : make_float2(0.0f, 0.0f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 2 * i + sub;
+          const int row = row_base + rr;
+          const uint32_t addr = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((cp >> 1) ^ (rr & 7)) << 4) +
+                                (uint32_t)((cp & 1) << 3);
+          float x0, x1;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(x0), "=f"(x1) : "r"(addr) : "memory");
+          x0 += b0;
+          x1 += b1;
+          if (ACT == ICKA_ACT_GELU_ERF) {
+            x0 = OUT_BF16 ? gelu_erf_fast(x0) : gelu_erf(x0);
+            x1 = OUT_BF16 ? gelu_erf_fast(x1) : gelu_erf(x1);
+          }
+          if (args.residual) {
+            x0 += res[i].x;
+            x1 += res[i].y;
+          }
+          if (col_ok && row < M) {
+            if (OUT_BF16) {
+              *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)row * args.ldo + col) =
+                  pack_bf16x2(x0, x1);
+            } else {
+              *reinterpret_cast<float2*>(static_cast<float*>(args.out) + (size_t)row * args.ldo + col) =
+                  make_float2(x0, x1);
             }
           }
         }
+        __syncwarp();   // staging tile is rewritten by the next column block
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
   }
 

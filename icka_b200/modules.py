@@ -365,8 +365,10 @@ class CrossModalFusion(nn.Module):
             z32 = zs[-1]
 
         # gated fusion, CMIM:1029-1036
-        w_fold, c_fold = ops.gate_fold(self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
-                                       self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach())
+        gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight, self.aux_head.bias)
+        w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
+            self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+            self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
         ln = self.cls_layer.proj_norm
         result, gate = ops.gate_blend(fused32.view(B, S, H), _rows(token_embedding).view(B, S, H), ln.weight.detach(),
                                       ln.bias.detach(), ln.eps, w_fold, c_fold)
