@@ -34,23 +34,32 @@ constexpr int kRegC = 64;
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) region_rows_kernel(const float* __restrict__ grid, OutT* __restrict__ rows,
-                                                          int C, int R) {
-  extern __shared__ float tile[];   // [kRegC][Rp]
-  const int Rp = R | 1;
+                                                          int C, int R, int Rp) {
+  extern __shared__ __align__(16) float tile[];   // [kRegC][Rp]; Rp == R (odd R: conflict-free as is) or R + 1
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * kRegC;
   const int nc = min(kRegC, C - c0);
   const float* src = grid + ((size_t)b * C + c0) * R;
   const int total = nc * R;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int c = i / R, r = i - c * R;
-    tile[c * Rp + r] = src[i];
+  if (Rp == R && (total & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    // the slab is one contiguous run: straight 16-byte copies, several in flight per thread
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    const int nv = total >> 2;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nv; i += 256) t4[i] = __ldcs(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < total; i += 256) {
+      const int c = i / R, r = i - c * R;
+      tile[c * Rp + r] = src[i];
+    }
   }
   __syncthreads();
   OutT* dst = rows + (size_t)b * R * C + c0;
-  // each thread writes two adjacent channels of one region row
-  const int pairs = kRegC / 2;
-  for (int i = threadIdx.x; i < R * pairs; i += blockDim.x) {
+  // each thread writes two adjacent channels of one region row; a warp covers one 64-channel row segment
+  constexpr int pairs = kRegC / 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < R * pairs; i += 256) {
     const int r = i / pairs, c = (i - r * pairs) * 2;
     if (c + 1 < nc) {
       const float v0 = tile[c * Rp + r], v1 = tile[(c + 1) * Rp + r];
@@ -235,16 +244,17 @@ extern "C" int icka_region_rows(icka_handle* h, const float* grid, void* rows, i
   ICKA_REQUIRE(B <= 65535, "region_rows: B=%d exceeds the grid.y limit; shard the batch", B);
   ICKA_REQUIRE(out_dtype == ICKA_F32 || out_dtype == ICKA_BF16, "region_rows: bad dtype %d", out_dtype);
   if (B == 0) return ICKA_OK;
-  const size_t smem = (size_t)kRegC * (R | 1) * sizeof(float);
+  const int Rp = R | 1;
+  const size_t smem = (size_t)kRegC * Rp * sizeof(float);
   ICKA_REQUIRE(smem <= h->smem_optin, "region_rows: R=%d too large", R);
   dim3 g((C + kRegC - 1) / kRegC, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == ICKA_BF16) {
     ICKA_CUDA(cudaFuncSetAttribute(region_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    region_rows_kernel<__nv_bfloat16><<<g, 256, smem, st>>>(grid, static_cast<__nv_bfloat16*>(rows), C, R);
+    region_rows_kernel<__nv_bfloat16><<<g, 256, smem, st>>>(grid, static_cast<__nv_bfloat16*>(rows), C, R, Rp);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(region_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    region_rows_kernel<float><<<g, 256, smem, st>>>(grid, static_cast<float*>(rows), C, R);
+    region_rows_kernel<float><<<g, 256, smem, st>>>(grid, static_cast<float*>(rows), C, R, Rp);
   }
   ICKA_LAUNCHED(h);
   return ICKA_OK;

@@ -7,13 +7,13 @@
 // FFN up + erf-GELU (CMIM:549-550) and FFN down (CMIM:533).  nn.Linear weights are [out, in] row-major,
 // i.e. already the K-major B operand; activations are [rows, in] row-major = K-major A.
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor 2-D boxes {64 x 128} of A and {64 x BN} of W into a
 //              kStages-deep shared-memory ring, 128-byte swizzle, completion on "full" mbarriers
 //   warp 1     allocates TMEM, then one elected thread issues tcgen05.mma (M=128, N=BN, K=16) x 4 per
 //              k-block; tcgen05.commit releases the smem slot ("empty") and, after the last k-block,
 //              publishes the accumulator ("tmem_full")
-//   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (lane = row) 32 columns at a time,
+//   warps 2-9  epilogue: tcgen05.ld the 128 x BN fp32 accumulator (lane = row) 32 columns at a time,
 //              transpose each 32x32 block through a swizzled shared-memory tile so that global traffic is
 //              row-contiguous (lane = column pair): coalesced bias / fp32-residual loads and stores, with
 //              erf-GELU and the bf16 conversion applied on the way; the accumulator is handed back
@@ -33,8 +33,8 @@ using namespace sm100;
 constexpr int kBM = 128;
 constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
-constexpr int kEpiWarp0 = 2;
+constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant; they split the column blocks
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
@@ -43,7 +43,7 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kStagingBytes = 4 * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
+  static constexpr int kStagingBytes = kEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
   static constexpr size_t kSmemBytes =
       (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -63,7 +63,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (size_t)Cfg::kStages * Cfg::kABytes;
   uint8_t* smem_stage = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
@@ -91,7 +91,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);   // one arrive per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -152,12 +152,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else {
-    // ===================== epilogue (4 warps, 128 rows) =====================
+    // ===================== epilogue (8 warps: 4 lane quadrants x 2 column halves) =====================
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may access
-    uint8_t* stage_tile = smem_stage + (size_t)(warp - 2) * (32 * 128);
-    const uint32_t stage_u32 = smem_u32(stage_tile);
+    const int half = (warp - 2) >> 2;                     // even / odd 32-column blocks
+    uint8_t* stage_tile = smem_stage + (warp - 2) * (32 * 128);
     const int sub = lane >> 4;                            // row parity handled in the transposed phase
     const int cp = lane & 15;                             // column pair handled in the transposed phase
+    // Staging tile: 32 rows x 128 B; the 16-byte slot s of row r is stored at slot s ^ (r & 7).
+    //   write side (lane = row):  slot offsets for s = 0..7
+    //   read side  (row = 2i+sub, 8 bytes at column pair cp): (2i+sub)&7 == (2(i&3)) ^ sub, so the slot is
+    //   ((cp>>1) ^ sub) ^ 2(i&3): four lane-dependent base pointers, everything else is an immediate.
+    uint8_t* wr_row = stage_tile + lane * 128;
+    int wr_off[8];
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) wr_off[sl] = (sl ^ (lane & 7)) << 4;
+    const uint8_t* rd_base[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      rd_base[k] = stage_tile + sub * 128 + ((((cp >> 1) ^ sub) ^ (2 * k)) << 4) + ((cp & 1) << 3);
+
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -166,30 +179,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n_tile0 = n_blk * BN;
       const int nchunks = min(BN / 32, (N - n_tile0 + 31) / 32);
       const int row_base = m_blk * kBM + quad * 32;
+      const int rows_left = M - row_base - sub;           // row 2i+sub of this warp's block is valid iff 2i < rows_left
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(taddr0, r);
+      bool released = false;
+      if (half < nchunks) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), r);
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = half; c < nchunks; c += 2) {
         tmem_ld_wait();
-        // row-per-lane -> swizzled staging tile (16-byte slot s of row l lives at slot s ^ (l & 7))
 #pragma unroll
-        for (int sl = 0; sl < 8; ++sl) {
-          const uint32_t addr = stage_u32 + (uint32_t)lane * 128u + (uint32_t)((sl ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(r[4 * sl]), "r"(r[4 * sl + 1]),
-                       "r"(r[4 * sl + 2]), "r"(r[4 * sl + 3])
-                       : "memory");
-        }
+        for (int sl = 0; sl < 8; ++sl)
+          *reinterpret_cast<uint4*>(wr_row + wr_off[sl]) = make_uint4(r[4 * sl], r[4 * sl + 1], r[4 * sl + 2], r[4 * sl + 3]);
         __syncwarp();
-        if (c + 1 < nchunks) {
-          tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 1) * 32), r);   // overlaps the transposed phase below
+        if (c + 2 < nchunks) {
+          tmem_ld_32x32b_x32(taddr0 + (uint32_t)((c + 2) * 32), r);   // overlaps the phase below
         } else {
-          // accumulator fully read: give it back to the MMA warp before doing the global stores
+          // this warp's last TMEM read has landed: hand the accumulator back before the global stores
           tc_fence_before();
-          __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          released = true;
         }
         const int col = n_tile0 + c * 32 + 2 * cp;
         const bool col_ok = col < N;
@@ -199,26 +209,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           b0 = bb.x;
           b1 = bb.y;
         }
+        const bool full = (rows_left >= 32) && (n_tile0 + c * 32 + 32 <= N);   // warp-uniform
+        const size_t row0 = (size_t)(row_base + sub);
         float2 res[16];
         if (args.residual) {
+          const float* rp = args.residual + row0 * N + col;
+          const size_t rstep = (size_t)2 * N;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int row = row_base + 2 * i + sub;
-            res[i] = (col_ok && row < M)
-                         ? __ldg(reinterpret_cast<const float2*>(args.residual + (size_t)row * N + col))
-                         : make_float2(0.0f, 0.0f);
-          }
+          for (int i = 0; i < 16; ++i, rp += rstep)
+            res[i] = (full || (col_ok && 2 * i < rows_left)) ? __ldg(reinterpret_cast<const float2*>(rp))
+                                                               : make_float2(0.0f, 0.0f);
         }
+        float2 x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float2*>(rd_base[i & 3] + i * 256);
+        __syncwarp();   // staging tile may be rewritten (next column block) once every lane has read it
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + sub;
-          const int row = row_base + rr;
-          const uint32_t addr = stage_u32 + (uint32_t)rr * 128u + (uint32_t)(((cp >> 1) ^ (rr & 7)) << 4) +
-                                (uint32_t)((cp & 1) << 3);
-          float x0, x1;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(x0), "=f"(x1) : "r"(addr) : "memory");
-          x0 += b0;
-          x1 += b1;
+          float x0 = x[i].x + b0, x1 = x[i].y + b1;
           if (ACT == ICKA_ACT_GELU_ERF) {
             x0 = OUT_BF16 ? gelu_erf_fast(x0) : gelu_erf(x0);
             x1 = OUT_BF16 ? gelu_erf_fast(x1) : gelu_erf(x1);
@@ -227,17 +235,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             x0 += res[i].x;
             x1 += res[i].y;
           }
-          if (col_ok && row < M) {
-            if (OUT_BF16) {
-              *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(args.out) + (size_t)row * args.ldo + col) =
-                  pack_bf16x2(x0, x1);
-            } else {
-              *reinterpret_cast<float2*>(static_cast<float*>(args.out) + (size_t)row * args.ldo + col) =
-                  make_float2(x0, x1);
-            }
-          }
+          x[i] = make_float2(x0, x1);
         }
-        __syncwarp();   // staging tile is rewritten by the next column block
+        const size_t ostep = (size_t)2 * args.ldo;
+        if (OUT_BF16) {
+          __nv_bfloat16* op = static_cast<__nv_bfloat16*>(args.out) + row0 * args.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, op += ostep)
+            if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(x[i].x, x[i].y);
+        } else {
+          float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, op += ostep)
+            if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<float2*>(op) = x[i];
+        }
+      }
+      if (!released) {   // warp had no column block in this (ragged) tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
   }
