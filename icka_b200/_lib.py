@@ -32,6 +32,7 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     'icka_cross_attn_core_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_i2t_pool_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_gate_fold': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p]),
     'icka_gate_blend_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,

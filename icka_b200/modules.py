@@ -219,10 +219,59 @@ class BertCrossAttention(nn.Module):
         super().__init__()
         self.self = BertCoAttention(config)
         self.output = BertSelfOutput(config)
+        self._fold_cache = _OperandCache()
 
     def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv):
+        if Sq == 1 and self._can_fold():
+            return self._run_single_query(x32, x_lp, y_lp, mask2d, B, Skv)
         ctx = self.self._run(x_lp, y_lp, mask2d, B, Sq, Skv)
         return self.output._run(ctx, x32)
+
+    # -- single-query fold (image->text encoders, CMIM:984-989) ------------------------
+    def _can_fold(self) -> bool:
+        att = self.self
+        return (_PRECISION == 'bf16' and att.attention_head_size == 64 and att.num_attention_heads <= 16
+                and att.all_head_size in (768, 1024))
+
+    def _folded_operands(self):
+        """Weight products of the fold, built with the fp32 kernel and cached until a parameter changes:
+             Wqk[(h,i), k] = sum_j Wk[hj, i] Wq[hj, k]      u0[(h,i)] = sum_j Wk[hj, i] bq[hj]
+             Wov[n, (h,i)] = sum_j Wo[n, hj] Wv[hj, i]      bo'[n]    = sum_hj Wo[n, hj] bv[hj] + bo[n]
+        so that  U = z Wqk^T + u0  and  dense(ctx) = xbar Wov^T + bo'  (see csrc/i2t_pool.cu)."""
+        att, out = self.self, self.output
+        ps = (att.query.weight, att.query.bias, att.key.weight, att.value.weight, att.value.bias,
+              out.dense.weight, out.dense.bias)
+
+        def build():
+            H, nh, d = att.all_head_size, att.num_attention_heads, att.attention_head_size
+            f32 = dict(dtype=torch.float32, device=att.query.weight.device)
+            wq_t = att.query.weight.detach().t().contiguous()       # [H_in, H_out]
+            wk_t = att.key.weight.detach().t().contiguous()
+            wv_t = att.value.weight.detach().t().contiguous()
+            wo = out.dense.weight.detach().contiguous()
+            bq = att.query.bias.detach().contiguous()
+            wqk = torch.empty(nh * H, H, **f32)
+            u0 = torch.empty(nh * H, **f32)
+            wov = torch.empty(H, nh * H, **f32)
+            for h in range(nh):
+                sl = slice(h * d, (h + 1) * d)
+                ops.linear(wk_t[:, sl], wq_t[:, sl], None, out=wqk[h * H:(h + 1) * H])
+                ops.linear(bq[sl].view(1, d), wk_t[:, sl], None, out=u0[h * H:(h + 1) * H].view(1, H))
+                ops.linear(wo[:, sl], wv_t[:, sl], None, out=wov[:, h * H:(h + 1) * H])
+            bo2 = ops.linear(att.value.bias.detach().view(1, H).contiguous(), wo, out.dense.bias.detach()).view(H)
+            return ops.cast_bf16(wqk), u0, ops.cast_bf16(wov), bo2
+
+        return self._fold_cache.get('fold', ps, build)
+
+    def _run_single_query(self, z32, z_lp, y_lp, mask2d, B, Skv):
+        att, out = self.self, self.output
+        H, nh = att.all_head_size, att.num_attention_heads
+        wqk, u0, wov, bo2 = self._folded_operands()
+        u = ops.linear(z_lp, wqk, u0, out_dtype=torch.bfloat16)                       # [B, nh*H]
+        xbar = ops.i2t_pool(u, y_lp, mask2d, B, Skv, H, nh)                           # [B, nh*H]
+        pre = ops.linear(xbar, wov, bo2, residual=z32, out_dtype=torch.float32)       # dense(ctx) + input
+        return ops.layernorm(pre, out.LayerNorm.weight.detach(), out.LayerNorm.bias.detach(),
+                             out.LayerNorm.variance_epsilon, want_f32=True, want_bf16=True)
 
     def forward(self, s1_input_tensor, s2_input_tensor, s2_attention_mask):
         _check_inference(self, self.self.dropout.p, self.output.dropout.p)

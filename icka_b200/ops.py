@@ -123,6 +123,21 @@ def cross_attn_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add:
     return ctx
 
 
+def i2t_pool(u: torch.Tensor, x: torch.Tensor, mask_add: Optional[torch.Tensor], B: int, S: int, H: int, nh: int):
+    """Folded single-query attention pool: u [B, nh*H] bf16, x [B*S, H] bf16 -> xbar [B, nh*H] bf16."""
+    _need(u, torch.bfloat16, 'i2t_pool(u)')
+    _need(x, torch.bfloat16, 'i2t_pool(x)')
+    if u.shape != (B, nh * H) or x.shape != (B * S, H):
+        raise RuntimeError(f'i2t_pool: bad shapes {tuple(u.shape)} {tuple(x.shape)}')
+    if mask_add is not None:
+        _need(mask_add, torch.float32, 'i2t_pool(mask_add)')
+    lib, h, st = _ctx(u)
+    xbar = torch.empty_like(u)
+    _lib.check(lib.icka_i2t_pool_fwd(h, u.data_ptr(), x.data_ptr(), _p(mask_add), xbar.data_ptr(), B, S, H, nh, st),
+               'icka_i2t_pool_fwd')
+    return xbar
+
+
 def gate_fold(wp: torch.Tensor, bp: torch.Tensor, wa: torch.Tensor, ba: torch.Tensor):
     for t, n in ((wp, 'Wp'), (bp, 'bp'), (wa, 'wa'), (ba, 'ba')):
         _need(t, torch.float32, f'gate_fold({n})')

@@ -35,15 +35,26 @@ class FusionViterbiPipeline:
                                        clip_dim=shape.clip_dim).to(self.device).eval()
         self.crf = CRF(shape.T, batch_first=True).to(self.device)
         self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._side_stream: Optional[torch.cuda.Stream] = None
 
     # ---- device-resident step -------------------------------------------------------------------
     @torch.no_grad()
     def step_device(self, d: Dict[str, torch.Tensor]):
         """One pass of the hot path over a device-resident batch; returns (result, clip, tags, lens, gate)."""
         set_precision(self.precision)
+        main = torch.cuda.current_stream(self.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        side = self._side_stream
+        # The CRF decode depends only on the emissions: run it beside the fusion kernels.
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
+            tags.record_stream(main)
+            lens.record_stream(main)
         out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
                           d['img_mask'], d['text_mask'], return_dict=True)
-        tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
+        main.wait_stream(side)
         return out['result'], out['clip'], tags, lens, out['gate']
 
     # ---- host batches ---------------------------------------------------------------------------

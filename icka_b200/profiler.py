@@ -39,6 +39,9 @@ def _work(name, args, kwargs):
         q, k, v, mask, B, Sq, Skv, nh, d = args
         es = _ESZ[q.dtype]
         return name, 4.0 * B * nh * Sq * Skv * d, (2 * B * Sq * nh * d + 2 * B * Skv * nh * d) * es
+    if name == 'i2t_pool':
+        u, x, mask, B, S, H, nh = args
+        return name, 4.0 * B * nh * S * H, (x.numel() + 2 * u.numel()) * 2
     if name == 'gate_blend':
         return name, 0.0, args[0].numel() * 12
     if name == 'gate_fold':
@@ -53,7 +56,7 @@ def _work(name, args, kwargs):
 
 
 class KernelTimer:
-    OPS = ('cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'gate_fold', 'gate_blend',
+    OPS = ('cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend',
            'viterbi', 'crf_llh')
 
     def __init__(self):

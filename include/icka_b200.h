@@ -85,6 +85,15 @@ int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const v
                              int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                              int B, int Sq, int Skv, int nh, int d, void* stream);
 
+/* Single-query attention in folded form (image->text encoders, CMIM:984-989 with Sq = 1).
+ * With one query per sentence, scores[h][s] = (U_h . x_s)/sqrt(d) + mask[s] where U_h = Wk_h^T q_h, and
+ * ctx_h = Wv_h xbar_h + bv_h where xbar_h = sum_s softmax_s(scores[h])[s] x_s.  This entry computes the
+ * part that touches the text states:  U [B, nh*H] bf16, X [B*S, H] bf16, mask_add [B,S] fp32 additive or
+ * NULL  ->  xbar [B, nh*H] bf16.  The weight folds around it are plain icka_linear_fwd calls.
+ * H in {768, 1024}, nh <= 16. */
+int icka_i2t_pool_fwd(icka_handle* h, const void* U, const void* X, const float* mask_add, void* xbar,
+                      int B, int S, int H, int nh, void* stream);
+
 /* ---- gated fusion ---------------------------------------------------------------------------- */
 
 /* Folds cls_layer_both.proj (CMIM:877, :882) and aux_head (CMIM:934, :1034) into one H-vector:
