@@ -219,7 +219,29 @@ __global__ void __launch_bounds__(kGateThreads) gate_blend_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Additive attention mask (CMIM:962-965, 976-977): out[b][j] = (1 - mask[b][j]) * -10000
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_additive_kernel(const int64_t* __restrict__ mask, int64_t ld,
+                                                            float* __restrict__ out, int B, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * n) {
+    const int b = i / n, j = i - b * n;
+    out[i] = (1.0f - (float)mask[(size_t)b * ld + j]) * -10000.0f;
+  }
+}
+
 }  // namespace
+
+extern "C" int icka_mask_additive(icka_handle* h, const int64_t* mask, int64_t ld, float* out, int B, int n,
+                                  void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(mask && out && B >= 0 && n >= 1 && ld >= n, "mask_additive: bad arguments");
+  if (B == 0) return ICKA_OK;
+  mask_additive_kernel<<<(B * n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, ld, out, B, n);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
 
 extern "C" int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y, int64_t n, void* stream) {
   ICKA_CHECK_HANDLE(h);

@@ -395,12 +395,12 @@ class CrossModalFusion(nn.Module):
         regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
                                 self.vismap2text.bias.detach(), out_dtype=_cdt())
         # masks, CMIM:962-965 and 976-982
-        img_mask = (1.0 - added_attention_mask[:, :R].float()) * -10000.0
-        txt_mask = (1.0 - ori_input_mask.float()) * -10000.0
+        img_mask = ops.mask_additive(added_attention_mask, R)
+        txt_mask = ops.mask_additive(ori_input_mask, S)
 
         # text -> image, CMIM:968-969
         x32 = _rows(sequence_output)
-        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask.contiguous(), B, S, R,
+        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R,
                                                      keep_all=False)
         fused32 = outs[-1]
 
@@ -410,7 +410,7 @@ class CrossModalFusion(nn.Module):
                          out_dtype=torch.float32)
         z_lp = _to_lp(z32)
         for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask.contiguous(), B, 1, S, keep_all=False)
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False)
             z32 = zs[-1]
 
         # gated fusion, CMIM:1029-1036

@@ -58,6 +58,21 @@ def region_rows(grid: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     return rows
 
 
+def mask_additive(mask01: torch.Tensor, n: int) -> torch.Tensor:
+    """0/1 mask [B, >= n] (any integer/bool/float dtype) -> additive fp32 [B, n]: (1 - m) * -10000 (CMIM:962-965)."""
+    if mask01.dim() != 2 or mask01.shape[1] < n:
+        raise RuntimeError(f'mask_additive: mask of shape {tuple(mask01.shape)} has fewer than {n} columns')
+    m = mask01 if mask01.dtype == torch.int64 else mask01.long()
+    if m.stride(1) != 1:
+        m = m.contiguous()
+    B = m.shape[0]
+    lib, h, st = _ctx(m)
+    out = torch.empty(B, n, dtype=torch.float32, device=m.device)
+    _lib.check(lib.icka_mask_additive(h, m.data_ptr(), m.stride(0) if B > 1 else max(n, m.stride(0)), out.data_ptr(),
+                                      B, n, st), 'icka_mask_additive')
+    return out
+
+
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(a[M,K] . w[N,K]^T + bias) (+ residual).  a/w fp32 -> FFMA path, bf16 -> tcgen05 path.

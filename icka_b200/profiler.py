@@ -56,7 +56,7 @@ def _work(name, args, kwargs):
 
 
 class KernelTimer:
-    OPS = ('cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend',
+    OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend',
            'viterbi', 'crf_llh')
 
     def __init__(self):

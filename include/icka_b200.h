@@ -55,6 +55,10 @@ int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y_bf16, int64_t 
 int icka_region_rows(icka_handle* h, const float* grid, void* rows, int out_dtype,
                      int B, int C, int R, void* stream);
 
+/* CMIM:962-965 / 976-977  `(1.0 - mask) * -10000.0`: 0/1 int64 mask [B, >= n] (row pitch ld) -> additive
+ * fp32 mask [B, n] for the attention kernels. */
+int icka_mask_additive(icka_handle* h, const int64_t* mask, int64_t ld, float* out, int B, int n, void* stream);
+
 /* ---- dense layers ---------------------------------------------------------------------------- */
 
 /* nn.Linear with fused epilogue:  out[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual[M,N]).
