@@ -190,7 +190,7 @@ class ClockSampler:
 def run_gpu_arm(args, shape):
     import torch
     import torch.distributed as dist
-    from icka_b200 import _lib
+    from icka_b200 import _lib, shard
     from icka_b200.pipeline import FusionViterbiPipeline
     from icka_b200.profiler import KernelTimer
 
@@ -232,10 +232,7 @@ def run_gpu_arm(args, shape):
         barrier()
     ms_total = s_ev.elapsed_time(e_ev)
     launches = _lib.launch_count(local_rank) - launches0
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = shard.max_over_ranks(ms_total, device=dev)
     value = args.batch * world * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel roofline pass (same step, CUDA events around every C-ABI launch) ----
@@ -271,10 +268,7 @@ def run_gpu_arm(args, shape):
         results, (s2, e2) = pipe.infer_host(seq)
         barrier()
         ms_e2e = s2.elapsed_time(e2)
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+        ms_e2e = shard.max_over_ranks(ms_e2e, device=dev)
         d2h = sum(x.numel() * x.element_size() for x in results[0])
         e2e = {'value': args.batch * world * n_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
                'h2d_bytes_per_step': pipe.h2d_bytes(host), 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
