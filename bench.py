@@ -240,6 +240,7 @@ def run_gpu_arm(args, shape):
         for _ in range(args.steps):
             pipe.step_device(d)
         kernels = kt.summary()
+        gemm_shapes = kt.gemm_shapes()
     gemm = kernels.get('linear_bf16_tcgen05') or kernels.get('linear_fp32_ffma')
     peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
     roofline = {
@@ -297,6 +298,8 @@ def run_gpu_arm(args, shape):
                        'l2_policy': 'inputs larger than L2 (>= 1.2 GB of inputs per step vs 126 MB L2); no flush needed'},
             'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu, 'kernels': kernel_table,
+            'gemm_shapes': {k: {'launches_per_step': v['launches'] // args.steps, 'ms_per_launch': round(v['ms_per_launch'], 4),
+                                'tflops': round(v['tflops'], 1)} for k, v in gemm_shapes.items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,6 +29,7 @@ SIGNATURES = {
     'icka_mask_additive': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'icka_linear_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_set_gemm_mode': (c_int, [c_int]),
     'icka_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p]),
     'icka_cross_attn_core_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,

@@ -66,7 +66,14 @@ class CRF(nn.Module):
             tags = None if tags is None else tags.transpose(0, 1)
             mask = None if mask is None else mask.transpose(0, 1)
         e = emissions.float().contiguous()
-        m = None if mask is None else (mask != 0).to(torch.uint8).contiguous()
+        if mask is None:
+            m = None
+        elif mask.dtype == torch.uint8:
+            m = mask.contiguous()
+        elif mask.dtype == torch.bool:
+            m = mask.contiguous().view(torch.uint8)
+        else:
+            m = (mask != 0).contiguous().view(torch.uint8)
         y = None if tags is None else tags.long().contiguous()
         return e, y, m
 

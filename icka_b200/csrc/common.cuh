@@ -93,3 +93,61 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, copysignf(erf_abs, z), hx);
 }
+
+// Two lanes of the same function on Blackwell's packed fp32x2 FMA pipe (FFMA2 / FMUL2 / FADD2): the
+// polynomial, the exponent argument and the final blend take one instruction per PAIR of outputs.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_splat(float a) { return f2_pack(a, a); }
+
+__device__ __forceinline__ float2 gelu_erf_fast2(float x0, float x1) {
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t z = f2_mul(x, f2_splat(0.70710678118654752440f));
+  float z0, z1;
+  f2_unpack(z, z0, z1);
+  const uint64_t az = f2_pack(fabsf(z0), fabsf(z1));
+  float d0, d1;
+  f2_unpack(f2_fma(f2_splat(0.3275911f), az, f2_splat(1.0f)), d0, d1);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  uint64_t poly = f2_fma(f2_splat(1.061405429f), t, f2_splat(-1.453152027f));
+  poly = f2_fma(poly, t, f2_splat(1.421413741f));
+  poly = f2_fma(poly, t, f2_splat(-0.284496736f));
+  poly = f2_fma(poly, t, f2_splat(0.254829592f));
+  poly = f2_mul(poly, t);
+  float a0, a1;
+  f2_unpack(f2_mul(f2_mul(az, az), f2_splat(-1.4426950408889634f)), a0, a1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  float r0, r1;
+  f2_unpack(f2_fma(f2_mul(poly, f2_splat(-1.0f)), f2_pack(e0, e1), f2_splat(1.0f)), r0, r1);
+  const uint64_t erfv = f2_pack(copysignf(r0, z0), copysignf(r1, z1));
+  const uint64_t hx = f2_mul(x, f2_splat(0.5f));
+  float y0, y1;
+  f2_unpack(f2_fma(hx, erfv, hx), y0, y1);
+  return make_float2(y0, y1);
+}

@@ -36,13 +36,17 @@ constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant; they split the column blocks
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
-template <int BN>
+// CTAS == 1: one CTA computes a 128 x BN tile.  CTAS == 2: a CTA pair (cluster of 2, tcgen05 cta_group::2)
+// computes a 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the weight tile (BN/2 rows),
+// so the same shared memory holds 6 stages instead of 4 and the weight tile crosses the L2->SM fabric once
+// per pair.  The leader CTA (cluster rank 0) issues the MMAs for both.
+template <int BN, int CTAS = 1>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256 && CTAS == 1) ? 4 : 6;
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CTAS) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kTmemCols = 2 * BN;   // two accumulators (per CTA: 128 lanes x BN columns each)
   static constexpr int kStagingBytes = kEpiWarps * 32 * 128;   // one 32 x 32 fp32 transpose tile per epilogue warp
   static constexpr size_t kSmemBytes =
       (size_t)kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -54,13 +58,18 @@ struct GemmArgs {
   void* out;
   int64_t ldo;
   int M, N, K;
+  int debug;   // 0 = normal; developer probes: 1 = epilogue only releases the accumulator, 2 = no global stores
 };
 
-template <int BN, int ACT, bool OUT_BF16>
+template <int BN, int ACT, bool OUT_BF16, int CTAS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
+  const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
+  const int group_id = (CTAS == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-walking unit
+  const int num_groups = (CTAS == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int kTileM = kBM * CTAS;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -77,7 +86,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const int M = args.M, N = args.N, K = args.K;
-  const int m_tiles = (M + kBM - 1) / kBM;
+  const int m_tiles = (M + kTileM - 1) / kTileM;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + kBK - 1) / kBK;
@@ -91,51 +100,66 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kEpiWarps);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[a], kEpiWarps * CTAS);   // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc_pair(tmem_base_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // peer barriers must be initialised before use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int a_row = m_blk * kTileM + (int)cta_rank * kBM;
+        const int b_row = n_blk * BN + (int)cta_rank * (BN / CTAS);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (CTAS == 2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier, which it arms for the pair
+            const uint32_t full_leader = map_to_cta(&full_bar[stage], 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * 2);
+            tma_load_2d_pair(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, full_leader, kb * kBK, a_row);
+            tma_load_2d_pair(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, full_leader, kb * kBK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, a_row);
+            tma_load_2d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, b_row);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kBM, BN);
+    // ===================== MMA issuer (one thread; the leader CTA of a pair) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);             // TMA bytes have landed
+          mbar_wait(&full_bar[stage], phase);             // TMA bytes (of both CTAs) have landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * Cfg::kBBytes);
@@ -143,12 +167,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             const uint64_t da = make_kmajor_sw128_desc(a_addr + k * (kUmmaK * 2));
             const uint64_t db = make_kmajor_sw128_desc(b_addr + k * (kUmmaK * 2));
-            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          // smem slot free (in both CTAs) once these MMAs retire
+          if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);                 // accumulator complete
+        // accumulator complete: wake the epilogue warps of both CTAs
+        if (CTAS == 2) umma_commit_pair(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -172,19 +199,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       rd_base[k] = stage_tile + sub * 128 + ((((cp >> 1) ^ sub) ^ (2 * k)) << 4) + ((cp & 1) << 3);
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t empty_leader[2] = {CTAS == 2 ? map_to_cta(&tmem_empty_bar[0], 0) : 0u,
+                                      CTAS == 2 ? map_to_cta(&tmem_empty_bar[1], 0) : 0u};
+    for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile0 = n_blk * BN;
       const int nchunks = min(BN / 32, (N - n_tile0 + 31) / 32);
-      const int row_base = m_blk * kBM + quad * 32;
+      const int row_base = m_blk * kTileM + (int)cta_rank * kBM + quad * 32;
       const int rows_left = M - row_base - sub;           // row 2i+sub of this warp's block is valid iff 2i < rows_left
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       uint32_t r[32];
       bool released = false;
+      if (args.debug == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+        continue;
+      }
       if (half < nchunks) tmem_ld_32x32b_x32(taddr0 + (uint32_t)(half * 32), r);
 #pragma unroll 1
       for (int c = half; c < nchunks; c += 2) {
@@ -198,18 +233,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         } else {
           // this warp's last TMEM read has landed: hand the accumulator back before the global stores
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
           released = true;
         }
         const int col = n_tile0 + c * 32 + 2 * cp;
-        const bool col_ok = col < N;
+        const bool col_ok = col < N && args.debug != 2;
         float b0 = 0.0f, b1 = 0.0f;
         if (args.bias && col_ok) {
           const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
           b0 = bb.x;
           b1 = bb.y;
         }
-        const bool full = (rows_left >= 32) && (n_tile0 + c * 32 + 32 <= N);   // warp-uniform
+        const bool full = (rows_left >= 32) && (n_tile0 + c * 32 + 32 <= N) && args.debug != 2;   // warp-uniform
         const size_t row0 = (size_t)(row_base + sub);
         float2 res[16];
         if (args.residual) {
@@ -228,8 +263,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int i = 0; i < 16; ++i) {
           float x0 = x[i].x + b0, x1 = x[i].y + b1;
           if (ACT == ICKA_ACT_GELU_ERF) {
-            x0 = OUT_BF16 ? gelu_erf_fast(x0) : gelu_erf(x0);
-            x1 = OUT_BF16 ? gelu_erf_fast(x1) : gelu_erf(x1);
+            if (OUT_BF16) {
+              const float2 gg = gelu_erf_fast2(x0, x1);
+              x0 = gg.x;
+              x1 = gg.y;
+            } else {
+              x0 = gelu_erf(x0);
+              x1 = gelu_erf(x1);
+            }
           }
           if (args.residual) {
             x0 += res[i].x;
@@ -253,17 +294,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (!released) {   // warp had no column block in this (ragged) tile
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer's smem / barriers stay valid until both are done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -288,20 +329,43 @@ int make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t row
   return ICKA_OK;
 }
 
-template <int BN, int ACT, bool OUT_BF16>
+template <int BN, int ACT, bool OUT_BF16, int CTAS>
 int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16>;
+  using Cfg = GemmCfg<BN, CTAS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS>;
   ICKA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
-  const int m_tiles = (args.M + kBM - 1) / kBM, n_tiles = (args.N + BN - 1) / BN;
+  const int m_tiles = (args.M + kBM * CTAS - 1) / (kBM * CTAS), n_tiles = (args.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < h->sm_count ? tiles : h->sm_count;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, args);
+  const int groups_max = h->sm_count / CTAS;
+  const int groups = tiles < groups_max ? tiles : groups_max;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CTAS);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ICKA_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, args));
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
 
 }  // namespace
+
+// icka_gemm_mode: 0 = choose per shape (default), 1 = force single-CTA tiles, 2 = force CTA pairs.
+static int g_gemm_mode = 0;
+static int g_gemm_debug = 0;
+extern "C" int icka_set_gemm_mode(int mode) {
+  if (mode < 0 || (mode & 15) > 2) ICKA_FAIL(ICKA_ERR_INVALID, "gemm mode %d not in 0..2", mode);
+  g_gemm_mode = mode & 15;
+  g_gemm_debug = mode >> 4;   // developer probes, see GemmArgs::debug
+  return ICKA_OK;
+}
 
 int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                           const float* residual, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
@@ -312,23 +376,31 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
                "linear(bf16): A, W, out must be 16-byte aligned");
   ICKA_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "linear(bf16): N=%d and ldo=%lld must be multiples of 8", N, (long long)ldo);
   ICKA_REQUIRE(!residual || icka_aligned(residual, 16), "linear(bf16): residual must be 16-byte aligned");
-  ICKA_REQUIRE(h->smem_optin >= GemmCfg<256>::kSmemBytes, "linear(bf16): device offers too little shared memory");
+  constexpr size_t kNeedSmem = GemmCfg<256, 1>::kSmemBytes;
+  ICKA_REQUIRE(h->smem_optin >= kNeedSmem, "linear(bf16): device offers too little shared memory");
   const int BN = (N > 128) ? 256 : 128;
+  // CTA pairs pay off once there are enough 256-row tiles to fill the machine
+  bool pair = (BN == 256) && ((long long)((M + 255) / 256) * ((N + 255) / 256) >= h->sm_count / 2);
+  if (g_gemm_mode == 1) pair = false;
+  if (g_gemm_mode == 2) pair = (BN == 256);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16(h, &tb, W, N, K, ldw, BN);
+  rc = make_tmap_bf16(h, &tb, W, N, K, ldw, pair ? BN / 2 : BN);
   if (rc) return rc;
-  GemmArgs args{bias, residual, out, ldo, M, N, K};
+  GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug};
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
-#define ICKA_GEMM(BN_, ACT_, BF_) return launch_gemm<BN_, ACT_, BF_>(h, ta, tb, args, st)
-  if (BN == 256) {
-    if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false); }
-    else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true);     else ICKA_GEMM(256, ICKA_ACT_NONE, false); }
+#define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_>(h, ta, tb, args, st)
+  if (pair) {
+    if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true, 2); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false, 2); }
+    else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true, 2);     else ICKA_GEMM(256, ICKA_ACT_NONE, false, 2); }
+  } else if (BN == 256) {
+    if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true, 1); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false, 1); }
+    else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true, 1);     else ICKA_GEMM(256, ICKA_ACT_NONE, false, 1); }
   } else {
-    if (gelu) { if (bf) ICKA_GEMM(128, ICKA_ACT_GELU_ERF, true); else ICKA_GEMM(128, ICKA_ACT_GELU_ERF, false); }
-    else      { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true);     else ICKA_GEMM(128, ICKA_ACT_NONE, false); }
+    if (gelu) { if (bf) ICKA_GEMM(128, ICKA_ACT_GELU_ERF, true, 1); else ICKA_GEMM(128, ICKA_ACT_GELU_ERF, false, 1); }
+    else      { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true, 1);     else ICKA_GEMM(128, ICKA_ACT_NONE, false, 1); }
   }
 #undef ICKA_GEMM
 }

@@ -61,6 +61,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = []
+        self.shapes = []
         self._saved = {}
 
     def __enter__(self):
@@ -78,6 +79,8 @@ class KernelTimer:
     def _wrap(self, name, fn):
         def timed(*args, **kwargs):
             tag, flops, nbytes = _work(name, args, kwargs)
+            if name == 'linear':
+                self.shapes.append((f'{args[0].shape[0]}x{args[1].shape[0]}x{args[0].shape[1]}', len(self.records)))
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             out = fn(*args, **kwargs)
@@ -103,3 +106,15 @@ class KernelTimer:
                             gbs=(a['bytes'] / sec / 1e9) if sec > 0 else 0.0,
                             flops_per_launch=a['flops'] / a['launches'], bytes_per_launch=a['bytes'] / a['launches'])
         return out
+
+    def gemm_shapes(self):
+        """Per (M x N x K) GEMM shape: launches, mean ms per launch, TFLOP/s (call after summary())."""
+        agg = defaultdict(lambda: [0, 0.0, 0.0])
+        for shape, idx in self.shapes:
+            tag, s, e, flops, nbytes = self.records[idx]
+            a = agg[shape]
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+            a[2] += flops
+        return {k: dict(launches=v[0], ms_per_launch=v[1] / v[0], tflops=v[2] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else 0.0)
+                for k, v in agg.items()}

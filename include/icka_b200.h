@@ -73,6 +73,10 @@ int icka_linear_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, i
                     const float* bias, const float* residual, void* out, int64_t ldo,
                     int in_dtype, int out_dtype, int M, int N, int K, int act, void* stream);
 
+/* Tile-shape policy of the bf16 path (process-wide tuning/testing knob): 0 = choose per shape (default),
+ * 1 = always single-CTA 128 x N tiles, 2 = always CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256). */
+int icka_set_gemm_mode(int mode);
+
 /* BertLayerNorm CMIM:518-522 (TF style: biased variance, eps inside the sqrt) over rows of x[M,N]
  * (x already holds dense(...) + input).  Writes y_f32 and/or y_bf16 (either may be NULL). */
 int icka_layernorm_fwd(icka_handle* h, const float* x, const float* gamma, const float* beta, float eps,

@@ -26,8 +26,16 @@ SHAPES = [(128, 256, 64), (128, 256, 16), (128, 128, 64), (128, 256, 768), (256,
           (1024, 3072, 768), (1000, 768, 3072), (7, 768, 512), (130, 1536, 768), (300, 136, 40), (128 * 40, 768, 768)]
 
 
+@pytest.fixture(params=[0, 1, 2], ids=['auto', 'single_cta', 'cta_pair'])
+def gemm_mode(request):
+    from icka_b200 import _lib
+    _lib.check(_lib.load().icka_set_gemm_mode(request.param), 'icka_set_gemm_mode')
+    yield request.param
+    _lib.load().icka_set_gemm_mode(0)
+
+
 @pytest.mark.parametrize('M,N,K', SHAPES)
-def test_linear_bf16_fp32_out(M, N, K):
+def test_linear_bf16_fp32_out(M, N, K, gemm_mode):
     a = rnd(M, K, seed=1).bfloat16()
     w = (rnd(N, K, seed=2) / math.sqrt(K)).bfloat16()
     bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
@@ -38,7 +46,7 @@ def test_linear_bf16_fp32_out(M, N, K):
 
 
 @pytest.mark.parametrize('M,N,K', [(256, 3072, 768), (77, 256, 128), (128, 768, 768)])
-def test_linear_bf16_gelu_bf16_out(M, N, K):
+def test_linear_bf16_gelu_bf16_out(M, N, K, gemm_mode):
     a = rnd(M, K, seed=5).bfloat16()
     w = (rnd(N, K, seed=6) / math.sqrt(K)).bfloat16()
     bias = rnd(N, seed=7)
@@ -48,7 +56,7 @@ def test_linear_bf16_gelu_bf16_out(M, N, K):
     assert err <= 2 ** -8, err
 
 
-def test_linear_bf16_pitched_kv_views():
+def test_linear_bf16_pitched_kv_views(gemm_mode):
     """Consumers read K and V as column halves of one [K|V] buffer; A may be a pitched view too."""
     M, H = 200, 768
     a_full = rnd(M, 2 * H, seed=8).bfloat16().to(DEV)

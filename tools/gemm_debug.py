@@ -53,10 +53,14 @@ def run(M, N, K, pattern='rand'):
 
 if __name__ == '__main__':
     ok = True
+    from icka_b200 import _lib
+    if len(sys.argv) > 1:
+        _lib.load().icka_set_gemm_mode(int(sys.argv[1]))
+        print('gemm mode', sys.argv[1])
     for args in [(128, 128, 16, 'ones'), (128, 128, 16, 'rand'), (128, 128, 64, 'ones'), (128, 128, 64, 'rowid'),
                  (128, 128, 64, 'colid'), (128, 128, 64, 'kid'), (128, 128, 64, 'rand'), (128, 256, 64, 'rand'),
                  (128, 256, 128, 'rand'), (128, 256, 768, 'rand'), (256, 256, 64, 'rand'), (1024, 768, 768, 'rand'),
-                 (128 * 300, 768, 768, 'rand')]:
+                 (128 * 300, 768, 768, 'rand'), (256, 256, 64, 'rowid'), (256, 256, 64, 'colid'), (512, 512, 128, 'rand'), (1000, 768, 3072, 'rand')]:
         ok = run(*args) and ok
     print('ALL OK' if ok else 'FAILURES')
     sys.exit(0 if ok else 1)

@@ -25,7 +25,10 @@ def timeit(fn, iters=20, warm=3):
     return s.elapsed_time(e) / iters * 1e-3
 
 
-def main(B=1024):
+def main(B=1024, mode=0):
+    from icka_b200 import _lib
+    _lib.load().icka_set_gemm_mode(mode)
+    print('gemm mode', mode)
     S, R, H, I = 128, 49, 768, 3072
     bf = torch.bfloat16
     x = torch.randn(B * S, H, device=DEV)
@@ -88,4 +91,4 @@ def main(B=1024):
 
 
 if __name__ == '__main__':
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 1024)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 1024, int(sys.argv[2]) if len(sys.argv) > 2 else 0)
