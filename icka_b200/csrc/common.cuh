@@ -22,6 +22,10 @@ struct icka_handle {
 
 void icka_set_error(const char* fmt, ...);
 
+// 2-D bf16 TMA descriptor: tensor [rows, cols] with row pitch `ld` elements, box {64 cols, box_rows}, SWIZZLE_128B.
+int icka_make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                        int box_rows);
+
 #define ICKA_FAIL(code, ...)      \
   do {                            \
     icka_set_error(__VA_ARGS__);  \

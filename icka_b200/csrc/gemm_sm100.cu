@@ -312,8 +312,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+}  // namespace
+
 // 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = {64 cols, box_rows}, 128-byte swizzle.
-int make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+int icka_make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
@@ -328,6 +330,8 @@ int make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t row
               (long long)rows, (long long)cols, (long long)ld, box_rows);
   return ICKA_OK;
 }
+
+namespace {
 
 template <int BN, int ACT, bool OUT_BF16, int CTAS>
 int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
@@ -384,9 +388,9 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   if (g_gemm_mode == 1) pair = false;
   if (g_gemm_mode == 2) pair = (BN == 256);
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
+  int rc = icka_make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_bf16(h, &tb, W, N, K, ldw, pair ? BN / 2 : BN);
+  rc = icka_make_tmap_bf16(h, &tb, W, N, K, ldw, pair ? BN / 2 : BN);
   if (rc) return rc;
   GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug};
   const bool bf = out_dtype == ICKA_BF16;
