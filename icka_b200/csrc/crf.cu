@@ -27,6 +27,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 struct SeqSmem {
+  float* score;    // [2][16] score exchange buffers (viterbi16_kernel)
   float* em;       // [S*T] (rounded up to 4)
   uint8_t* bp;     // [(S-1)*LPS]
   uint8_t* mask;   // [S]
@@ -37,7 +38,7 @@ __host__ __device__ inline size_t seq_smem_bytes(int S, int T, int LPS) {
   size_t em = ((size_t)S * T + 3) / 4 * 16;
   size_t bp = ((size_t)(S > 1 ? S - 1 : 1) * LPS + 15) / 16 * 16;
   size_t mk = ((size_t)S + 15) / 16 * 16;
-  return em + bp + 2 * mk;
+  return 128 + em + bp + 2 * mk;
 }
 
 template <int LPS>
@@ -46,8 +47,9 @@ __device__ __forceinline__ SeqSmem carve(uint8_t* base, int S, int T) {
   size_t em = ((size_t)S * T + 3) / 4 * 16;
   size_t bp = ((size_t)(S > 1 ? S - 1 : 1) * LPS + 15) / 16 * 16;
   size_t mk = ((size_t)S + 15) / 16 * 16;
-  s.em = reinterpret_cast<float*>(base);
-  s.bp = base + em;
+  s.score = reinterpret_cast<float*>(base);
+  s.em = reinterpret_cast<float*>(base + 128);
+  s.bp = base + 128 + em;
   s.mask = s.bp + bp;
   s.tagb = s.mask + mk;
   return s;
@@ -185,6 +187,170 @@ __global__ void __launch_bounds__(kThreads) viterbi_kernel(
   if (gl == 0) lens_out[b] = len;
 }
 
+// ---- T <= 16: two sentences per warp, both halves in lock-step ------------------------------------------
+// The generic kernel above syncs each half-warp on its own member mask, which makes the two halves of a
+// warp run the serial chain one after the other, and scans the 15 predecessors with a 15-deep compare
+// chain.  Here every shuffle uses the full mask (the warp runs max(len_a, len_b) steps; a half that is
+// already past its own length just keeps its score), lane j publishes score[j] in shared memory and reads all
+// 16 back as four broadcast 16-byte loads (the shuffle unit, 16 SHFL per step, was the limiter: ~4 cycles
+// per SHFL per SM), the 16 candidates of a step are formed independently
+// and reduced by a 4-level (value, index) tournament whose left operand always holds the lower indices, so
+// "first index wins ties" is preserved exactly, and the next step's emission is fetched from shared memory
+// one step ahead of the chain.
+struct Cand {
+  float v;
+  int i;
+};
+__device__ __forceinline__ Cand take_first_max(const Cand a, const Cand b) {   // a holds the lower indices
+  Cand r;
+  r.v = fmaxf(a.v, b.v);          // value chain: one FMNMX per level (inputs are NaN-free; a signed-zero
+  r.i = (b.v > a.v) ? b.i : a.i;  // difference cannot change a later comparison); the index trails it
+  return r;
+}
+
+constexpr int kV16Threads = 128;
+constexpr int kV16Seqs = kV16Threads / 16;
+
+__global__ void __launch_bounds__(kV16Threads) viterbi16_kernel(
+    const float* __restrict__ emissions, const uint8_t* __restrict__ mask, const float* __restrict__ start,
+    const float* __restrict__ end, const float* __restrict__ trans, int32_t* __restrict__ tags_out,
+    int32_t* __restrict__ lens_out, int B, int S, int T, size_t per_seq_bytes) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g_in_block = threadIdx.x >> 4;
+  const int gl = threadIdx.x & 15;
+  const int gshift = threadIdx.x & 16;
+  const int b_raw = blockIdx.x * kV16Seqs + g_in_block;
+  if (blockIdx.x * kV16Seqs + (g_in_block & ~1) >= B) return;   // whole warp out of range
+  const bool seq_ok = b_raw < B;
+  const int b = seq_ok ? b_raw : B - 1;   // an odd tail half shadows the last sentence and stores nothing
+
+  SeqSmem sm = carve<16>(smem_raw + (size_t)g_in_block * per_seq_bytes, S, T);
+  const float* e_g = emissions + (size_t)b * S * T;
+  const uint8_t* mrow = mask ? mask + (size_t)b * S : nullptr;
+
+  // mask row -> smem, len = sum(mask), prefix = (mask is len ones followed by zeros)
+  int len = 0;
+  bool prefix = true, seen_zero = false;
+  for (int t0 = 0; t0 < S; t0 += 16) {
+    const int t = t0 + gl;
+    uint8_t m = 0;
+    if (t < S) {
+      m = mrow ? (mrow[t] != 0) : 1;
+      sm.mask[t] = m;
+    }
+    const unsigned bits = (__ballot_sync(kFull, m != 0) >> gshift) & 0xffffu;
+    const int c = __popc(bits);
+    if (bits != 0 && seen_zero) prefix = false;
+    if (bits != ((1u << c) - 1u)) prefix = false;
+    if (c < min(16, S - t0)) seen_zero = true;
+    len += c;
+  }
+  const bool fast = prefix && len >= 1;
+  const int n_steps = fast ? len : S;                                      // this sentence runs t = 0 .. n_steps-1
+  const int n_warp = max(n_steps, __shfl_xor_sync(kFull, n_steps, 16));    // the warp's trip count
+  const bool all_fast = __all_sync(kFull, fast);
+
+  // emission slab -> smem: the first 16 steps as one cp.async group, the rest as a second one
+  const int n_floats = n_steps * T;
+  const int head_floats = min(n_floats, 16 * T);
+  const bool vec_ok = ((((size_t)S * T) % 4) == 0) && ((reinterpret_cast<uintptr_t>(emissions) % 16) == 0);
+  if (vec_ok) {
+    const int nvec = (n_floats + 3) / 4, hvec = (head_floats + 3) / 4;   // <= 3 floats of slack stay inside S*T
+    for (int v = gl; v < hvec; v += 16) cp_async16(sm.em + 4 * v, e_g + 4 * v);
+    cp_async_commit();
+    for (int v = hvec + gl; v < nvec; v += 16) cp_async16(sm.em + 4 * v, e_g + 4 * v);
+    cp_async_commit();
+  } else {
+    for (int i = gl; i < n_floats; i += 16) sm.em[i] = e_g[i];
+    cp_async_commit();
+    cp_async_commit();
+  }
+
+  const bool active = gl < T;
+  float tr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tr[i] = (i < T) ? (active ? trans[i * T + gl] : 0.0f) : -INFINITY;
+  const float st = active ? start[gl] : 0.0f;
+  const float en = active ? end[gl] : 0.0f;
+
+  cp_async_wait<1>();
+  __syncwarp();
+  float score = active ? st + sm.em[gl] : 0.0f;   // idle lanes carry 0; their tr[] row is never selected
+  sm.score[gl] = score;
+  __syncwarp();
+  const float* e_ptr = sm.em + gl;
+  uint8_t* bp_ptr = sm.bp + gl;
+  // reads past a sentence's own n_steps hit unwritten (but allocated) smem; the result is discarded
+  float e_next = (n_warp > 1) ? e_ptr[T] : 0.0f;
+  for (int t = 1; t < n_warp; ++t) {
+    if (t == 15) {   // the prefetch below leaves the head group
+      cp_async_wait<0>();
+      __syncwarp();
+    }
+    const float e = e_next;
+    e_next = e_ptr[min(t + 1, S - 1) * T];
+    // all 16 scores of the previous step: four broadcast 16-byte shared loads (one address per half-warp)
+    const float4* sp = reinterpret_cast<const float4*>(sm.score + ((t - 1) & 1) * 16);
+    const float4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3];
+    const float sv[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
+                          s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+    Cand c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      c[i].v = (sv[i] + tr[i]) + e;
+      c[i].i = i;
+    }
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) c[k] = take_first_max(c[2 * k], c[2 * k + 1]);
+    // note: level order above pairs (0,1)(2,3).. then (01,23).. so the left operand is always the lower range
+    bp_ptr[(t - 1) * 16] = (uint8_t)c[0].i;
+    bool upd = active && t < n_steps;
+    if (!all_fast) upd = upd && sm.mask[t] != 0;
+    score = upd ? c[0].v : score;
+    sm.score[(t & 1) * 16 + gl] = score;
+    __syncwarp();   // step t+1 reads this buffer and overwrites the other one, which every lane has finished reading
+  }
+  cp_async_wait<0>();   // nothing may be in flight at exit
+
+  // last = first argmax_j (score[j] + end[j])
+  float fin = active ? score + en : -INFINITY;
+  int idx = gl;
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const float ov = __shfl_xor_sync(kFull, fin, off, 16);
+    const int oi = __shfl_xor_sync(kFull, idx, off, 16);
+    if (ov > fin || (ov == fin && oi < idx)) { fin = ov; idx = oi; }
+  }
+  __syncwarp();   // back-pointer writes visible to the tracing lane
+  if (gl == 0 && len >= 1) {
+    int cur = idx;
+    sm.tagb[len - 1] = (uint8_t)cur;
+    for (int k = len - 2; k >= 0; --k) {
+      cur = sm.bp[k * 16 + cur];
+      sm.tagb[k] = (uint8_t)cur;
+    }
+  }
+  __syncwarp();
+  if (!seq_ok) return;
+  int32_t* out = tags_out + (size_t)b * S;
+  if ((S % 4) == 0 && (reinterpret_cast<uintptr_t>(tags_out) % 16) == 0) {
+    for (int t = 4 * gl; t < S; t += 64) {
+      int4 v;
+      v.x = (t + 0 < len) ? (int)sm.tagb[t + 0] : -1;
+      v.y = (t + 1 < len) ? (int)sm.tagb[t + 1] : -1;
+      v.z = (t + 2 < len) ? (int)sm.tagb[t + 2] : -1;
+      v.w = (t + 3 < len) ? (int)sm.tagb[t + 3] : -1;
+      *reinterpret_cast<int4*>(out + t) = v;
+    }
+  } else {
+    for (int t = gl; t < S; t += 16) out[t] = (t < len) ? (int32_t)sm.tagb[t] : -1;
+  }
+  if (gl == 0) lens_out[b] = len;
+}
+
 // Per-sentence log-likelihood: gold-path score minus log-partition (forward algorithm), fp32.
 // Same lane mapping as Viterbi; logsumexp over predecessors i is max-shifted like torch.logsumexp.
 template <int LPS>
@@ -282,9 +448,9 @@ extern "C" int icka_viterbi_decode(icka_handle* h, const float* emissions, const
               smem, h->smem_optin);
   const int grid = (B + spb - 1) / spb;
   if (LPS == 16) {
-    ICKA_CUDA(cudaFuncSetAttribute(viterbi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    viterbi_kernel<16><<<grid, kThreads, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B,
-                                                      S, T, per_seq);
+    ICKA_CUDA(cudaFuncSetAttribute(viterbi16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    viterbi16_kernel<<<grid, kV16Threads, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B, S,
+                                                      T, per_seq);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(viterbi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     viterbi_kernel<32><<<grid, kThreads, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B,
