@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libicka_b200.so')
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU_ERF = 0, 1
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_ERF_BWD = 0, 1, 2
 
 # name -> (restype, argtypes); must list every symbol of include/icka_b200.h
 SIGNATURES = {
@@ -29,6 +29,25 @@ SIGNATURES = {
     'icka_mask_additive': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'icka_linear_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_linear_fwd_ex': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_linear_dgrad': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_linear_wgrad': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_void_p]),
+    'icka_colsum': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'icka_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'icka_cross_attn_core_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                         c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_gate_blend_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                    c_int, c_int, c_void_p]),
+    'icka_gate_fold_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_void_p]),
+    'icka_crf_llh_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'icka_set_gemm_mode': (c_int, [c_int]),
     'icka_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p]),

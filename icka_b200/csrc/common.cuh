@@ -98,6 +98,26 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, copysignf(erf_abs, z), hx);
 }
 
+// d/dx of the erf-GELU: Phi(x) + x * phi(x)  (exact form for the fp32 path, fast form for bf16 outputs)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;   // exp(-z^2) = exp(-x^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return fmaf(0.5f, copysignf(erf_abs, z), 0.5f) + x * 0.3989422804014327f * e;
+}
+
 // Two lanes of the same function on Blackwell's packed fp32x2 FMA pipe (FFMA2 / FMUL2 / FADD2): the
 // polynomial, the exponent argument and the final blend take one instruction per PAIR of outputs.
 __device__ __forceinline__ uint64_t f2_pack(float a, float b) {

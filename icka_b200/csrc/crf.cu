@@ -428,6 +428,157 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
   }
 }
 
+// Gradient of sum_b w[b] * llh[b]: forward-backward marginals minus the gold path (the autograd of
+// pytorch-crf's forward()).  Same lane mapping as crf_llh_kernel (lane j <-> tag j); the chain runs over the
+// "on" steps only (step 0 always counts, exactly as in _compute_normalizer where masked steps leave alpha
+// untouched); the alphas of all on-steps are kept in shared memory for the backward sweep.  Parameter
+// gradients are gathered per block in shared memory and added to the global vectors once per block.
+template <int LPS>
+__global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
+    const float* __restrict__ emissions, const int64_t* __restrict__ tags, const uint8_t* __restrict__ mask,
+    const float* __restrict__ start, const float* __restrict__ end, const float* __restrict__ trans,
+    const float* __restrict__ w, float* __restrict__ d_emissions, float* __restrict__ d_start,
+    float* __restrict__ d_end, float* __restrict__ d_trans, int B, int S, int T, size_t per_seq_bytes) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int kSeqs = kThreads / LPS;
+  float* s_dtrans = reinterpret_cast<float*>(smem_raw);      // [T*T]
+  float* s_dstart = s_dtrans + T * T;                        // [T]
+  float* s_dend = s_dstart + T;                              // [T]
+  const size_t head = (((size_t)T * T + 2 * T) * sizeof(float) + 15) / 16 * 16;
+  const int g_in_block = threadIdx.x / LPS;
+  const int gl = threadIdx.x % LPS;
+  const int gshift = (threadIdx.x % 32) / LPS * LPS;
+  const unsigned gmask = (LPS == 32) ? 0xffffffffu : (0xffffu << gshift);
+  const int b = blockIdx.x * kSeqs + g_in_block;
+  for (int i = threadIdx.x; i < T * T + 2 * T; i += kThreads) s_dtrans[i] = 0.0f;
+  __syncthreads();
+
+  if (b < B) {
+    float* alpha = reinterpret_cast<float*>(smem_raw + head + (size_t)g_in_block * per_seq_bytes);   // [S][LPS]
+    int* on_idx = reinterpret_cast<int*>(alpha + (size_t)S * LPS);                                   // [S]
+    const float* e_g = emissions + (size_t)b * S * T;
+    const uint8_t* m_g = mask ? mask + (size_t)b * S : nullptr;
+    const int64_t* y_g = tags + (size_t)b * S;
+    float* de_g = d_emissions + (size_t)b * S * T;
+    const bool active = gl < T;
+    const float wb = w[b];
+
+    // on-steps (t = 0 always), len = sum(mask) as pytorch-crf counts it
+    int n_on = 0, len = 0;
+    for (int t0 = 0; t0 < S; t0 += LPS) {
+      const int t = t0 + gl;
+      const bool m = (t < S) && (m_g ? (m_g[t] != 0) : true);
+      const bool on = (t < S) && (m || t == 0);
+      const unsigned bits_on = (__ballot_sync(gmask, on) >> gshift) & (LPS == 32 ? 0xffffffffu : 0xffffu);
+      const unsigned bits_m = (__ballot_sync(gmask, m) >> gshift) & (LPS == 32 ? 0xffffffffu : 0xffffu);
+      if (on) on_idx[n_on + __popc(bits_on & ((1u << gl) - 1u))] = t;
+      n_on += __popc(bits_on);
+      len += __popc(bits_m);
+    }
+    for (int i = gl; i < S * T; i += LPS) de_g[i] = 0.0f;
+    __syncwarp(gmask);
+
+    float tr[LPS], trr[LPS];   // column gl and row gl of the transition matrix
+#pragma unroll
+    for (int i = 0; i < LPS; ++i) {
+      tr[i] = (active && i < T) ? trans[i * T + gl] : 0.0f;
+      trr[i] = (active && i < T) ? trans[gl * T + i] : 0.0f;
+    }
+
+    // ---- forward sweep: alpha[n][j] ----
+    float a = active ? start[gl] + e_g[gl] : -INFINITY;
+    alpha[gl] = a;
+    for (int n = 1; n < n_on; ++n) {
+      const int t = on_idx[n];
+      const float e = active ? e_g[t * T + gl] : 0.0f;
+      float c[LPS];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < LPS; ++i) {
+        if (i < T) {
+          c[i] = (__shfl_sync(gmask, a, i, LPS) + tr[i]) + e;
+          mx = fmaxf(mx, c[i]);
+        }
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int i = 0; i < LPS; ++i)
+        if (i < T) sum += expf(c[i] - mx);
+      if (active) a = mx + logf(sum);
+      alpha[n * LPS + gl] = a;
+    }
+    float fin = active ? a + end[gl] : -INFINITY;
+    float mx = fin;
+#pragma unroll
+    for (int off = LPS / 2; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, off, LPS));
+    float ex = active ? expf(fin - mx) : 0.0f;
+#pragma unroll
+    for (int off = LPS / 2; off >= 1; off >>= 1) ex += __shfl_xor_sync(gmask, ex, off, LPS);
+    const float logz = mx + logf(ex);
+    __syncwarp(gmask);
+
+    // ---- backward sweep ----
+    float acc_tr[LPS];   // sum over steps of P(y_prev = i, y_cur = gl)
+#pragma unroll
+    for (int i = 0; i < LPS; ++i) acc_tr[i] = 0.0f;
+    float beta = active ? end[gl] : -INFINITY;
+    const int y_last = (int)y_g[max(len - 1, 0)];
+    for (int n = n_on - 1; n >= 0; --n) {
+      const int t = on_idx[n];
+      const float an = alpha[n * LPS + gl];
+      const float p = active ? expf(an + beta - logz) : 0.0f;
+      const int y = (int)y_g[t];
+      if (active) {
+        de_g[t * T + gl] = wb * ((y == gl ? 1.0f : 0.0f) - p);
+        if (n == n_on - 1) atomicAdd(s_dend + gl, wb * ((y_last == gl ? 1.0f : 0.0f) - p));
+        if (n == 0) atomicAdd(s_dstart + gl, wb * ((y == gl ? 1.0f : 0.0f) - p));
+      }
+      if (n == 0) break;
+      const float e = active ? e_g[t * T + gl] : 0.0f;
+      const float eb = active ? e + beta : -INFINITY;     // e[t][j] + beta_n[j], lane j
+      // pairwise marginals of (on-step n-1 -> n), column gl
+#pragma unroll
+      for (int i = 0; i < LPS; ++i) {
+        if (i < T) {
+          const float ai = alpha[(n - 1) * LPS + i];
+          if (active) acc_tr[i] += expf(((ai + tr[i]) + eb) - logz);
+        }
+      }
+      // beta_{n-1}[i] = logsumexp_j (trans[i][j] + e[t][j] + beta_n[j]), lane i
+      float c[LPS];
+      float bm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < LPS; ++j) {
+        if (j < T) {
+          c[j] = trr[j] + __shfl_sync(gmask, eb, j, LPS);
+          bm = fmaxf(bm, c[j]);
+        }
+      }
+      float bs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LPS; ++j)
+        if (j < T) bs += expf(c[j] - bm);
+      beta = active ? bm + logf(bs) : -INFINITY;
+    }
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < LPS; ++i)
+        if (i < T) atomicAdd(s_dtrans + i * T + gl, -wb * acc_tr[i]);
+    }
+    // gold transitions: pytorch-crf's _compute_score pairs every on-step t >= 1 with position t-1
+    for (int t = 1 + gl; t < S; t += LPS) {
+      const bool on = m_g ? (m_g[t] != 0) : true;
+      if (on) atomicAdd(s_dtrans + (int)y_g[t - 1] * T + (int)y_g[t], wb);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += kThreads) atomicAdd(d_trans + i, s_dtrans[i]);
+  for (int i = threadIdx.x; i < T; i += kThreads) {
+    atomicAdd(d_start + i, s_dstart[i]);
+    atomicAdd(d_end + i, s_dend[i]);
+  }
+}
+
 }  // namespace
 
 extern "C" int icka_viterbi_decode(icka_handle* h, const float* emissions, const uint8_t* mask,
@@ -476,6 +627,39 @@ extern "C" int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const in
     crf_llh_kernel<16><<<grid, kThreads, 0, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
   else
     crf_llh_kernel<32><<<grid, kThreads, 0, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const int64_t* tags, const uint8_t* mask,
+                                const float* start, const float* end, const float* trans, const float* w,
+                                float* d_emissions, float* d_start, float* d_end, float* d_trans, int B, int S, int T,
+                                void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && T >= 1, "crf_llh_bwd: bad shape B=%d S=%d T=%d", B, S, T);
+  ICKA_REQUIRE(T <= 32, "crf_llh_bwd: num_tags %d > 32 not supported by this kernel", T);
+  ICKA_REQUIRE(emissions && tags && start && end && trans && w && d_emissions && d_start && d_end && d_trans,
+               "crf_llh_bwd: null pointer");
+  if (B == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int LPS = (T <= 16) ? 16 : 32;
+  const int spb = kThreads / LPS;
+  const size_t head = (((size_t)T * T + 2 * T) * sizeof(float) + 15) / 16 * 16;
+  const size_t per_seq = ((size_t)S * LPS * sizeof(float) + (size_t)S * sizeof(int) + 15) / 16 * 16;
+  const size_t smem = head + per_seq * spb;
+  if (smem > h->smem_optin)
+    ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh_bwd: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,
+              h->smem_optin);
+  const int grid = (B + spb - 1) / spb;
+  if (LPS == 16) {
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_llh_bwd_kernel<16><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, w, d_emissions,
+                                                         d_start, d_end, d_trans, B, S, T, per_seq);
+  } else {
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_llh_bwd_kernel<32><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, w, d_emissions,
+                                                         d_start, d_end, d_trans, B, S, T, per_seq);
+  }
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -23,6 +23,16 @@
 // HBM once (weights are a few MB and stay in the 126 MB L2).
 // Ragged edges: TMA zero-fills out-of-bounds rows/columns (M, N and K tails), the epilogue masks
 // rows >= M and columns >= N.
+//
+// Operand layouts (template parameter MAJOR) -- the same pipeline serves the backward GEMMs of training
+// without transposed copies of weights or activations, by switching the UMMA descriptors to MN-major:
+//   MAJOR 0  forward   out = A[M,K] . W[N,K]^T          A, W contraction-contiguous (K-major)
+//   MAJOR 1  dgrad     dX  = dY[M,K'] . W[K',N]         second operand read as stored by nn.Linear ([out,in]):
+//                                                        its N (output) index is contiguous -> MN-major B
+//   MAJOR 2  wgrad     dW += dY[T,M]^T . X[T,N]         both operands token-major: MN-major A and B, the token
+//                                                        range is split over CTAs (split-K) and partial tiles
+//                                                        are added to dW with fp32 red.global
+// MN-major tiles are fetched by one 3-D TMA box {64 elements, 64 contraction rows, tile/64 chunks} each.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -59,12 +69,21 @@ struct GemmArgs {
   int64_t ldo;
   int M, N, K;
   int debug;   // 0 = normal; developer probes: 1 = epilogue only releases the accumulator, 2 = no global stores
+  const __nv_bfloat16* aux_in;   // ACT_GELU_ERF_BWD: pre-activation u [M, N] (pitch ld_aux)
+  __nv_bfloat16* aux_out;        // ACT_GELU_ERF: optional copy of the pre-activation (acc + bias) [M, N]
+  int64_t ld_aux;
+  int splits;                    // MAJOR 2: number of contraction ranges; 1 otherwise
+  int kb_per_split;
 };
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS>
+constexpr int kChunkBytes = kBK * 128;   // one 64-element-wide MN-major chunk of a stage: 64 contraction rows x 128 B
+
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
+  static_assert(MAJOR == 0 || CTAS == 1, "MN-major operands are built for single-CTA tiles only");
+  static_assert(MAJOR != 2 || (!OUT_BF16 && ACT == ICKA_ACT_NONE), "wgrad accumulates plain fp32");
   using Cfg = GemmCfg<BN, CTAS>;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const int group_id = (CTAS == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // tile-walking unit
@@ -88,7 +107,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int M = args.M, N = args.N, K = args.K;
   const int m_tiles = (M + kTileM - 1) / kTileM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * args.splits;   // split-major: concurrent CTAs share a contraction range
   const int num_kb = (K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -125,10 +145,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int split = tile / mn_tiles, mn = tile % mn_tiles;
+        const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
         const int a_row = m_blk * kTileM + (int)cta_rank * kBM;
         const int b_row = n_blk * BN + (int)cta_rank * (BN / CTAS);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * args.kb_per_split, kb1 = min(num_kb, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (CTAS == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier, which it arms for the pair
@@ -138,8 +160,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tma_load_2d_pair(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, full_leader, kb * kBK, b_row);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, a_row);
-            tma_load_2d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, b_row);
+            if (MAJOR == 2)
+              tma_load_3d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], 0, kb * kBK, a_row / 64);
+            else
+              tma_load_2d(smem_a + (size_t)stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kBK, a_row);
+            if (MAJOR >= 1)
+              tma_load_3d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], 0, kb * kBK, b_row / 64);
+            else
+              tma_load_2d(smem_b + (size_t)stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kBK, b_row);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -148,7 +176,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread; the leader CTA of a pair) =====================
     if (lane == 0 && cta_rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, BN, MAJOR == 2, MAJOR >= 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -158,17 +186,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int split = tile / mn_tiles;
+        const int kb0 = split * args.kb_per_split, kb1 = min(num_kb, kb0 + args.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);             // TMA bytes (of both CTAs) have landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * Cfg::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            const uint64_t da = make_kmajor_sw128_desc(a_addr + k * (kUmmaK * 2));
-            const uint64_t db = make_kmajor_sw128_desc(b_addr + k * (kUmmaK * 2));
-            if (CTAS == 2) umma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            // K-major: 16 contraction elements = 32 B inside the 128-B swizzle row;
+            // MN-major: 16 contraction rows = 2 swizzle atoms of 8 rows x 128 B
+            const uint64_t da = (MAJOR == 2) ? make_mnmajor_sw128_desc(a_addr + k * (kUmmaK * 128), kChunkBytes)
+                                             : make_kmajor_sw128_desc(a_addr + k * (kUmmaK * 2));
+            const uint64_t db = (MAJOR >= 1) ? make_mnmajor_sw128_desc(b_addr + k * (kUmmaK * 128), kChunkBytes)
+                                             : make_kmajor_sw128_desc(b_addr + k * (kUmmaK * 2));
+            if (CTAS == 2) umma_bf16_pair(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // smem slot free (in both CTAs) once these MMAs retire
           if (CTAS == 2) umma_commit_pair(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
@@ -202,7 +236,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t empty_leader[2] = {CTAS == 2 ? map_to_cta(&tmem_empty_bar[0], 0) : 0u,
                                       CTAS == 2 ? map_to_cta(&tmem_empty_bar[1], 0) : 0u};
     for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int mn = tile % mn_tiles;
+      const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile0 = n_blk * BN;
@@ -255,13 +290,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             res[i] = (full || (col_ok && 2 * i < rows_left)) ? __ldg(reinterpret_cast<const float2*>(rp))
                                                                : make_float2(0.0f, 0.0f);
         }
+        uint32_t aux[16];
+        if (ACT == ICKA_ACT_GELU_ERF_BWD) {
+          const __nv_bfloat16* ap = args.aux_in + row0 * args.ld_aux + col;
+          const size_t astep = (size_t)2 * args.ld_aux;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, ap += astep)
+            aux[i] = (full || (col_ok && 2 * i < rows_left)) ? __ldg(reinterpret_cast<const uint32_t*>(ap)) : 0u;
+        }
         float2 x[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float2*>(rd_base[i & 3] + i * 256);
         __syncwarp();   // staging tile may be rewritten (next column block) once every lane has read it
+        if (ACT == ICKA_ACT_GELU_ERF && args.aux_out != nullptr) {   // training: keep the pre-activation
+          __nv_bfloat16* up = args.aux_out + row0 * args.ld_aux + col;
+          const size_t ustep = (size_t)2 * args.ld_aux;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, up += ustep)
+            if (full || (col_ok && 2 * i < rows_left))
+              *reinterpret_cast<uint32_t*>(up) = pack_bf16x2(x[i].x + b0, x[i].y + b1);
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x0 = x[i].x + b0, x1 = x[i].y + b1;
+          if (ACT == ICKA_ACT_GELU_ERF_BWD) {
+            x0 *= gelu_erf_grad_fast(__uint_as_float(aux[i] << 16));
+            x1 *= gelu_erf_grad_fast(__uint_as_float(aux[i] & 0xffff0000u));
+          }
           if (ACT == ICKA_ACT_GELU_ERF) {
             if (OUT_BF16) {
               const float2 gg = gelu_erf_fast2(x0, x1);
@@ -284,6 +339,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int i = 0; i < 16; ++i, op += ostep)
             if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(x[i].x, x[i].y);
+        } else if (MAJOR == 2) {
+          float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, op += ostep)
+            if (full || (col_ok && 2 * i < rows_left)) atomicAdd(reinterpret_cast<float2*>(op), x[i]);
         } else {
           float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
 #pragma unroll
@@ -316,7 +376,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D bf16 tensor [rows, cols] with row pitch `ld` elements; box = {64 cols, box_rows}, 128-byte swizzle.
 int icka_make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
-                   int box_rows) {
+                        int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
   const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
@@ -331,15 +391,33 @@ int icka_make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_
   return ICKA_OK;
 }
 
+// MN-major operand: matrix [rows = contraction index, cols = M or N index] with row pitch `ld`, seen as a 3-D
+// tensor {64 elements, rows, cols / 64}; box = {64, 64 rows, box_chunks}, 128-byte swizzle.  cols % 64 == 0.
+int icka_make_tmap_bf16_mn(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                           int box_chunks) {
+  const cuuint64_t gdim[3] = {64, (cuuint64_t)rows, (cuuint64_t)(cols / 64)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, 128};
+  const cuuint32_t box[3] = {64, (cuuint32_t)kBK, (cuuint32_t)box_chunks};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    ICKA_FAIL(ICKA_ERR_CUDA, "cuTensorMapEncodeTiled(3-D) failed (%d) rows=%lld cols=%lld ld=%lld chunks=%d", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, box_chunks);
+  return ICKA_OK;
+}
+
 namespace {
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS>
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR>
 int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS, MAJOR>;
   ICKA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
   const int m_tiles = (args.M + kBM * CTAS - 1) / (kBM * CTAS), n_tiles = (args.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
+  const int tiles = m_tiles * n_tiles * args.splits;
   const int groups_max = h->sm_count / CTAS;
   const int groups = tiles < groups_max ? tiles : groups_max;
   cudaLaunchConfig_t cfg = {};
@@ -371,15 +449,19 @@ extern "C" int icka_set_gemm_mode(int mode) {
   return ICKA_OK;
 }
 
+// Forward GEMM  out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual); aux_out (optional, with ACT_GELU_ERF)
+// receives the bf16 pre-activation for the backward pass.
 int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
                           const float* residual, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
-                          cudaStream_t st) {
+                          void* aux_out, cudaStream_t st) {
   ICKA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "linear(bf16): lda=%lld, ldw=%lld must be multiples of 8",
                (long long)lda, (long long)ldw);
   ICKA_REQUIRE(icka_aligned(A, 16) && icka_aligned(W, 16) && icka_aligned(out, 16),
                "linear(bf16): A, W, out must be 16-byte aligned");
   ICKA_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "linear(bf16): N=%d and ldo=%lld must be multiples of 8", N, (long long)ldo);
   ICKA_REQUIRE(!residual || icka_aligned(residual, 16), "linear(bf16): residual must be 16-byte aligned");
+  ICKA_REQUIRE(!aux_out || (act == ICKA_ACT_GELU_ERF && icka_aligned(aux_out, 16)),
+               "linear(bf16): aux_out needs act = gelu and 16-byte alignment");
   constexpr size_t kNeedSmem = GemmCfg<256, 1>::kSmemBytes;
   ICKA_REQUIRE(h->smem_optin >= kNeedSmem, "linear(bf16): device offers too little shared memory");
   const int BN = (N > 128) ? 256 : 128;
@@ -392,10 +474,11 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   if (rc) return rc;
   rc = icka_make_tmap_bf16(h, &tb, W, N, K, ldw, pair ? BN / 2 : BN);
   if (rc) return rc;
-  GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug};
+  GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug, nullptr, static_cast<__nv_bfloat16*>(aux_out),
+                (int64_t)N, 1, (K + kBK - 1) / kBK};
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
-#define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_>(h, ta, tb, args, st)
+#define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_, 0>(h, ta, tb, args, st)
   if (pair) {
     if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true, 2); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false, 2); }
     else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true, 2);     else ICKA_GEMM(256, ICKA_ACT_NONE, false, 2); }
@@ -407,4 +490,61 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
     else      { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true, 1);     else ICKA_GEMM(128, ICKA_ACT_NONE, false, 1); }
   }
 #undef ICKA_GEMM
+}
+
+// dgrad  dX[M,K] = (dY[M,N] . W[N,K]) (* gelu'(gelu_pre)) (+ residual): in kernel terms an M x K output contracted
+// over N, with W consumed in its stored [N,K] layout as the MN-major B operand.
+int icka_gemm_bf16_dgrad_launch(icka_handle* h, const void* dY, int64_t ldd, const void* W, int64_t ldw,
+                                const float* residual, const void* gelu_pre, int64_t ldg, void* dX, int64_t ldo,
+                                int out_dtype, int M, int N, int K, cudaStream_t st) {
+  ICKA_REQUIRE(ldd % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "dgrad(bf16): pitches must be multiples of 8");
+  ICKA_REQUIRE(K % 64 == 0, "dgrad(bf16): in_features %d must be a multiple of 64", K);
+  ICKA_REQUIRE(icka_aligned(dY, 16) && icka_aligned(W, 16) && icka_aligned(dX, 16), "dgrad(bf16): 16-byte alignment");
+  ICKA_REQUIRE(!residual || icka_aligned(residual, 16), "dgrad(bf16): residual must be 16-byte aligned");
+  ICKA_REQUIRE(!gelu_pre || (icka_aligned(gelu_pre, 4) && ldg % 2 == 0), "dgrad(bf16): gelu_pre alignment");
+  const int BN = (K > 128) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = icka_make_tmap_bf16(h, &ta, dY, M, N, ldd, kBM);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16_mn(h, &tb, W, N, K, ldw, BN / 64);
+  if (rc) return rc;
+  GemmArgs args{nullptr, residual, dX, ldo, M, K, N, 0, static_cast<const __nv_bfloat16*>(gelu_pre), nullptr, ldg, 1,
+                (N + kBK - 1) / kBK};
+  const bool bf = out_dtype == ICKA_BF16;
+#define ICKA_GEMM(BN_, ACT_, BF_) return launch_gemm<BN_, ACT_, BF_, 1, 1>(h, ta, tb, args, st)
+  if (BN == 256) {
+    if (gelu_pre) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF_BWD, true); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF_BWD, false); }
+    else          { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true);         else ICKA_GEMM(256, ICKA_ACT_NONE, false); }
+  } else {
+    if (gelu_pre) { if (bf) ICKA_GEMM(128, ICKA_ACT_GELU_ERF_BWD, true); else ICKA_GEMM(128, ICKA_ACT_GELU_ERF_BWD, false); }
+    else          { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true);         else ICKA_GEMM(128, ICKA_ACT_NONE, false); }
+  }
+#undef ICKA_GEMM
+}
+
+// wgrad  dW[N,K] += dY[M,N]^T . X[M,K]: an N x K output contracted over the M tokens, both operands MN-major,
+// token range split over CTAs.  dW must already hold the value to accumulate onto (zeros for a fresh gradient).
+int icka_gemm_bf16_wgrad_launch(icka_handle* h, const void* dY, int64_t ldd, const void* X, int64_t ldx, float* dW,
+                                int64_t ldo, int M, int N, int K, cudaStream_t st) {
+  ICKA_REQUIRE(ldd % 8 == 0 && ldx % 8 == 0 && ldo % 2 == 0, "wgrad(bf16): pitches must be multiples of 8 (dW: 2)");
+  ICKA_REQUIRE(N % 64 == 0 && K % 64 == 0, "wgrad(bf16): out_features %d and in_features %d must be multiples of 64",
+               N, K);
+  ICKA_REQUIRE(icka_aligned(dY, 16) && icka_aligned(X, 16) && icka_aligned(dW, 8), "wgrad(bf16): alignment");
+  const int BN = (K > 128) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = icka_make_tmap_bf16_mn(h, &ta, dY, M, N, ldd, kBM / 64);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16_mn(h, &tb, X, M, K, ldx, BN / 64);
+  if (rc) return rc;
+  const int num_kb = (M + kBK - 1) / kBK;
+  const int mn_tiles = ((N + kBM - 1) / kBM) * ((K + BN - 1) / BN);
+  // enough token ranges for ~2 tiles per SM, each at least 8 k-blocks (512 tokens) long
+  int splits = (2 * h->sm_count + mn_tiles - 1) / mn_tiles;
+  if (splits > (num_kb + 7) / 8) splits = (num_kb + 7) / 8;
+  if (splits < 1) splits = 1;
+  const int kbps = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kbps - 1) / kbps;
+  GemmArgs args{nullptr, nullptr, dW, ldo, N, K, M, 0, nullptr, nullptr, 0, splits, kbps};
+  if (BN == 256) return launch_gemm<256, ICKA_ACT_NONE, false, 1, 2>(h, ta, tb, args, st);
+  return launch_gemm<128, ICKA_ACT_NONE, false, 1, 2>(h, ta, tb, args, st);
 }

@@ -22,8 +22,8 @@ __device__ __forceinline__ float4 ldg_row(const float* __restrict__ base, int64_
 template <int ACT, bool OUT_BF16>
 __global__ void __launch_bounds__(kThreads) sgemm_tn_kernel(
     const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw,
-    const float* __restrict__ bias, const float* __restrict__ residual, void* __restrict__ out, int64_t ldo, int M,
-    int N, int K) {
+    const float* __restrict__ bias, const float* __restrict__ residual, void* __restrict__ out, int64_t ldo,
+    float* __restrict__ pre_act_out, int M, int N, int K) {
   __shared__ __align__(16) float As[BK][LDS_];
   __shared__ __align__(16) float Ws[BK][LDS_];
   const int tid = threadIdx.x;
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(kThreads) sgemm_tn_kernel(
         if (n >= N) continue;
         float v = acc[i][jh * 4 + j];
         if (bias) v += bias[n];
+        if (ACT == ICKA_ACT_GELU_ERF && pre_act_out) pre_act_out[(size_t)m * N + n] = v;
         if (ACT == ICKA_ACT_GELU_ERF) v = gelu_erf(v);
         if (residual) v += residual[(size_t)m * N + n];
         if (OUT_BF16)
@@ -100,17 +101,79 @@ __global__ void __launch_bounds__(kThreads) sgemm_tn_kernel(
   }
 }
 
+// Backward GEMMs of the fp32 parity path, any operand orientation through element strides:
+//   out[m,n] (+)= (sum_k A(m,k) B(k,n)) * gelu'(gelu_pre[m,n]) + residual[m,n]
+// with A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].  64x64 tile, 4x4 outputs per thread.
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(
+    const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B, int64_t b_rs, int64_t b_cs,
+    const float* __restrict__ residual, const float* __restrict__ gelu_pre, int64_t ldg, float* __restrict__ out,
+    int64_t ldo, int M, int N, int K, int accumulate) {
+  __shared__ float As[GK][GT + 1];
+  __shared__ float Bs[GK][GT + 1];
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int i = tid; i < GT * GK; i += 256) {
+      // consecutive threads walk the operand's contiguous direction
+      const int am = (a_cs == 1) ? i / GK : i % GT, ak = (a_cs == 1) ? i % GK : i / GT;
+      As[ak][am] = (m0 + am < M && k0 + ak < K) ? A[(size_t)(m0 + am) * a_rs + (size_t)(k0 + ak) * a_cs] : 0.0f;
+      const int bn = (b_rs == 1) ? i / GK : i % GT, bk = (b_rs == 1) ? i % GK : i / GT;
+      Bs[bk][bn] = (n0 + bn < N && k0 + bk < K) ? B[(size_t)(k0 + bk) * b_rs + (size_t)(n0 + bn) * b_cs] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (gelu_pre) v *= gelu_erf_grad(gelu_pre[(size_t)m * ldg + n]);
+      if (residual) v += residual[(size_t)m * N + n];
+      float* o = out + (size_t)m * ldo + n;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
 }  // namespace
+
+int icka_sgemm_strided_launch(icka_handle* h, const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs,
+                              int64_t b_cs, const float* residual, const float* gelu_pre, int64_t ldg, float* out,
+                              int64_t ldo, int M, int N, int K, int accumulate, cudaStream_t st) {
+  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
+  ICKA_REQUIRE(grid.y <= 65535, "sgemm_strided: M=%d too large for one launch", M);
+  sgemm_strided_kernel<<<grid, 256, 0, st>>>(A, a_rs, a_cs, B, b_rs, b_cs, residual, gelu_pre, ldg, out, ldo, M, N, K,
+                                             accumulate);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
 
 int icka_sgemm_launch(icka_handle* h, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                       const float* residual, void* out, int64_t ldo, int out_dtype, int M, int N, int K, int act,
-                      cudaStream_t st) {
+                      float* pre_act_out, cudaStream_t st) {
   ICKA_REQUIRE(K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0, "linear(fp32): K, lda, ldw must be multiples of 4");
   ICKA_REQUIRE(icka_aligned(A, 16) && icka_aligned(W, 16), "linear(fp32): A and W must be 16-byte aligned");
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   ICKA_REQUIRE(grid.y <= 65535, "linear(fp32): M=%d too large for one launch", M);
 #define ICKA_SGEMM(ACT_, BF_) \
-  sgemm_tn_kernel<ACT_, BF_><<<grid, kThreads, 0, st>>>(A, lda, W, ldw, bias, residual, out, ldo, M, N, K)
+  sgemm_tn_kernel<ACT_, BF_><<<grid, kThreads, 0, st>>>(A, lda, W, ldw, bias, residual, out, ldo, pre_act_out, M, N, K)
   const bool bf = out_dtype == ICKA_BF16;
   if (act == ICKA_ACT_GELU_ERF) {
     if (bf) ICKA_SGEMM(ICKA_ACT_GELU_ERF, true); else ICKA_SGEMM(ICKA_ACT_GELU_ERF, false);

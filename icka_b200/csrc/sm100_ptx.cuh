@@ -69,6 +69,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// 3-D tiled load (used for MN-major operands: {64 elements, contraction rows, 64-wide chunks}).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- tcgen05 / TMEM -----------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)),
@@ -194,11 +204,27 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major bf16 tile written by TMA with SWIZZLE_128B as
+// [chunk of 64 MN elements][contraction row][64 MN elements = 128 B]: within a chunk the 8-row x 128-B
+// swizzle atoms follow each other every 1024 B along the contraction (stride byte offset), and the
+// next 64 MN elements start `chunk_bytes` further (leading byte offset).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((chunk_bytes >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)2u << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, dense.
 //   [4,6) c_format = 1 (f32)  [7,10) a_format = 1 (bf16)  [10,13) b_format = 1 (bf16)
 //   [15] a_major = 0 (K)  [16] b_major = 0 (K)  [17,23) N >> 3  [24,29) M >> 4
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, bool a_mn_major = false,
+                                                           bool b_mn_major = false) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace sm100

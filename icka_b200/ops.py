@@ -74,10 +74,12 @@ def mask_additive(mask01: torch.Tensor, n: int) -> torch.Tensor:
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
-           act: int = ACT_NONE, out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           act: int = ACT_NONE, out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
+           pre_act_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = act(a[M,K] . w[N,K]^T + bias) (+ residual).  a/w fp32 -> FFMA path, bf16 -> tcgen05 path.
 
-    ``a`` and ``w`` may be row-pitched 2-D views (stride(1) == 1)."""
+    ``a`` and ``w`` may be row-pitched 2-D views (stride(1) == 1).  ``pre_act_out`` (contiguous [M,N] in the
+    operand dtype, GELU layers only) receives a . w^T + bias for the backward pass."""
     if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
         raise RuntimeError(f'linear: bad shapes {tuple(a.shape)} x {tuple(w.shape)}')
     if a.dtype != w.dtype or a.dtype not in _DT:
@@ -98,11 +100,142 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, re
         _need(residual, torch.float32, 'linear(residual)')
         if residual.shape != (M, N):
             raise RuntimeError('linear: residual shape mismatch')
-    _lib.check(lib.icka_linear_fwd(h, a.data_ptr(), a.stride(0) if M > 1 else max(K, a.stride(0)), w.data_ptr(),
-                                   w.stride(0) if N > 1 else max(K, w.stride(0)), _p(bias), _p(residual),
-                                   out.data_ptr(), out.stride(0) if M > 1 else max(N, out.stride(0)),
-                                   _DT[a.dtype], _DT[out_dtype], M, N, K, act, st), 'icka_linear_fwd')
+    if pre_act_out is not None:
+        _need(pre_act_out, a.dtype, 'linear(pre_act_out)')
+        if pre_act_out.shape != (M, N):
+            raise RuntimeError('linear: pre_act_out shape mismatch')
+    _lib.check(lib.icka_linear_fwd_ex(h, a.data_ptr(), _ld(a, K), w.data_ptr(), _ld(w, K), _p(bias), _p(residual),
+                                      out.data_ptr(), _ld(out, N), _p(pre_act_out), _DT[a.dtype], _DT[out_dtype],
+                                      M, N, K, act, st), 'icka_linear_fwd_ex')
     return out
+
+
+def _ld(t: torch.Tensor, cols: int) -> int:
+    """Row pitch of a 2-D view (a single-row tensor may report any stride)."""
+    return t.stride(0) if t.shape[0] > 1 else max(cols, t.stride(0))
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, residual: Optional[torch.Tensor] = None,
+                 gelu_pre: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """dX[M,K] = (dy[M,N] . w[N,K]) * gelu'(gelu_pre[M,K]) + residual[M,K]; w exactly as nn.Linear stores it."""
+    if dy.dim() != 2 or w.dim() != 2 or dy.shape[1] != w.shape[0]:
+        raise RuntimeError(f'linear_dgrad: bad shapes {tuple(dy.shape)} x {tuple(w.shape)}')
+    if dy.dtype != w.dtype or dy.dtype not in _DT or dy.stride(1) != 1 or w.stride(1) != 1:
+        raise RuntimeError('linear_dgrad: operands must share dtype (fp32 or bf16) and be unit-stride')
+    M, N = dy.shape
+    K = w.shape[1]
+    lib, h, st = _ctx(dy)
+    out_dtype = out_dtype or dy.dtype
+    dx = torch.empty(M, K, dtype=out_dtype, device=dy.device)
+    if residual is not None:
+        _need(residual, torch.float32, 'linear_dgrad(residual)')
+        if residual.shape != (M, K):
+            raise RuntimeError('linear_dgrad: residual shape mismatch')
+    if gelu_pre is not None:
+        if gelu_pre.dtype != dy.dtype or gelu_pre.shape != (M, K) or gelu_pre.stride(1) != 1:
+            raise RuntimeError('linear_dgrad: bad gelu_pre')
+    _lib.check(lib.icka_linear_dgrad(h, dy.data_ptr(), _ld(dy, N), w.data_ptr(), _ld(w, K), _p(residual),
+                                     _p(gelu_pre), _ld(gelu_pre, K) if gelu_pre is not None else 0, dx.data_ptr(), K,
+                                     _DT[dy.dtype], _DT[out_dtype], M, N, K, st), 'icka_linear_dgrad')
+    return dx
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 accumulate: bool = False) -> torch.Tensor:
+    """dW[N,K] (+)= dy[M,N]^T . x[M,K] (fp32)."""
+    if dy.dim() != 2 or x.dim() != 2 or dy.shape[0] != x.shape[0]:
+        raise RuntimeError(f'linear_wgrad: bad shapes {tuple(dy.shape)} x {tuple(x.shape)}')
+    if dy.dtype != x.dtype or dy.dtype not in _DT or dy.stride(1) != 1 or x.stride(1) != 1:
+        raise RuntimeError('linear_wgrad: operands must share dtype (fp32 or bf16) and be unit-stride')
+    M, N = dy.shape
+    K = x.shape[1]
+    lib, h, st = _ctx(dy)
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+        accumulate = False
+    else:
+        _need(out, torch.float32, 'linear_wgrad(out)')
+        if out.shape != (N, K):
+            raise RuntimeError('linear_wgrad: bad `out`')
+    _lib.check(lib.icka_linear_wgrad(h, dy.data_ptr(), _ld(dy, N), x.data_ptr(), _ld(x, K), out.data_ptr(),
+                                     _DT[dy.dtype], M, N, K, int(accumulate), st), 'icka_linear_wgrad')
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D fp32/bf16 view -> fp32 [N] (bias gradient)."""
+    if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:
+        raise RuntimeError('colsum: need a unit-stride 2-D fp32/bf16 tensor')
+    M, N = x.shape
+    lib, h, st = _ctx(x)
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.icka_colsum(h, x.data_ptr(), _ld(x, N), _DT[x.dtype], out.data_ptr(), M, N, 0, st), 'icka_colsum')
+    return out
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, *, want_f32: bool = True,
+                  want_bf16: bool = False, want_dbias: bool = True):
+    """Backward of layernorm(x): returns (dx32 | None, dx16 | None, dgamma, dbeta, colsum(dx) | None)."""
+    _need(dy, torch.float32, 'layernorm_bwd(dy)')
+    _need(x, torch.float32, 'layernorm_bwd(x)')
+    _need(gamma, torch.float32, 'layernorm_bwd(gamma)')
+    M, N = x.shape
+    lib, h, st = _ctx(x)
+    dx32 = torch.empty_like(x) if want_f32 else None
+    dx16 = torch.empty_like(x, dtype=torch.bfloat16) if want_bf16 else None
+    acc = torch.zeros(3, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.icka_layernorm_bwd(h, dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), float(eps), _p(dx32), _p(dx16),
+                                      acc[0].data_ptr(), acc[1].data_ptr(), acc[2].data_ptr() if want_dbias else None,
+                                      M, N, st), 'icka_layernorm_bwd')
+    return dx32, dx16, acc[0], acc[1], (acc[2] if want_dbias else None)
+
+
+def cross_attn_core_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add: Optional[torch.Tensor],
+                        dctx: torch.Tensor, B: int, Sq: int, Skv: int, nh: int, d: int):
+    """Returns (dq [B*Sq, nh*d], dkv [B*Skv, 2*nh*d]) in the dtype of q."""
+    if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype or dctx.dtype != q.dtype:
+        raise RuntimeError('cross_attn_core_bwd: q/k/v/dctx must share dtype fp32 or bf16')
+    if q.stride(1) != 1 or k.stride(1) != 1 or v.stride(1) != 1 or dctx.stride(1) != 1 or k.stride(0) != v.stride(0):
+        raise RuntimeError('cross_attn_core_bwd: bad strides')
+    H = nh * d
+    lib, h, st = _ctx(q)
+    dq = torch.empty(B * Sq, H, dtype=q.dtype, device=q.device)
+    dkv = torch.empty(B * Skv, 2 * H, dtype=q.dtype, device=q.device)
+    dk, dv = dkv[:, :H], dkv[:, H:]
+    _lib.check(lib.icka_cross_attn_core_bwd(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                            _p(mask_add), dctx.data_ptr(), dctx.stride(0), dq.data_ptr(), H,
+                                            dk.data_ptr(), dv.data_ptr(), 2 * H, _DT[q.dtype], B, Sq, Skv, nh, d, st),
+               'icka_cross_attn_core_bwd')
+    return dq, dkv
+
+
+def gate_blend_bwd(dout, fused, tok, gate, ln_w, ln_b, ln_eps: float, w_fold, want_dtok: bool = True):
+    """Returns (dfused, dtok | None, d_ln_w, d_ln_b, d_w_fold, d_c_fold)."""
+    for t, n in ((dout, 'dout'), (fused, 'fused'), (tok, 'tok'), (gate, 'gate')):
+        _need(t, torch.float32, f'gate_blend_bwd({n})')
+    B, S, H = fused.shape
+    lib, h, st = _ctx(fused)
+    dfused = torch.empty_like(fused)
+    dtok = torch.empty_like(tok) if want_dtok else None
+    acc = torch.zeros(3 * H + 1, dtype=torch.float32, device=fused.device)
+    d_ln_w, d_ln_b, d_w_fold, d_c_fold = acc[:H], acc[H:2 * H], acc[2 * H:3 * H], acc[3 * H:]
+    _lib.check(lib.icka_gate_blend_bwd(h, dout.data_ptr(), fused.data_ptr(), tok.data_ptr(), gate.data_ptr(),
+                                       ln_w.data_ptr(), ln_b.data_ptr(), float(ln_eps), w_fold.data_ptr(),
+                                       dfused.data_ptr(), _p(dtok), d_ln_w.data_ptr(), d_ln_b.data_ptr(),
+                                       d_w_fold.data_ptr(), d_c_fold.data_ptr(), B, S, H, st), 'icka_gate_blend_bwd')
+    return dfused, dtok, d_ln_w, d_ln_b, d_w_fold, d_c_fold
+
+
+def gate_fold_bwd(wp, bp, wa, d_w_fold, d_c_fold):
+    """Returns (dWp [H,H], dbp [H], dwa [H], dba [1])."""
+    H = wp.shape[0]
+    lib, h, st = _ctx(wp)
+    f32 = dict(dtype=torch.float32, device=wp.device)
+    dwp, dbp, dwa, dba = torch.empty(H, H, **f32), torch.empty(H, **f32), torch.empty(H, **f32), torch.empty(1, **f32)
+    _lib.check(lib.icka_gate_fold_bwd(h, wp.data_ptr(), bp.data_ptr(), wa.data_ptr(), d_w_fold.data_ptr(),
+                                      d_c_fold.data_ptr(), dwp.data_ptr(), dbp.data_ptr(), dwa.data_ptr(),
+                                      dba.data_ptr(), H, st), 'icka_gate_fold_bwd')
+    return dwp, dbp, dwa, dba
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, want_f32: bool = True,
@@ -209,3 +342,22 @@ def crf_llh(emissions: torch.Tensor, tags_i64: torch.Tensor, mask_u8: Optional[t
                                     end.data_ptr(), trans.data_ptr(), llh.data_ptr(), B, S, T, st),
                'icka_crf_llh_fwd')
     return llh
+
+
+def crf_llh_bwd(emissions: torch.Tensor, tags_i64: torch.Tensor, mask_u8: Optional[torch.Tensor], start, end, trans,
+                w: torch.Tensor):
+    """Gradient of sum_b w[b] * llh[b]: returns (d_emissions [B,S,T], d_start [T], d_end [T], d_trans [T,T])."""
+    _need(emissions, torch.float32, 'crf_llh_bwd(emissions)')
+    _need(tags_i64, torch.int64, 'crf_llh_bwd(tags)')
+    _need(w, torch.float32, 'crf_llh_bwd(w)')
+    B, S, T = emissions.shape
+    if mask_u8 is not None:
+        _need(mask_u8, torch.uint8, 'crf_llh_bwd(mask)')
+    lib, h, st = _ctx(emissions)
+    de = torch.empty_like(emissions)
+    acc = torch.zeros(T * T + 2 * T, dtype=torch.float32, device=emissions.device)
+    d_start, d_end, d_trans = acc[:T], acc[T:2 * T], acc[2 * T:].view(T, T)
+    _lib.check(lib.icka_crf_llh_bwd(h, emissions.data_ptr(), tags_i64.data_ptr(), _p(mask_u8), start.data_ptr(),
+                                    end.data_ptr(), trans.data_ptr(), w.data_ptr(), de.data_ptr(), d_start.data_ptr(),
+                                    d_end.data_ptr(), d_trans.data_ptr(), B, S, T, st), 'icka_crf_llh_bwd')
+    return de, d_start, d_end, d_trans

@@ -35,7 +35,11 @@ enum icka_status {
 };
 
 enum icka_dtype { ICKA_F32 = 0, ICKA_BF16 = 1 };
-enum icka_act { ICKA_ACT_NONE = 0, ICKA_ACT_GELU_ERF = 1 };  /* CMIM:31-37 */
+enum icka_act {
+  ICKA_ACT_NONE = 0,
+  ICKA_ACT_GELU_ERF = 1,     /* CMIM:31-37 */
+  ICKA_ACT_GELU_ERF_BWD = 2  /* internal: multiply by gelu'(pre-activation) (backward of CMIM:550) */
+};
 
 int icka_version(void);
 const char* icka_last_error(void);
@@ -73,6 +77,37 @@ int icka_linear_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, i
                     const float* bias, const float* residual, void* out, int64_t ldo,
                     int in_dtype, int out_dtype, int M, int N, int K, int act, void* stream);
 
+/* Training-time forward: icka_linear_fwd that can also keep the pre-activation (A.W^T + bias, in the
+ * operand dtype, pitch N) of a GELU layer for the backward pass.  pre_act_out may be NULL. */
+int icka_linear_fwd_ex(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
+                       const float* bias, const float* residual, void* out, int64_t ldo, void* pre_act_out,
+                       int in_dtype, int out_dtype, int M, int N, int K, int act, void* stream);
+
+/* Backward of nn.Linear w.r.t. its input (autograd of CMIM:533, :549, :562, :592-594 ...):
+ *   dX[M,K] = (dY[M,N] . W[N,K]) * gelu'(gelu_pre[M,K]) + residual[M,K]
+ * dY and W in `in_dtype` (W exactly as nn.Linear stores it, no transposed copy); gelu_pre (same dtype, pitch
+ * ldg) and residual (fp32, pitch K) may be NULL.  bf16 path: K % 64 == 0. */
+int icka_linear_dgrad(icka_handle* h, const void* dY, int64_t ldd, const void* W, int64_t ldw,
+                      const float* residual, const void* gelu_pre, int64_t ldg, void* dX, int64_t ldo,
+                      int in_dtype, int out_dtype, int M, int N, int K, void* stream);
+
+/* Backward of nn.Linear w.r.t. its weight:  dW[N,K] (+)= dY[M,N]^T . X[M,K]  (fp32 dW, pitch K).
+ * accumulate = 0 overwrites dW, 1 adds to it (gradient accumulation, My_cross_attention.py:826-844).
+ * bf16 path: N % 64 == 0 and K % 64 == 0; token range split over CTAs, partial sums added with red.global. */
+int icka_linear_wgrad(icka_handle* h, const void* dY, int64_t ldd, const void* X, int64_t ldx, float* dW,
+                      int in_dtype, int M, int N, int K, int accumulate, void* stream);
+
+/* Column sums of x[M,N] (pitch ld, fp32 or bf16) -> out[N] fp32: the bias gradient of a dense layer. */
+int icka_colsum(icka_handle* h, const void* x, int64_t ld, int dtype, float* out, int M, int N, int accumulate,
+                void* stream);
+
+/* Backward of BertLayerNorm (CMIM:518-522) for y = LN(x):  dx from dy and the saved pre-LN x; dgamma[N],
+ * dbeta[N] and dbias[N] (= column sums of dx: the bias gradient of the dense layer that produced x) are
+ * ADDED to (each may be NULL).  dx_f32 and/or dx_bf16 (either may be NULL). */
+int icka_layernorm_bwd(icka_handle* h, const float* dy, const float* x, const float* gamma, float eps,
+                       float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dbias, int M, int N,
+                       void* stream);
+
 /* Tile-shape policy of the bf16 path (process-wide tuning/testing knob): 0 = choose per shape (default),
  * 1 = always single-CTA 128 x N tiles, 2 = always CTA pairs (cluster of 2, tcgen05 cta_group::2, 256 x 256). */
 int icka_set_gemm_mode(int mode);
@@ -92,6 +127,14 @@ int icka_layernorm_fwd(icka_handle* h, const float* x, const float* gamma, const
 int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
                              int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                              int B, int Sq, int Skv, int nh, int d, void* stream);
+
+/* Backward of icka_cross_attn_core_fwd: probabilities are recomputed from q, k, v (same layouts as the
+ * forward); dctx [B*Sq, nh*d] -> dq [B*Sq, nh*d] (pitch lddq), dk / dv [B*Skv, nh*d] (pitch lddkv; may be the
+ * halves of one [dK|dV] buffer).  Skv <= ~150 (shared-memory resident). */
+int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                             int64_t ldkv, const float* mask_add, const void* dctx, int64_t ldc, void* dq,
+                             int64_t lddq, void* dk, void* dv, int64_t lddkv, int dtype, int B, int Sq, int Skv,
+                             int nh, int d, void* stream);
 
 /* Single-query attention in folded form (image->text encoders, CMIM:984-989 with Sq = 1).
  * With one query per sentence, scores[h][s] = (U_h . x_s)/sqrt(d) + mask[s] where U_h = Wk_h^T q_h, and
@@ -115,6 +158,18 @@ int icka_gate_blend_fwd(icka_handle* h, const float* fused, const float* tok, co
                         const float* ln_b, float ln_eps, const float* w_fold, const float* c_fold,
                         float* out, float* gate_out, int B, int S, int H, void* stream);
 
+/* Backward of icka_gate_blend_fwd: dout [B,S,H] -> dfused, dtok [B,S,H] (dtok may be NULL); the gradients of
+ * the LayerNorm affine (d_ln_w, d_ln_b [H]) and of the folded gate vector (d_w_fold [H], d_c_fold [1]) are
+ * ADDED to.  `gate` is the gate_out of the forward. */
+int icka_gate_blend_bwd(icka_handle* h, const float* dout, const float* fused, const float* tok, const float* gate,
+                        const float* ln_w, const float* ln_b, float ln_eps, const float* w_fold, float* dfused,
+                        float* dtok, float* d_ln_w, float* d_ln_b, float* d_w_fold, float* d_c_fold, int B, int S,
+                        int H, void* stream);
+
+/* Backward of icka_gate_fold: (d_w_fold [H], d_c_fold [1]) -> dWp [H,H], dbp [H], dwa [H], dba [1] (overwritten). */
+int icka_gate_fold_bwd(icka_handle* h, const float* Wp, const float* bp, const float* wa, const float* d_w_fold,
+                       const float* d_c_fold, float* dWp, float* dbp, float* dwa, float* dba, int H, void* stream);
+
 /* ---- CRF ------------------------------------------------------------------------------------- */
 
 /* torchcrf.CRF.decode (call sites CMIM:1051, :1056): Viterbi best path per sentence.
@@ -130,6 +185,14 @@ int icka_viterbi_decode(icka_handle* h, const float* emissions, const uint8_t* m
 int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const int64_t* tags, const uint8_t* mask,
                      const float* start, const float* end, const float* trans, float* llh_out,
                      int B, int S, int T, void* stream);
+
+/* Gradient of sum_b w[b] * llh[b] (llh as icka_crf_llh_fwd; autograd of CMIM:1047-1048): forward-backward
+ * marginals minus the gold path.  d_emissions [B,S,T] is overwritten (zeros at masked-off steps); d_start [T],
+ * d_end [T], d_trans [T,T] are ADDED to.  w [B] fp32 is the upstream gradient per sentence. */
+int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const int64_t* tags, const uint8_t* mask,
+                     const float* start, const float* end, const float* trans, const float* w,
+                     float* d_emissions, float* d_start, float* d_end, float* d_trans, int B, int S, int T,
+                     void* stream);
 
 #ifdef __cplusplus
 }
