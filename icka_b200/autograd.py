@@ -1,0 +1,154 @@
+"""Training path: ``torch.autograd.Function`` nodes whose forward AND backward are C-ABI kernel launches.
+
+The reference trains the fusion stack through eager-PyTorch autograd (My_cross_attention.py:814-844:
+``loss = model(...)``, ``loss.backward()``, clip, AdamW step).  Here autograd is only the bookkeeping: one
+node per cross-attention layer (CMIM:639-650), one for a plain dense layer (vismap2text / vismapping,
+CMIM:897-899), one for the gate + blend (CMIM:1029-1036) and one for the CRF log-likelihood (CMIM:1047-1048).
+Each backward is a hand-scheduled sequence of the kernels declared in include/icka_b200.h:
+
+    dgrad / wgrad   tcgen05 GEMMs reading weights and activations in place (MN-major operands, split-K)
+    LayerNorm bwd   fused with the bias-gradient column sums
+    attention bwd   probabilities recomputed from the saved Q and K|V
+    GELU bwd        fused into the epilogue of the FFN-down dgrad GEMM
+
+Precision follows ``modules.set_precision``: 'bf16' keeps fp32 for the residual stream, its gradient,
+LayerNorm statistics and all parameter gradients, and bf16 for GEMM operands; 'fp32' runs every GEMM on
+the FFMA kernels (the gradient-parity path).  Dropout is not implemented: training requires p = 0.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import ACT_GELU_ERF
+
+F32 = torch.float32
+
+
+def _op(t32, t16):
+    return t16 if t16 is not None else t32
+
+
+class DenseFn(torch.autograd.Function):
+    """out32[M,N] = x_op[M,K] . W^T + b for an input that needs no gradient (region rows, CLIP feature)."""
+
+    @staticmethod
+    def forward(ctx, x_op, weight, bias, w_op):
+        out = ops.linear(x_op, w_op, bias, out_dtype=F32)
+        ctx.save_for_backward(x_op)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x_op,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        d_op = ops.cast_bf16(dout) if x_op.dtype == torch.bfloat16 else dout
+        return None, ops.linear_wgrad(d_op, x_op), ops.colsum(dout), None
+
+
+class CrossLayerFn(torch.autograd.Function):
+    """One BertCrossAttentionLayer (CMIM:639-650): attention block + FFN block, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x32, y32, x_op, y_op, mask2d, meta,
+                wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, wd, bd, g2, b2,
+                wq_op, wkv_op, bkv, wo_op, wi_op, wd_op):
+        B, Sq, Skv, nh, d, eps = meta
+        H = nh * d
+        dt = x_op.dtype
+        bf = dt == torch.bfloat16
+        q = ops.linear(x_op, wq_op, bq, out_dtype=dt)
+        kv = ops.linear(y_op, wkv_op, bkv, out_dtype=dt)
+        att = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask2d, B, Sq, Skv, nh, d)
+        pre1 = ops.linear(att, wo_op, bo, residual=x32, out_dtype=F32)
+        a32, a16 = ops.layernorm(pre1, g1, b1, eps, want_f32=True, want_bf16=bf)
+        a_op = _op(a32, a16)
+        u = torch.empty(a_op.shape[0], wi_op.shape[0], dtype=dt, device=a_op.device)
+        f = ops.linear(a_op, wi_op, bi, act=ACT_GELU_ERF, out_dtype=dt, pre_act_out=u)
+        pre2 = ops.linear(f, wd_op, bd, residual=a32, out_dtype=F32)
+        o32, o16 = ops.layernorm(pre2, g2, b2, eps, want_f32=True, want_bf16=bf)
+        ctx.meta = meta
+        ctx.has_mask = mask2d is not None
+        ctx.save_for_backward(x_op, y_op, q, kv, att, pre1, a_op, u, f, pre2, g1, g2, wq_op, wkv_op, wo_op, wi_op,
+                              wd_op, *([mask2d] if mask2d is not None else []))
+        if o16 is not None:
+            ctx.mark_non_differentiable(o16)
+        return o32, o16          # o16: bf16 operand copy for the next GEMM (None in fp32 mode)
+
+    @staticmethod
+    def backward(ctx, do32, _unused):
+        B, Sq, Skv, nh, d, eps = ctx.meta
+        H = nh * d
+        saved = ctx.saved_tensors
+        x_op, y_op, q, kv, att, pre1, a_op, u, f, pre2, g1, g2, wq_op, wkv_op, wo_op, wi_op, wd_op = saved[:17]
+        mask2d = saved[17] if ctx.has_mask else None
+        dt = x_op.dtype
+        bf = dt == torch.bfloat16
+        do32 = do32.contiguous()
+
+        # ---- FFN block: X' = LN2(F Wd^T + bd + A1),  F = gelu(A1 Wi^T + bi) ----
+        dpre2, dpre2_16, dg2, db2, dbd = ops.layernorm_bwd(do32, pre2, g2, eps, want_f32=True, want_bf16=bf)
+        dpre2_op = _op(dpre2, dpre2_16)
+        dwd = ops.linear_wgrad(dpre2_op, f)
+        dgl = ops.linear_dgrad(dpre2_op, wd_op, gelu_pre=u, out_dtype=dt)          # d(pre-activation) [M, I]
+        dwi = ops.linear_wgrad(dgl, a_op)
+        dbi = ops.colsum(dgl)
+        da1 = ops.linear_dgrad(dgl, wi_op, residual=dpre2, out_dtype=F32)          # + the residual branch
+
+        # ---- attention block: A1 = LN1(ctx Wo^T + bo + X) ----
+        dpre1, dpre1_16, dg1, db1, dbo = ops.layernorm_bwd(da1, pre1, g1, eps, want_f32=True, want_bf16=bf)
+        dpre1_op = _op(dpre1, dpre1_16)
+        dwo = ops.linear_wgrad(dpre1_op, att)
+        datt = ops.linear_dgrad(dpre1_op, wo_op, out_dtype=dt)
+        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, datt, B, Sq, Skv, nh, d)
+        dwq = ops.linear_wgrad(dq, x_op)
+        dbq = ops.colsum(dq)
+        dwkv = ops.linear_wgrad(dkv, y_op)                                         # [2H, H]: rows = key | value
+        dbkv = ops.colsum(dkv)
+        dx32 = ops.linear_dgrad(dq, wq_op, residual=dpre1, out_dtype=F32) if ctx.needs_input_grad[0] else None
+        dy32 = ops.linear_dgrad(dkv, wkv_op, out_dtype=F32) if ctx.needs_input_grad[1] else None
+
+        return (dx32, dy32, None, None, None, None,
+                dwq, dbq, dwkv[:H], dbkv[:H], dwkv[H:], dbkv[H:], dwo, dbo, dg1, db1, dwi, dbi, dwd, dbd, dg2, db2,
+                None, None, None, None, None, None)
+
+
+class GateBlendFn(torch.autograd.Function):
+    """result = g tok + (1 - g) fused with the sentence gate of CMIM:1029-1036."""
+
+    @staticmethod
+    def forward(ctx, fused, tok, ln_w, ln_b, wp, bp, wa, ba, ln_eps):
+        wa_v = wa.reshape(-1).contiguous()
+        w_fold, c_fold = ops.gate_fold(wp, bp, wa_v, ba)
+        out, gate = ops.gate_blend(fused, tok, ln_w, ln_b, ln_eps, w_fold, c_fold)
+        ctx.ln_eps = ln_eps
+        ctx.save_for_backward(fused, tok, gate, ln_w, ln_b, w_fold, wp, bp, wa_v)
+        ctx.mark_non_differentiable(gate)
+        return out, gate
+
+    @staticmethod
+    def backward(ctx, dout, _dgate):
+        fused, tok, gate, ln_w, ln_b, w_fold, wp, bp, wa_v = ctx.saved_tensors
+        dfused, dtok, d_ln_w, d_ln_b, d_wf, d_cf = ops.gate_blend_bwd(
+            dout.contiguous(), fused, tok, gate, ln_w, ln_b, ctx.ln_eps, w_fold, want_dtok=ctx.needs_input_grad[1])
+        dwp, dbp, dwa, dba = ops.gate_fold_bwd(wp, bp, wa_v, d_wf, d_cf)
+        return dfused, dtok, d_ln_w, d_ln_b, dwp, dbp, dwa.view(1, -1), dba, None
+
+
+class CrfLlhFn(torch.autograd.Function):
+    """Per-sentence CRF log-likelihood (pytorch-crf forward, reduction='none')."""
+
+    @staticmethod
+    def forward(ctx, emissions, start, end, trans, tags, mask_u8):
+        llh = ops.crf_llh(emissions, tags, mask_u8, start, end, trans)
+        ctx.has_mask = mask_u8 is not None
+        ctx.save_for_backward(emissions, start, end, trans, tags, *([mask_u8] if mask_u8 is not None else []))
+        return llh
+
+    @staticmethod
+    def backward(ctx, dllh):
+        saved = ctx.saved_tensors
+        emissions, start, end, trans, tags = saved[:5]
+        mask_u8 = saved[5] if ctx.has_mask else None
+        de, ds, dend, dtr = ops.crf_llh_bwd(emissions, tags, mask_u8, start, end, trans, dllh.float().contiguous())
+        return de, ds, dend, dtr, None, None

@@ -7,7 +7,10 @@ tags, mask=None, reduction='sum')`` and ``decode(emissions, mask=None) -> List[L
 (``icka_viterbi_decode`` / ``icka_crf_llh_fwd``); ``decode`` does a single device->host copy of the
 ``[B,S]`` int32 tags and ``[B]`` lengths instead of pytorch-crf's ``.item()`` per decoded token.
 
-Forward-only in this round: ``forward`` returns the log-likelihood without an autograd graph.
+``forward`` is differentiable: when autograd is recording, the log-likelihood is one
+``icka_b200.autograd.CrfLlhFn`` node whose backward is the forward-backward kernel ``icka_crf_llh_bwd``
+(gradients for the emissions and the three parameter tensors, as the reference trains them through
+``loss = -crf(..., reduction='token_mean')``, CMIM:1047-1048).
 """
 from __future__ import annotations
 
@@ -17,6 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .autograd import CrfLlhFn
 
 
 class CRF(nn.Module):
@@ -89,7 +93,11 @@ class CRF(nn.Module):
         if reduction not in ('none', 'sum', 'mean', 'token_mean'):
             raise ValueError(f'invalid reduction: {reduction}')
         e, y, m = self._batch_first(emissions, tags, mask)
-        llh = ops.crf_llh(e, y, m, *self._params())
+        params = (self.start_transitions, self.end_transitions, self.transitions)
+        if torch.is_grad_enabled() and (e.requires_grad or any(p.requires_grad for p in params)):
+            llh = CrfLlhFn.apply(e, *(p.float().contiguous() for p in params), y, m)
+        else:
+            llh = ops.crf_llh(e, y, m, *self._params())
         if reduction == 'none':
             return llh
         if reduction == 'sum':

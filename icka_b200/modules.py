@@ -19,8 +19,11 @@ sequence of C-ABI kernel launches (icka_b200.ops).  Two precision modes (``set_p
           and softmax statistics stay fp32 (SURVEY 7.3 #3b) -- the fast path (max-abs 2e-2 gate)
   'fp32'  everything fp32 on CUDA cores -- the parity path (max-rel 1e-5 gate)
 
-This round is forward-only: dropout must be inactive (eval mode or p = 0), like the reference's
-dev/test calls (My_cross_attention.py:872, 1047).
+Training: when autograd is recording (``torch.is_grad_enabled()``), ``BertCrossAttentionLayer``,
+``BertCrossEncoder``, ``CrossModalFusion`` and ``CRF.forward`` build their graph out of the nodes in
+``icka_b200.autograd`` (kernel-backed forward and backward); the small building blocks below them
+(``BertSelfOutput`` ... called on their own) stay forward-only.  Dropout is not implemented: it must be
+inactive (eval mode or p = 0), like the reference's dev/test calls (My_cross_attention.py:872, 1047).
 """
 from __future__ import annotations
 
@@ -32,6 +35,7 @@ from torch import nn
 
 from . import ops
 from ._lib import ACT_GELU_ERF, ACT_NONE
+from .autograd import CrossLayerFn, DenseFn, GateBlendFn
 
 _PRECISION = 'bf16'
 
@@ -95,7 +99,17 @@ def _mask2d(mask: Optional[torch.Tensor], B: int, Skv: int) -> Optional[torch.Te
 
 def _check_inference(module: nn.Module, *ps: float) -> None:
     if module.training and any(p > 0 for p in ps):
-        raise NotImplementedError('icka_b200 is forward-only in this round: call .eval() (dropout must be off)')
+        raise NotImplementedError('icka_b200 has no dropout kernels: call .eval() or build the config with '
+                                  'hidden_dropout_prob = attention_probs_dropout_prob = 0')
+
+
+def _recording(*tensors, module: Optional[nn.Module] = None) -> bool:
+    """True when this call must build an autograd graph (kernel-backed nodes of icka_b200.autograd)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return module is not None and any(p.requires_grad for p in module.parameters())
 
 
 class BertLayerNorm(nn.Module):
@@ -292,11 +306,33 @@ class BertCrossAttentionLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=None):
+        if _recording(x32, y32, module=self):
+            return self._run_recorded(x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv)
         a32, a_lp = self.attention._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
         f = self.intermediate._run(a_lp if a_lp is not None else a32)
         o32, o_lp = self.output._run(f, a32)
         return o32, (o_lp if o_lp is not None else o32)
+
+    def _run_recorded(self, x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv):
+        """Autograd-recording pass: one CrossLayerFn node (kernel-backed forward and backward)."""
+        att, so, out = self.attention.self, self.attention.output, self.output
+        if so.LayerNorm.variance_epsilon != out.LayerNorm.variance_epsilon:
+            raise RuntimeError('the two LayerNorms of a cross layer must share layer_norm_eps')
+        if y32 is None:
+            raise RuntimeError('recording pass needs the fp32 key/value states (y32)')
+        wkv, bkv = att._kv_operands()
+        meta = (B, Sq, Skv, att.num_attention_heads, att.attention_head_size, so.LayerNorm.variance_epsilon)
+        o32, o16 = CrossLayerFn.apply(
+            x32, y32, x_lp.detach(), y_lp.detach(), mask2d, meta,
+            att.query.weight, att.query.bias, att.key.weight, att.key.bias, att.value.weight, att.value.bias,
+            so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+            self.intermediate.dense.weight, self.intermediate.dense.bias,
+            out.dense.weight, out.dense.bias, out.LayerNorm.weight, out.LayerNorm.bias,
+            _operand(att._cache, 'q', att.query.weight), wkv, bkv, _operand(so._cache, 'w', so.dense.weight),
+            _operand(self.intermediate._cache, 'w', self.intermediate.dense.weight),
+            _operand(out._cache, 'w', out.dense.weight))
+        return o32, (o16 if o16 is not None else o32.detach())
 
     def _dropouts(self):
         return (self.attention.self.dropout.p, self.attention.output.dropout.p, self.output.dropout.p)
@@ -305,9 +341,9 @@ class BertCrossAttentionLayer(nn.Module):
         _check_inference(self, *self._dropouts())
         B, Sq, H = s1_hidden_states.shape
         Skv = s2_hidden_states.shape[1]
-        x32 = _rows(s1_hidden_states)
-        o32, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_hidden_states)), _mask2d(s2_attention_mask, B, Skv),
-                           B, Sq, Skv)
+        x32, y32 = _rows(s1_hidden_states), _rows(s2_hidden_states)
+        o32, _ = self._run(x32, _to_lp(x32.detach()), _to_lp(y32.detach()), _mask2d(s2_attention_mask, B, Skv),
+                           B, Sq, Skv, y32=y32)
         return o32.view(B, Sq, H)
 
 
@@ -319,10 +355,10 @@ class BertCrossEncoder(nn.Module):
         layer = BertCrossAttentionLayer(config)
         self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(layer_num)])
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True, y32=None):
         outs = []
         for layer_module in self.layer:
-            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
+            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=y32)
             if keep_all:
                 outs.append(x32)
         if not keep_all:
@@ -334,9 +370,9 @@ class BertCrossEncoder(nn.Module):
             _check_inference(l, *l._dropouts())
         B, Sq, H = s1_hidden_states.shape
         Skv = s2_hidden_states.shape[1]
-        x32 = _rows(s1_hidden_states)
-        outs, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_hidden_states)), _mask2d(s2_attention_mask, B, Skv),
-                            B, Sq, Skv, keep_all=output_all_encoded_layers)
+        x32, y32 = _rows(s1_hidden_states), _rows(s2_hidden_states)
+        outs, _ = self._run(x32, _to_lp(x32.detach()), _to_lp(y32.detach()), _mask2d(s2_attention_mask, B, Skv),
+                            B, Sq, Skv, keep_all=output_all_encoded_layers, y32=y32)
         return [o.view(B, Sq, H) for o in outs]
 
 
@@ -390,37 +426,53 @@ class CrossModalFusion(nn.Module):
         grid = visual_embeds_att.float().contiguous()
         R = grid.numel() // (B * grid.shape[1])
 
-        # region projection, CMIM:956-958
+        rec = _recording(sequence_output, token_embedding, module=self)
+        # region projection, CMIM:956-958 (the ResNet grid carries no gradient: My_cross_attention.py:804-805)
         rows = ops.region_rows(grid, _cdt())
-        regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
-                                self.vismap2text.bias.detach(), out_dtype=_cdt())
+        w_vm2t = _operand(self._cache, 'vm2t', self.vismap2text.weight)
+        if rec:
+            regions32 = DenseFn.apply(rows, self.vismap2text.weight, self.vismap2text.bias, w_vm2t)
+            regions_lp = _to_lp(regions32.detach())
+        else:
+            regions32 = None
+            regions_lp = ops.linear(rows, w_vm2t, self.vismap2text.bias.detach(), out_dtype=_cdt())
         # masks, CMIM:962-965 and 976-982
         img_mask = ops.mask_additive(added_attention_mask, R)
         txt_mask = ops.mask_additive(ori_input_mask, S)
 
         # text -> image, CMIM:968-969
         x32 = _rows(sequence_output)
-        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R,
-                                                     keep_all=False)
+        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32.detach()), regions_lp, img_mask, B, S, R,
+                                                     keep_all=False, y32=regions32)
         fused32 = outs[-1]
 
         # image -> text, CMIM:954, 981-989 (single CLIP token as the query)
-        clip_in = _to_lp(clip_features.float().reshape(B, -1).contiguous())
-        z32 = ops.linear(clip_in, _operand(self._cache, 'vmap', self.vismapping.weight), self.vismapping.bias.detach(),
-                         out_dtype=torch.float32)
-        z_lp = _to_lp(z32)
+        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
+        w_vmap = _operand(self._cache, 'vmap', self.vismapping.weight)
+        if rec:
+            z32 = DenseFn.apply(clip_in, self.vismapping.weight, self.vismapping.bias, w_vmap)
+        else:
+            z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
+        z_lp = _to_lp(z32.detach())
         for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False)
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32)
             z32 = zs[-1]
 
         # gated fusion, CMIM:1029-1036
-        gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight, self.aux_head.bias)
-        w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
-            self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
-            self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
         ln = self.cls_layer.proj_norm
-        result, gate = ops.gate_blend(fused32.view(B, S, H), _rows(token_embedding).view(B, S, H), ln.weight.detach(),
-                                      ln.bias.detach(), ln.eps, w_fold, c_fold)
+        tok32 = _rows(token_embedding).view(B, S, H)
+        if rec:
+            result, gate = GateBlendFn.apply(fused32.view(B, S, H), tok32, ln.weight, ln.bias,
+                                             self.cls_layer.proj.weight, self.cls_layer.proj.bias,
+                                             self.aux_head.weight, self.aux_head.bias, ln.eps)
+        else:
+            gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight,
+                           self.aux_head.bias)
+            w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
+                self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+                self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
+            result, gate = ops.gate_blend(fused32.view(B, S, H), tok32, ln.weight.detach(), ln.bias.detach(), ln.eps,
+                                          w_fold, c_fold)
         if return_dict:
             return dict(regions=regions_lp.view(B, R, H), fused=fused32.view(B, S, H), clip=z32.view(B, 1, H),
                         result=result, gate=gate)
