@@ -42,7 +42,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='icka', choices=['icka', 'reference'])
-    ap.add_argument('--batch', type=int, default=1024, help='sentences per GPU per step')
+    ap.add_argument('--batch', type=int, default=None, help='sentences per GPU per step (default 1024; 128 for --mode train)')
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
+                    help="'infer' (default, the BASELINE metric) or 'train' (configs[1]/[4]: fwd + bwd + all-reduce + AdamW)")
     ap.add_argument('--layers', type=int, default=1, help='cross layers per encoder (layer_num1)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--hires', action='store_true', help='S=256, R=196 variant (BASELINE configs[3])')
@@ -306,12 +308,122 @@ def run_gpu_arm(args, shape):
         dist.destroy_process_group()
 
 
+def run_train_arm(args, shape):
+    """Extra (non-headline) mode for BASELINE configs[1] / [4]: one data-parallel training step of the hot path.
+
+    step = fusion forward (recording) -> emission head -> CRF negative log-likelihood (token_mean, CMIM:1047-1048)
+           -> backward through the kernel-backed autograd nodes -> bucketed gradient all-reduce (NCCL, overlapped
+           with backward) -> AdamW.  The emission head is a torch nn.Linear(H, T) standing in for the reference's
+           BiLSTM + classifier (CMIM:1042-1043, SURVEY 8f "next" row) and AdamW is torch's (the reference uses
+           transformers.AdamW): both are outside the hot path and are named in `config`."""
+    import torch
+    import torch.distributed as dist
+    from icka_b200 import CRF, CrossModalFusion, FusionConfig, _lib, set_precision, shard, synth
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    set_precision(args.precision)
+    torch.manual_seed(19260817)
+    cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
+                       layer_norm_eps=shape.eps)
+    fusion = CrossModalFusion(cfg, layer_num1=shape.L).to(dev).eval()       # eval(): dropout kernels are not built
+    head = torch.nn.Linear(shape.H, shape.T).to(dev)
+    crf = CRF(shape.T, batch_first=True).to(dev)
+    params = list(fusion.parameters()) + list(head.parameters()) + list(crf.parameters())
+    for m in (fusion, head, crf):
+        shard.broadcast_parameters(m)
+    reducer = shard.GradientAllReducer(params)
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
+    f = synth.fusion_inputs(args.batch, shape, seed=19260817 + rank)
+    c = synth.crf_batch(args.batch, shape, seed=19260817 + rank)
+    d = {k: f[k].to(dev) for k in ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask',
+                                   'text_mask')}
+    tags, mask = c['tags'].to(dev), c['mask'].to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        result, clip = fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                              d['img_mask'], d['text_mask'])
+        loss = -crf(head(result), tags, mask, reduction='token_mean') + 1e-3 * clip.mean()
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = _lib.launch_count(local_rank)
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        s_ev.record()
+        for _ in range(args.steps):
+            loss = step()
+        e_ev.record()
+        barrier()
+    ms = shard.max_over_ranks(s_ev.elapsed_time(e_ev), device=dev)
+    launches = _lib.launch_count(local_rank) - l0
+    from icka_b200.profiler import KernelTimer
+    n_prof = min(args.steps, 5)
+    with KernelTimer() as kt:                 # per-kernel CUDA-event pass of the same step
+        for _ in range(n_prof):
+            step()
+        ksum = kt.summary()
+    hbm = load_peaks().get('hbm_gbs', FALLBACK_PEAKS['hbm_gbs'])
+    kernel_table = {name: {'launches_per_step': k['launches'] // n_prof, 'ms_per_step': round(k['ms_total'] / n_prof, 4),
+                           'tflops': round(k['tflops'], 1), 'gbs': round(k['gbs'], 1)} for name, k in ksum.items()}
+    n_param = sum(p.numel() for p in params)
+    # dense-GEMM FLOPs per sentence: forward (unfolded single-query encoders) x3 for forward + dgrad + wgrad
+    S, R, H, I, L = shape.S, shape.R, shape.H, shape.inter, shape.L
+    layer = lambda sq, skv: 2.0 * (sq * H * H + 2 * skv * H * H + sq * H * H + 2 * sq * H * I)
+    fwd = 2.0 * R * shape.region_dim * H + L * layer(S, R) + 2 * L * layer(1, S)
+    peaks = load_peaks()
+    peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
+    tf = 3.0 * fwd * args.batch * args.steps / (ms * 1e-3) / 1e12
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'sentences/sec fusion+CRF training step', 'value': args.batch * world * args.steps / (ms * 1e-3),
+            'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32',
+            'data': 'synthetic', 'mode': 'train',
+            'config': {'workload': f'twitter2015_training_B{args.batch}_per_gpu_S{S}_R{R}_H{H}_I{I}_T{shape.T}_L{L}',
+                       'global_batch': args.batch * world, 'parallelism': f'data-parallel x{world}, bucketed NCCL gradient all-reduce',
+                       'params_allreduced': n_param, 'buckets': len(reducer.buckets),
+                       'buckets_launched_inside_backward_per_step': reducer.launched_early // (args.steps + max(args.warmup, 3)),
+                       'outside_hot_path': 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier; optimizer = torch AdamW(fused)',
+                       'dropout': 'p = 0 (no dropout kernels)'},
+            'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss),
+            'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor', 'achieved': tf,
+                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
+                         'note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, '
+                                 'the all-reduce and the optimizer'},
+            'kernels': kernel_table,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.batch is None:
+        args.batch = 128 if args.mode == 'train' else 1024
     from icka_b200 import synth
     shape = synth.Shape(L=args.layers, S=256 if args.hires else 128, R=196 if args.hires else 49)
     if args.impl == 'reference':
         run_reference_arm(args, shape)
+    elif args.mode == 'train':
+        run_train_arm(args, shape)
     else:
         run_gpu_arm(args, shape)
 

@@ -39,8 +39,8 @@ SIGNATURES = {
     'icka_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'icka_cross_attn_core_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
-                                         c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,
-                                         c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                         c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                         c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_gate_blend_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                     c_int, c_int, c_void_p]),

@@ -100,7 +100,7 @@ class CrossLayerFn(torch.autograd.Function):
         dpre1_op = _op(dpre1, dpre1_16)
         dwo = ops.linear_wgrad(dpre1_op, att)
         datt = ops.linear_dgrad(dpre1_op, wo_op, out_dtype=dt)
-        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, datt, B, Sq, Skv, nh, d)
+        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, datt, B, Sq, Skv, nh, d, ctx=att)
         dwq = ops.linear_wgrad(dq, x_op)
         dbq = ops.colsum(dq)
         dwkv = ops.linear_wgrad(dkv, y_op)                                         # [2H, H]: rows = key | value

@@ -384,6 +384,310 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 attention backward on the tensor cores (mma.sync m16n8k16, fp32 accumulate) for Sq <= 128: the same
+// tiling as the forward kernel (attention.cu): one block = one (sentence, head), 8 warps x 16 query rows,
+// keys in blocks of 64.  The softmax statistics are rebuilt in a first sweep over the key blocks; the
+// second sweep forms P and dS = P * (dP - delta) / 8 per key block with delta = rowsum(dO * O) taken from
+// the saved forward output, accumulates dQ += dS K in registers, parks P and dS (bf16) in shared memory,
+// and then the 8 warps split dV = P^T dO and dK = dS^T Q of that key block (operands fetched with
+// ldmatrix.trans straight from the [row][key] / [row][dim] tiles).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMmaThreads = 256;
+constexpr int kPitch = 72;        // bf16 elements per smem row (64 + 8 pad): conflict-free ldmatrix
+constexpr int kKeyBlk = 64;
+constexpr int kRowsQ = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_fence_wait() {
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(sa));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(sa));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// grid = (nh, B); Sq <= 128
+__global__ void __launch_bounds__(kMmaThreads) cross_attn_bwd_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
+    const __nv_bfloat16* __restrict__ v, int64_t ldkv, const float* __restrict__ mask_add,
+    const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dctx, int64_t ldc,
+    __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
+    int64_t lddkv, int Sq, int Skv) {
+  extern __shared__ __align__(16) uint8_t smem_dyn[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_dyn);   // [128][72]
+  __nv_bfloat16* dOs = Qs + kRowsQ * kPitch;                          // [128][72]
+  __nv_bfloat16* Ps = dOs + kRowsQ * kPitch;                          // [128][72]  P   of the current key block
+  __nv_bfloat16* dSs = Ps + kRowsQ * kPitch;                          // [128][72]  dS  of the current key block
+  __nv_bfloat16* Ks = dSs + kRowsQ * kPitch;                          // [64][72]
+  __nv_bfloat16* Vs = Ks + kKeyBlk * kPitch;                          // [64][72]
+  float* Ms = reinterpret_cast<float*>(Vs + kKeyBlk * kPitch);        // [64]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kScale = 0.125f * kLog2e;
+
+  // ---- stage Q and dO (rows beyond Sq are zero-filled) ----
+  const __nv_bfloat16* qb = q + (size_t)b * Sq * ldq + (size_t)h * kD;
+  const __nv_bfloat16* dob = dctx + (size_t)b * Sq * ldc + (size_t)h * kD;
+  for (int i = tid; i < kRowsQ * 8; i += kMmaThreads) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    if (r < Sq) {
+      cp_async16(Qs + r * kPitch + c, qb + (size_t)r * ldq + c);
+      cp_async16(dOs + r * kPitch + c, dob + (size_t)r * ldc + c);
+    } else {
+      *reinterpret_cast<uint4*>(Qs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dOs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_fence_wait();
+  __syncthreads();
+
+  // ---- delta[row] = sum_d dO[row][d] * O[row][d]; two lanes per row, then fetched for rows g and g+8 ----
+  float delta0, delta1;
+  {
+    const int r = warp * 16 + (lane >> 1), c0 = (lane & 1) * 32;
+    float acc = 0.0f;
+    if (r < Sq) {
+      const __nv_bfloat16* op = o + ((size_t)b * Sq + r) * ldo + (size_t)h * kD + c0;
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        const uint4 uo = *reinterpret_cast<const uint4*>(op + c);
+        const uint4 ud = *reinterpret_cast<const uint4*>(dOs + r * kPitch + c0 + c);
+        const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wd[4] = {ud.x, ud.y, ud.z, ud.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc = fmaf(__uint_as_float(wo[j] << 16), __uint_as_float(wd[j] << 16), acc);
+          acc = fmaf(__uint_as_float(wo[j] & 0xffff0000u), __uint_as_float(wd[j] & 0xffff0000u), acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    delta0 = __shfl_sync(0xffffffffu, acc, 2 * g);
+    delta1 = __shfl_sync(0xffffffffu, acc, 2 * (g + 8));
+  }
+
+  uint32_t qf[4][4], dof[4][4];
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    ldmatrix_x4(qf[kk], Qs + (warp * 16 + (lane & 15)) * kPitch + kk * 16 + (lane >> 4) * 8);
+    ldmatrix_x4(dof[kk], dOs + (warp * 16 + (lane & 15)) * kPitch + kk * 16 + (lane >> 4) * 8);
+  }
+
+  const __nv_bfloat16* kb = k + (size_t)b * Skv * ldkv + (size_t)h * kD;
+  const __nv_bfloat16* vb = v + (size_t)b * Skv * ldkv + (size_t)h * kD;
+
+  auto load_keys = [&](int key0, bool with_v) {
+    for (int i = tid; i < kKeyBlk * 8; i += kMmaThreads) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      if (key0 + r < Skv) {
+        cp_async16(Ks + r * kPitch + c, kb + (size_t)(key0 + r) * ldkv + c);
+        if (with_v) cp_async16(Vs + r * kPitch + c, vb + (size_t)(key0 + r) * ldkv + c);
+      } else {
+        *reinterpret_cast<uint4*>(Ks + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+        if (with_v) *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (tid < kKeyBlk) {
+      const int key = key0 + tid;
+      Ms[tid] = (key < Skv) ? (mask_add ? mask_add[(size_t)b * Skv + key] * kLog2e : 0.0f) : -INFINITY;
+    }
+    cp_async_fence_wait();
+    __syncthreads();
+  };
+  // scores of this warp's 16 rows against the staged key block, log2 domain (scale and mask applied)
+  auto scores = [&](float (&sacc)[8][4]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+      uint32_t kf[4];
+      ldmatrix_x4(kf, Ks + (j * 8 + (lane & 7)) * kPitch + (lane >> 3) * 8);
+      mma_bf16_16816(sacc[j], qf[0], kf[0], kf[1]);
+      mma_bf16_16816(sacc[j], qf[1], kf[2], kf[3]);
+      ldmatrix_x4(kf, Ks + (j * 8 + (lane & 7)) * kPitch + 32 + (lane >> 3) * 8);
+      mma_bf16_16816(sacc[j], qf[2], kf[0], kf[1]);
+      mma_bf16_16816(sacc[j], qf[3], kf[2], kf[3]);
+      const float mk0 = Ms[j * 8 + 2 * t], mk1 = Ms[j * 8 + 2 * t + 1];
+      sacc[j][0] = fmaf(sacc[j][0], kScale, mk0);
+      sacc[j][1] = fmaf(sacc[j][1], kScale, mk1);
+      sacc[j][2] = fmaf(sacc[j][2], kScale, mk0);
+      sacc[j][3] = fmaf(sacc[j][3], kScale, mk1);
+    }
+  };
+
+  // ---- sweep 1: softmax statistics (running max m, sum l) over all key blocks ----
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  for (int key0 = 0; key0 < Skv; key0 += kKeyBlk) {
+    if (key0 > 0) __syncthreads();
+    load_keys(key0, false);
+    float sacc[8][4];
+    scores(sacc);
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      bm0 = fmaxf(bm0, fmaxf(sacc[j][0], sacc[j][1]));
+      bm1 = fmaxf(bm1, fmaxf(sacc[j][2], sacc[j][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    float ps0 = 0.0f, ps1 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ps0 += fast_exp2(sacc[j][0] - mn0) + fast_exp2(sacc[j][1] - mn0);
+      ps1 += fast_exp2(sacc[j][2] - mn1) + fast_exp2(sacc[j][3] - mn1);
+    }
+    l0 = l0 * fast_exp2(m0 - mn0) + ps0;
+    l1 = l1 * fast_exp2(m1 - mn1) + ps1;
+    m0 = mn0;
+    m1 = mn1;
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float il0 = 1.0f / l0, il1 = 1.0f / l1;
+
+  // ---- sweep 2: P, dS, dQ per key block, then dK / dV of that block ----
+  float dqa[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dqa[j][0] = dqa[j][1] = dqa[j][2] = dqa[j][3] = 0.0f;
+  for (int key0 = 0; key0 < Skv; key0 += kKeyBlk) {
+    __syncthreads();   // previous users of Ks / Vs / Ps / dSs are done
+    load_keys(key0, true);
+    float sacc[8][4];
+    scores(sacc);
+    uint32_t dsf[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float dp[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // dP = dO V^T for this 8-key tile
+      uint32_t vf[4];
+      ldmatrix_x4(vf, Vs + (j * 8 + (lane & 7)) * kPitch + (lane >> 3) * 8);
+      mma_bf16_16816(dp, dof[0], vf[0], vf[1]);
+      mma_bf16_16816(dp, dof[1], vf[2], vf[3]);
+      ldmatrix_x4(vf, Vs + (j * 8 + (lane & 7)) * kPitch + 32 + (lane >> 3) * 8);
+      mma_bf16_16816(dp, dof[2], vf[0], vf[1]);
+      mma_bf16_16816(dp, dof[3], vf[2], vf[3]);
+      const float p0 = fast_exp2(sacc[j][0] - m0) * il0, p1 = fast_exp2(sacc[j][1] - m0) * il0;
+      const float p2 = fast_exp2(sacc[j][2] - m1) * il1, p3 = fast_exp2(sacc[j][3] - m1) * il1;
+      const float d0 = p0 * (dp[0] - delta0) * 0.125f, d1 = p1 * (dp[1] - delta0) * 0.125f;
+      const float d2 = p2 * (dp[2] - delta1) * 0.125f, d3 = p3 * (dp[3] - delta1) * 0.125f;
+      dsf[j][0] = pack_bf16x2(d0, d1);
+      dsf[j][1] = pack_bf16x2(d2, d3);
+      const int r0 = warp * 16 + g, col = j * 8 + 2 * t;
+      *reinterpret_cast<uint32_t*>(Ps + r0 * kPitch + col) = pack_bf16x2(p0, p1);
+      *reinterpret_cast<uint32_t*>(Ps + (r0 + 8) * kPitch + col) = pack_bf16x2(p2, p3);
+      *reinterpret_cast<uint32_t*>(dSs + r0 * kPitch + col) = dsf[j][0];
+      *reinterpret_cast<uint32_t*>(dSs + (r0 + 8) * kPitch + col) = dsf[j][1];
+    }
+    // dQ += dS K   (A = dS fragments from registers, B = K via ldmatrix.trans, as P.V in the forward)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t a[4] = {dsf[2 * ks][0], dsf[2 * ks][1], dsf[2 * ks + 1][0], dsf[2 * ks + 1][1]};
+#pragma unroll
+      for (int jn = 0; jn < 8; jn += 2) {
+        uint32_t kf[4];
+        ldmatrix_x4_trans(kf, Ks + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + jn * 8 + (lane >> 4) * 8);
+        mma_bf16_16816(dqa[jn], a, kf[0], kf[1]);
+        mma_bf16_16816(dqa[jn + 1], a, kf[2], kf[3]);
+      }
+    }
+    __syncthreads();   // P and dS of every warp are in shared memory
+    // dV = P^T dO, dK = dS^T Q for this key block: warp -> 16 keys (mt) x 32 dims (nh2)
+    {
+      const int mt = warp & 3, nh2 = warp >> 2;
+      float dka[4][4], dva[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dka[j][0] = dka[j][1] = dka[j][2] = dka[j][3] = 0.0f;
+        dva[j][0] = dva[j][1] = dva[j][2] = dva[j][3] = 0.0f;
+      }
+      const int mat = lane >> 3;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {   // 16 query rows per step
+        // A[m = key][k = row] = X[row][key]: transposed 8x8 blocks of the [row][key] tiles
+        const int arow = ks * 16 + (lane & 7) + ((mat >> 1) & 1) * 8;
+        const int acol = mt * 16 + (mat & 1) * 8;
+        uint32_t ap[4], ads[4];
+        ldmatrix_x4_trans(ap, Ps + arow * kPitch + acol);
+        ldmatrix_x4_trans(ads, dSs + arow * kPitch + acol);
+#pragma unroll
+        for (int jn = 0; jn < 4; jn += 2) {
+          const int brow = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int bcol = nh2 * 32 + jn * 8 + (lane >> 4) * 8;
+          uint32_t bo[4], bq[4];
+          ldmatrix_x4_trans(bo, dOs + brow * kPitch + bcol);
+          ldmatrix_x4_trans(bq, Qs + brow * kPitch + bcol);
+          mma_bf16_16816(dva[jn], ap, bo[0], bo[1]);
+          mma_bf16_16816(dva[jn + 1], ap, bo[2], bo[3]);
+          mma_bf16_16816(dka[jn], ads, bq[0], bq[1]);
+          mma_bf16_16816(dka[jn + 1], ads, bq[2], bq[3]);
+        }
+      }
+      const int key_a = key0 + mt * 16 + g, key_b = key_a + 8;
+      __nv_bfloat16* dkp = dk + (size_t)b * Skv * lddkv + (size_t)h * kD + nh2 * 32 + 2 * t;
+      __nv_bfloat16* dvp = dv + (size_t)b * Skv * lddkv + (size_t)h * kD + nh2 * 32 + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (key_a < Skv) {
+          *reinterpret_cast<uint32_t*>(dkp + (size_t)key_a * lddkv + j * 8) = pack_bf16x2(dka[j][0], dka[j][1]);
+          *reinterpret_cast<uint32_t*>(dvp + (size_t)key_a * lddkv + j * 8) = pack_bf16x2(dva[j][0], dva[j][1]);
+        }
+        if (key_b < Skv) {
+          *reinterpret_cast<uint32_t*>(dkp + (size_t)key_b * lddkv + j * 8) = pack_bf16x2(dka[j][2], dka[j][3]);
+          *reinterpret_cast<uint32_t*>(dvp + (size_t)key_b * lddkv + j * 8) = pack_bf16x2(dva[j][2], dva[j][3]);
+        }
+      }
+    }
+  }
+
+  // ---- dQ: stage through the P tile (each warp owns its 16 rows), coalesced write-out ----
+  __syncthreads();
+  {
+    __nv_bfloat16* ow = Ps + (warp * 16) * kPitch;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint32_t*>(ow + g * kPitch + j * 8 + 2 * t) = pack_bf16x2(dqa[j][0], dqa[j][1]);
+      *reinterpret_cast<uint32_t*>(ow + (g + 8) * kPitch + j * 8 + 2 * t) = pack_bf16x2(dqa[j][2], dqa[j][3]);
+    }
+    __syncwarp();
+    __nv_bfloat16* ob = dq + ((size_t)b * Sq + warp * 16) * lddq + (size_t)h * kD;
+#pragma unroll
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, c = (i & 7) * 8;
+      if (warp * 16 + r < Sq)
+        *reinterpret_cast<uint4*>(ob + (size_t)r * lddq + c) = *reinterpret_cast<const uint4*>(ow + r * kPitch + c);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Gate + blend backward (forward: elementwise.cu gate_blend_kernel).  One block per sentence.
 //   out = g tok + (1-g) fused,  g = sigmoid(w_fold . n + c_fold),  n = LN(fused[0] + tok[0]) * ln_w + ln_b
 // ------------------------------------------------------------------------------------------------
@@ -520,9 +824,9 @@ extern "C" int icka_layernorm_bwd(icka_handle* h, const float* dy, const float* 
 }
 
 extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
-                                        int64_t ldkv, const float* mask_add, const void* dctx, int64_t ldc, void* dq,
-                                        int64_t lddq, void* dk, void* dv, int64_t lddkv, int dtype, int B, int Sq,
-                                        int Skv, int nh, int d, void* stream) {
+                                        int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx,
+                                        const void* dctx, int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv,
+                                        int64_t lddkv, int dtype, int B, int Sq, int Skv, int nh, int d, void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(q && k && v && dctx && dq && dk && dv, "cross_attn_bwd: null pointer");
   ICKA_REQUIRE(B >= 0 && Sq >= 1 && Skv >= 1 && nh >= 1, "cross_attn_bwd: bad shape");
@@ -535,6 +839,18 @@ extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t l
                "cross_attn_bwd: pointers must be 16-byte aligned");
   ICKA_REQUIRE(B <= 65535, "cross_attn_bwd: B exceeds grid limits; shard the batch");
   if (B == 0) return ICKA_OK;
+  if (dtype == ICKA_BF16 && ctx != nullptr && Sq <= kRowsQ && ldctx % 8 == 0 && icka_aligned(ctx, 16)) {
+    // tensor-core path
+    const size_t smem_mma = (size_t)(4 * kRowsQ + 2 * kKeyBlk) * kPitch * sizeof(__nv_bfloat16) + kKeyBlk * sizeof(float);
+    using T = __nv_bfloat16;
+    ICKA_CUDA(cudaFuncSetAttribute(cross_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+    cross_attn_bwd_mma_kernel<<<dim3(nh, B), kMmaThreads, smem_mma, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const T*>(q), ldq, static_cast<const T*>(k), static_cast<const T*>(v), ldkv, mask_add,
+        static_cast<const T*>(ctx), ldctx, static_cast<const T*>(dctx), ldc, static_cast<T*>(dq), lddq,
+        static_cast<T*>(dk), static_cast<T*>(dv), lddkv, Sq, Skv);
+    ICKA_LAUNCHED(h);
+    return ICKA_OK;
+  }
   // query tile: as many rows (<= 128 threads) as shared memory allows next to the four [Skv][64] key-side arrays
   const size_t fixed = ((size_t)4 * Skv * kD + Skv) * sizeof(float);
   const size_t per_row = ((size_t)2 * kD + 2 * (Skv + 1)) * sizeof(float);

@@ -351,6 +351,18 @@ __global__ void __launch_bounds__(kV16Threads) viterbi16_kernel(
   if (gl == 0) lens_out[b] = len;
 }
 
+// Coalesced copy of one sentence's [S*T] fp32 slab into shared memory by the LPS lanes of its group.
+template <int LPS>
+__device__ __forceinline__ void stage_slab(const float* __restrict__ g, float* s, int n, int gl) {
+  if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+    const int nv = n / 4;
+    for (int v = gl; v < nv; v += LPS) reinterpret_cast<float4*>(s)[v] = reinterpret_cast<const float4*>(g)[v];
+    for (int i = nv * 4 + gl; i < n; i += LPS) s[i] = g[i];
+  } else {
+    for (int i = gl; i < n; i += LPS) s[i] = g[i];
+  }
+}
+
 // Per-sentence log-likelihood: gold-path score minus log-partition (forward algorithm), fp32.
 // Same lane mapping as Viterbi; logsumexp over predecessors i is max-shifted like torch.logsumexp.
 template <int LPS>
@@ -358,16 +370,20 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
     const float* __restrict__ emissions, const int64_t* __restrict__ tags, const uint8_t* __restrict__ mask,
     const float* __restrict__ start, const float* __restrict__ end, const float* __restrict__ trans,
     float* __restrict__ llh_out, int B, int S, int T) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int g_in_block = threadIdx.x / LPS;
   const int gl = threadIdx.x % LPS;
   const int gshift = (threadIdx.x % 32) / LPS * LPS;
   const unsigned gmask = (LPS == 32) ? 0xffffffffu : (0xffffu << gshift);
   const int b = blockIdx.x * (kThreads / LPS) + g_in_block;
   if (b >= B) return;
-  const float* e_g = emissions + (size_t)b * S * T;
   const uint8_t* m_g = mask ? mask + (size_t)b * S : nullptr;
   const int64_t* y_g = tags + (size_t)b * S;
   const bool active = gl < T;
+  // the serial chain must not wait on HBM every step: stage the sentence's emission slab in shared memory
+  float* e_g = reinterpret_cast<float*>(smem_raw) + (size_t)g_in_block * (((size_t)S * T + 3) / 4 * 4);
+  stage_slab<LPS>(emissions + (size_t)b * S * T, e_g, S * T, gl);
+  __syncwarp(gmask);
 
   float tr[LPS];
 #pragma unroll
@@ -455,8 +471,9 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
 
   if (b < B) {
     float* alpha = reinterpret_cast<float*>(smem_raw + head + (size_t)g_in_block * per_seq_bytes);   // [S][LPS]
-    int* on_idx = reinterpret_cast<int*>(alpha + (size_t)S * LPS);                                   // [S]
-    const float* e_g = emissions + (size_t)b * S * T;
+    float* e_g = alpha + (size_t)S * LPS;                                                            // [S*T] (16-B aligned)
+    int* on_idx = reinterpret_cast<int*>(e_g + ((size_t)S * T + 3) / 4 * 4);                         // [S]
+    stage_slab<LPS>(emissions + (size_t)b * S * T, e_g, S * T, gl);
     const uint8_t* m_g = mask ? mask + (size_t)b * S : nullptr;
     const int64_t* y_g = tags + (size_t)b * S;
     float* de_g = d_emissions + (size_t)b * S * T;
@@ -623,10 +640,17 @@ extern "C" int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const in
   const int LPS = (T <= 16) ? 16 : 32;
   const int spb = kThreads / LPS;
   const int grid = (B + spb - 1) / spb;
-  if (LPS == 16)
-    crf_llh_kernel<16><<<grid, kThreads, 0, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
-  else
-    crf_llh_kernel<32><<<grid, kThreads, 0, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
+  const size_t smem = (((size_t)S * T + 3) / 4 * 4) * sizeof(float) * spb;
+  if (smem > h->smem_optin)
+    ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,
+              h->smem_optin);
+  if (LPS == 16) {
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_llh_kernel<16><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
+  } else {
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    crf_llh_kernel<32><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
+  }
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
@@ -645,7 +669,9 @@ extern "C" int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const in
   const int LPS = (T <= 16) ? 16 : 32;
   const int spb = kThreads / LPS;
   const size_t head = (((size_t)T * T + 2 * T) * sizeof(float) + 15) / 16 * 16;
-  const size_t per_seq = ((size_t)S * LPS * sizeof(float) + (size_t)S * sizeof(int) + 15) / 16 * 16;
+  const size_t per_seq =
+      ((size_t)S * LPS * sizeof(float) + (size_t)S * sizeof(int) + (((size_t)S * T + 3) / 4 * 4) * sizeof(float) + 15) /
+      16 * 16;
   const size_t smem = head + per_seq * spb;
   if (smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh_bwd: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,

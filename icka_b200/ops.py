@@ -191,8 +191,10 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: f
 
 
 def cross_attn_core_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add: Optional[torch.Tensor],
-                        dctx: torch.Tensor, B: int, Sq: int, Skv: int, nh: int, d: int):
-    """Returns (dq [B*Sq, nh*d], dkv [B*Skv, 2*nh*d]) in the dtype of q."""
+                        dctx: torch.Tensor, B: int, Sq: int, Skv: int, nh: int, d: int,
+                        ctx: Optional[torch.Tensor] = None):
+    """Returns (dq [B*Sq, nh*d], dkv [B*Skv, 2*nh*d]) in the dtype of q.  ``ctx`` = the forward output
+    (enables the tensor-core kernel for bf16)."""
     if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype or dctx.dtype != q.dtype:
         raise RuntimeError('cross_attn_core_bwd: q/k/v/dctx must share dtype fp32 or bf16')
     if q.stride(1) != 1 or k.stride(1) != 1 or v.stride(1) != 1 or dctx.stride(1) != 1 or k.stride(0) != v.stride(0):
@@ -202,8 +204,11 @@ def cross_attn_core_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_
     dq = torch.empty(B * Sq, H, dtype=q.dtype, device=q.device)
     dkv = torch.empty(B * Skv, 2 * H, dtype=q.dtype, device=q.device)
     dk, dv = dkv[:, :H], dkv[:, H:]
+    if ctx is not None and (ctx.dtype != q.dtype or ctx.stride(1) != 1):
+        raise RuntimeError('cross_attn_core_bwd: bad ctx')
     _lib.check(lib.icka_cross_attn_core_bwd(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
-                                            _p(mask_add), dctx.data_ptr(), dctx.stride(0), dq.data_ptr(), H,
+                                            _p(mask_add), _p(ctx), ctx.stride(0) if ctx is not None else 0,
+                                            dctx.data_ptr(), dctx.stride(0), dq.data_ptr(), H,
                                             dk.data_ptr(), dv.data_ptr(), 2 * H, _DT[q.dtype], B, Sq, Skv, nh, d, st),
                'icka_cross_attn_core_bwd')
     return dq, dkv

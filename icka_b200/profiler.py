@@ -16,7 +16,7 @@ from . import ops
 _ESZ = {torch.float32: 4, torch.bfloat16: 2, torch.uint8: 1, torch.int32: 4, torch.int64: 8}
 
 
-def _work_linear(a, w, bias, residual=None, act=0, out_dtype=None, out=None):
+def _work_linear(a, w, bias, residual=None, act=0, out_dtype=None, out=None, pre_act_out=None):
     M, K = a.shape
     N = w.shape[0]
     od = out_dtype or (out.dtype if out is not None else a.dtype)
@@ -52,12 +52,44 @@ def _work(name, args, kwargs):
     if name == 'crf_llh':
         B, S, T = args[0].shape
         return name, 0.0, B * (S * T * 4 + S + S * 8)
+    # ---- backward (training) ----
+    if name == 'linear_dgrad':
+        dy, w = args[0], args[1]
+        M, N = dy.shape
+        K = w.shape[1]
+        od = kwargs.get('out_dtype') or dy.dtype
+        nb = (M * N + N * K) * _ESZ[dy.dtype] + M * K * _ESZ[od]
+        nb += M * K * 4 if kwargs.get('residual') is not None else 0
+        nb += M * K * _ESZ[dy.dtype] if kwargs.get('gelu_pre') is not None else 0
+        return ('dgrad_bf16_tcgen05' if dy.dtype == torch.bfloat16 else 'dgrad_fp32_ffma'), 2.0 * M * N * K, nb
+    if name == 'linear_wgrad':
+        dy, x = args[0], args[1]
+        M, N = dy.shape
+        K = x.shape[1]
+        return (('wgrad_bf16_tcgen05' if dy.dtype == torch.bfloat16 else 'wgrad_fp32_ffma'), 2.0 * M * N * K,
+                (M * N + M * K) * _ESZ[dy.dtype] + N * K * 4)
+    if name == 'colsum':
+        return name, 0.0, args[0].numel() * _ESZ[args[0].dtype]
+    if name == 'layernorm_bwd':
+        x = args[1]
+        nb = x.numel() * 4 * (2 + (1 if kwargs.get('want_f32', True) else 0)) + (x.numel() * 2 if kwargs.get('want_bf16') else 0)
+        return name, 0.0, nb
+    if name == 'cross_attn_core_bwd':
+        q, k, v, mask, dctx, B, Sq, Skv, nh, d = args[:10]
+        es = _ESZ[q.dtype]
+        return name, 10.0 * B * nh * Sq * Skv * d, (3 * B * Sq * nh * d + 4 * B * Skv * nh * d) * es
+    if name == 'gate_blend_bwd':
+        return name, 0.0, args[0].numel() * 4 * (6 if kwargs.get('want_dtok', True) else 5)
+    if name == 'crf_llh_bwd':
+        B, S, T = args[0].shape
+        return name, 0.0, B * (2 * S * T * 4 + S + S * 8)
     return name, 0.0, 0
 
 
 class KernelTimer:
     OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend',
-           'viterbi', 'crf_llh')
+           'viterbi', 'crf_llh', 'linear_dgrad', 'linear_wgrad', 'colsum', 'layernorm_bwd', 'cross_attn_core_bwd',
+           'gate_blend_bwd', 'gate_fold_bwd', 'crf_llh_bwd')
 
     def __init__(self):
         self.records = []

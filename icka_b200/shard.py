@@ -42,3 +42,120 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Training: the one collective of the path -- data-parallel gradient averaging (the reference
+# does it with apex DistributedDataParallel / nn.DataParallel, My_cross_attention.py:768-779).
+# ---------------------------------------------------------------------------------------------------------
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Every rank starts from rank ``src``'s weights (what DDP does at construction)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src, group=group)
+
+
+class _Bucket:
+    __slots__ = ('params', 'offsets', 'numel', 'flat', 'pending', 'work')
+
+    def __init__(self, params):
+        self.params = params
+        self.offsets, n = [], 0
+        for p in params:
+            self.offsets.append(n)
+            n += p.numel()
+        self.numel = n
+        self.flat = None
+        self.pending = len(params)
+        self.work = None
+
+
+class GradientAllReducer:
+    """Bucketed, backward-overlapped gradient all-reduce for one process per GPU.
+
+    Parameters are grouped into buckets of about ``bucket_bytes`` in REVERSE registration order (roughly the
+    order backward produces their gradients: the kernel-backed autograd nodes of ``icka_b200.autograd`` emit
+    all 16 parameter gradients of a cross layer at once, so buckets fill layer by layer).  A
+    post-accumulate-grad hook counts a bucket's gradients in; when the last one lands, the bucket is packed
+    into one flat fp32 buffer and all-reduced asynchronously (NCCL over NVLink 5 / NVSwitch on GPU ranks --
+    the collective runs on NCCL's own stream beside the rest of backward; gloo in the CPU tests).
+    ``finish()`` (call it after ``loss.backward()``, before clipping / the optimizer step) waits for the
+    transfers, divides by the world size -- ranks hold equal shards, so this is the global-batch mean the
+    reference's DDP produces -- and writes the averaged gradients back into ``p.grad``.
+    """
+
+    def __init__(self, params, bucket_bytes: int = 25 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        plist = [p for p in params if p.requires_grad]
+        seen, uniq = set(), []
+        for p in plist:
+            if id(p) not in seen:
+                seen.add(id(p))
+                uniq.append(p)
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(uniq):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self.buckets.append(_Bucket(cur))
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._where = {}
+        self._handles = []
+        for b in self.buckets:
+            for p in b.params:
+                self._where[id(p)] = b
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        self.launched_early = 0      # buckets whose all-reduce started from inside backward (diagnostics)
+
+    def remove_hooks(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    # -- internals -------------------------------------------------------------------------------------
+    def _on_grad(self, p: torch.Tensor) -> None:
+        b = self._where[id(p)]
+        b.pending -= 1
+        if b.pending == 0 and self.world > 1:
+            self._launch(b)
+            self.launched_early += 1
+
+    def _launch(self, b: _Bucket) -> None:
+        ref = b.params[0]
+        if b.flat is None or b.flat.device != ref.device:
+            b.flat = torch.empty(b.numel, dtype=torch.float32, device=ref.device)
+        with torch.no_grad():
+            for p, off in zip(b.params, b.offsets):
+                dst = b.flat[off:off + p.numel()]
+                if p.grad is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(p.grad.reshape(-1))
+        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        """Wait for every bucket, average, scatter back; re-arm the hooks' counters for the next step."""
+        if self.world > 1:
+            for b in self.buckets:
+                if b.work is None:               # some gradient of this bucket never arrived (unused parameter)
+                    self._launch(b)
+            with torch.no_grad():
+                for b in self.buckets:
+                    b.work.wait()
+                    b.flat.div_(self.world)
+                    for p, off in zip(b.params, b.offsets):
+                        avg = b.flat[off:off + p.numel()].view_as(p)
+                        if p.grad is None:
+                            p.grad = avg.clone()
+                        else:
+                            p.grad.copy_(avg)
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None

@@ -130,11 +130,12 @@ int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const v
 
 /* Backward of icka_cross_attn_core_fwd: probabilities are recomputed from q, k, v (same layouts as the
  * forward); dctx [B*Sq, nh*d] -> dq [B*Sq, nh*d] (pitch lddq), dk / dv [B*Skv, nh*d] (pitch lddkv; may be the
- * halves of one [dK|dV] buffer).  Skv <= ~150 (shared-memory resident). */
+ * halves of one [dK|dV] buffer).  ctx (the forward output, pitch ldctx) may be NULL; with it, bf16 and
+ * Sq <= 128 the tensor-core kernel runs (any Skv); otherwise the fp32 CUDA-core kernel (Skv <= ~150). */
 int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
-                             int64_t ldkv, const float* mask_add, const void* dctx, int64_t ldc, void* dq,
-                             int64_t lddq, void* dk, void* dv, int64_t lddkv, int dtype, int B, int Sq, int Skv,
-                             int nh, int d, void* stream);
+                             int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx, const void* dctx,
+                             int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, int dtype,
+                             int B, int Sq, int Skv, int nh, int d, void* stream);
 
 /* Single-query attention in folded form (image->text encoders, CMIM:984-989 with Sq = 1).
  * With one query per sentence, scores[h][s] = (U_h . x_s)/sqrt(d) + mask[s] where U_h = Wk_h^T q_h, and

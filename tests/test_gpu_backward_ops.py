@@ -121,9 +121,13 @@ def attn_ref(q, k, v, mask_add, B, Sq, Skv, nh, d):
 
 
 @pytest.mark.parametrize('B,Sq,Skv,nh', [(3, 128, 49, 12), (2, 1, 128, 12), (2, 77, 49, 4), (1, 200, 64, 2),
-                                          (2, 128, 100, 3)])
-@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
-def test_cross_attn_core_bwd(B, Sq, Skv, nh, dtype):
+                                          (2, 128, 100, 3), (2, 128, 196, 2)])
+@pytest.mark.parametrize('kind', ['fp32', 'bf16', 'bf16_tensor_core'])
+def test_cross_attn_core_bwd(B, Sq, Skv, nh, kind):
+    """fp32 / bf16: CUDA-core kernel; bf16_tensor_core: mma.sync kernel (needs the forward output, Sq <= 128)."""
+    if kind != 'bf16_tensor_core' and Skv > 150:
+        pytest.skip('the CUDA-core kernel keeps all keys in shared memory')
+    dtype = torch.float32 if kind == 'fp32' else torch.bfloat16
     d, H = 64, nh * 64
     q = rnd(B * Sq, H, seed=17).to(dtype)
     kv = rnd(B * Skv, 2 * H, seed=18).to(dtype)
@@ -133,10 +137,14 @@ def test_cross_attn_core_bwd(B, Sq, Skv, nh, dtype):
     qd = q.double().requires_grad_(True)
     kvd = kv.double().requires_grad_(True)
     attn_ref(qd, kvd[:, :H], kvd[:, H:], mask_add.double(), B, Sq, Skv, nh, d).backward(dctx.double())
-    kv_dev = kv.to(DEV)
-    dq, dkv = ops.cross_attn_core_bwd(q.to(DEV), kv_dev[:, :H], kv_dev[:, H:], mask_add.to(DEV), dctx.to(DEV), B, Sq,
-                                      Skv, nh, d)
-    tol = 2e-5 if dtype == torch.float32 else 2 ** -7
+    q_dev, kv_dev, m_dev = q.to(DEV), kv.to(DEV), mask_add.to(DEV)
+    ctx = None
+    if kind == 'bf16_tensor_core':
+        ctx = ops.cross_attn_core(q_dev, kv_dev[:, :H], kv_dev[:, H:], m_dev, B, Sq, Skv, nh, d)
+    dq, dkv = ops.cross_attn_core_bwd(q_dev, kv_dev[:, :H], kv_dev[:, H:], m_dev, dctx.to(DEV), B, Sq, Skv, nh, d,
+                                      ctx=ctx)
+    # bf16: outputs rounded to bf16; the tensor-core kernel also rounds P and dS to bf16 before the second GEMMs
+    tol = {'fp32': 2e-5, 'bf16': 2 ** -7, 'bf16_tensor_core': 4e-2}[kind]
     for got, want in ((dq, qd.grad), (dkv, kvd.grad)):
         err = float(((got.cpu().double() - want).abs() / want.abs().clamp(min=1.0)).max())
         assert err <= tol, err

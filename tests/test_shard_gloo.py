@@ -67,3 +67,64 @@ def test_two_rank_sharded_decode_matches_single_rank():
         assert p.exitcode == 0
     assert ok
     assert slowest == 11.0
+
+
+# ---- data-parallel gradient averaging (the training collective) ------------------------------------------
+def _make_model():
+    torch.manual_seed(7)
+    return torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16), torch.nn.Tanh(),
+                               torch.nn.Linear(16, 3))
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model = _make_model()
+        if rank != 0:                       # ranks start out different; broadcast must fix that
+            with torch.no_grad():
+                for p in model.parameters():
+                    p.add_(1.0)
+        shard.broadcast_parameters(model)
+        model[4].bias.requires_grad_(True)
+        extra = torch.nn.Parameter(torch.ones(5))          # registered but never used: no gradient arrives
+        reducer = shard.GradientAllReducer(list(model.parameters()) + [extra], bucket_bytes=1024)
+        g = torch.Generator().manual_seed(11)
+        x, y = torch.randn(10, 12, generator=g), torch.randn(10, 3, generator=g)
+        mine = shard.shard_batch({'x': x, 'y': y}, world, rank)
+        grads = []
+        for step in range(2):                               # twice: the hook counters must re-arm
+            for p in model.parameters():
+                p.grad = None
+            loss = ((model(mine['x']) - mine['y']) ** 2).mean()
+            loss.backward()
+            reducer.finish()
+            grads.append([p.grad.clone() for p in model.parameters()])
+        if rank == 0:
+            q.put((grads, len(reducer.buckets), reducer.launched_early, extra.grad))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_full_batch():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads, n_buckets, early, extra_grad = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = _make_model()
+    g = torch.Generator().manual_seed(11)
+    x, y = torch.randn(10, 12, generator=g), torch.randn(10, 3, generator=g)
+    ((model(x) - y) ** 2).mean().backward()                 # equal shards: mean of shard means == full-batch mean
+    for step in range(2):
+        for got, p in zip(grads[step], model.parameters()):
+            assert torch.allclose(got, p.grad, rtol=1e-5, atol=1e-6)
+    assert n_buckets >= 3                                   # 1 KiB buckets split this model
+    assert early >= 2 * (n_buckets - 1)                     # all but the unused-parameter bucket start inside backward
+    assert extra_grad is not None and float(extra_grad.abs().max()) == 0.0
