@@ -381,8 +381,13 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
   const int64_t* y_g = tags + (size_t)b * S;
   const bool active = gl < T;
   // the serial chain must not wait on HBM every step: stage the sentence's emission slab in shared memory
-  float* e_g = reinterpret_cast<float*>(smem_raw) + (size_t)g_in_block * (((size_t)S * T + 3) / 4 * 4);
+  // (nor on a per-step global read of the mask byte that decides the branch)
+  const size_t e_floats = ((size_t)S * T + 3) / 4 * 4;
+  const size_t seq_bytes = e_floats * sizeof(float) + ((size_t)S + 15) / 16 * 16;
+  float* e_g = reinterpret_cast<float*>(smem_raw + (size_t)g_in_block * seq_bytes);
+  uint8_t* m_s = reinterpret_cast<uint8_t*>(e_g + e_floats);
   stage_slab<LPS>(emissions + (size_t)b * S * T, e_g, S * T, gl);
+  for (int t = gl; t < S; t += LPS) m_s[t] = m_g ? (m_g[t] != 0) : 1;
   __syncwarp(gmask);
 
   float tr[LPS];
@@ -392,8 +397,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
   // ---- normalizer (pytorch-crf _compute_normalizer) ----
   float alpha = active ? start[gl] + e_g[gl] : -INFINITY;
   for (int t = 1; t < S; ++t) {
-    const bool on = m_g ? (m_g[t] != 0) : true;   // group-uniform
-    if (!on) continue;
+    if (!m_s[t]) continue;   // group-uniform
     const float e = active ? e_g[t * T + gl] : 0.0f;
     float c[LPS];
     float mx = -INFINITY;
@@ -473,6 +477,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
     float* alpha = reinterpret_cast<float*>(smem_raw + head + (size_t)g_in_block * per_seq_bytes);   // [S][LPS]
     float* e_g = alpha + (size_t)S * LPS;                                                            // [S*T] (16-B aligned)
     int* on_idx = reinterpret_cast<int*>(e_g + ((size_t)S * T + 3) / 4 * 4);                         // [S]
+    int* y_s = on_idx + S;                                                                           // [S]
     stage_slab<LPS>(emissions + (size_t)b * S * T, e_g, S * T, gl);
     const uint8_t* m_g = mask ? mask + (size_t)b * S : nullptr;
     const int64_t* y_g = tags + (size_t)b * S;
@@ -493,6 +498,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
       len += __popc(bits_m);
     }
     for (int i = gl; i < S * T; i += LPS) de_g[i] = 0.0f;
+    for (int t = gl; t < S; t += LPS) y_s[t] = (int)y_g[t];   // the sweeps below must not wait on HBM per step
     __syncwarp(gmask);
 
     float tr[LPS], trr[LPS];   // column gl and row gl of the transition matrix
@@ -539,12 +545,12 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
 #pragma unroll
     for (int i = 0; i < LPS; ++i) acc_tr[i] = 0.0f;
     float beta = active ? end[gl] : -INFINITY;
-    const int y_last = (int)y_g[max(len - 1, 0)];
+    const int y_last = y_s[max(len - 1, 0)];
     for (int n = n_on - 1; n >= 0; --n) {
       const int t = on_idx[n];
       const float an = alpha[n * LPS + gl];
       const float p = active ? expf(an + beta - logz) : 0.0f;
-      const int y = (int)y_g[t];
+      const int y = y_s[t];
       if (active) {
         de_g[t * T + gl] = wb * ((y == gl ? 1.0f : 0.0f) - p);
         if (n == n_on - 1) atomicAdd(s_dend + gl, wb * ((y_last == gl ? 1.0f : 0.0f) - p));
@@ -585,7 +591,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
     // gold transitions: pytorch-crf's _compute_score pairs every on-step t >= 1 with position t-1
     for (int t = 1 + gl; t < S; t += LPS) {
       const bool on = m_g ? (m_g[t] != 0) : true;
-      if (on) atomicAdd(s_dtrans + (int)y_g[t - 1] * T + (int)y_g[t], wb);
+      if (on) atomicAdd(s_dtrans + y_s[t - 1] * T + y_s[t], wb);
     }
   }
   __syncthreads();
@@ -593,6 +599,224 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
   for (int i = threadIdx.x; i < T; i += kThreads) {
     atomicAdd(d_start + i, s_dstart[i]);
     atomicAdd(d_end + i, s_dend[i]);
+  }
+}
+
+// ---- T <= 16: lock-step log-likelihood kernels ------------------------------------------------------------
+// Like viterbi16_kernel: two sentences per warp, every warp-level primitive with the full mask (a per-half
+// member mask makes the two halves run one after the other and costs ~10 extra instructions per shuffle),
+// the 16 values a step needs from its predecessor read back from shared memory as four broadcast 16-byte
+// loads, and exp / log through ex2.approx / lg2.approx (arguments are max-shifted, so in [-inf, 0]; the
+// absolute error of ~1e-7 per term is far inside the 1e-5 relative gate on the log-likelihood).
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_log(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y * 0.6931471805599453f;
+}
+__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
+  const float4* q = reinterpret_cast<const float4*>(p);
+  const float4 a = q[0], b = q[1], c = q[2], d = q[3];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+}
+// logsumexp of 16 candidates (entries that must not count hold -inf; at least one is finite)
+__device__ __forceinline__ float lse16(const float (&c)[16]) {
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(c[2 * i], c[2 * i + 1]);
+  const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+  float e[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) e[i] = fast_exp(c[i] - mx);
+#pragma unroll
+  for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) e[i] += e[i + w];
+  return mx + fast_log(e[0]);
+}
+__device__ __forceinline__ float group16_lse(float v, bool active) {   // over the 16 lanes of a half-warp
+  float mx = v;
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off, 16));
+  float ex = active ? fast_exp(v - mx) : 0.0f;
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, off, 16);
+  return mx + fast_log(ex);
+}
+
+constexpr int kL16Threads = 128;
+constexpr int kL16Seqs = kL16Threads / 16;
+
+// shared memory per sentence (16-byte aligned pieces): alpha[S][16] | e[S*T] | on_idx[S] | y[S] | xch[2][16]
+__host__ __device__ inline size_t llh16_seq_bytes(int S, int T, bool with_alpha) {
+  size_t n = with_alpha ? (size_t)S * 16 * sizeof(float) : 0;
+  n += (((size_t)S * T + 3) / 4 * 4) * sizeof(float);
+  n += (((size_t)2 * S + 3) / 4 * 4) * sizeof(int);
+  n += 32 * sizeof(float);
+  return n;
+}
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kL16Threads) crf_llh16_kernel(
+    const float* __restrict__ emissions, const int64_t* __restrict__ tags, const uint8_t* __restrict__ mask,
+    const float* __restrict__ start, const float* __restrict__ end, const float* __restrict__ trans,
+    const float* __restrict__ w, float* __restrict__ llh_out, float* __restrict__ d_emissions,
+    float* __restrict__ d_start, float* __restrict__ d_end, float* __restrict__ d_trans, int B, int S, int T) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr unsigned kFull = 0xffffffffu;
+  float* s_dtrans = reinterpret_cast<float*>(smem_raw);      // [T*T] | d_start [T] | d_end [T]   (backward only)
+  float* s_dstart = s_dtrans + T * T;
+  float* s_dend = s_dstart + T;
+  const size_t head = kBackward ? (((size_t)T * T + 2 * T) * sizeof(float) + 15) / 16 * 16 : 0;
+  const int g_in_block = threadIdx.x >> 4;
+  const int gl = threadIdx.x & 15;
+  const int gshift = threadIdx.x & 16;
+  if (kBackward) {
+    for (int i = threadIdx.x; i < T * T + 2 * T; i += kL16Threads) s_dtrans[i] = 0.0f;
+    __syncthreads();
+  }
+  const int b_raw = blockIdx.x * kL16Seqs + g_in_block;
+  const bool warp_ok = blockIdx.x * kL16Seqs + (g_in_block & ~1) < B;
+  if (warp_ok) {
+    const bool seq_ok = b_raw < B;
+    const int b = seq_ok ? b_raw : B - 1;   // an odd tail half shadows the last sentence and stores nothing
+    uint8_t* base = smem_raw + head + (size_t)g_in_block * llh16_seq_bytes(S, T, kBackward);
+    float* alpha = reinterpret_cast<float*>(base);                                   // [S][16] (backward only)
+    float* e_s = reinterpret_cast<float*>(base) + (kBackward ? (size_t)S * 16 : 0);  // [S*T]
+    int* on_idx = reinterpret_cast<int*>(e_s + ((size_t)S * T + 3) / 4 * 4);        // [S]
+    int* y_s = on_idx + S;                                                            // [S]
+    float* xch = reinterpret_cast<float*>(on_idx + ((size_t)2 * S + 3) / 4 * 4);    // [2][16]
+    const uint8_t* m_g = mask ? mask + (size_t)b * S : nullptr;
+    const int64_t* y_g = tags + (size_t)b * S;
+    const bool active = gl < T;
+
+    stage_slab<16>(emissions + (size_t)b * S * T, e_s, S * T, gl);
+    for (int t = gl; t < S; t += 16) y_s[t] = (int)y_g[t];
+    // on-steps (t = 0 always counts, as in _compute_normalizer); len = sum(mask) as pytorch-crf counts it
+    int n_on = 0, len = 0;
+    for (int t0 = 0; t0 < S; t0 += 16) {
+      const int t = t0 + gl;
+      const bool m = (t < S) && (m_g ? (m_g[t] != 0) : true);
+      const bool on = (t < S) && (m || t == 0);
+      const unsigned bits_on = (__ballot_sync(kFull, on) >> gshift) & 0xffffu;
+      const unsigned bits_m = (__ballot_sync(kFull, m) >> gshift) & 0xffffu;
+      if (on) on_idx[n_on + __popc(bits_on & ((1u << gl) - 1u))] = t;
+      n_on += __popc(bits_on);
+      len += __popc(bits_m);
+    }
+    const int n_warp = max(n_on, __shfl_xor_sync(kFull, n_on, 16));
+    __syncwarp();
+
+    float tr[16];   // column gl of the transition matrix; rows >= T are -inf so they never count
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tr[i] = (i < T) ? (active ? trans[i * T + gl] : 0.0f) : -INFINITY;
+
+    // ---- forward sweep over the on-steps: a[j] = logsumexp_i((a[i] + trans[i][j]) + e[t][j]) ----
+    float a = active ? start[gl] + e_s[gl] : 0.0f;   // idle lanes carry 0
+    float* pub = kBackward ? alpha : xch;
+    pub[gl] = a;
+    __syncwarp();
+    for (int n = 1; n < n_warp; ++n) {
+      const bool mine = n < n_on;
+      const int t = on_idx[mine ? n : 0];
+      const float e = e_s[t * T + (active ? gl : 0)];
+      float prev[16], c[16];
+      load16(kBackward ? alpha + (n - 1) * 16 : xch + ((n - 1) & 1) * 16, prev);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) c[i] = (prev[i] + tr[i]) + e;
+      const float nxt = lse16(c);
+      a = (mine && active) ? nxt : a;
+      if (kBackward) { if (mine) alpha[n * 16 + gl] = a; }
+      else xch[(n & 1) * 16 + gl] = a;
+      __syncwarp();
+    }
+    const float en = active ? end[gl] : 0.0f;
+    const float logz = group16_lse(active ? a + en : -INFINITY, active);
+
+    if (!kBackward) {
+      // ---- gold path score (pytorch-crf _compute_score): lanes take strided time steps, then reduce ----
+      float sc = 0.0f;
+      for (int t = gl; t < S; t += 16) {
+        const int y = y_s[t];
+        const bool on = m_g ? (m_g[t] != 0) : true;
+        if (t == 0) sc += start[y] + e_s[y];
+        else if (on) sc += trans[y_s[t - 1] * T + y] + e_s[t * T + y];
+      }
+#pragma unroll
+      for (int off = 8; off >= 1; off >>= 1) sc += __shfl_xor_sync(kFull, sc, off, 16);
+      if (gl == 0 && seq_ok) llh_out[b] = (sc + end[y_s[max(len - 1, 0)]]) - logz;
+    } else {
+      // ---- backward sweep: marginals, pairwise marginals, beta ----
+      float* de_g = d_emissions + (size_t)b * S * T;
+      if (seq_ok)
+        for (int i = gl; i < S * T; i += 16) de_g[i] = 0.0f;
+      __syncwarp();
+      const float wb = seq_ok ? w[b] : 0.0f;
+      float trr[16];   // row gl of the transition matrix; columns >= T are -inf
+#pragma unroll
+      for (int j = 0; j < 16; ++j) trr[j] = (j < T) ? (active ? trans[gl * T + j] : 0.0f) : -INFINITY;
+      float acc_tr[16];   // sum over steps of P(y_prev = i, y_cur = gl)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc_tr[i] = 0.0f;
+      float beta = en;
+      const int y_last = y_s[max(len - 1, 0)];
+      for (int kk = 0; kk < n_warp; ++kk) {
+        const int n = n_on - 1 - kk;         // this half's on-step (counted from its own end)
+        const bool mine = n >= 0;
+        const int nn = mine ? n : 0;
+        const int t = on_idx[nn];
+        const float an = alpha[nn * 16 + gl];
+        const float e = e_s[t * T + (active ? gl : 0)];
+        const float p = fast_exp(an + beta - logz);
+        const int y = y_s[t];
+        if (mine && active && seq_ok) {
+          de_g[t * T + gl] = wb * ((y == gl ? 1.0f : 0.0f) - p);
+          if (n == n_on - 1) atomicAdd(s_dend + gl, wb * ((y_last == gl ? 1.0f : 0.0f) - p));
+          if (n == 0) atomicAdd(s_dstart + gl, wb * ((y == gl ? 1.0f : 0.0f) - p));
+        }
+        // publish e[t][j] + beta_n[j]; idle lanes publish -inf so they never count
+        xch[(kk & 1) * 16 + gl] = active ? e + beta : -INFINITY;
+        __syncwarp();
+        const bool step = n >= 1;            // a transition (on-step n-1 -> n) exists
+        float eb[16], c[16], prev[16];
+        load16(xch + (kk & 1) * 16, eb);
+        load16(alpha + (step ? n - 1 : 0) * 16, prev);
+        const float ebm = active ? e + beta : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float pr = fast_exp(((prev[i] + tr[i]) + ebm) - logz);   // tr[i] = -inf for i >= T -> 0
+          acc_tr[i] += (step && active) ? pr : 0.0f;
+          c[i] = trr[i] + eb[i];
+        }
+        const float nb = lse16(c);
+        beta = (step && active) ? nb : beta;
+      }
+      if (active && seq_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < T) atomicAdd(s_dtrans + i * T + gl, -wb * acc_tr[i]);
+      }
+      // gold transitions: pytorch-crf's _compute_score pairs every on-step t >= 1 with position t-1
+      if (seq_ok) {
+        for (int t = 1 + gl; t < S; t += 16) {
+          const bool on = m_g ? (m_g[t] != 0) : true;
+          if (on) atomicAdd(s_dtrans + y_s[t - 1] * T + y_s[t], wb);
+        }
+      }
+    }
+  }
+  if (kBackward) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * T; i += kL16Threads) atomicAdd(d_trans + i, s_dtrans[i]);
+    for (int i = threadIdx.x; i < T; i += kL16Threads) {
+      atomicAdd(d_start + i, s_dstart[i]);
+      atomicAdd(d_end + i, s_dend[i]);
+    }
   }
 }
 
@@ -640,13 +864,17 @@ extern "C" int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const in
   const int LPS = (T <= 16) ? 16 : 32;
   const int spb = kThreads / LPS;
   const int grid = (B + spb - 1) / spb;
-  const size_t smem = (((size_t)S * T + 3) / 4 * 4) * sizeof(float) * spb;
+  const size_t smem = ((((size_t)S * T + 3) / 4 * 4) * sizeof(float) + ((size_t)S + 15) / 16 * 16) * spb;
   if (smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,
               h->smem_optin);
   if (LPS == 16) {
-    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    crf_llh_kernel<16><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
+    const size_t smem16 = llh16_seq_bytes(S, T, false) * kL16Seqs;
+    if (smem16 > h->smem_optin)
+      ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh: S=%d T=%d needs %zu B shared memory per block", S, T, smem16);
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    crf_llh16_kernel<false><<<(B + kL16Seqs - 1) / kL16Seqs, kL16Threads, smem16, st>>>(
+        emissions, tags, mask, start, end, trans, nullptr, llh_out, nullptr, nullptr, nullptr, nullptr, B, S, T);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crf_llh_kernel<32><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, llh_out, B, S, T);
@@ -670,7 +898,7 @@ extern "C" int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const in
   const int spb = kThreads / LPS;
   const size_t head = (((size_t)T * T + 2 * T) * sizeof(float) + 15) / 16 * 16;
   const size_t per_seq =
-      ((size_t)S * LPS * sizeof(float) + (size_t)S * sizeof(int) + (((size_t)S * T + 3) / 4 * 4) * sizeof(float) + 15) /
+      ((size_t)S * LPS * sizeof(float) + 2 * (size_t)S * sizeof(int) + (((size_t)S * T + 3) / 4 * 4) * sizeof(float) + 15) /
       16 * 16;
   const size_t smem = head + per_seq * spb;
   if (smem > h->smem_optin)
@@ -678,9 +906,12 @@ extern "C" int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const in
               h->smem_optin);
   const int grid = (B + spb - 1) / spb;
   if (LPS == 16) {
-    ICKA_CUDA(cudaFuncSetAttribute(crf_llh_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    crf_llh_bwd_kernel<16><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, w, d_emissions,
-                                                         d_start, d_end, d_trans, B, S, T, per_seq);
+    const size_t smem16 = head + llh16_seq_bytes(S, T, true) * kL16Seqs;
+    if (smem16 > h->smem_optin)
+      ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh_bwd: S=%d T=%d needs %zu B shared memory per block", S, T, smem16);
+    ICKA_CUDA(cudaFuncSetAttribute(crf_llh16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    crf_llh16_kernel<true><<<(B + kL16Seqs - 1) / kL16Seqs, kL16Threads, smem16, st>>>(
+        emissions, tags, mask, start, end, trans, w, nullptr, d_emissions, d_start, d_end, d_trans, B, S, T);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     crf_llh_bwd_kernel<32><<<grid, kThreads, smem, st>>>(emissions, tags, mask, start, end, trans, w, d_emissions,
