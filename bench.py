@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 METRIC = 'sentences/sec fusion+Viterbi'
 UNIT = 'sentences/s'
@@ -238,11 +241,13 @@ def run_gpu_arm(args, shape):
     value = args.batch * world * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel roofline pass (same step, CUDA events around every C-ABI launch) ----
+    pipe.overlap_decode = False          # events on one stream: the decode must not be timed while it waits
     with KernelTimer() as kt:
         for _ in range(args.steps):
             pipe.step_device(d)
         kernels = kt.summary()
         gemm_shapes = kt.gemm_shapes()
+    pipe.overlap_decode = True
     gemm = kernels.get('linear_bf16_tcgen05') or kernels.get('linear_fp32_ffma')
     peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
     roofline = {
@@ -403,7 +408,7 @@ def run_train_arm(args, shape):
                        'buckets_launched_inside_backward_per_step': reducer.launched_early // (args.steps + max(args.warmup, 3)),
                        'outside_hot_path': 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier; optimizer = torch AdamW(fused)',
                        'dropout': 'p = 0 (no dropout kernels)'},
-            'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss),
+            'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
             'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor', 'achieved': tf,
                          'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
                          'note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, '

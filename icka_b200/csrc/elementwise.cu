@@ -220,6 +220,131 @@ __global__ void __launch_bounds__(kGateThreads) gate_blend_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Last LayerNorm of the text->image encoder fused with the gate + blend (inference path):
+//   fused = LN2(pre)            (BertOutput.LayerNorm, CMIM:535; `pre` = dense(h) + attention_output)
+//   g     = sigmoid(w_fold . LN_g(fused[0] + tok[0]) + c_fold)            (CMIM:1029-1035)
+//   out   = g tok + (1-g) fused                                            (CMIM:1036)
+// Two launches: a tiny one (one warp per sentence) for the gates, then a streaming one (one warp per row, the
+// row lives in registers).  Compared with running layernorm_kernel and gate_blend_kernel back to back this
+// never writes the fp32 `fused` tensor nor reads it again: per sentence 393 KB (pre) + 393 KB (tok) in, 393 KB (out) + 197 KB (bf16 fused, the key/value
+// operand of the image->text encoders) out, instead of 2.2 MB.
+// ------------------------------------------------------------------------------------------------
+// LayerNorm of one row held in v[] by a warp (two-pass statistics like the reference); gamma / beta are read
+// through L1 each time (3 KB each, always resident) instead of living in registers.
+__device__ __forceinline__ void warp_ln_row(float4 (&v)[kMaxVec], int lane, int nvec, float invH, float eps,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta) {
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (lane + 32 * i < nvec) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(sum) * invH;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    if (lane + 32 * i < nvec) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) * invH + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      v[i].x = g.x * (v[i].x * rstd) + bt.x;
+      v[i].y = g.y * (v[i].y * rstd) + bt.y;
+      v[i].z = g.z * (v[i].z * rstd) + bt.z;
+      v[i].w = g.w * (v[i].w * rstd) + bt.w;
+    }
+  }
+}
+
+// Step 1 (tiny): the gate of each sentence from its [CLS] rows.  One warp per sentence.
+__global__ void __launch_bounds__(128) ln_gate_kernel(
+    const float* __restrict__ pre, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b, float ln2_eps,
+    const float* __restrict__ tok, const float* __restrict__ lng_w, const float* __restrict__ lng_b, float lng_eps,
+    const float* __restrict__ w_fold, const float* __restrict__ c_fold, float* __restrict__ gate_out, int B, int S,
+    int H) {
+  const int b = blockIdx.x * 4 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (b >= B) return;
+  const int nvec = H / 4;
+  const float invH = 1.0f / (float)H;
+  const float4* p4 = reinterpret_cast<const float4*>(pre + (size_t)b * S * H);
+  const float4* t4 = reinterpret_cast<const float4*>(tok + (size_t)b * S * H);
+  float4 f[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    f[i] = (c < nvec) ? p4[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  warp_ln_row(f, lane, nvec, invH, ln2_eps, ln2_w, ln2_b);          // fused[0]
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 t = t4[c];
+      f[i].x += t.x; f[i].y += t.y; f[i].z += t.z; f[i].w += t.w;
+    }
+  }
+  warp_ln_row(f, lane, nvec, invH, lng_eps, lng_w, lng_b);
+  float dot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 wf = __ldg(reinterpret_cast<const float4*>(w_fold) + c);
+      dot += (f[i].x * wf.x + f[i].y * wf.y) + (f[i].z * wf.z + f[i].w * wf.w);
+    }
+  }
+  const float logit = warp_sum(dot) + c_fold[0];
+  if (lane == 0) gate_out[b] = 1.0f / (1.0f + expf(-logit));
+}
+
+// Step 2 (streaming, HBM-bound): one warp per row -- LayerNorm, fused copies, blend with the sentence's gate.
+__global__ void __launch_bounds__(256) ln_blend_kernel(
+    const float* __restrict__ pre, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b, float ln2_eps,
+    const float* __restrict__ tok, const float* __restrict__ gate, float* __restrict__ out,
+    float* __restrict__ fused32, __nv_bfloat16* __restrict__ fused16, int M, int S, int H) {
+  const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= M) return;
+  const int nvec = H / 4;
+  const float4* p4 = reinterpret_cast<const float4*>(pre + (size_t)row * H);
+  const float4* t4 = reinterpret_cast<const float4*>(tok + (size_t)row * H);
+  float4 f[kMaxVec], t[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      f[i] = __ldcs(p4 + c);
+      t[i] = __ldcs(t4 + c);
+    }
+  }
+  const float g = __ldg(gate + row / S), og = 1.0f - g;
+  warp_ln_row(f, lane, nvec, 1.0f / (float)H, ln2_eps, ln2_w, ln2_b);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      if (fused32) reinterpret_cast<float4*>(fused32 + (size_t)row * H)[c] = f[i];
+      if (fused16) {
+        uint2 p;
+        p.x = pack_bf16x2(f[i].x, f[i].y);
+        p.y = pack_bf16x2(f[i].z, f[i].w);
+        reinterpret_cast<uint2*>(fused16 + (size_t)row * H)[c] = p;
+      }
+      float4 o;
+      o.x = g * t[i].x + og * f[i].x;
+      o.y = g * t[i].y + og * f[i].y;
+      o.z = g * t[i].z + og * f[i].z;
+      o.w = g * t[i].w + og * f[i].w;
+      __stcs(reinterpret_cast<float4*>(out + (size_t)row * H) + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Additive attention mask (CMIM:962-965, 976-977): out[b][j] = (1 - mask[b][j]) * -10000
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mask_additive_kernel(const int64_t* __restrict__ mask, int64_t ld,
@@ -320,6 +445,33 @@ extern "C" int icka_gate_blend_fwd(icka_handle* h, const float* fused, const flo
   if (B == 0) return ICKA_OK;
   gate_blend_kernel<<<B, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(fused, tok, ln_w, ln_b, ln_eps, w_fold,
                                                                             c_fold, out, gate_out, S, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_ln_gate_blend_fwd(icka_handle* h, const float* pre, const float* ln2_w, const float* ln2_b,
+                                      float ln2_eps, const float* tok, const float* lng_w, const float* lng_b,
+                                      float lng_eps, const float* w_fold, const float* c_fold, float* out,
+                                      float* fused_f32, void* fused_bf16, float* gate_out, int B, int S, int H,
+                                      void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && H >= 4 && pre && ln2_w && ln2_b && tok && lng_w && lng_b && w_fold && c_fold && out,
+               "ln_gate_blend: bad arguments");
+  ICKA_REQUIRE(H % 4 == 0 && H <= 128 * kMaxVec, "ln_gate_blend: H=%d must be a multiple of 4 and <= %d", H,
+               128 * kMaxVec);
+  ICKA_REQUIRE(icka_aligned(pre, 16) && icka_aligned(tok, 16) && icka_aligned(out, 16) && icka_aligned(ln2_w, 16) &&
+                   icka_aligned(ln2_b, 16) && icka_aligned(lng_w, 16) && icka_aligned(lng_b, 16) &&
+                   icka_aligned(w_fold, 16) && icka_aligned(fused_f32, 16) && icka_aligned(fused_bf16, 8),
+               "ln_gate_blend: pointers must be 16-byte aligned");
+  ICKA_REQUIRE(gate_out != nullptr, "ln_gate_blend: gate_out is required (it carries the gates between the two launches)");
+  if (B == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ln_gate_kernel<<<(B + 3) / 4, 128, 0, st>>>(pre, ln2_w, ln2_b, ln2_eps, tok, lng_w, lng_b, lng_eps, w_fold, c_fold,
+                                              gate_out, B, S, H);
+  ICKA_LAUNCHED(h);
+  const int M = B * S;
+  ln_blend_kernel<<<(M + 7) / 8, 256, 0, st>>>(pre, ln2_w, ln2_b, ln2_eps, tok, gate_out, out, fused_f32,
+                                               static_cast<__nv_bfloat16*>(fused_bf16), M, S, H);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -319,7 +319,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (ACT == ICKA_ACT_GELU_ERF) {
             if (OUT_BF16) {
-              const float2 gg = gelu_erf_fast2(x0, x1);
+              const float2 gg = gelu_erf_tanh2(x0, x1);
               x0 = gg.x;
               x1 = gg.y;
             } else {

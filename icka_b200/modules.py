@@ -137,9 +137,11 @@ class _DenseResidualNorm(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
         self._cache = _OperandCache()
 
-    def _run(self, h_lp: torch.Tensor, res32: torch.Tensor):
+    def _run(self, h_lp: torch.Tensor, res32: torch.Tensor, defer_ln: bool = False):
         w = _operand(self._cache, 'w', self.dense.weight)
         pre = ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32)
+        if defer_ln:          # the caller fuses this LayerNorm into its consumer (icka_ln_gate_blend_fwd)
+            return pre, None
         return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
                              self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=_PRECISION == 'bf16')
 
@@ -306,12 +308,12 @@ class BertCrossAttentionLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=None):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=None, defer_ln=False):
         if _recording(x32, y32, module=self):
             return self._run_recorded(x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv)
         a32, a_lp = self.attention._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
         f = self.intermediate._run(a_lp if a_lp is not None else a32)
-        o32, o_lp = self.output._run(f, a32)
+        o32, o_lp = self.output._run(f, a32, defer_ln=defer_ln)      # deferred: o32 is the PRE-LayerNorm tensor
         return o32, (o_lp if o_lp is not None else o32)
 
     def _run_recorded(self, x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv):
@@ -355,10 +357,13 @@ class BertCrossEncoder(nn.Module):
         layer = BertCrossAttentionLayer(config)
         self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(layer_num)])
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True, y32=None):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True, y32=None, defer_last_ln=False):
+        """``defer_last_ln`` (inference only): the last layer returns its PRE-LayerNorm tensor; the caller applies
+        ``self.layer[-1].output.LayerNorm`` fused into the next kernel."""
         outs = []
-        for layer_module in self.layer:
-            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=y32)
+        for i, layer_module in enumerate(self.layer):
+            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=y32,
+                                          defer_ln=defer_last_ln and i == len(self.layer) - 1)
             if keep_all:
                 outs.append(x32)
         if not keep_all:
@@ -442,9 +447,29 @@ class CrossModalFusion(nn.Module):
 
         # text -> image, CMIM:968-969
         x32 = _rows(sequence_output)
-        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32.detach()), regions_lp, img_mask, B, S, R,
-                                                     keep_all=False, y32=regions32)
-        fused32 = outs[-1]
+        tok32 = _rows(token_embedding).view(B, S, H)
+        ln = self.cls_layer.proj_norm
+        if rec:
+            outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32.detach()), regions_lp, img_mask, B, S, R,
+                                                         keep_all=False, y32=regions32)
+            fused32 = outs[-1]
+        else:
+            # inference: the encoder's last LayerNorm is fused with the gate + blend (CMIM:1029-1036), which also
+            # emits the operand copy of `fused` the image->text encoders read
+            outs, _ = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R, keep_all=False,
+                                                  defer_last_ln=True)
+            ln2 = self.txt2img_attention.layer[-1].output.LayerNorm
+            gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight,
+                           self.aux_head.bias)
+            w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
+                self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+                self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
+            bf = _PRECISION == 'bf16'
+            result, gate, fused32, fused16 = ops.ln_gate_blend(
+                outs[-1].view(B, S, H), ln2.weight.detach(), ln2.bias.detach(), ln2.variance_epsilon, tok32,
+                ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold,
+                want_fused_f32=return_dict or not bf, want_fused_bf16=bf)
+            fused_lp = fused16 if bf else fused32.view(B * S, H)
 
         # image -> text, CMIM:954, 981-989 (single CLIP token as the query)
         clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
@@ -455,24 +480,14 @@ class CrossModalFusion(nn.Module):
             z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
         z_lp = _to_lp(z32.detach())
         for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32)
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None)
             z32 = zs[-1]
 
-        # gated fusion, CMIM:1029-1036
-        ln = self.cls_layer.proj_norm
-        tok32 = _rows(token_embedding).view(B, S, H)
+        # gated fusion, CMIM:1029-1036 (recording pass; the inference pass did it above)
         if rec:
             result, gate = GateBlendFn.apply(fused32.view(B, S, H), tok32, ln.weight, ln.bias,
                                              self.cls_layer.proj.weight, self.cls_layer.proj.bias,
                                              self.aux_head.weight, self.aux_head.bias, ln.eps)
-        else:
-            gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight,
-                           self.aux_head.bias)
-            w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
-                self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
-                self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
-            result, gate = ops.gate_blend(fused32.view(B, S, H), tok32, ln.weight.detach(), ln.bias.detach(), ln.eps,
-                                          w_fold, c_fold)
         if return_dict:
             return dict(regions=regions_lp.view(B, R, H), fused=fused32.view(B, S, H), clip=z32.view(B, 1, H),
                         result=result, gate=gate)

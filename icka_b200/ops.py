@@ -318,6 +318,26 @@ def gate_blend(fused: torch.Tensor, tok: torch.Tensor, ln_w, ln_b, ln_eps: float
     return out, gate
 
 
+def ln_gate_blend(pre, ln2_w, ln2_b, ln2_eps: float, tok, lng_w, lng_b, lng_eps: float, w_fold, c_fold, *,
+                  want_fused_f32: bool = False, want_fused_bf16: bool = True):
+    """fused = LN(pre); result = gate-blend(fused, tok).  Returns (result, gate, fused32 | None, fused16 | None)."""
+    _need(pre, torch.float32, 'ln_gate_blend(pre)')
+    _need(tok, torch.float32, 'ln_gate_blend(tok)')
+    if pre.shape != tok.shape or pre.dim() != 3:
+        raise RuntimeError('ln_gate_blend: pre/tok must both be [B, S, H]')
+    B, S, H = pre.shape
+    lib, h, st = _ctx(pre)
+    out = torch.empty_like(pre)
+    gate = torch.empty(B, dtype=torch.float32, device=pre.device)
+    f32 = torch.empty_like(pre) if want_fused_f32 else None
+    f16 = torch.empty(B * S, H, dtype=torch.bfloat16, device=pre.device) if want_fused_bf16 else None
+    _lib.check(lib.icka_ln_gate_blend_fwd(h, pre.data_ptr(), ln2_w.data_ptr(), ln2_b.data_ptr(), float(ln2_eps),
+                                          tok.data_ptr(), lng_w.data_ptr(), lng_b.data_ptr(), float(lng_eps),
+                                          w_fold.data_ptr(), c_fold.data_ptr(), out.data_ptr(), _p(f32), _p(f16),
+                                          gate.data_ptr(), B, S, H, st), 'icka_ln_gate_blend_fwd')
+    return out, gate, f32, f16
+
+
 def viterbi(emissions: torch.Tensor, mask_u8: Optional[torch.Tensor], start, end, trans):
     """Batch-first fp32 emissions [B,S,T]; returns device tensors (tags [B,S] int32 with -1 pad, lens [B] int32)."""
     _need(emissions, torch.float32, 'viterbi(emissions)')

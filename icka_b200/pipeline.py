@@ -36,12 +36,18 @@ class FusionViterbiPipeline:
         self.crf = CRF(shape.T, batch_first=True).to(self.device)
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._side_stream: Optional[torch.cuda.Stream] = None
+        self.overlap_decode = True     # False: run the CRF decode on the main stream (per-kernel timing passes)
 
     # ---- device-resident step -------------------------------------------------------------------
     @torch.no_grad()
     def step_device(self, d: Dict[str, torch.Tensor]):
         """One pass of the hot path over a device-resident batch; returns (result, clip, tags, lens, gate)."""
         set_precision(self.precision)
+        if not self.overlap_decode:
+            tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
+            out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                              d['img_mask'], d['text_mask'], return_dict=True)
+            return out['result'], out['clip'], tags, lens, out['gate']
         main = torch.cuda.current_stream(self.device)
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(self.device)

@@ -44,6 +44,9 @@ def _work(name, args, kwargs):
         return name, 4.0 * B * nh * S * H, (x.numel() + 2 * u.numel()) * 2
     if name == 'gate_blend':
         return name, 0.0, args[0].numel() * 12
+    if name == 'ln_gate_blend':
+        n = args[0].numel()
+        return name, 0.0, n * 4 * 3 + (n * 2 if kwargs.get('want_fused_bf16', True) else 0) + (n * 4 if kwargs.get('want_fused_f32') else 0)
     if name == 'gate_fold':
         return name, 0.0, args[0].numel() * 4
     if name == 'viterbi':
@@ -87,7 +90,7 @@ def _work(name, args, kwargs):
 
 
 class KernelTimer:
-    OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend',
+    OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend', 'ln_gate_blend',
            'viterbi', 'crf_llh', 'linear_dgrad', 'linear_wgrad', 'colsum', 'layernorm_bwd', 'cross_attn_core_bwd',
            'gate_blend_bwd', 'gate_fold_bwd', 'crf_llh_bwd')
 

@@ -159,6 +159,16 @@ int icka_gate_blend_fwd(icka_handle* h, const float* fused, const float* tok, co
                         const float* ln_b, float ln_eps, const float* w_fold, const float* c_fold,
                         float* out, float* gate_out, int B, int S, int H, void* stream);
 
+/* Inference fusion of the text->image encoder's last LayerNorm (CMIM:535) with the gate + blend:
+ *   fused = LN_{ln2}(pre);  out = icka_gate_blend_fwd(fused, tok, ...)
+ * `pre` [B,S,H] fp32 is dense(h) + attention_output of the last layer (what icka_linear_fwd wrote with its
+ * residual epilogue).  fused_f32 [B,S,H] and fused_bf16 [B*S,H] (the key/value operand of the image->text
+ * encoders) are optional outputs (NULL to skip); gate_out [B] is required. */
+int icka_ln_gate_blend_fwd(icka_handle* h, const float* pre, const float* ln2_w, const float* ln2_b, float ln2_eps,
+                           const float* tok, const float* lng_w, const float* lng_b, float lng_eps,
+                           const float* w_fold, const float* c_fold, float* out, float* fused_f32,
+                           void* fused_bf16, float* gate_out, int B, int S, int H, void* stream);
+
 /* Backward of icka_gate_blend_fwd: dout [B,S,H] -> dfused, dtok [B,S,H] (dtok may be NULL); the gradients of
  * the LayerNorm affine (d_ln_w, d_ln_b [H]) and of the folded gate vector (d_w_fold [H], d_c_fold [1]) are
  * ADDED to.  `gate` is the gate_out of the forward. */

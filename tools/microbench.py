@@ -75,6 +75,8 @@ def main(B=1024, mode=0):
     tot += gemm('FFN down +res (f32 out)', fb, Wd, bH, res=x, od=torch.float32)
     tot += mem('layernorm', lambda: ops.layernorm(x, g1, g1, 1e-12, want_f32=True, want_bf16=True), B * S * H * 10)
     tot += mem('gate blend', lambda: ops.gate_blend(fused, tok, g1, g1, 1e-5, wf, cf), B * S * H * 12)
+    mem('ln + gate blend (fused)', lambda: ops.ln_gate_blend(fused, g1, g1, 1e-12, tok, g1, g1, 1e-5, wf, cf),
+        B * S * H * 14)
     print(f'sum of t2i-side kernels: {tot*1e3:.3f} ms for B={B} -> {B/tot:,.0f} sentences/s (excl. i2t)')
 
     sh = synth.STD
