@@ -68,6 +68,21 @@ def load_peaks():
     return d
 
 
+def measured_traffic(workload_tag):
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` capture
+    (profiles/traffic_*.json, written by tools/summarize_profiles.py); None when no capture matches."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'traffic_*.json'))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if d.get('workload') == workload_tag:
+            best = (d, os.path.basename(f))
+    return best
+
+
 def workload_name(args, shape):
     return (f'twitter2017_inference_B{args.batch}_per_gpu_S{shape.S}_R{shape.R}_H{shape.H}_nh{shape.heads}'
             f'_I{shape.inter}_T{shape.T}_L{shape.L}')
@@ -255,9 +270,17 @@ def run_gpu_arm(args, shape):
         'bound': 'tensor', 'achieved': gemm['tflops'], 'peak': peak_tf, 'unit': 'TFLOP/s',
         'frac': gemm['tflops'] / peak_tf, 'traffic': None,
         'peak_source': peaks['_source'] + ', bf16_tflops_sustained (kernel timed inside a long step)',
+        'frac_of_burst_peak': gemm['tflops'] / peaks.get('bf16_tflops', FALLBACK_PEAKS['bf16_tflops']),
         'launches_per_step': gemm['launches'] // args.steps, 'ms_per_launch': gemm['ms_per_launch'],
         'flops_per_launch': gemm['flops_per_launch'],
     }
+    if args.precision == 'bf16' and not args.hires:
+        cap = measured_traffic(f'B{args.batch}_L{shape.L}')
+        if cap is not None:
+            roofline['traffic'] = cap[0]['dram_bytes_per_launch_mean']
+            roofline['traffic_source'] = (f'profiles/{cap[1]}: dram__bytes_read.sum + dram__bytes_write.sum, mean over the '
+                                          f"{cap[0]['launches']} GEMM launches of one step (ncu --set full)")
+            roofline['algorithmic_bytes_per_launch'] = gemm['bytes_per_launch']
     hbm = peaks.get('hbm_gbs', FALLBACK_PEAKS['hbm_gbs'])
     kernel_table = {}
     for name, k in kernels.items():

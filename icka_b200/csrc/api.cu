@@ -44,11 +44,22 @@ extern "C" int icka_create(int device, icka_handle** out) {
     ICKA_FAIL(ICKA_ERR_CUDA, "icka_create: cuTensorMapEncodeTiled not available from the driver");
   }
   h->encode_tiled = fn;
+  h->workspace = nullptr;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaError_t ea = cudaSetDevice(device);
+  if (ea == cudaSuccess) ea = cudaMalloc(&h->workspace, ICKA_WORKSPACE_BYTES);
+  cudaSetDevice(prev);
+  if (ea != cudaSuccess) {
+    delete h;
+    ICKA_FAIL(ICKA_ERR_CUDA, "icka_create: cannot allocate the handle's device scratch: %s", cudaGetErrorString(ea));
+  }
   *out = h;
   return ICKA_OK;
 }
 
 extern "C" int icka_destroy(icka_handle* h) {
+  if (h && h->workspace) cudaFree(h->workspace);
   delete h;
   return ICKA_OK;
 }

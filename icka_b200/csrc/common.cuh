@@ -18,7 +18,10 @@ struct icka_handle {
   size_t smem_optin;
   std::atomic<long long> launches;
   void* encode_tiled;   // PFN cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
+  void* workspace;      // device scratch [ICKA_WORKSPACE_BYTES]: split-K partial tiles of skinny forward GEMMs
 };
+
+#define ICKA_WORKSPACE_BYTES ((size_t)32 << 20)
 
 void icka_set_error(const char* fmt, ...);
 

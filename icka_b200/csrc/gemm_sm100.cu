@@ -72,8 +72,9 @@ struct GemmArgs {
   const __nv_bfloat16* aux_in;   // ACT_GELU_ERF_BWD: pre-activation u [M, N] (pitch ld_aux)
   __nv_bfloat16* aux_out;        // ACT_GELU_ERF: optional copy of the pre-activation (acc + bias) [M, N]
   int64_t ld_aux;
-  int splits;                    // MAJOR 2: number of contraction ranges; 1 otherwise
+  int splits;                    // number of contraction ranges (split-K); 1 otherwise
   int kb_per_split;
+  int64_t split_stride;          // forward split-K: split s writes its partial tile to out + s * split_stride
 };
 
 constexpr int kChunkBytes = kBK * 128;   // one 64-element-wide MN-major chunk of a stage: 64 contraction rows x 128 B
@@ -238,6 +239,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
       const int mn = tile % mn_tiles;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+      const bool lead = args.splits == 1 || MAJOR == 2;   // split-K forward: bias / residual are added by the reduce pass
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile0 = n_blk * BN;
@@ -247,6 +249,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
+      // Forward split-K: every split stores its partial tile to its own slab of the workspace (plain stores);
+      // splitk_reduce_kernel then adds the slabs in split order + bias + residual, so results are reproducible.
+      const bool slabs = (MAJOR != 2) && args.splits > 1;
       uint32_t r[32];
       bool released = false;
       if (args.debug == 1) {
@@ -274,7 +279,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int col = n_tile0 + c * 32 + 2 * cp;
         const bool col_ok = col < N && args.debug != 2;
         float b0 = 0.0f, b1 = 0.0f;
-        if (args.bias && col_ok) {
+        if (args.bias && col_ok && lead) {
           const float2 bb = __ldg(reinterpret_cast<const float2*>(args.bias + col));
           b0 = bb.x;
           b1 = bb.y;
@@ -282,7 +287,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const bool full = (rows_left >= 32) && (n_tile0 + c * 32 + 32 <= N) && args.debug != 2;   // warp-uniform
         const size_t row0 = (size_t)(row_base + sub);
         float2 res[16];
-        if (args.residual) {
+        const bool use_res = args.residual != nullptr && lead;
+        if (use_res) {
           const float* rp = args.residual + row0 * N + col;
           const size_t rstep = (size_t)2 * N;
 #pragma unroll
@@ -327,7 +333,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               x1 = gelu_erf(x1);
             }
           }
-          if (args.residual) {
+          if (use_res) {
             x0 += res[i].x;
             x1 += res[i].y;
           }
@@ -339,11 +345,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int i = 0; i < 16; ++i, op += ostep)
             if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<uint32_t*>(op) = pack_bf16x2(x[i].x, x[i].y);
-        } else if (MAJOR == 2) {
+        } else if (MAJOR == 2) {   // wgrad: partial tiles are added onto the running gradient with red.global
           float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
 #pragma unroll
           for (int i = 0; i < 16; ++i, op += ostep)
             if (full || (col_ok && 2 * i < rows_left)) atomicAdd(reinterpret_cast<float2*>(op), x[i]);
+        } else if (slabs) {
+          float* op = static_cast<float*>(args.out) + (size_t)(tile / mn_tiles) * args.split_stride + row0 * args.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, op += ostep)
+            if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<float2*>(op) = x[i];
         } else {
           float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
 #pragma unroll
@@ -356,6 +367,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
         if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
+
     }
   }
 
@@ -365,6 +377,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// out[m, n] = sum_s part[s][m][n] (s ascending) + bias[n] + residual[m][n]
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int64_t split_stride,
+                                                            int splits, const float* __restrict__ bias,
+                                                            const float* __restrict__ residual, float* __restrict__ out,
+                                                            int64_t total, int N) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += stride) {
+    float4 a = __ldcg(reinterpret_cast<const float4*>(part + i));
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(part + (size_t)s * split_stride + i));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + (int)(i % N));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + i);
+      a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = a;
   }
 }
 
@@ -475,9 +511,36 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   rc = icka_make_tmap_bf16(h, &tb, W, N, K, ldw, pair ? BN / 2 : BN);
   if (rc) return rc;
   GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug, nullptr, static_cast<__nv_bfloat16*>(aux_out),
-                (int64_t)N, 1, (K + kBK - 1) / kBK};
+                (int64_t)N, 1, (K + kBK - 1) / kBK, 0};
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
+  // Skinny problems (the single-query encoders: M = batch, N = 768, K = 3072 / 9216) have only a few dozen output
+  // tiles for 148 SMs: split the contraction over CTAs into per-split slabs of the handle's workspace, then add the
+  // slabs in split order (+ bias, residual) with a small reduce pass -- bit-reproducible, unlike atomics.
+  if (!bf && !gelu && !pair && ldo == N) {
+    const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+    const int num_kb = (K + kBK - 1) / kBK;
+    int splits = h->sm_count / tiles;
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits >= 2 && (size_t)splits * M * N * sizeof(float) <= ICKA_WORKSPACE_BYTES && h->workspace != nullptr &&
+        N % 4 == 0) {
+      const int kbps = (num_kb + splits - 1) / splits;
+      args.splits = (num_kb + kbps - 1) / kbps;
+      args.kb_per_split = kbps;
+      args.split_stride = (int64_t)M * N;
+      args.out = h->workspace;
+      int rc2 = (BN == 256) ? launch_gemm<256, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st)
+                            : launch_gemm<128, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st);
+      if (rc2) return rc2;
+      const int64_t total = (int64_t)M * N;
+      int blocks = (int)((total / 4 + 255) / 256);
+      if (blocks > 4 * h->sm_count) blocks = 4 * h->sm_count;
+      splitk_reduce_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(h->workspace), args.split_stride, args.splits,
+                                                   bias, residual, static_cast<float*>(out), total, N);
+      ICKA_LAUNCHED(h);
+      return ICKA_OK;
+    }
+  }
 #define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_, 0>(h, ta, tb, args, st)
   if (pair) {
     if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true, 2); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false, 2); }
@@ -509,7 +572,7 @@ int icka_gemm_bf16_dgrad_launch(icka_handle* h, const void* dY, int64_t ldd, con
   rc = icka_make_tmap_bf16_mn(h, &tb, W, N, K, ldw, BN / 64);
   if (rc) return rc;
   GemmArgs args{nullptr, residual, dX, ldo, M, K, N, 0, static_cast<const __nv_bfloat16*>(gelu_pre), nullptr, ldg, 1,
-                (N + kBK - 1) / kBK};
+                (N + kBK - 1) / kBK, 0};
   const bool bf = out_dtype == ICKA_BF16;
 #define ICKA_GEMM(BN_, ACT_, BF_) return launch_gemm<BN_, ACT_, BF_, 1, 1>(h, ta, tb, args, st)
   if (BN == 256) {
@@ -544,7 +607,7 @@ int icka_gemm_bf16_wgrad_launch(icka_handle* h, const void* dY, int64_t ldd, con
   if (splits < 1) splits = 1;
   const int kbps = (num_kb + splits - 1) / splits;
   splits = (num_kb + kbps - 1) / kbps;
-  GemmArgs args{nullptr, nullptr, dW, ldo, N, K, M, 0, nullptr, nullptr, 0, splits, kbps};
+  GemmArgs args{nullptr, nullptr, dW, ldo, N, K, M, 0, nullptr, nullptr, 0, splits, kbps, 0};
   if (BN == 256) return launch_gemm<256, ICKA_ACT_NONE, false, 1, 2>(h, ta, tb, args, st);
   return launch_gemm<128, ICKA_ACT_NONE, false, 1, 2>(h, ta, tb, args, st);
 }

@@ -420,7 +420,7 @@ class CrossModalFusion(nn.Module):
         self._cache = _OperandCache()
 
     def forward(self, sequence_output, visual_embeds_att, clip_features, token_embedding, added_attention_mask,
-                ori_input_mask, return_dict=False):
+                ori_input_mask, return_dict=False, want_fused=True):
         """sequence_output [B,S,H] (CMIM:953), visual_embeds_att [B,2048,g,g], clip_features [B,1,512],
         token_embedding [B,S,H] (CMIM:1024), added_attention_mask [B,>=R], ori_input_mask [B,S].
         Returns (result [B,S,H], clip_features [B,1,H]) -- CMIM:1036 and the loop result of CMIM:984-989."""
@@ -468,7 +468,7 @@ class CrossModalFusion(nn.Module):
             result, gate, fused32, fused16 = ops.ln_gate_blend(
                 outs[-1].view(B, S, H), ln2.weight.detach(), ln2.bias.detach(), ln2.variance_epsilon, tok32,
                 ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold,
-                want_fused_f32=return_dict or not bf, want_fused_bf16=bf)
+                want_fused_f32=(return_dict and want_fused) or not bf, want_fused_bf16=bf)
             fused_lp = fused16 if bf else fused32.view(B * S, H)
 
         # image -> text, CMIM:954, 981-989 (single CLIP token as the query)
@@ -489,6 +489,8 @@ class CrossModalFusion(nn.Module):
                                              self.cls_layer.proj.weight, self.cls_layer.proj.bias,
                                              self.aux_head.weight, self.aux_head.bias, ln.eps)
         if return_dict:
-            return dict(regions=regions_lp.view(B, R, H), fused=fused32.view(B, S, H), clip=z32.view(B, 1, H),
-                        result=result, gate=gate)
+            out = dict(regions=regions_lp.view(B, R, H), clip=z32.view(B, 1, H), result=result, gate=gate)
+            if fused32 is not None:      # the inference path only materialises fp32 `fused` when asked to
+                out['fused'] = fused32.view(B, S, H)
+            return out
         return result, z32.view(B, 1, H)

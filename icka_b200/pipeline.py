@@ -46,7 +46,7 @@ class FusionViterbiPipeline:
         if not self.overlap_decode:
             tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
             out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
-                              d['img_mask'], d['text_mask'], return_dict=True)
+                              d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
             return out['result'], out['clip'], tags, lens, out['gate']
         main = torch.cuda.current_stream(self.device)
         if self._side_stream is None:
@@ -59,7 +59,7 @@ class FusionViterbiPipeline:
             tags.record_stream(main)
             lens.record_stream(main)
         out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
-                          d['img_mask'], d['text_mask'], return_dict=True)
+                          d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
         main.wait_stream(side)
         return out['result'], out['clip'], tags, lens, out['gate']
 

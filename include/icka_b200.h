@@ -11,9 +11,11 @@
  *     device unless stated otherwise; tensors are dense row-major.
  *   - return 0 on success, <0 on error; icka_last_error() returns a thread-local message.
  *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
- *     no entry point synchronises with the host or allocates device memory.
+ *     no entry point synchronises with the host or allocates device memory (icka_create does, once).
  *   - re-entrant: one handle per device; no global mutable state (CMIM is driven by one thread per GPU
  *     under nn.DataParallel, My_cross_attention.py:777-779).
+ *   - the handle owns one 32 MiB device workspace (split-K partial tiles of skinny icka_linear_fwd calls):
+ *     calls on the SAME handle must be issued to one stream at a time (or be ordered by events).
  *   - there is NO CPU fallback: every entry point fails if the device is not sm_100.
  */
 #ifndef ICKA_B200_H_
