@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=32, help='sentences in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -239,24 +240,38 @@ def run_gpu_arm(args, shape):
     torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    # One step = ~40 kernel launches on two streams; by default it is captured once into a CUDA graph and the timed
+    # region replays it (one driver call per step), so a slow host cannot starve the GPU.  gpu_launches counts the
+    # kernels the graph contains (icka_launch_count over the capture) times the replays.
+    use_graph = not args.no_graph
+    if use_graph:
+        graph, _outs = pipe.capture(d)
+        per_step = pipe.graph_kernels
+        run_step = graph.replay
+    else:
+        per_step = None
+        run_step = lambda: pipe.step_device(d)
     for _ in range(max(args.warmup, 3)):
-        pipe.step_device(d)
+        run_step()
     barrier()
     launches0 = _lib.launch_count(local_rank)
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         s_ev.record()
         for _ in range(args.steps):
-            pipe.step_device(d)
+            run_step()
         e_ev.record()
         barrier()
     ms_total = s_ev.elapsed_time(e_ev)
-    launches = _lib.launch_count(local_rank) - launches0
+    launches = per_step * args.steps if use_graph else _lib.launch_count(local_rank) - launches0
     ms_total = shard.max_over_ranks(ms_total, device=dev)
     value = args.batch * world * args.steps / (ms_total * 1e-3)
 
     # ---- per-kernel roofline pass (same step, CUDA events around every C-ABI launch) ----
     pipe.overlap_decode = False          # events on one stream: the decode must not be timed while it waits
+    for _ in range(2):                   # eager warm-up: the caching allocator must not cudaMalloc inside the events
+        pipe.step_device(d)
+    torch.cuda.synchronize()
     with KernelTimer() as kt:
         for _ in range(args.steps):
             pipe.step_device(d)
@@ -294,9 +309,9 @@ def run_gpu_arm(args, shape):
         hosts = [host, pipe.make_host_batch(args.batch, shape, seed + 1000)]
         n_e2e = max(4, min(args.steps, 10))
         seq = [hosts[i & 1] for i in range(n_e2e)]
-        pipe.infer_host(seq[:2])
+        pipe.infer_host(seq[:2], use_graphs=use_graph)
         barrier()
-        results, (s2, e2) = pipe.infer_host(seq)
+        results, (s2, e2) = pipe.infer_host(seq, use_graphs=use_graph)
         barrier()
         ms_e2e = s2.elapsed_time(e2)
         ms_e2e = shard.max_over_ranks(ms_e2e, device=dev)
@@ -325,6 +340,7 @@ def run_gpu_arm(args, shape):
                        'layers': shape.L, 'parallelism': f'batch-sharded x{world}, no collectives',
                        'precision': 'bf16 GEMM operands, fp32 accumulate/residual/LayerNorm/softmax' if args.precision == 'bf16' else 'fp32',
                        'weights': 'random init (nn.Linear default)',
+                       'launch': 'CUDA graph replay of the captured step' if use_graph else 'eager host launches',
                        'l2_policy': 'inputs larger than L2 (>= 1.2 GB of inputs per step vs 126 MB L2); no flush needed'},
             'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu, 'kernels': kernel_table,

@@ -180,24 +180,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// grid = (ceil(Sq / 128), nh, B)
-__global__ void __launch_bounds__(kMmaThreads) cross_attn_mma_kernel(
+// grid = (ceil(Sq / (16 * WARPS)), nh, B); WARPS x 16 query rows per block.  The kernel is a load -> compute ->
+// store sequence per block, so HBM stays busy only through the overlap of independent blocks: 64-row blocks
+// (4 per SM at 128 registers) interleave better than 128-row ones (2 per SM) at the price of staging K / V twice
+// from L2.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
     const __nv_bfloat16* __restrict__ v, int64_t ldkv, const float* __restrict__ mask_add,
     __nv_bfloat16* __restrict__ ctx, int64_t ldc, int Sq, int Skv) {
-  __shared__ __align__(16) __nv_bfloat16 Qs[kRows * kPitch];
+  constexpr int kRowsT = WARPS * 16, kThreadsT = WARPS * 32;
+  __shared__ __align__(16) __nv_bfloat16 Qs[kRowsT * kPitch];
   __shared__ __align__(16) __nv_bfloat16 Ks[kKeyBlk * kPitch];
   __shared__ __align__(16) __nv_bfloat16 Vs[kKeyBlk * kPitch];
   __shared__ float Ms[kKeyBlk];
   const int b = blockIdx.z, h = blockIdx.y;
-  const int row0 = blockIdx.x * kRows;
+  const int row0 = blockIdx.x * kRowsT;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int g = lane >> 2, t = lane & 3;
   constexpr float kLog2e = 1.4426950408889634f;
 
   // ---- stage the Q tile (rows beyond Sq are zero-filled) ----
   const __nv_bfloat16* qb = q + ((size_t)b * Sq + row0) * ldq + (size_t)h * kD;
-  for (int i = tid; i < kRows * 8; i += kMmaThreads) {
+  for (int i = tid; i < kRowsT * 8; i += kThreadsT) {
     const int r = i >> 3, c = (i & 7) * 8;
     if (row0 + r < Sq) cp_async16(Qs + r * kPitch + c, qb + (size_t)r * ldq + c);
     else *reinterpret_cast<uint4*>(Qs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kMmaThreads) cross_attn_mma_kernel(
   const __nv_bfloat16* vb = v + (size_t)b * Skv * ldkv + (size_t)h * kD;
   for (int key0 = 0; key0 < Skv; key0 += kKeyBlk) {
     if (key0 > 0) __syncthreads();   // previous block fully consumed
-    for (int i = tid; i < kKeyBlk * 8; i += kMmaThreads) {
+    for (int i = tid; i < kKeyBlk * 8; i += kThreadsT) {
       const int r = i >> 3, c = (i & 7) * 8;
       if (key0 + r < Skv) {
         cp_async16(Ks + r * kPitch + c, kb + (size_t)(key0 + r) * ldkv + c);
@@ -224,9 +229,9 @@ __global__ void __launch_bounds__(kMmaThreads) cross_attn_mma_kernel(
         *reinterpret_cast<uint4*>(Vs + r * kPitch + c) = make_uint4(0, 0, 0, 0);
       }
     }
-    if (tid < kKeyBlk) {
-      const int key = key0 + tid;
-      Ms[tid] = (key < Skv) ? (mask_add ? mask_add[(size_t)b * Skv + key] * kLog2e : 0.0f) : -INFINITY;
+    for (int i = tid; i < kKeyBlk; i += kThreadsT) {
+      const int key = key0 + i;
+      Ms[i] = (key < Skv) ? (mask_add ? mask_add[(size_t)b * Skv + key] * kLog2e : 0.0f) : -INFINITY;
     }
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group 0;\n" ::);
@@ -355,7 +360,11 @@ extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t l
   dim3 grid((Sq + kRows - 1) / kRows, nh, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == ICKA_BF16) {
-    cross_attn_mma_kernel<<<grid, kMmaThreads, 0, st>>>(
+    constexpr int kWarpsPerBlock = 4;
+    dim3 grid_mma((Sq + 16 * kWarpsPerBlock - 1) / (16 * kWarpsPerBlock), nh, B);
+    ICKA_CUDA(cudaFuncSetAttribute(cross_attn_mma_kernel<kWarpsPerBlock>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    cross_attn_mma_kernel<kWarpsPerBlock><<<grid_mma, 32 * kWarpsPerBlock, 0, st>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
         static_cast<const __nv_bfloat16*>(v), ldkv, mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, Sq, Skv);
   } else {

@@ -23,7 +23,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kKeyBlk = 32;
-constexpr int kSpPitch = 40;   // floats; conflict-free for 8-byte accesses in accumulator layout
+constexpr int kSpPitch = 32;   // floats; 4-float groups XOR-swizzled by the row (sp_at) -> conflict-free 8-byte accesses
+                               // without padding, which keeps the CTA under half an SM's shared memory (2 CTAs / SM)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -54,6 +55,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Element (row, col) of a [16][32] fp32 partial-score tile (col even; the pair col, col+1 stays adjacent).
+__device__ __forceinline__ float* sp_at(float* tile, int row, int col) {
+  return tile + row * kSpPitch + (col ^ ((row & 7) << 2));
+}
+
 // Row-major bf16 tile with H elements per row; 16-byte chunk c of row r is stored at chunk c ^ (r & 7).
 template <int H>
 __device__ __forceinline__ __nv_bfloat16* tile_chunk(__nv_bfloat16* base, int row, int chunk) {
@@ -61,7 +67,7 @@ __device__ __forceinline__ __nv_bfloat16* tile_chunk(__nv_bfloat16* base, int ro
 }
 
 template <int H>
-__global__ void __launch_bounds__(kThreads) i2t_pool_kernel(const __nv_bfloat16* __restrict__ U,
+__global__ void __launch_bounds__(kThreads, (H <= 768) ? 2 : 1) i2t_pool_kernel(const __nv_bfloat16* __restrict__ U,
                                                             const __nv_bfloat16* __restrict__ X,
                                                             const float* __restrict__ mask_add,
                                                             __nv_bfloat16* __restrict__ xbar, int S, int nh) {
@@ -141,8 +147,8 @@ __global__ void __launch_bounds__(kThreads) i2t_pool_kernel(const __nv_bfloat16*
     float* spw = Sp + warp * 16 * kSpPitch;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      *reinterpret_cast<float2*>(spw + g * kSpPitch + nt * 8 + 2 * t) = make_float2(sacc[nt][0], sacc[nt][1]);
-      *reinterpret_cast<float2*>(spw + (g + 8) * kSpPitch + nt * 8 + 2 * t) = make_float2(sacc[nt][2], sacc[nt][3]);
+      *reinterpret_cast<float2*>(sp_at(spw, g, nt * 8 + 2 * t)) = make_float2(sacc[nt][0], sacc[nt][1]);
+      *reinterpret_cast<float2*>(sp_at(spw, g + 8, nt * 8 + 2 * t)) = make_float2(sacc[nt][2], sacc[nt][3]);
     }
     __syncthreads();
     // ---- sum the 8 partials, scale, mask, online softmax (every warp keeps the full statistics) ----
@@ -151,8 +157,8 @@ __global__ void __launch_bounds__(kThreads) i2t_pool_kernel(const __nv_bfloat16*
       float2 a = make_float2(0.0f, 0.0f), c = make_float2(0.0f, 0.0f);
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) {
-        const float2 p0 = *reinterpret_cast<const float2*>(Sp + (w * 16 + g) * kSpPitch + nt * 8 + 2 * t);
-        const float2 p1 = *reinterpret_cast<const float2*>(Sp + (w * 16 + g + 8) * kSpPitch + nt * 8 + 2 * t);
+        const float2 p0 = *reinterpret_cast<const float2*>(sp_at(Sp + w * 16 * kSpPitch, g, nt * 8 + 2 * t));
+        const float2 p1 = *reinterpret_cast<const float2*>(sp_at(Sp + w * 16 * kSpPitch, g + 8, nt * 8 + 2 * t));
         a.x += p0.x; a.y += p0.y; c.x += p1.x; c.y += p1.y;
       }
       constexpr float kScale = 0.125f * kLog2e;
@@ -226,6 +232,9 @@ int launch_pool(icka_handle* h, const void* U, const void* X, const float* mask_
   const size_t smem = (size_t)2 * kKeyBlk * H * 2 + (size_t)kWarps * 16 * kSpPitch * 4 + 2 * kKeyBlk * 4;
   if (smem > h->smem_optin) ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "i2t_pool: needs %zu B shared memory", smem);
   ICKA_CUDA(cudaFuncSetAttribute(i2t_pool_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // two CTAs per SM only fit with the largest shared-memory carve-out
+  ICKA_CUDA(cudaFuncSetAttribute(i2t_pool_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
   i2t_pool_kernel<H><<<B, kThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(U),
                                                 static_cast<const __nv_bfloat16*>(X), mask_add,
                                                 static_cast<__nv_bfloat16*>(xbar), S, nh);

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import synth
+from . import _lib, synth
 from .config import FusionConfig
 from .crf import CRF
 from .modules import CrossModalFusion, set_precision
@@ -37,6 +37,7 @@ class FusionViterbiPipeline:
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._side_stream: Optional[torch.cuda.Stream] = None
         self.overlap_decode = True     # False: run the CRF decode on the main stream (per-kernel timing passes)
+        self._capturing = False
 
     # ---- device-resident step -------------------------------------------------------------------
     @torch.no_grad()
@@ -56,12 +57,39 @@ class FusionViterbiPipeline:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
-            tags.record_stream(main)
-            lens.record_stream(main)
+            if not self._capturing:      # (a captured graph owns its allocations; nothing to hand over)
+                tags.record_stream(main)
+                lens.record_stream(main)
         out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
                           d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
         main.wait_stream(side)
         return out['result'], out['clip'], tags, lens, out['gate']
+
+    # ---- CUDA graph of the device-resident step -----------------------------------------------------
+    def capture(self, d: Dict[str, torch.Tensor]):
+        """Capture one ``step_device(d)`` -- ~40 kernel launches on two streams -- into a CUDA graph bound to the
+        (static) device buffers ``d``.  Returns ``(graph, outputs)``; ``graph.replay()`` re-runs the step on new
+        contents of ``d`` and refreshes ``outputs`` in place.  The step is launch-bound on a slow host (each
+        launch goes Python -> ctypes -> cudaLaunchKernelEx); a replay is one driver call."""
+        cur = torch.cuda.current_stream(self.device)
+        warm = torch.cuda.Stream(self.device)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):          # operand / fold caches and kernel attributes settle before capture
+            for _ in range(2):
+                self.step_device(d)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        self._capturing = True
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        n0 = _lib.launch_count(idx)
+        try:
+            with torch.cuda.graph(graph):
+                outputs = self.step_device(d)
+        finally:
+            self._capturing = False
+        self.graph_kernels = _lib.launch_count(idx) - n0      # kernels one replay launches
+        return graph, outputs
 
     # ---- host batches ---------------------------------------------------------------------------
     @staticmethod
@@ -83,7 +111,7 @@ class FusionViterbiPipeline:
         return sum(v.numel() * v.element_size() for v in host.values())
 
     @torch.no_grad()
-    def infer_host(self, batches: List[Dict[str, torch.Tensor]]):
+    def infer_host(self, batches: List[Dict[str, torch.Tensor]], use_graphs: bool = True):
         """End-to-end over pinned host batches: H2D copy of every input, fusion + Viterbi, D2H of tags,
         lengths and gate values.  Copies of batch i+1 overlap the kernels of batch i (two device buffer
         sets).  Returns per-batch (tags [B,S] int32, lens [B] int32, gate [B] fp32) pinned host tensors
@@ -93,7 +121,11 @@ class FusionViterbiPipeline:
         cs = self._copy_stream
         main = torch.cuda.current_stream(self.device)
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        dev_bufs = [None, None]
+        if not hasattr(self, '_host_slots'):
+            self._host_slots = {}
+        key = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in batches[0].items())) if batches else None
+        slots = self._host_slots.setdefault(key, {'bufs': [None, None], 'graphs': [None, None]})
+        dev_bufs = slots['bufs']
         compute_done = [None, None]
         results = []
         cs.wait_stream(main)
@@ -110,7 +142,15 @@ class FusionViterbiPipeline:
                 copied = torch.cuda.Event()
                 copied.record(cs)
             main.wait_event(copied)
-            _, _, tags, lens, gate = self.step_device(dev_bufs[slot])
+            if use_graphs:
+                if slots['graphs'][slot] is None:      # first use of this buffer set: capture its step once
+                    main.synchronize()
+                    slots['graphs'][slot] = self.capture(dev_bufs[slot])
+                graph, outs = slots['graphs'][slot]
+                graph.replay()
+                _, _, tags, lens, gate = outs
+            else:
+                _, _, tags, lens, gate = self.step_device(dev_bufs[slot])
             out = (torch.empty(tags.shape, dtype=tags.dtype, pin_memory=True),
                    torch.empty(lens.shape, dtype=lens.dtype, pin_memory=True),
                    torch.empty(gate.shape, dtype=gate.dtype, pin_memory=True))
