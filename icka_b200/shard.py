@@ -82,8 +82,9 @@ class GradientAllReducer:
     into one flat fp32 buffer and all-reduced asynchronously (NCCL over NVLink 5 / NVSwitch on GPU ranks --
     the collective runs on NCCL's own stream beside the rest of backward; gloo in the CPU tests).
     ``finish()`` (call it after ``loss.backward()``, before clipping / the optimizer step) waits for the
-    transfers, divides by the world size -- ranks hold equal shards, so this is the global-batch mean the
-    reference's DDP produces -- and writes the averaged gradients back into ``p.grad``.
+    transfers and averages over the ranks -- ranks hold equal shards, so this is the global-batch mean the
+    reference's DDP produces; ``p.grad`` becomes a view of its bucket (no unpack copy, like DDP's
+    ``gradient_as_bucket_view``).
     """
 
     def __init__(self, params, bucket_bytes: int = 25 << 20, group=None):
@@ -132,13 +133,24 @@ class GradientAllReducer:
         if b.flat is None or b.flat.device != ref.device:
             b.flat = torch.empty(b.numel, dtype=torch.float32, device=ref.device)
         with torch.no_grad():
-            for p, off in zip(b.params, b.offsets):
-                dst = b.flat[off:off + p.numel()]
-                if p.grad is None:
-                    dst.zero_()
-                else:
-                    dst.copy_(p.grad.reshape(-1))
-        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            views = [b.flat[off:off + p.numel()] for p, off in zip(b.params, b.offsets)]
+            lo, hi = b.flat.data_ptr(), b.flat.data_ptr() + b.flat.numel() * 4
+            aliased = [p.grad is not None and lo <= p.grad.data_ptr() < hi for p in b.params]
+            if not any(aliased) and all(p.grad is not None for p in b.params):
+                torch.cat([p.grad.reshape(-1) for p in b.params], out=b.flat)          # one pack kernel per bucket
+            else:
+                for p, v, a in zip(b.params, views, aliased):
+                    if a and p.grad.data_ptr() == v.data_ptr():
+                        continue            # accumulated straight into last step's bucket view: already packed
+                    if p.grad is None:
+                        v.zero_()
+                    else:
+                        v.copy_(p.grad.reshape(-1))
+        op = dist.ReduceOp.SUM
+        b_avg = False
+        if self.world > 1 and dist.get_backend(self.group) == 'nccl':
+            op, b_avg = dist.ReduceOp.AVG, True            # NCCL scales inside the collective
+        b.work = (dist.all_reduce(b.flat, op=op, group=self.group, async_op=True), b_avg)
 
     def finish(self) -> None:
         """Wait for every bucket, average, scatter back; re-arm the hooks' counters for the next step."""
@@ -148,14 +160,12 @@ class GradientAllReducer:
                     self._launch(b)
             with torch.no_grad():
                 for b in self.buckets:
-                    b.work.wait()
-                    b.flat.div_(self.world)
+                    work, averaged = b.work
+                    work.wait()
+                    if not averaged:
+                        b.flat.div_(self.world)
                     for p, off in zip(b.params, b.offsets):
-                        avg = b.flat[off:off + p.numel()].view_as(p)
-                        if p.grad is None:
-                            p.grad = avg.clone()
-                        else:
-                            p.grad.copy_(avg)
+                        p.grad = b.flat[off:off + p.numel()].view_as(p)      # gradients become views of the bucket
         for b in self.buckets:
             b.pending = len(b.params)
             b.work = None
