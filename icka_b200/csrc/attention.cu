@@ -341,6 +341,18 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
 
 }  // namespace
 
+int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
+                             cudaStream_t st);
+
+// 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel
+static int g_attn_mode = 0;
+extern "C" int icka_set_attn_mode(int mode) {
+  if (mode < 0 || mode > 1) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..1", mode);
+  g_attn_mode = mode;
+  return ICKA_OK;
+}
+
 extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
                                         int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                                         int B, int Sq, int Skv, int nh, int d, void* stream) {
@@ -359,6 +371,10 @@ extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t l
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "cross_attn: Skv=%d needs %zu B shared memory (max %zu)", Skv, smem, h->smem_optin);
   dim3 grid((Sq + kRows - 1) / kRows, nh, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ICKA_BF16 && g_attn_mode == 0) {
+    const int rc = icka_attn_tcgen05_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, B, Sq, Skv, nh, st);
+    if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope
+  }
   if (dtype == ICKA_BF16) {
     constexpr int kWarpsPerBlock = 4;
     dim3 grid_mma((Sq + 16 * kWarpsPerBlock - 1) / (16 * kWarpsPerBlock), nh, B);

@@ -1,0 +1,277 @@
+// Cross-attention core on tcgen05 / TMEM for sm_100a (bf16, Skv <= 64: the 49-region text->image attention).
+//
+// Same contract as cross_attn_mma_kernel (attention.cu; BertCoAttention, CMIM:598-623):
+//   P = softmax(Q_h K_h^T / 8 + mask),  ctx_h = P V_h,  heads merged in place.
+// The mma.sync kernel spends its time in instruction issue (ncu: 54 % issue-slot utilisation, 4 CTAs / SM
+// at 128 registers): fragments, quad shuffles for the row statistics, staging.  Here the two GEMMs of a
+// (sentence, head, 128-query) item run on the 5th-generation tensor cores and the softmax works on whole
+// rows:
+//   S[128 x 64]  = Q[128 x 64] . K[64 x 64]^T     tcgen05.mma, operands by TMA (SWIZZLE_128B), fp32 in TMEM
+//   row softmax : each of 128 threads pulls ITS row of S out of TMEM (tcgen05.ld, lane = row), so max / sum
+//                 / exp2 need no cross-lane traffic; P is rounded to bf16 and written to shared memory in
+//                 the K-major 128-B-swizzled layout the UMMA A descriptor expects
+//   O[128 x 64]  = P[128 x 64] . V[64 x 64]        tcgen05.mma, V read in place as the MN-major B operand
+//   epilogue    : thread = row again: O from TMEM, times 1/rowsum, bf16, one contiguous 128-B store per row
+// One persistent CTA per SM, 320 threads: warp 0 TMA producer (3-stage ring of {Q, K, V} tiles), warp 1
+// MMA issuer, warps 2-5 and 6-9 two softmax/epilogue groups that alternate items (each item owns one of
+// two TMEM {S, O} slots and one of two P buffers), so the loads, the two MMAs, the softmax of one item and
+// the epilogue of another overlap.  Keys beyond Skv inside the 64-row K / V box belong to the next sentence
+// (or are TMA zero-fill): they get probability exactly 0.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kD = 64;          // head dim
+constexpr int kRows = 128;      // query rows per item
+constexpr int kKeys = 64;       // keys per item (Skv <= 64)
+constexpr int kStages = 3;
+constexpr int kQBytes = kRows * kD * 2, kKBytes = kKeys * kD * 2, kVBytes = kKeys * kD * 2;
+constexpr int kStageBytes = kQBytes + kKBytes + kVBytes;   // 32 KB
+constexpr int kPBytes = kRows * kKeys * 2;                  // 16 KB
+constexpr int kThreads = 320;
+constexpr int kTmemCols = 256;                              // 2 slots x {S: 64, O: 64}
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kPBytes + 2 * kKeys * sizeof(float) + 1024 + 256;
+
+struct AttnArgs {
+  const float* mask_add;   // [B, Skv] or null
+  __nv_bfloat16* ctx;
+  int64_t ldc;
+  int B, Sq, Skv, nh, q_tiles;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                          const __grid_constant__ CUtensorMap tmap_v, const AttnArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B alignment
+  uint8_t* stage_base = smem;
+  uint8_t* p_base = smem + (size_t)kStages * kStageBytes;                         // 2 x [128][64] bf16
+  float* mask_s = reinterpret_cast<float*>(p_base + 2 * kPBytes);                  // 2 x [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 2 * kKeys);
+  uint64_t* full_bar = bars;                   // [kStages] TMA bytes landed
+  uint64_t* empty_bar = bars + kStages;        // [kStages] both MMAs of the item retired
+  uint64_t* s_full = bars + 2 * kStages;       // [2] S = QK^T complete in TMEM slot
+  uint64_t* p_full = s_full + 2;               // [2] P written to shared memory (and S consumed)
+  uint64_t* o_full = p_full + 2;               // [2] O = PV complete in TMEM slot
+  uint64_t* o_free = o_full + 2;               // [2] O consumed by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int items = args.B * args.nh * args.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);    // one arrive per warp of the group
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_free[s], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+        const int h = bh % args.nh, b = bh / args.nh;
+        uint8_t* st = stage_base + (size_t)stage * kStageBytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+        tma_load_2d(st, &tmap_q, &full_bar[stage], h * kD, b * args.Sq + qt * kRows);
+        tma_load_2d(st + kQBytes, &tmap_k, &full_bar[stage], h * kD, b * args.Skv);
+        tma_load_2d(st + kQBytes + kKBytes, &tmap_v, &full_bar[stage], h * kD, b * args.Skv);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(kRows, kKeys);              // Q, K both K-major
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(kRows, kD, false, true);    // P K-major, V MN-major
+      int stage = 0, prev_stage = 0;
+      uint32_t phase = 0;
+      int n = 0;
+      auto issue_pv = [&](int m, int st_idx) {   // O = P V for the m-th item of this CTA
+        const int slot = m & 1;
+        const uint32_t par = (m >> 1) & 1;
+        mbar_wait(&p_full[slot], par);
+        if (m >= 2) mbar_wait(&o_free[slot], ((m >> 1) - 1) & 1);   // the epilogue drained this slot's O
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(p_base + slot * kPBytes);
+        const uint32_t v_addr = smem_u32(stage_base + (size_t)st_idx * kStageBytes + kQBytes + kKBytes);
+        const uint32_t tmem_o = tmem_base + (uint32_t)(slot * 128 + 64);
+#pragma unroll
+        for (int k = 0; k < kKeys / 16; ++k) {
+          const uint64_t da = make_kmajor_sw128_desc(p_addr + k * 32);
+          const uint64_t db = make_mnmajor_sw128_desc(v_addr + k * (16 * 128), kKeys * 128);
+          umma_bf16(tmem_o, da, db, idesc_o, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[st_idx]);   // Q, K, V of this stage are no longer read
+        umma_commit(&o_full[slot]);
+      };
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int slot = n & 1;
+        mbar_wait(&full_bar[stage], phase);
+        // S of this slot was consumed when p_full of item n-2 completed, which issue_pv(n-2) waited for.
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(stage_base + (size_t)stage * kStageBytes);
+        const uint32_t k_addr = q_addr + kQBytes;
+        const uint32_t tmem_s = tmem_base + (uint32_t)(slot * 128);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem_s, make_kmajor_sw128_desc(q_addr + k * 32), make_kmajor_sw128_desc(k_addr + k * 32), idesc_s,
+                    k > 0 ? 1u : 0u);
+        umma_commit(&s_full[slot]);
+        if (n >= 1) issue_pv(n - 1, prev_stage);
+        prev_stage = stage;
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (n >= 1) issue_pv(n - 1, prev_stage);
+    }
+  } else {
+    // ===================== softmax + epilogue groups (warps 2-5: even items, warps 6-9: odd items) =====================
+    const int group = (warp - 2) >> 2;                 // == TMEM slot == P buffer
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;                  // query row inside the item
+    const int gtid = (warp - 2 - group * 4) * 32 + lane;
+    uint8_t* p_buf = p_base + group * kPBytes;
+    float* mk = mask_s + group * kKeys;
+    const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(group * 128);
+    const uint32_t tmem_o = tmem_s + 64;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      if ((n & 1) != group) continue;
+      const uint32_t par = (n >> 1) & 1;
+      const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+      const int h = bh % args.nh, b = bh / args.nh;
+      // additive mask of this sentence (log2 domain); keys >= Skv get -inf
+      if (gtid < kKeys)
+        mk[gtid] = (gtid < args.Skv) ? (args.mask_add ? args.mask_add[(size_t)b * args.Skv + gtid] * kLog2e : 0.0f)
+                                     : -INFINITY;
+      named_bar_sync(1 + group, 128);
+      mbar_wait(&s_full[group], par);
+      tc_fence_after();
+      uint32_t sr[64];
+      tmem_ld_32x32b_x32(tmem_s, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld_32x32b_x32(tmem_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float s = fmaf(__uint_as_float(sr[j]), kScale, mk[j]);
+        sr[j] = __float_as_uint(s);
+        mx = fmaxf(mx, s);
+      }
+      float l = 0.0f;
+      uint8_t* prow = p_buf + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {          // 8 keys = one 16-byte chunk of the P row
+        float p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          p[j] = ex2(__uint_as_float(sr[8 * c + j]) - mx);
+          l += p[j];
+        }
+        uint4 u;
+        u.x = pack_bf16x2(p[0], p[1]);
+        u.y = pack_bf16x2(p[2], p[3]);
+        u.z = pack_bf16x2(p[4], p[5]);
+        u.w = pack_bf16x2(p[6], p[7]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;
+      }
+      fence_proxy_async();        // generic-proxy stores -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[group]);
+
+      // ---- epilogue: O row from TMEM, normalise, one 128-byte row store ----
+      mbar_wait(&o_full[group], par);
+      tc_fence_after();
+      uint32_t orr[64];
+      tmem_ld_32x32b_x32(tmem_o, *reinterpret_cast<uint32_t(*)[32]>(&orr[0]));
+      tmem_ld_32x32b_x32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&orr[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[group]);
+      const float inv = 1.0f / l;
+      const int q_row = qt * kRows + row;
+      if (q_row < args.Sq) {
+        __nv_bfloat16* op = args.ctx + ((size_t)b * args.Sq + q_row) * args.ldc + (size_t)h * kD;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
+          *reinterpret_cast<uint4*>(op + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+// Returns ICKA_OK after launching, or a positive value when the shape is outside this kernel's envelope
+// (the caller then uses the mma.sync kernel).
+int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
+                             cudaStream_t st) {
+  if (Skv > kKeys || h->smem_optin < kSmemBytes) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc = icka_make_tmap_bf16(h, &tq, q, (int64_t)B * Sq, (int64_t)nh * kD, ldq, kRows);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tk, k, (int64_t)B * Skv, (int64_t)nh * kD, ldkv, kKeys);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tv, v, (int64_t)B * Skv, (int64_t)nh * kD, ldkv, kKeys);
+  if (rc) return rc;
+  AttnArgs args{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows};
+  const int items = B * nh * args.q_tiles;
+  ICKA_CUDA(cudaFuncSetAttribute(cross_attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const int grid = items < h->sm_count ? items : h->sm_count;
+  cross_attn_tcgen05_kernel<<<grid, kThreads, kSmemBytes, st>>>(tq, tk, tv, args);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}

@@ -130,6 +130,10 @@ int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const v
                              int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                              int B, int Sq, int Skv, int nh, int d, void* stream);
 
+/* Kernel choice of the bf16 attention core (process-wide tuning/testing knob): 0 = per shape (tcgen05 / TMEM
+ * kernel for Skv <= 64, mma.sync kernel otherwise; default), 1 = always the mma.sync kernel. */
+int icka_set_attn_mode(int mode);
+
 /* Backward of icka_cross_attn_core_fwd: probabilities are recomputed from q, k, v (same layouts as the
  * forward); dctx [B*Sq, nh*d] -> dq [B*Sq, nh*d] (pitch lddq), dk / dv [B*Skv, nh*d] (pitch lddkv; may be the
  * halves of one [dK|dV] buffer).  ctx (the forward output, pitch ldctx) may be NULL; with it, bf16 and

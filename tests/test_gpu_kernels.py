@@ -91,6 +91,35 @@ def test_cross_attn_core_fp32_and_bf16():
         assert rel(gotb.float().cpu(), want) <= 3e-2
 
 
+@pytest.mark.parametrize('B,Sq,Skv,nh', [(3, 128, 49, 12), (2, 16, 9, 2), (5, 128, 64, 1), (2, 300, 49, 3), (40, 128, 49, 12),
+                                          (1, 1, 1, 1)])
+@pytest.mark.parametrize('attn_mode', [0, 1], ids=['tcgen05', 'mma_sync'])
+def test_cross_attn_core_bf16_kernels(B, Sq, Skv, nh, attn_mode):
+    """Both bf16 attention kernels (tcgen05/TMEM for Skv <= 64, mma.sync) against the fp64 formula on the same
+    bf16-rounded operands; ragged Sq (rows of the next sentence / zero fill inside the Q box) and key masks."""
+    from icka_b200 import _lib
+    H = nh * 64
+    q = rnd(B * Sq, H, seed=3).bfloat16()
+    kv = rnd(B * Skv, 2 * H, seed=4).bfloat16()
+    mask = torch.zeros(B, Skv)
+    mask[:, (Skv + 1) // 2:] = -10000.0
+    mask[0] = 0
+    qh = q.double().view(B, Sq, nh, 64).permute(0, 2, 1, 3)
+    kh = kv[:, :H].double().reshape(B, Skv, nh, 64).permute(0, 2, 1, 3)
+    vh = kv[:, H:].double().reshape(B, Skv, nh, 64).permute(0, 2, 1, 3)
+    sc = qh @ kh.transpose(-1, -2) / 8.0 + mask.double().view(B, 1, 1, Skv)
+    want = (torch.softmax(sc, -1) @ vh).permute(0, 2, 1, 3).reshape(B * Sq, H)
+    _lib.check(_lib.load().icka_set_attn_mode(attn_mode), 'icka_set_attn_mode')
+    try:
+        kvd = kv.to(DEV)
+        got = ops.cross_attn_core(q.to(DEV), kvd[:, :H], kvd[:, H:], mask.to(DEV), B, Sq, Skv, nh, 64)
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().icka_set_attn_mode(0)
+    err = float(((got.double().cpu() - want).abs() / want.abs().clamp(min=1.0)).max())
+    assert err <= 2e-2, err     # P rounded to bf16 for the second GEMM + bf16 output
+
+
 def test_gate_fold_and_blend():
     B, S, H = 5, 128, 768
     fused, tok = rnd(B, S, H, seed=1), rnd(B, S, H, seed=2)
