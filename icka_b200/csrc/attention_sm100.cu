@@ -27,13 +27,13 @@ using namespace sm100;
 constexpr int kD = 64;          // head dim
 constexpr int kRows = 128;      // query rows per item
 constexpr int kKeys = 64;       // keys per item (Skv <= 64)
-constexpr int kStages = 3;
+constexpr int kStages = 5;
 constexpr int kQBytes = kRows * kD * 2, kKBytes = kKeys * kD * 2, kVBytes = kKeys * kD * 2;
 constexpr int kStageBytes = kQBytes + kKBytes + kVBytes;   // 32 KB
 constexpr int kPBytes = kRows * kKeys * 2;                  // 16 KB
 constexpr int kThreads = 320;
 constexpr int kTmemCols = 256;                              // 2 slots x {S: 64, O: 64}
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kPBytes + 2 * kKeys * sizeof(float) + 1024 + 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kPBytes + 4 * kKeys * sizeof(float) + 1024 + 256;
 
 struct AttnArgs {
   const float* mask_add;   // [B, Skv] or null
@@ -58,8 +58,8 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B alignment
   uint8_t* stage_base = smem;
   uint8_t* p_base = smem + (size_t)kStages * kStageBytes;                         // 2 x [128][64] bf16
-  float* mask_s = reinterpret_cast<float*>(p_base + 2 * kPBytes);                  // 2 x [64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 2 * kKeys);
+  float* mask_s = reinterpret_cast<float*>(p_base + 2 * kPBytes);                  // 2 groups x 2 buffers x [64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 4 * kKeys);
   uint64_t* full_bar = bars;                   // [kStages] TMA bytes landed
   uint64_t* empty_bar = bars + kStages;        // [kStages] both MMAs of the item retired
   uint64_t* s_full = bars + 2 * kStages;       // [2] S = QK^T complete in TMEM slot
@@ -166,22 +166,29 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
     const int row = quad * 32 + lane;                  // query row inside the item
     const int gtid = (warp - 2 - group * 4) * 32 + lane;
     uint8_t* p_buf = p_base + group * kPBytes;
-    float* mk = mask_s + group * kKeys;
+    float* mk2 = mask_s + group * 2 * kKeys;           // double-buffered: the next item's mask is fetched early
     const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(group * 128);
     const uint32_t tmem_o = tmem_s + 64;
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kScale = 0.125f * kLog2e;
+    // additive mask of a sentence (log2 domain); keys >= Skv get -inf.  Written by the first 64 threads of the group.
+    auto fetch_mask = [&](int item, float* dst) {
+      if (gtid < kKeys && item < items) {
+        const int b = item / (args.q_tiles * args.nh);
+        dst[gtid] = (gtid < args.Skv) ? (args.mask_add ? args.mask_add[(size_t)b * args.Skv + gtid] * kLog2e : 0.0f)
+                                      : -INFINITY;
+      }
+    };
+    fetch_mask((int)blockIdx.x + group * (int)gridDim.x, mk2);
     int n = 0;
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       if ((n & 1) != group) continue;
       const uint32_t par = (n >> 1) & 1;
       const int qt = it % args.q_tiles, bh = it / args.q_tiles;
       const int h = bh % args.nh, b = bh / args.nh;
-      // additive mask of this sentence (log2 domain); keys >= Skv get -inf
-      if (gtid < kKeys)
-        mk[gtid] = (gtid < args.Skv) ? (args.mask_add ? args.mask_add[(size_t)b * args.Skv + gtid] * kLog2e : 0.0f)
-                                     : -INFINITY;
-      named_bar_sync(1 + group, 128);
+      const float* mk = mk2 + ((n >> 1) & 1) * kKeys;
+      named_bar_sync(1 + group, 128);      // this item's mask is in place; the other buffer is no longer read
+      fetch_mask(it + 2 * (int)gridDim.x, mk2 + (((n >> 1) & 1) ^ 1) * kKeys);   // latency hides behind this item
       mbar_wait(&s_full[group], par);
       tc_fence_after();
       uint32_t sr[64];
@@ -227,20 +234,32 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[group]);
+      // normalise, round to bf16 and park the row in this group's P buffer (PV has retired: o_full), then write
+      // out with 16 bytes per lane and 128 contiguous bytes per 8 lanes (4 full rows per warp instruction)
       const float inv = 1.0f / l;
-      const int q_row = qt * kRows + row;
-      if (q_row < args.Sq) {
-        __nv_bfloat16* op = args.ctx + ((size_t)b * args.Sq + q_row) * args.ldc + (size_t)h * kD;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + c * 8) = u;
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = u;
+      }
+      __syncwarp();
+      {
+        const int cch = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = quad * 32 + i * 4 + (lane >> 3);
+          const int q_row = qt * kRows + r;
+          if (q_row < args.Sq) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p_buf + r * 128 + ((cch ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(args.ctx + ((size_t)b * args.Sq + q_row) * args.ldc + (size_t)h * kD + cch * 8) = u;
+          }
         }
       }
+      __syncwarp();   // the rows are re-used by this warp's next softmax
     }
   }
 
