@@ -29,6 +29,8 @@ SIGNATURES = {
     'icka_mask_additive': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'icka_linear_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_linear_ln_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_linear_fwd_ex': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_linear_dgrad': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,

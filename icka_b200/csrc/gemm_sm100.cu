@@ -75,14 +75,41 @@ struct GemmArgs {
   int splits;                    // number of contraction ranges (split-K); 1 otherwise
   int kb_per_split;
   int64_t split_stride;          // forward split-K: split s writes its partial tile to out + s * split_stride
+  // LayerNorm-fused epilogue (LNF): out = LN(acc + bias + residual) in fp32 plus a bf16 copy
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  __nv_bfloat16* out16;          // [M, N] bf16 copy of the normalised rows (pitch N) or null
 };
 
 constexpr int kChunkBytes = kBK * 128;   // one 64-element-wide MN-major chunk of a stage: 64 contraction rows x 128 B
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR>
+// Tile walk.  Default: tile t = group + i * groups, n fastest, so the CTAs that share an A row-block run together.
+// LNF (LayerNorm-fused epilogue): a CTA owns WHOLE output rows -- it walks all n-tiles of row-block
+// group + j * groups before moving on -- because the row statistics span every n-tile.
+template <bool LNF>
+__device__ __forceinline__ bool tile_at(int i, int group_id, int num_groups, int m_tiles, int n_tiles, int num_tiles,
+                                        int& mn, int& split) {
+  if (LNF) {
+    const int mb = group_id + (i / n_tiles) * num_groups;
+    if (mb >= m_tiles) return false;
+    mn = mb * n_tiles + i % n_tiles;
+    split = 0;
+    return true;
+  }
+  const int tile = group_id + i * num_groups;
+  if (tile >= num_tiles) return false;
+  const int mn_tiles = m_tiles * n_tiles;
+  mn = tile % mn_tiles;
+  split = tile / mn_tiles;
+  return true;
+}
+
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
+  static_assert(!LNF || (MAJOR == 0 && CTAS == 1 && !OUT_BF16 && ACT == ICKA_ACT_NONE), "LNF: plain fp32 forward only");
   static_assert(MAJOR == 0 || CTAS == 1, "MN-major operands are built for single-CTA tiles only");
   static_assert(MAJOR != 2 || (!OUT_BF16 && ACT == ICKA_ACT_NONE), "wgrad accumulates plain fp32");
   using Cfg = GemmCfg<BN, CTAS>;
@@ -145,8 +172,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = group_id; tile < num_tiles; tile += num_groups) {
-        const int split = tile / mn_tiles, mn = tile % mn_tiles;
+      for (int i = 0;; ++i) {
+        int mn, split;
+        if (!tile_at<LNF>(i, group_id, num_groups, m_tiles, n_tiles, num_tiles, mn, split)) break;
         const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
         const int a_row = m_blk * kTileM + (int)cta_rank * kBM;
         const int b_row = n_blk * BN + (int)cta_rank * (BN / CTAS);
@@ -181,13 +209,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
+      for (;; ++it) {
+        int mn, split;
+        if (!tile_at<LNF>(it, group_id, num_groups, m_tiles, n_tiles, num_tiles, mn, split)) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        const int split = tile / mn_tiles;
         const int kb0 = split * args.kb_per_split, kb1 = min(num_kb, kb0 + args.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);             // TMA bytes (of both CTAs) have landed
@@ -236,9 +265,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int it = 0;
     const uint32_t empty_leader[2] = {CTAS == 2 ? map_to_cta(&tmem_empty_bar[0], 0) : 0u,
                                       CTAS == 2 ? map_to_cta(&tmem_empty_bar[1], 0) : 0u};
-    for (int tile = group_id; tile < num_tiles; tile += num_groups, ++it) {
-      const int mn = tile % mn_tiles;
+    float rs[16], rq[16];   // LNF: per-thread partial row sums / sums of squares of rows 2i+sub over this warp's columns
+    // LNF keeps its pre-LayerNorm rows in L2 between the two passes: they are written and re-read with evict_last,
+    // everything that streams (residual reads, final fp32 / bf16 stores) goes through with evict_first
+    const uint64_t pol_keep = LNF ? l2_policy_evict_last() : 0, pol_stream = LNF ? l2_policy_evict_first() : 0;
+    for (;; ++it) {
+      int mn, split_idx;
+      if (!tile_at<LNF>(it, group_id, num_groups, m_tiles, n_tiles, num_tiles, mn, split_idx)) break;
       const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
+      if (LNF && n_blk == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rs[i] = rq[i] = 0.0f;
+      }
       const bool lead = args.splits == 1 || MAJOR == 2;   // split-K forward: bias / residual are added by the reduce pass
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -293,8 +331,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const size_t rstep = (size_t)2 * N;
 #pragma unroll
           for (int i = 0; i < 16; ++i, rp += rstep)
-            res[i] = (full || (col_ok && 2 * i < rows_left)) ? __ldg(reinterpret_cast<const float2*>(rp))
-                                                               : make_float2(0.0f, 0.0f);
+            res[i] = (full || (col_ok && 2 * i < rows_left))
+                         ? (LNF ? ldg_f2_hint(rp, pol_stream) : __ldg(reinterpret_cast<const float2*>(rp)))
+                         : make_float2(0.0f, 0.0f);
         }
         uint32_t aux[16];
         if (ACT == ICKA_ACT_GELU_ERF_BWD) {
@@ -338,6 +377,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             x1 += res[i].y;
           }
           x[i] = make_float2(x0, x1);
+          if (LNF && col_ok) {   // columns beyond N hold zeros of the TMA fill + nothing: keep them out of the statistics
+            rs[i] += x0 + x1;
+            rq[i] = fmaf(x0, x0, fmaf(x1, x1, rq[i]));
+          }
         }
         const size_t ostep = (size_t)2 * args.ldo;
         if (OUT_BF16) {
@@ -351,10 +394,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int i = 0; i < 16; ++i, op += ostep)
             if (full || (col_ok && 2 * i < rows_left)) atomicAdd(reinterpret_cast<float2*>(op), x[i]);
         } else if (slabs) {
-          float* op = static_cast<float*>(args.out) + (size_t)(tile / mn_tiles) * args.split_stride + row0 * args.ldo + col;
+          float* op = static_cast<float*>(args.out) + (size_t)split_idx * args.split_stride + row0 * args.ldo + col;
 #pragma unroll
           for (int i = 0; i < 16; ++i, op += ostep)
             if (full || (col_ok && 2 * i < rows_left)) *reinterpret_cast<float2*>(op) = x[i];
+        } else if (LNF) {
+          float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i, op += ostep)
+            if (full || (col_ok && 2 * i < rows_left)) stg_f2_hint(op, x[i], pol_keep);
         } else {
           float* op = static_cast<float*>(args.out) + row0 * args.ldo + col;
 #pragma unroll
@@ -367,7 +415,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         __syncwarp();
         if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
       }
-
+      if (LNF && n_blk == n_tiles - 1) {
+        // ---- LayerNorm over the rows this CTA has just completed (BertLayerNorm, CMIM:518-522) ----
+        // (1) transpose-reduce the 16 per-thread row partials over the 16 lanes that share `sub`: after the four
+        //     exchange steps lane (sub, cp) holds the total of row 2*cp + sub over this warp's columns
+        float tsum, tsq;
+        {
+          float a[16], q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { a[i] = rs[i]; q[i] = rq[i]; }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+            const bool up = (cp & w) != 0;
+#pragma unroll
+            for (int k = 0; k < w; ++k) {
+              const float sa = up ? a[k] : a[k + w], sq = up ? q[k] : q[k + w];
+              const float ra = __shfl_xor_sync(0xffffffffu, sa, w), rq2 = __shfl_xor_sync(0xffffffffu, sq, w);
+              a[k] = (up ? a[k + w] : a[k]) + ra;
+              q[k] = (up ? q[k + w] : q[k]) + rq2;
+            }
+          }
+          tsum = a[0];
+          tsq = q[0];
+        }
+        // (2) the two warps of a lane quadrant own interleaved column blocks of the same 32 rows: combine through
+        //     shared memory (the idle transpose tile of the quadrant's first warp), then every thread fetches the
+        //     statistics of its 16 rows; the second barrier frees the tile for the next column block
+        float2* st = reinterpret_cast<float2*>(smem_stage + ((quad + 2) & 3) * (32 * 128));   // [half][32 rows]
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");   // the tile's owner is done transposing through it
+        st[half * 32 + 2 * cp + sub] = make_float2(tsum, tsq);
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");
+        const float inv_n = 1.0f / (float)N;
+        float mean[16], rstd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 p0 = st[2 * i + sub], p1 = st[32 + 2 * i + sub];
+          const float mu = (p0.x + p1.x) * inv_n;
+          const float var = fmaxf((p0.y + p1.y) * inv_n - mu * mu, 0.0f);
+          mean[i] = mu;
+          rstd[i] = rsqrtf(var + args.ln_eps);
+        }
+        asm volatile("bar.sync %0, 64;\n" ::"r"(1 + quad) : "memory");
+        // (3) second pass over this thread's own stores (L2-resident): normalise in place, emit the bf16 copy
+        const int row_base2 = m_blk * kTileM + quad * 32;
+        const int rows_left2 = M - row_base2 - sub;
+        for (int nb = 0; nb < n_tiles; ++nb) {
+          const int nch = min(BN / 32, (N - nb * BN + 31) / 32);
+          for (int c = half; c < nch; c += 2) {
+            const int col = nb * BN + c * 32 + 2 * cp;
+            if (col >= N) continue;
+            const float2 g = __ldg(reinterpret_cast<const float2*>(args.ln_gamma + col));
+            const float2 bt = __ldg(reinterpret_cast<const float2*>(args.ln_beta + col));
+            float* op = static_cast<float*>(args.out) + (size_t)(row_base2 + sub) * args.ldo + col;
+            __nv_bfloat16* hp = args.out16 ? args.out16 + (size_t)(row_base2 + sub) * N + col : nullptr;
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = (2 * i < rows_left2) ? ldg_f2_hint(op + (size_t)(2 * i) * args.ldo, pol_keep) : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (2 * i < rows_left2) {
+                const float y0 = g.x * ((v[i].x - mean[i]) * rstd[i]) + bt.x;
+                const float y1 = g.y * ((v[i].y - mean[i]) * rstd[i]) + bt.y;
+                stg_f2_hint(op + (size_t)(2 * i) * args.ldo, make_float2(y0, y1), pol_stream);
+                if (hp) stg_u32_hint(hp + (size_t)(2 * i) * N, pack_bf16x2(y0, y1), pol_stream);
+              }
+            }
+          }
+        }
+      }
     }
   }
 
@@ -447,13 +563,13 @@ int icka_make_tmap_bf16_mn(icka_handle* h, CUtensorMap* tm, const void* ptr, int
 
 namespace {
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR>
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false>
 int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS, MAJOR>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS, MAJOR, LNF>;
   ICKA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
   const int m_tiles = (args.M + kBM * CTAS - 1) / (kBM * CTAS), n_tiles = (args.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles * args.splits;
+  const int tiles = LNF ? m_tiles : m_tiles * n_tiles * args.splits;   // LNF: a CTA owns whole row-blocks
   const int groups_max = h->sm_count / CTAS;
   const int groups = tiles < groups_max ? tiles : groups_max;
   cudaLaunchConfig_t cfg = {};
@@ -553,6 +669,24 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
     else      { if (bf) ICKA_GEMM(128, ICKA_ACT_NONE, true, 1);     else ICKA_GEMM(128, ICKA_ACT_NONE, false, 1); }
   }
 #undef ICKA_GEMM
+}
+
+// out32 / out16 = LayerNorm(A . W^T + bias + residual) with the normalisation fused into the epilogue (LNF).
+int icka_gemm_bf16_ln_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             const float* residual, const float* gamma, const float* beta, float eps, float* out32,
+                             void* out16, int M, int N, int K, cudaStream_t st) {
+  ICKA_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && N % 8 == 0, "linear_ln(bf16): lda, ldw, N must be multiples of 8");
+  ICKA_REQUIRE(icka_aligned(A, 16) && icka_aligned(W, 16) && icka_aligned(out32, 16) && icka_aligned(out16, 16) &&
+                   icka_aligned(residual, 16) && icka_aligned(gamma, 8) && icka_aligned(beta, 8),
+               "linear_ln(bf16): pointers must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc = icka_make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tb, W, N, K, ldw, 256);
+  if (rc) return rc;
+  GemmArgs args{bias, residual, out32, (int64_t)N, M, N, K, 0, nullptr, nullptr, (int64_t)N, 1, (K + kBK - 1) / kBK, 0,
+                gamma, beta, eps, static_cast<__nv_bfloat16*>(out16)};
+  return launch_gemm<256, ICKA_ACT_NONE, false, 1, 0, true>(h, ta, tb, args, st);
 }
 
 // dgrad  dX[M,K] = (dY[M,N] . W[N,K]) (* gelu'(gelu_pre)) (+ residual): in kernel terms an M x K output contracted

@@ -17,6 +17,30 @@ int icka_gemm_bf16_dgrad_launch(icka_handle* h, const void* dY, int64_t ldd, con
 int icka_gemm_bf16_wgrad_launch(icka_handle* h, const void* dY, int64_t ldd, const void* X, int64_t ldx, float* dW,
                                 int64_t ldo, int M, int N, int K, cudaStream_t st);
 
+int icka_gemm_bf16_ln_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                             const float* residual, const float* gamma, const float* beta, float eps, float* out32,
+                             void* out16, int M, int N, int K, cudaStream_t st);
+
+extern "C" int icka_linear_ln_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                  const float* bias, const float* residual, const float* gamma, const float* beta,
+                                  float eps, float* out_f32, void* out_bf16, int in_dtype, int M, int N, int K,
+                                  void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(A && W && gamma && beta && out_f32, "linear_ln: null pointer");
+  ICKA_REQUIRE(M >= 0 && N >= 1 && K >= 1, "linear_ln: bad shape M=%d N=%d K=%d", M, N, K);
+  ICKA_REQUIRE(lda >= K && ldw >= K, "linear_ln: pitches smaller than the logical extents");
+  ICKA_REQUIRE(in_dtype == ICKA_F32 || in_dtype == ICKA_BF16, "linear_ln: bad in_dtype %d", in_dtype);
+  if (M == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (in_dtype == ICKA_BF16)
+    return icka_gemm_bf16_ln_launch(h, A, lda, W, ldw, bias, residual, gamma, beta, eps, out_f32, out_bf16, M, N, K, st);
+  // fp32 parity path: the FFMA GEMM writes the pre-LayerNorm rows, the row kernel normalises them in place
+  int rc = icka_sgemm_launch(h, static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias, residual,
+                             out_f32, N, ICKA_F32, M, N, K, ICKA_ACT_NONE, nullptr, st);
+  if (rc) return rc;
+  return icka_layernorm_fwd(h, out_f32, gamma, beta, eps, out_f32, out_bf16, M, N, stream);
+}
+
 extern "C" int icka_linear_fwd_ex(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
                                   const float* bias, const float* residual, void* out, int64_t ldo, void* pre_act_out,
                                   int in_dtype, int out_dtype, int M, int N, int K, int act, void* stream) {

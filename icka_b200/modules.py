@@ -38,6 +38,9 @@ from ._lib import ACT_GELU_ERF, ACT_NONE
 from .autograd import CrossLayerFn, DenseFn, GateBlendFn
 
 _PRECISION = 'bf16'
+_FUSE_LN = False     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
+                     # B200 the second (normalising) pass re-reads rows that have left L2 and is latency-bound:
+                     # 511 us fused vs 227 + 152 us unfused at B=1024, so it stays off
 
 
 def set_precision(mode: str) -> None:
@@ -139,9 +142,15 @@ class _DenseResidualNorm(nn.Module):
 
     def _run(self, h_lp: torch.Tensor, res32: torch.Tensor, defer_ln: bool = False):
         w = _operand(self._cache, 'w', self.dense.weight)
-        pre = ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32)
         if defer_ln:          # the caller fuses this LayerNorm into its consumer (icka_ln_gate_blend_fwd)
-            return pre, None
+            return ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32), None
+        if _FUSE_LN and h_lp.shape[0] >= 2048:
+            # dense + residual + LayerNorm in one launch (normalisation in the GEMM epilogue); below ~2k rows a CTA
+            # per 128-row block leaves most SMs idle, so skinny problems keep the split-K GEMM + row kernel
+            return ops.linear_ln(h_lp, w, self.dense.bias.detach(), res32, self.LayerNorm.weight.detach(),
+                                 self.LayerNorm.bias.detach(), self.LayerNorm.variance_epsilon,
+                                 want_bf16=_PRECISION == 'bf16')
+        pre = ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32)
         return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
                              self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=_PRECISION == 'bf16')
 

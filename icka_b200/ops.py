@@ -110,6 +110,33 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, re
     return out
 
 
+def linear_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+              gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, want_bf16: bool = False):
+    """LayerNorm(a . w^T + bias + residual) -> (y32 [M,N], y16 | None): the dense layer with the normalisation
+    fused into the GEMM epilogue (bf16 operands) -- BertSelfOutput / BertOutput in one launch."""
+    if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1] or a.dtype != w.dtype or a.dtype not in _DT:
+        raise RuntimeError(f'linear_ln: bad operands {tuple(a.shape)} {a.dtype} x {tuple(w.shape)} {w.dtype}')
+    if a.stride(1) != 1 or w.stride(1) != 1:
+        raise RuntimeError('linear_ln: operands must be unit-stride along K')
+    M, K = a.shape
+    N = w.shape[0]
+    for t, n in ((gamma, 'gamma'), (beta, 'beta')):
+        _need(t, torch.float32, f'linear_ln({n})')
+    if bias is not None:
+        _need(bias, torch.float32, 'linear_ln(bias)')
+    if residual is not None:
+        _need(residual, torch.float32, 'linear_ln(residual)')
+        if residual.shape != (M, N):
+            raise RuntimeError('linear_ln: residual shape mismatch')
+    lib, h, st = _ctx(a)
+    y32 = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    y16 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    _lib.check(lib.icka_linear_ln_fwd(h, a.data_ptr(), _ld(a, K), w.data_ptr(), _ld(w, K), _p(bias), _p(residual),
+                                      gamma.data_ptr(), beta.data_ptr(), float(eps), y32.data_ptr(), _p(y16),
+                                      _DT[a.dtype], M, N, K, st), 'icka_linear_ln_fwd')
+    return y32, y16
+
+
 def _ld(t: torch.Tensor, cols: int) -> int:
     """Row pitch of a 2-D view (a single-row tensor may report any stride)."""
     return t.stride(0) if t.shape[0] > 1 else max(cols, t.stride(0))

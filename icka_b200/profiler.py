@@ -27,6 +27,12 @@ def _work_linear(a, w, bias, residual=None, act=0, out_dtype=None, out=None, pre
 def _work(name, args, kwargs):
     if name == 'linear':
         return _work_linear(*args, **kwargs)
+    if name == 'linear_ln':
+        a, w = args[0], args[1]
+        M, K = a.shape
+        N = w.shape[0]
+        nb = M * K * _ESZ[a.dtype] + N * K * _ESZ[w.dtype] + M * N * 8 + (M * N * 2 if kwargs.get('want_bf16') else 0)
+        return ('linear_bf16_tcgen05' if a.dtype == torch.bfloat16 else 'linear_fp32_ffma'), 2.0 * M * N * K, nb
     if name == 'cast_bf16':
         return name, 0.0, args[0].numel() * 6
     if name == 'region_rows':
@@ -90,7 +96,7 @@ def _work(name, args, kwargs):
 
 
 class KernelTimer:
-    OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend', 'ln_gate_blend',
+    OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'linear_ln', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend', 'ln_gate_blend',
            'viterbi', 'crf_llh', 'linear_dgrad', 'linear_wgrad', 'colsum', 'layernorm_bwd', 'cross_attn_core_bwd',
            'gate_blend_bwd', 'gate_fold_bwd', 'crf_llh_bwd')
 
@@ -114,7 +120,7 @@ class KernelTimer:
     def _wrap(self, name, fn):
         def timed(*args, **kwargs):
             tag, flops, nbytes = _work(name, args, kwargs)
-            if name == 'linear':
+            if name in ('linear', 'linear_ln'):
                 self.shapes.append((f'{args[0].shape[0]}x{args[1].shape[0]}x{args[0].shape[1]}', len(self.records)))
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()

@@ -66,3 +66,24 @@ def test_linear_bf16_pitched_kv_views(gemm_mode):
     got = ops.linear(a_full[:, H:], w, None, out_dtype=torch.float32).cpu()
     want = a_full[:, H:].cpu().double() @ w.cpu().double().t()
     assert float((got.double() - want).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 768, 768), (1000, 768, 3072), (300, 256, 64), (77, 1024, 512), (128 * 160, 768, 768),
+                                    (5, 136, 40)])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_linear_ln_fused_epilogue(M, N, K, dtype):
+    """Dense + bias + residual + BertLayerNorm in one call (LayerNorm in the tcgen05 epilogue for bf16 operands)."""
+    from oracle import fusion_ref
+    a = rnd(M, K, seed=11).to(dtype)
+    w = (rnd(N, K, seed=12) / math.sqrt(K)).to(dtype)
+    bias, res = rnd(N, seed=13), rnd(M, N, seed=14)
+    gamma, beta = 1.0 + 0.1 * rnd(N, seed=15), 0.1 * rnd(N, seed=16)
+    eps = 1e-12
+    y32, y16 = ops.linear_ln(a.to(DEV), w.to(DEV), bias.to(DEV), res.to(DEV), gamma.to(DEV), beta.to(DEV), eps,
+                             want_bf16=True)
+    pre = a.double() @ w.double().t() + bias.double() + res.double()
+    want = fusion_ref.bert_layer_norm(pre, gamma.double(), beta.double(), eps)
+    err = float((y32.cpu().double() - want).abs().max())
+    assert err <= 2e-5, err
+    err16 = float((y16.float().cpu().double() - want).abs().max())
+    assert err16 <= 2 ** -8 * float(want.abs().max()) + 1e-5, err16

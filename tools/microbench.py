@@ -71,6 +71,14 @@ def main(B=1024, mode=0):
                B * (S * H * 2 * 2 + R * 2 * H * 2))
     tot += gemm('out proj +res (f32 out)', xb, Wo, bH, res=x, od=torch.float32)
     tot += mem('layernorm', lambda: ops.layernorm(x, g1, g1, 1e-12, want_f32=True, want_bf16=True), B * S * H * 10)
+    def gemm_ln(name, a, W, b, res):
+        M, K = a.shape
+        N = W.shape[0]
+        t = timeit(lambda: ops.linear_ln(a, W, b, res, g1, g1, 1e-12, want_bf16=True))
+        tf = 2.0 * M * N * K / t / 1e12
+        print(f'{name:28s} M={M:7d} N={N:5d} K={K:5d}  {t*1e6:9.1f} us  {tf:7.1f} TF/s  (GEMM + LayerNorm in one launch)')
+    gemm_ln('out proj +res +LN fused', xb, Wo, bH, x)
+    gemm_ln('FFN down +res +LN fused', fb, Wd, bH, x)
     tot += gemm('FFN up + gelu', xb, Wi, bI, act=ACT_GELU_ERF)
     tot += gemm('FFN down +res (f32 out)', fb, Wd, bH, res=x, od=torch.float32)
     tot += mem('layernorm', lambda: ops.layernorm(x, g1, g1, 1e-12, want_f32=True, want_bf16=True), B * S * H * 10)
