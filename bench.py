@@ -376,7 +376,7 @@ def run_train_arm(args, shape):
     torch.manual_seed(19260817)
     cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
                        layer_norm_eps=shape.eps)
-    fusion = CrossModalFusion(cfg, layer_num1=shape.L).to(dev).eval()       # eval(): dropout kernels are not built
+    fusion = CrossModalFusion(cfg, layer_num1=shape.L).to(dev).train()      # dropout p = 0.1 on all three sites
     head = torch.nn.Linear(shape.H, shape.T).to(dev)
     crf = CRF(shape.T, batch_first=True).to(dev)
     params = list(fusion.parameters()) + list(head.parameters()) + list(crf.parameters())
@@ -446,7 +446,7 @@ def run_train_arm(args, shape):
                        'params_allreduced': n_param, 'buckets': len(reducer.buckets),
                        'buckets_launched_inside_backward_per_step': reducer.launched_early // (args.steps + max(args.warmup, 3)),
                        'outside_hot_path': 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier; optimizer = torch AdamW(fused)',
-                       'dropout': 'p = 0 (no dropout kernels)'},
+                       'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)'},
             'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
             'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor', 'achieved': tf,
                          'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libicka_b200.so')
@@ -56,6 +56,16 @@ SIGNATURES = {
                                    c_int, c_void_p]),
     'icka_cross_attn_core_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
                                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'icka_cross_attn_core_fwd_drop': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                              c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                              c_uint64, c_void_p]),
+    'icka_cross_attn_core_bwd_drop': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p,
+                                              c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                              c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                              c_uint64, c_void_p]),
+    'icka_dropout_fwd': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64, c_float, c_uint64,
+                                 c_void_p]),
+    'icka_dropout_mask': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_uint64, c_void_p]),
     'icka_i2t_pool_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_gate_fold': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p]),

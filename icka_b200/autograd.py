@@ -13,7 +13,8 @@ Each backward is a hand-scheduled sequence of the kernels declared in include/ic
 
 Precision follows ``modules.set_precision``: 'bf16' keeps fp32 for the residual stream, its gradient,
 LayerNorm statistics and all parameter gradients, and bf16 for GEMM operands; 'fp32' runs every GEMM on
-the FFMA kernels (the gradient-parity path).  Dropout is not implemented: training requires p = 0.
+the FFMA kernels (the gradient-parity path).  Dropout (CMIM:616, 563, 534) uses counter-based Philox masks that
+backward regenerates from a per-call seed, so no mask tensor is stored.
 """
 from __future__ import annotations
 
@@ -53,19 +54,25 @@ class CrossLayerFn(torch.autograd.Function):
     def forward(ctx, x32, y32, x_op, y_op, mask2d, meta,
                 wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, wd, bd, g2, b2,
                 wq_op, wkv_op, bkv, wo_op, wi_op, wd_op):
-        B, Sq, Skv, nh, d, eps = meta
+        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed = meta
         H = nh * d
         dt = x_op.dtype
         bf = dt == torch.bfloat16
         q = ops.linear(x_op, wq_op, bq, out_dtype=dt)
         kv = ops.linear(y_op, wkv_op, bkv, out_dtype=dt)
-        att = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask2d, B, Sq, Skv, nh, d)
-        pre1 = ops.linear(att, wo_op, bo, residual=x32, out_dtype=F32)
+        att = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask2d, B, Sq, Skv, nh, d, p_drop=p_attn, seed=3 * seed)
+        if p_hid > 0:     # dropout(dense(ctx)) + input, CMIM:562-564 (Philox mask regenerated in backward)
+            pre1 = ops.dropout(ops.linear(att, wo_op, bo, out_dtype=F32), p_hid, 3 * seed + 1, residual=x32)
+        else:
+            pre1 = ops.linear(att, wo_op, bo, residual=x32, out_dtype=F32)
         a32, a16 = ops.layernorm(pre1, g1, b1, eps, want_f32=True, want_bf16=bf)
         a_op = _op(a32, a16)
         u = torch.empty(a_op.shape[0], wi_op.shape[0], dtype=dt, device=a_op.device)
         f = ops.linear(a_op, wi_op, bi, act=ACT_GELU_ERF, out_dtype=dt, pre_act_out=u)
-        pre2 = ops.linear(f, wd_op, bd, residual=a32, out_dtype=F32)
+        if p_hid > 0:     # CMIM:533-535
+            pre2 = ops.dropout(ops.linear(f, wd_op, bd, out_dtype=F32), p_hid, 3 * seed + 2, residual=a32)
+        else:
+            pre2 = ops.linear(f, wd_op, bd, residual=a32, out_dtype=F32)
         o32, o16 = ops.layernorm(pre2, g2, b2, eps, want_f32=True, want_bf16=bf)
         ctx.meta = meta
         ctx.has_mask = mask2d is not None
@@ -77,7 +84,7 @@ class CrossLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, do32, _unused):
-        B, Sq, Skv, nh, d, eps = ctx.meta
+        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed = ctx.meta
         H = nh * d
         saved = ctx.saved_tensors
         x_op, y_op, q, kv, att, pre1, a_op, u, f, pre2, g1, g2, wq_op, wkv_op, wo_op, wi_op, wd_op = saved[:17]
@@ -87,8 +94,14 @@ class CrossLayerFn(torch.autograd.Function):
         do32 = do32.contiguous()
 
         # ---- FFN block: X' = LN2(F Wd^T + bd + A1),  F = gelu(A1 Wi^T + bi) ----
-        dpre2, dpre2_16, dg2, db2, dbd = ops.layernorm_bwd(do32, pre2, g2, eps, want_f32=True, want_bf16=bf)
-        dpre2_op = _op(dpre2, dpre2_16)
+        drop = p_hid > 0
+        dpre2, dpre2_16, dg2, db2, dbd = ops.layernorm_bwd(do32, pre2, g2, eps, want_f32=True, want_bf16=bf and not drop,
+                                                           want_dbias=not drop)
+        if drop:          # gradient of the dense output = upstream gradient through the same Philox mask
+            dpre2_op = ops.dropout(dpre2, p_hid, 3 * seed + 2, out_dtype=dt)
+            dbd = ops.colsum(dpre2_op)
+        else:
+            dpre2_op = _op(dpre2, dpre2_16)
         dwd = ops.linear_wgrad(dpre2_op, f)
         dgl = ops.linear_dgrad(dpre2_op, wd_op, gelu_pre=u, out_dtype=dt)          # d(pre-activation) [M, I]
         dwi = ops.linear_wgrad(dgl, a_op)
@@ -96,11 +109,17 @@ class CrossLayerFn(torch.autograd.Function):
         da1 = ops.linear_dgrad(dgl, wi_op, residual=dpre2, out_dtype=F32)          # + the residual branch
 
         # ---- attention block: A1 = LN1(ctx Wo^T + bo + X) ----
-        dpre1, dpre1_16, dg1, db1, dbo = ops.layernorm_bwd(da1, pre1, g1, eps, want_f32=True, want_bf16=bf)
-        dpre1_op = _op(dpre1, dpre1_16)
+        dpre1, dpre1_16, dg1, db1, dbo = ops.layernorm_bwd(da1, pre1, g1, eps, want_f32=True, want_bf16=bf and not drop,
+                                                           want_dbias=not drop)
+        if drop:
+            dpre1_op = ops.dropout(dpre1, p_hid, 3 * seed + 1, out_dtype=dt)
+            dbo = ops.colsum(dpre1_op)
+        else:
+            dpre1_op = _op(dpre1, dpre1_16)
         dwo = ops.linear_wgrad(dpre1_op, att)
         datt = ops.linear_dgrad(dpre1_op, wo_op, out_dtype=dt)
-        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, datt, B, Sq, Skv, nh, d, ctx=att)
+        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, datt, B, Sq, Skv, nh, d, ctx=att,
+                                          p_drop=p_attn, seed=3 * seed)
         dwq = ops.linear_wgrad(dq, x_op)
         dbq = ops.colsum(dq)
         dwkv = ops.linear_wgrad(dkv, y_op)                                         # [2H, H]: rows = key | value

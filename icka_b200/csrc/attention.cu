@@ -11,11 +11,20 @@
 // AFTER the dot product, CMIM:605-607; x0.125 is exact); softmax is evaluated online (running max)
 // which reassociates the reference's exp(s - max)/sum within fp32 rounding.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
 constexpr int kD = 64;
 constexpr int kRows = 128;   // query rows per block == threads per block
+
+// Dropout on the attention probabilities (CMIM:616), training only: P' = P * keep / (1 - p) goes into P.V while the
+// softmax normaliser keeps the undropped sum.  thresh == 0 means "off".
+struct DropArgs {
+  uint32_t thresh;
+  float scale;
+  uint64_t seed;
+};
 
 template <typename T>
 __device__ __forceinline__ void load8(const T* p, float* out);
@@ -59,7 +68,7 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 template <typename T>
 __global__ void __launch_bounds__(kRows) cross_attn_kernel(
     const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
-    const float* __restrict__ mask_add, T* __restrict__ ctx, int64_t ldc, int Sq, int Skv) {
+    const float* __restrict__ mask_add, T* __restrict__ ctx, int64_t ldc, int Sq, int Skv, DropArgs drop) {
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;                      // [Skv][64]
   float* Vs = Ks + (size_t)Skv * kD;     // [Skv][64]
@@ -93,8 +102,12 @@ __global__ void __launch_bounds__(kRows) cross_attn_kernel(
 #pragma unroll
   for (int c = 0; c < kD; ++c) acc[c] = 0.0f;
   float m = -INFINITY, l = 0.0f;
+  const uint64_t drow = ((uint64_t)b * gridDim.y + h) * (uint64_t)Sq + (uint64_t)row;
+  uint32_t keep = 0xfu;
 
   for (int r = 0; r < Skv; ++r) {
+    if (drop.thresh && (r & 3) == 0)
+      keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, r), drop.thresh);
     const float4* kr = reinterpret_cast<const float4*>(Ks + r * kD);
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
@@ -113,8 +126,9 @@ __global__ void __launch_bounds__(kRows) cross_attn_kernel(
       for (int c = 0; c < kD; ++c) acc[c] *= scale;
       m = s;
     }
-    const float p = expf(s - m);
+    float p = expf(s - m);
     l += p;
+    if (drop.thresh) p = (keep >> (r & 3) & 1u) ? p * drop.scale : 0.0f;
     const float4* vr = reinterpret_cast<const float4*>(Vs + r * kD);
 #pragma unroll
     for (int c = 0; c < kD / 4; ++c) {
@@ -188,7 +202,7 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
     const __nv_bfloat16* __restrict__ v, int64_t ldkv, const float* __restrict__ mask_add,
-    __nv_bfloat16* __restrict__ ctx, int64_t ldc, int Sq, int Skv) {
+    __nv_bfloat16* __restrict__ ctx, int64_t ldc, int Sq, int Skv, DropArgs drop) {
   constexpr int kRowsT = WARPS * 16, kThreadsT = WARPS * 32;
   __shared__ __align__(16) __nv_bfloat16 Qs[kRowsT * kPitch];
   __shared__ __align__(16) __nv_bfloat16 Ks[kKeyBlk * kPitch];
@@ -283,12 +297,22 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
     m1 = mn1;
     float ps0 = 0.0f, ps1 = 0.0f;
     uint32_t pf[8][2];
+    const uint64_t drow0 = ((uint64_t)b * gridDim.y + h) * (uint64_t)Sq + (uint64_t)(row0 + warp * 16 + g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float p0 = fast_exp2(sacc[j][0] - mn0), p1 = fast_exp2(sacc[j][1] - mn0);
-      const float p2 = fast_exp2(sacc[j][2] - mn1), p3 = fast_exp2(sacc[j][3] - mn1);
+      float p0 = fast_exp2(sacc[j][0] - mn0), p1 = fast_exp2(sacc[j][1] - mn0);
+      float p2 = fast_exp2(sacc[j][2] - mn1), p3 = fast_exp2(sacc[j][3] - mn1);
       ps0 += p0 + p1;
       ps1 += p2 + p3;
+      if (drop.thresh) {   // this thread's two keys of the tile share one Philox group of four
+        const int key = key0 + j * 8 + 2 * t;
+        const uint32_t k0 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow0, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t k1 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow0 + 8, Skv, key), drop.thresh) >> (key & 3);
+        p0 = (k0 & 1u) ? p0 * drop.scale : 0.0f;
+        p1 = (k0 & 2u) ? p1 * drop.scale : 0.0f;
+        p2 = (k1 & 1u) ? p2 * drop.scale : 0.0f;
+        p3 = (k1 & 2u) ? p3 * drop.scale : 0.0f;
+      }
       pf[j][0] = pack_bf16x2(p0, p1);
       pf[j][1] = pack_bf16x2(p2, p3);
     }
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
 
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
-                             cudaStream_t st);
+                             uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st);
 
 // 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel
 static int g_attn_mode = 0;
@@ -356,7 +380,16 @@ extern "C" int icka_set_attn_mode(int mode) {
 extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
                                         int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                                         int B, int Sq, int Skv, int nh, int d, void* stream) {
+  return icka_cross_attn_core_fwd_drop(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, dtype, B, Sq, Skv, nh, d, 0.0f, 0, stream);
+}
+
+extern "C" int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                                             int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
+                                             int B, int Sq, int Skv, int nh, int d, float p_drop, uint64_t seed,
+                                             void* stream) {
   ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "cross_attn: dropout p=%f outside [0, 1)", (double)p_drop);
+  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed};
   ICKA_REQUIRE(q && k && v && ctx, "cross_attn: null pointer");
   ICKA_REQUIRE(B >= 0 && Sq >= 1 && Skv >= 1 && nh >= 1, "cross_attn: bad shape");
   ICKA_REQUIRE(d == kD, "cross_attn: head dim %d != 64 (ICKA uses 768/12 and 1024/16)", d);
@@ -372,7 +405,8 @@ extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t l
   dim3 grid((Sq + kRows - 1) / kRows, nh, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == ICKA_BF16 && g_attn_mode == 0) {
-    const int rc = icka_attn_tcgen05_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, B, Sq, Skv, nh, st);
+    const int rc = icka_attn_tcgen05_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, B, Sq, Skv, nh, drop.thresh,
+                                            drop.scale, drop.seed, st);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope
   }
   if (dtype == ICKA_BF16) {
@@ -382,12 +416,12 @@ extern "C" int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t l
                                    cudaSharedmemCarveoutMaxShared));
     cross_attn_mma_kernel<kWarpsPerBlock><<<grid_mma, 32 * kWarpsPerBlock, 0, st>>>(
         static_cast<const __nv_bfloat16*>(q), ldq, static_cast<const __nv_bfloat16*>(k),
-        static_cast<const __nv_bfloat16*>(v), ldkv, mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, Sq, Skv);
+        static_cast<const __nv_bfloat16*>(v), ldkv, mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, Sq, Skv, drop);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(cross_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cross_attn_kernel<float><<<grid, kRows, smem, st>>>(static_cast<const float*>(q), ldq, static_cast<const float*>(k),
                                                         static_cast<const float*>(v), ldkv, mask_add,
-                                                        static_cast<float*>(ctx), ldc, Sq, Skv);
+                                                        static_cast<float*>(ctx), ldc, Sq, Skv, drop);
   }
   ICKA_LAUNCHED(h);
   return ICKA_OK;

@@ -19,6 +19,7 @@
 // (or are TMA zero-fill): they get probability exactly 0.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -40,6 +41,9 @@ struct AttnArgs {
   __nv_bfloat16* ctx;
   int64_t ldc;
   int B, Sq, Skv, nh, q_tiles;
+  uint32_t drop_thresh;   // attention-probability dropout (CMIM:616), training only; 0 = off
+  float drop_scale;
+  uint64_t seed;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -204,6 +208,7 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
       }
       float l = 0.0f;
       uint8_t* prow = p_buf + row * 128;
+      const uint64_t drow = ((uint64_t)b * args.nh + h) * (uint64_t)args.Sq + (uint64_t)(qt * kRows + row);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {          // 8 keys = one 16-byte chunk of the P row
         float p[8];
@@ -211,6 +216,15 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         for (int j = 0; j < 8; ++j) {
           p[j] = ex2(__uint_as_float(sr[8 * c + j]) - mx);
           l += p[j];
+        }
+        if (args.drop_thresh) {              // the normaliser keeps the undropped sum; P' = P keep / (1 - p) feeds P.V
+#pragma unroll
+          for (int g4 = 0; g4 < 2; ++g4) {
+            const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+                                                       icka_rng::attn_group(drow, args.Skv, 8 * c + 4 * g4), args.drop_thresh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
+          }
         }
         uint4 u;
         u.x = pack_bf16x2(p[0], p[1]);
@@ -277,7 +291,7 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 // (the caller then uses the mma.sync kernel).
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
-                             cudaStream_t st) {
+                             uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st) {
   if (Skv > kKeys || h->smem_optin < kSmemBytes) return 1;
   CUtensorMap tq, tk, tv;
   int rc = icka_make_tmap_bf16(h, &tq, q, (int64_t)B * Sq, (int64_t)nh * kD, ldq, kRows);
@@ -286,7 +300,8 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
   if (rc) return rc;
   rc = icka_make_tmap_bf16(h, &tv, v, (int64_t)B * Skv, (int64_t)nh * kD, ldkv, kKeys);
   if (rc) return rc;
-  AttnArgs args{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows};
+  AttnArgs args{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows,
+                drop_thresh, drop_scale, seed};
   const int items = B * nh * args.q_tiles;
   ICKA_CUDA(cudaFuncSetAttribute(cross_attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int grid = items < h->sm_count ? items : h->sm_count;

@@ -7,8 +7,15 @@
 // All of them are HBM / L2 bound streaming passes except the attention backward, which recomputes the
 // probabilities from Q, K, V (nothing but Q and K|V is saved by the forward).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
+
+struct DropArgs {   // attention-probability dropout (CMIM:616); thresh == 0: off
+  uint32_t thresh;
+  float scale;
+  uint64_t seed;
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -229,7 +236,7 @@ template <typename T>
 __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
     const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, const T* __restrict__ v, int64_t ldkv,
     const float* __restrict__ mask_add, const T* __restrict__ dctx, int64_t ldc, T* __restrict__ dq, int64_t lddq,
-    T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv, int Sq, int Skv, int TQ) {
+    T* __restrict__ dk, T* __restrict__ dv, int64_t lddkv, int Sq, int Skv, int TQ, DropArgs drop) {
   extern __shared__ __align__(16) float sm[];
   float* Ks = sm;                              // [Skv][64]
   float* Vs = Ks + (size_t)Skv * kD;           // [Skv][64]
@@ -310,7 +317,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
       }
       const float inv = 1.0f / l;
       float delta = 0.0f;
+      const uint64_t drow = ((uint64_t)b * gridDim.x + h) * (uint64_t)Sq + (uint64_t)row;
+      uint32_t keep = 0xfu;
       for (int j = 0; j < Skv; ++j) {
+        if (drop.thresh && (j & 3) == 0)
+          keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
         const float4* vr = reinterpret_cast<const float4*>(Vs + j * kD);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -321,7 +332,9 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
           s2 = fmaf(dor[4 * c + 2], vv.z, s2);
           s3 = fmaf(dor[4 * c + 3], vv.w, s3);
         }
-        const float dp = (s0 + s1) + (s2 + s3);
+        // with dropout the forward used P' = P keep/(1-p): dP = dP' keep/(1-p), and delta = sum P' dP' = sum P dP
+        const float ks = drop.thresh ? ((keep >> (j & 3) & 1u) ? drop.scale : 0.0f) : 1.0f;
+        const float dp = ((s0 + s1) + (s2 + s3)) * ks;
         const float p = prow[j] * inv;
         prow[j] = p;
         dsrow[j] = dp;
@@ -333,6 +346,11 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
       for (int j = 0; j < Skv; ++j) {
         const float ds = prow[j] * (dsrow[j] - delta) * 0.125f;
         dsrow[j] = ds;
+        if (drop.thresh) {   // phase 2 forms dV from the DROPPED probabilities
+          if ((j & 3) == 0)
+            keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
+          prow[j] = (keep >> (j & 3) & 1u) ? prow[j] * drop.scale : 0.0f;
+        }
         const float4* kr = reinterpret_cast<const float4*>(Ks + j * kD);
 #pragma unroll
         for (int c = 0; c < kD / 4; ++c) {
@@ -436,7 +454,7 @@ __global__ void __launch_bounds__(kMmaThreads) cross_attn_bwd_mma_kernel(
     const __nv_bfloat16* __restrict__ v, int64_t ldkv, const float* __restrict__ mask_add,
     const __nv_bfloat16* __restrict__ o, int64_t ldo, const __nv_bfloat16* __restrict__ dctx, int64_t ldc,
     __nv_bfloat16* __restrict__ dq, int64_t lddq, __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
-    int64_t lddkv, int Sq, int Skv) {
+    int64_t lddkv, int Sq, int Skv, DropArgs drop) {
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_dyn);   // [128][72]
   __nv_bfloat16* dOs = Qs + kRowsQ * kPitch;                          // [128][72]
@@ -594,10 +612,23 @@ __global__ void __launch_bounds__(kMmaThreads) cross_attn_bwd_mma_kernel(
       ldmatrix_x4(vf, Vs + (j * 8 + (lane & 7)) * kPitch + 32 + (lane >> 3) * 8);
       mma_bf16_16816(dp, dof[2], vf[0], vf[1]);
       mma_bf16_16816(dp, dof[3], vf[2], vf[3]);
-      const float p0 = fast_exp2(sacc[j][0] - m0) * il0, p1 = fast_exp2(sacc[j][1] - m0) * il0;
-      const float p2 = fast_exp2(sacc[j][2] - m1) * il1, p3 = fast_exp2(sacc[j][3] - m1) * il1;
-      const float d0 = p0 * (dp[0] - delta0) * 0.125f, d1 = p1 * (dp[1] - delta0) * 0.125f;
-      const float d2 = p2 * (dp[2] - delta1) * 0.125f, d3 = p3 * (dp[3] - delta1) * 0.125f;
+      float p0 = fast_exp2(sacc[j][0] - m0) * il0, p1 = fast_exp2(sacc[j][1] - m0) * il0;
+      float p2 = fast_exp2(sacc[j][2] - m1) * il1, p3 = fast_exp2(sacc[j][3] - m1) * il1;
+      float k0 = 1.0f, k1 = 1.0f, k2 = 1.0f, k3 = 1.0f;   // keep / (1 - p) of this thread's four probabilities
+      if (drop.thresh) {
+        const int key = key0 + j * 8 + 2 * t;
+        const uint64_t drow = ((uint64_t)b * gridDim.x + h) * (uint64_t)Sq + (uint64_t)(warp * 16 + g);
+        const uint32_t b0 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t b1 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow + 8, Skv, key), drop.thresh) >> (key & 3);
+        k0 = (b0 & 1u) ? drop.scale : 0.0f;
+        k1 = (b0 & 2u) ? drop.scale : 0.0f;
+        k2 = (b1 & 1u) ? drop.scale : 0.0f;
+        k3 = (b1 & 2u) ? drop.scale : 0.0f;
+      }
+      // dP = dP' keep/(1-p) (dp[] is the gradient w.r.t. the dropped probabilities); dV below uses P' = P keep/(1-p)
+      const float d0 = p0 * (dp[0] * k0 - delta0) * 0.125f, d1 = p1 * (dp[1] * k1 - delta0) * 0.125f;
+      const float d2 = p2 * (dp[2] * k2 - delta1) * 0.125f, d3 = p3 * (dp[3] * k3 - delta1) * 0.125f;
+      p0 *= k0; p1 *= k1; p2 *= k2; p3 *= k3;
       dsf[j][0] = pack_bf16x2(d0, d1);
       dsf[j][1] = pack_bf16x2(d2, d3);
       const int r0 = warp * 16 + g, col = j * 8 + 2 * t;
@@ -827,7 +858,18 @@ extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t l
                                         int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx,
                                         const void* dctx, int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv,
                                         int64_t lddkv, int dtype, int B, int Sq, int Skv, int nh, int d, void* stream) {
+  return icka_cross_attn_core_bwd_drop(h, q, ldq, k, v, ldkv, mask_add, ctx, ldctx, dctx, ldc, dq, lddq, dk, dv, lddkv,
+                                       dtype, B, Sq, Skv, nh, d, 0.0f, 0, stream);
+}
+
+extern "C" int icka_cross_attn_core_bwd_drop(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                                             int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx,
+                                             const void* dctx, int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv,
+                                             int64_t lddkv, int dtype, int B, int Sq, int Skv, int nh, int d,
+                                             float p_drop, uint64_t seed, void* stream) {
   ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "cross_attn_bwd: dropout p=%f outside [0, 1)", (double)p_drop);
+  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed};
   ICKA_REQUIRE(q && k && v && dctx && dq && dk && dv, "cross_attn_bwd: null pointer");
   ICKA_REQUIRE(B >= 0 && Sq >= 1 && Skv >= 1 && nh >= 1, "cross_attn_bwd: bad shape");
   ICKA_REQUIRE(d == kD, "cross_attn_bwd: head dim %d != 64", d);
@@ -847,7 +889,7 @@ extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t l
     cross_attn_bwd_mma_kernel<<<dim3(nh, B), kMmaThreads, smem_mma, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const T*>(q), ldq, static_cast<const T*>(k), static_cast<const T*>(v), ldkv, mask_add,
         static_cast<const T*>(ctx), ldctx, static_cast<const T*>(dctx), ldc, static_cast<T*>(dq), lddq,
-        static_cast<T*>(dk), static_cast<T*>(dv), lddkv, Sq, Skv);
+        static_cast<T*>(dk), static_cast<T*>(dv), lddkv, Sq, Skv, drop);
     ICKA_LAUNCHED(h);
     return ICKA_OK;
   }
@@ -868,13 +910,13 @@ extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t l
     cross_attn_bwd_kernel<T><<<grid, kAttnBwdThreads, smem, st>>>(
         static_cast<const T*>(q), ldq, static_cast<const T*>(k), static_cast<const T*>(v), ldkv, mask_add,
         static_cast<const T*>(dctx), ldc, static_cast<T*>(dq), lddq, static_cast<T*>(dk), static_cast<T*>(dv), lddkv, Sq,
-        Skv, TQ);
+        Skv, TQ, drop);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(cross_attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cross_attn_bwd_kernel<float><<<grid, kAttnBwdThreads, smem, st>>>(
         static_cast<const float*>(q), ldq, static_cast<const float*>(k), static_cast<const float*>(v), ldkv, mask_add,
         static_cast<const float*>(dctx), ldc, static_cast<float*>(dq), lddq, static_cast<float*>(dk),
-        static_cast<float*>(dv), lddkv, Sq, Skv, TQ);
+        static_cast<float*>(dv), lddkv, Sq, Skv, TQ, drop);
   }
   ICKA_LAUNCHED(h);
   return ICKA_OK;

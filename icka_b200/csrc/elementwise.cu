@@ -1,6 +1,7 @@
 // HBM-bound helpers of the fusion path: operand casts, region-grid relayout, LayerNorm, gate + blend.
 // All loops are 128-bit vectorised and coalesced; none of these kernels has data reuse beyond a row.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -345,6 +346,67 @@ __global__ void __launch_bounds__(256) ln_blend_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hidden-state dropout (CMIM:563, 534: `dropout(dense(h)) + input`), forward and backward share one kernel:
+//   y = x * keep * 1/(1-p) (+ residual)      keep = Philox(seed, site, element index) < (1-p) 2^32
+// x / y in fp32 or bf16 (the forward reads the fp32 dense output and writes the fp32 pre-LayerNorm rows; the
+// backward turns the fp32 upstream gradient into the masked GEMM operand).  n must be a multiple of 4.
+// ------------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) dropout_kernel(const TI* __restrict__ x, const float* __restrict__ residual,
+                                                      TO* __restrict__ y, int64_t n4, uint32_t thresh, float scale,
+                                                      uint64_t seed, uint32_t site) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+    float v[4];
+    if constexpr (sizeof(TI) == 2) {
+      const uint2 u = reinterpret_cast<const uint2*>(x)[g];
+      v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+      v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    } else {
+      const float4 f = reinterpret_cast<const float4*>(x)[g];
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+    const uint32_t keep = icka_rng::keep_bits4(seed, site, (uint64_t)g, thresh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (keep >> j & 1u) ? v[j] * scale : 0.0f;
+    if (residual) {
+      const float4 r = reinterpret_cast<const float4*>(residual)[g];
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    if constexpr (sizeof(TO) == 2) {
+      uint2 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      reinterpret_cast<uint2*>(y)[g] = o;
+    } else {
+      reinterpret_cast<float4*>(y)[g] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// Test helper: the keep mask itself (u8 0/1).  kind 0: hidden site over n elements (n % 4 == 0);
+// kind 1: attention site, [rows, Skv] with rows = B*nh*Sq.
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* __restrict__ m, int64_t rows, int Skv, int kind,
+                                                           uint32_t thresh, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (kind == 0) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < rows / 4; g += stride) {
+      const uint32_t keep = icka_rng::keep_bits4(seed, icka_rng::kSiteHidden, (uint64_t)g, thresh);
+      for (int j = 0; j < 4; ++j) m[4 * g + j] = (keep >> j) & 1u;
+    }
+  } else {
+    const int gpr = (Skv + 3) / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * gpr; i += stride) {
+      const int64_t row = i / gpr;
+      const int k4 = (int)(i % gpr);
+      const uint32_t keep = icka_rng::keep_bits4(seed, icka_rng::kSiteAttention, icka_rng::attn_group((uint64_t)row, Skv, 4 * k4), thresh);
+      for (int j = 0; j < 4; ++j)
+        if (4 * k4 + j < Skv) m[row * Skv + 4 * k4 + j] = (keep >> j) & 1u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Additive attention mask (CMIM:962-965, 976-977): out[b][j] = (1 - mask[b][j]) * -10000
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mask_additive_kernel(const int64_t* __restrict__ mask, int64_t ld,
@@ -472,6 +534,41 @@ extern "C" int icka_ln_gate_blend_fwd(icka_handle* h, const float* pre, const fl
   const int M = B * S;
   ln_blend_kernel<<<(M + 7) / 8, 256, 0, st>>>(pre, ln2_w, ln2_b, ln2_eps, tok, gate_out, out, fused_f32,
                                                static_cast<__nv_bfloat16*>(fused_bf16), M, S, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_dropout_fwd(icka_handle* h, const void* x, int x_dtype, const float* residual, void* y, int y_dtype,
+                                int64_t n, float p_drop, uint64_t seed, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(x && y && n >= 0 && n % 4 == 0, "dropout: bad arguments (n must be a multiple of 4)");
+  ICKA_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "dropout: p=%f outside [0, 1)", (double)p_drop);
+  ICKA_REQUIRE((x_dtype == ICKA_F32 || x_dtype == ICKA_BF16) && (y_dtype == ICKA_F32 || y_dtype == ICKA_BF16), "dropout: bad dtype");
+  ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(y, 16) && icka_aligned(residual, 16), "dropout: pointers must be 16-byte aligned");
+  if (n == 0) return ICKA_OK;
+  const int64_t n4 = n / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > (int64_t)h->sm_count * 8) blocks = (int64_t)h->sm_count * 8;
+  const uint32_t th = icka_rng::keep_threshold(p_drop);
+  const float sc = 1.0f / (1.0f - p_drop);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  using B16 = __nv_bfloat16;
+#define ICKA_DROP(TI, TO) dropout_kernel<TI, TO><<<(int)blocks, 256, 0, st>>>(static_cast<const TI*>(x), residual, static_cast<TO*>(y), n4, th, sc, seed, icka_rng::kSiteHidden)
+  if (x_dtype == ICKA_F32) { if (y_dtype == ICKA_F32) ICKA_DROP(float, float); else ICKA_DROP(float, B16); }
+  else                     { if (y_dtype == ICKA_F32) ICKA_DROP(B16, float);   else ICKA_DROP(B16, B16); }
+#undef ICKA_DROP
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_dropout_mask(icka_handle* h, uint8_t* mask, int64_t rows, int Skv, int kind, float p_drop,
+                                 uint64_t seed, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(mask && rows >= 0 && (kind == 0 || (kind == 1 && Skv >= 1)), "dropout_mask: bad arguments");
+  ICKA_REQUIRE(kind != 0 || rows % 4 == 0, "dropout_mask: element count must be a multiple of 4");
+  if (rows == 0) return ICKA_OK;
+  dropout_mask_kernel<<<h->sm_count * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(mask, rows, Skv, kind,
+                                                                                      icka_rng::keep_threshold(p_drop), seed);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -22,8 +22,9 @@ sequence of C-ABI kernel launches (icka_b200.ops).  Two precision modes (``set_p
 Training: when autograd is recording (``torch.is_grad_enabled()``), ``BertCrossAttentionLayer``,
 ``BertCrossEncoder``, ``CrossModalFusion`` and ``CRF.forward`` build their graph out of the nodes in
 ``icka_b200.autograd`` (kernel-backed forward and backward); the small building blocks below them
-(``BertSelfOutput`` ... called on their own) stay forward-only.  Dropout is not implemented: it must be
-inactive (eval mode or p = 0), like the reference's dev/test calls (My_cross_attention.py:872, 1047).
+(``BertSelfOutput`` ... called on their own) stay forward-only.  Dropout (attention probabilities CMIM:616,
+dense outputs CMIM:563 / 534) is applied on that recording path when the module is in training mode: a
+per-call seed expands into Philox keep-masks inside the kernels and backward regenerates them.
 """
 from __future__ import annotations
 
@@ -100,10 +101,14 @@ def _mask2d(mask: Optional[torch.Tensor], B: int, Skv: int) -> Optional[torch.Te
     return mask.reshape(B, Skv).float().contiguous()
 
 
-def _check_inference(module: nn.Module, *ps: float) -> None:
-    if module.training and any(p > 0 for p in ps):
-        raise NotImplementedError('icka_b200 has no dropout kernels: call .eval() or build the config with '
-                                  'hidden_dropout_prob = attention_probs_dropout_prob = 0')
+def _check_inference(module: nn.Module, *ps: float, graph_capable: bool = False) -> None:
+    """Dropout (CMIM:616, 563, 534) lives in the autograd-recording path only (Philox masks regenerated in backward).
+    A module in training mode with p > 0 must therefore be one of the graph-capable ones (cross layer / encoder /
+    CrossModalFusion) called with autograd enabled; the small forward-only blocks refuse instead of silently
+    skipping dropout."""
+    if module.training and any(p > 0 for p in ps) and not (graph_capable and torch.is_grad_enabled()):
+        raise NotImplementedError('dropout is applied on the autograd-recording path of BertCrossAttentionLayer / '
+                                  'BertCrossEncoder / CrossModalFusion only: call .eval() for forward-only use')
 
 
 def _recording(*tensors, module: Optional[nn.Module] = None) -> bool:
@@ -333,7 +338,15 @@ class BertCrossAttentionLayer(nn.Module):
         if y32 is None:
             raise RuntimeError('recording pass needs the fp32 key/value states (y32)')
         wkv, bkv = att._kv_operands()
-        meta = (B, Sq, Skv, att.num_attention_heads, att.attention_head_size, so.LayerNorm.variance_epsilon)
+        p_attn = att.dropout.p if self.training else 0.0
+        p_hid = so.dropout.p if self.training else 0.0
+        if self.training and so.dropout.p != out.dropout.p:
+            raise RuntimeError('the two hidden dropouts of a cross layer must share hidden_dropout_prob')
+        # one host-side draw per call (torch's CPU generator: reproducible under torch.manual_seed); the kernels expand
+        # it into per-element Philox masks and backward regenerates them from the same number
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if (p_attn > 0 or p_hid > 0) else 0
+        meta = (B, Sq, Skv, att.num_attention_heads, att.attention_head_size, so.LayerNorm.variance_epsilon,
+                float(p_attn), float(p_hid), seed)
         o32, o16 = CrossLayerFn.apply(
             x32, y32, x_lp.detach(), y_lp.detach(), mask2d, meta,
             att.query.weight, att.query.bias, att.key.weight, att.key.bias, att.value.weight, att.value.bias,
@@ -349,7 +362,7 @@ class BertCrossAttentionLayer(nn.Module):
         return (self.attention.self.dropout.p, self.attention.output.dropout.p, self.output.dropout.p)
 
     def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask):
-        _check_inference(self, *self._dropouts())
+        _check_inference(self, *self._dropouts(), graph_capable=True)
         B, Sq, H = s1_hidden_states.shape
         Skv = s2_hidden_states.shape[1]
         x32, y32 = _rows(s1_hidden_states), _rows(s2_hidden_states)
@@ -381,7 +394,7 @@ class BertCrossEncoder(nn.Module):
 
     def forward(self, s1_hidden_states, s2_hidden_states, s2_attention_mask, output_all_encoded_layers=True):
         for l in self.layer:
-            _check_inference(l, *l._dropouts())
+            _check_inference(l, *l._dropouts(), graph_capable=True)
         B, Sq, H = s1_hidden_states.shape
         Skv = s2_hidden_states.shape[1]
         x32, y32 = _rows(s1_hidden_states), _rows(s2_hidden_states)
@@ -435,7 +448,7 @@ class CrossModalFusion(nn.Module):
         Returns (result [B,S,H], clip_features [B,1,H]) -- CMIM:1036 and the loop result of CMIM:984-989."""
         for enc in (self.txt2img_attention, *self.cls_layer_Y):
             for l in enc.layer:
-                _check_inference(l, *l._dropouts())
+                _check_inference(l, *l._dropouts(), graph_capable=True)
         B, S, H = sequence_output.shape
         grid = visual_embeds_att.float().contiguous()
         R = grid.numel() // (B * grid.shape[1])

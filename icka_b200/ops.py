@@ -219,7 +219,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: f
 
 def cross_attn_core_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add: Optional[torch.Tensor],
                         dctx: torch.Tensor, B: int, Sq: int, Skv: int, nh: int, d: int,
-                        ctx: Optional[torch.Tensor] = None):
+                        ctx: Optional[torch.Tensor] = None, p_drop: float = 0.0, seed: int = 0):
     """Returns (dq [B*Sq, nh*d], dkv [B*Skv, 2*nh*d]) in the dtype of q.  ``ctx`` = the forward output
     (enables the tensor-core kernel for bf16)."""
     if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype or dctx.dtype != q.dtype:
@@ -233,10 +233,11 @@ def cross_attn_core_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_
     dk, dv = dkv[:, :H], dkv[:, H:]
     if ctx is not None and (ctx.dtype != q.dtype or ctx.stride(1) != 1):
         raise RuntimeError('cross_attn_core_bwd: bad ctx')
-    _lib.check(lib.icka_cross_attn_core_bwd(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+    _lib.check(lib.icka_cross_attn_core_bwd_drop(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
                                             _p(mask_add), _p(ctx), ctx.stride(0) if ctx is not None else 0,
                                             dctx.data_ptr(), dctx.stride(0), dq.data_ptr(), H,
-                                            dk.data_ptr(), dv.data_ptr(), 2 * H, _DT[q.dtype], B, Sq, Skv, nh, d, st),
+                                            dk.data_ptr(), dv.data_ptr(), 2 * H, _DT[q.dtype], B, Sq, Skv, nh, d,
+                                            float(p_drop), int(seed), st),
                'icka_cross_attn_core_bwd')
     return dq, dkv
 
@@ -285,8 +286,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def cross_attn_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add: Optional[torch.Tensor], B: int,
-                    Sq: int, Skv: int, nh: int, d: int) -> torch.Tensor:
-    """q [B*Sq, nh*d], k/v [B*Skv, nh*d] row-pitched views (k, v may be halves of one [K|V] buffer)."""
+                    Sq: int, Skv: int, nh: int, d: int, p_drop: float = 0.0, seed: int = 0) -> torch.Tensor:
+    """q [B*Sq, nh*d], k/v [B*Skv, nh*d] row-pitched views (k, v may be halves of one [K|V] buffer).
+    ``p_drop`` > 0 (training): dropout on the probabilities with the Philox mask of ``seed``."""
     if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype:
         raise RuntimeError('cross_attn_core: q/k/v must share dtype fp32 or bf16')
     if q.stride(1) != 1 or k.stride(1) != 1 or v.stride(1) != 1 or k.stride(0) != v.stride(0):
@@ -297,9 +299,9 @@ def cross_attn_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask_add:
             raise RuntimeError(f'cross_attn_core: mask_add must be [B, Skv], got {tuple(mask_add.shape)}')
     lib, h, st = _ctx(q)
     ctx = torch.empty(B * Sq, nh * d, dtype=q.dtype, device=q.device)
-    _lib.check(lib.icka_cross_attn_core_fwd(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
-                                            _p(mask_add), ctx.data_ptr(), ctx.stride(0), _DT[q.dtype], B, Sq, Skv,
-                                            nh, d, st), 'icka_cross_attn_core_fwd')
+    _lib.check(lib.icka_cross_attn_core_fwd_drop(h, q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0),
+                                                 _p(mask_add), ctx.data_ptr(), ctx.stride(0), _DT[q.dtype], B, Sq, Skv,
+                                                 nh, d, float(p_drop), int(seed), st), 'icka_cross_attn_core_fwd')
     return ctx
 
 
@@ -413,3 +415,33 @@ def crf_llh_bwd(emissions: torch.Tensor, tags_i64: torch.Tensor, mask_u8: Option
                                     end.data_ptr(), trans.data_ptr(), w.data_ptr(), de.data_ptr(), d_start.data_ptr(),
                                     d_end.data_ptr(), d_trans.data_ptr(), B, S, T, st), 'icka_crf_llh_bwd')
     return de, d_start, d_end, d_trans
+
+
+def dropout(x: torch.Tensor, p_drop: float, seed: int, *, residual: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """y = x * keep / (1 - p) (+ residual); keep = Philox(seed, element index).  x fp32/bf16 contiguous, numel % 4 == 0."""
+    if x.dtype not in _DT or not x.is_contiguous():
+        raise RuntimeError('dropout: need a contiguous fp32/bf16 tensor')
+    out_dtype = out_dtype or x.dtype
+    if residual is not None:
+        _need(residual, torch.float32, 'dropout(residual)')
+        if residual.shape != x.shape:
+            raise RuntimeError('dropout: residual shape mismatch')
+    lib, h, st = _ctx(x)
+    y = torch.empty_like(x, dtype=out_dtype)
+    _lib.check(lib.icka_dropout_fwd(h, x.data_ptr(), _DT[x.dtype], _p(residual), y.data_ptr(), _DT[out_dtype], x.numel(),
+                                    float(p_drop), int(seed), st), 'icka_dropout_fwd')
+    return y
+
+
+def dropout_mask(shape, p_drop: float, seed: int, device, attention: bool = False) -> torch.Tensor:
+    """Test helper: the u8 keep mask the dropout kernels regenerate.  ``attention``: shape = (B, nh, Sq, Skv)."""
+    m = torch.empty(shape, dtype=torch.uint8, device=device)
+    d = m.device.index if m.device.index is not None else torch.cuda.current_device()
+    lib, h, st = _lib.load(), _lib.handle(d), torch.cuda.current_stream(d).cuda_stream
+    if attention:
+        rows, skv = m.numel() // shape[-1], shape[-1]
+        _lib.check(lib.icka_dropout_mask(h, m.data_ptr(), rows, skv, 1, float(p_drop), int(seed), st), 'icka_dropout_mask')
+    else:
+        _lib.check(lib.icka_dropout_mask(h, m.data_ptr(), m.numel(), 1, 0, float(p_drop), int(seed), st), 'icka_dropout_mask')
+    return m

@@ -89,6 +89,10 @@ def _work(name, args, kwargs):
         return name, 10.0 * B * nh * Sq * Skv * d, (3 * B * Sq * nh * d + 4 * B * Skv * nh * d) * es
     if name == 'gate_blend_bwd':
         return name, 0.0, args[0].numel() * 4 * (6 if kwargs.get('want_dtok', True) else 5)
+    if name == 'dropout':
+        x = args[0]
+        od = kwargs.get('out_dtype') or x.dtype
+        return name, 0.0, x.numel() * (_ESZ[x.dtype] + _ESZ[od] + (4 if kwargs.get('residual') is not None else 0))
     if name == 'crf_llh_bwd':
         B, S, T = args[0].shape
         return name, 0.0, B * (2 * S * T * 4 + S + S * 8)
@@ -98,7 +102,7 @@ def _work(name, args, kwargs):
 class KernelTimer:
     OPS = ('mask_additive', 'cast_bf16', 'region_rows', 'linear', 'linear_ln', 'layernorm', 'cross_attn_core', 'i2t_pool', 'gate_fold', 'gate_blend', 'ln_gate_blend',
            'viterbi', 'crf_llh', 'linear_dgrad', 'linear_wgrad', 'colsum', 'layernorm_bwd', 'cross_attn_core_bwd',
-           'gate_blend_bwd', 'gate_fold_bwd', 'crf_llh_bwd')
+           'gate_blend_bwd', 'gate_fold_bwd', 'crf_llh_bwd', 'dropout')
 
     def __init__(self):
         self.records = []

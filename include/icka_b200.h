@@ -140,6 +140,28 @@ int icka_cross_attn_core_fwd(icka_handle* h, const void* q, int64_t ldq, const v
                              int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
                              int B, int Sq, int Skv, int nh, int d, void* stream);
 
+/* Training-time variants with dropout on the attention probabilities (CMIM:616): P' = P * keep / (1 - p_drop)
+ * enters P.V, the softmax normaliser keeps the undropped sum.  keep = Philox4x32-10(seed, element) -- forward and
+ * backward regenerate the same mask from (seed, p_drop); p_drop = 0 is the plain kernel. */
+int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                                  int64_t ldkv, const float* mask_add, void* ctx, int64_t ldc, int dtype,
+                                  int B, int Sq, int Skv, int nh, int d, float p_drop, uint64_t seed, void* stream);
+int icka_cross_attn_core_bwd_drop(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
+                                  int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx,
+                                  const void* dctx, int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv,
+                                  int64_t lddkv, int dtype, int B, int Sq, int Skv, int nh, int d, float p_drop,
+                                  uint64_t seed, void* stream);
+
+/* Hidden-state dropout (CMIM:563, 534), forward and backward alike:  y = x * keep / (1 - p_drop) (+ residual)
+ * over n elements (n % 4 == 0); x / y fp32 or bf16, residual fp32 or NULL; keep = Philox(seed, element index). */
+int icka_dropout_fwd(icka_handle* h, const void* x, int x_dtype, const float* residual, void* y, int y_dtype,
+                     int64_t n, float p_drop, uint64_t seed, void* stream);
+
+/* Test helper: the keep mask (u8 0/1) the kernels above regenerate.  kind 0: hidden site, `rows` = element count;
+ * kind 1: attention site, mask [rows = B*nh*Sq, Skv]. */
+int icka_dropout_mask(icka_handle* h, uint8_t* mask, int64_t rows, int Skv, int kind, float p_drop, uint64_t seed,
+                      void* stream);
+
 /* Kernel choice of the bf16 attention core (process-wide tuning/testing knob): 0 = per shape (tcgen05 / TMEM
  * kernel for Skv <= 64, mma.sync kernel otherwise; default), 1 = always the mma.sync kernel. */
 int icka_set_attn_mode(int mode);

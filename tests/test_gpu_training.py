@@ -155,3 +155,58 @@ def test_encoder_module_api_records_a_graph():
     for k, v in enc.named_parameters():
         ref_k = p[k.replace('key.bias', 'query.bias')].grad      # d(key.bias) == 0 in exact arithmetic
         assert float((v.grad.cpu() - p[k].grad).abs().max()) <= 2e-4 * float(ref_k.abs().max()) + 1e-7, k
+
+
+@pytest.mark.parametrize('Sq,Skv', [(128, 49), (1, 128)], ids=['text2image', 'image2text'])
+@pytest.mark.parametrize('mode,tol', [('fp32', 3e-4), ('bf16', 5e-2)])
+def test_cross_layer_with_dropout_replays_the_same_philox_masks(mode, tol, Sq, Skv, monkeypatch):
+    """Training-mode layer with p = 0.1 on all three dropout sites: the keep masks the kernels draw are exported
+    (icka_dropout_mask) and replayed in the oracle, so forward and every gradient must match as without dropout."""
+    from icka_b200 import ops
+    B, H, nh, I = 3 if Sq > 1 else 40, 768, 12, 3072
+    cfg = icka_b200.FusionConfig(hidden_size=H, num_attention_heads=nh, intermediate_size=I, layer_norm_eps=1e-12,
+                                 hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+    torch.manual_seed(5)
+    layer = icka_b200.BertCrossAttentionLayer(cfg).to(DEV).train()
+    g = torch.Generator().manual_seed(6)
+    s1 = torch.nn.functional.layer_norm(torch.randn(B, Sq, H, generator=g), (H,))
+    s2 = torch.randn(B, Skv, H, generator=g)
+    m01 = (torch.rand(B, Skv, generator=g) > 0.2).long()
+    ext = fusion_ref.additive_mask(m01, torch.float32)
+    wgt = torch.randn(B, Sq, H, generator=g) / (Sq * H) ** 0.5
+    seeds = []
+    real_randint = torch.randint
+
+    def spy(*a, **k):
+        out = real_randint(*a, **k)
+        seeds.append(int(out.item()))
+        return out
+    monkeypatch.setattr(torch, 'randint', spy)
+    icka_b200.set_precision(mode)
+    try:
+        a, b = s1.to(DEV).requires_grad_(True), s2.to(DEV).requires_grad_(True)
+        out = layer(a, b, ext.to(DEV))
+        (out * wgt.to(DEV)).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        icka_b200.set_precision('bf16')
+    monkeypatch.undo()
+    assert len(seeds) == 1
+    seed = seeds[0]
+    drop = dict(p_attn=0.1, p_hid=0.1,
+                attn=ops.dropout_mask((B, nh, Sq, Skv), 0.1, 3 * seed, DEV, attention=True).cpu(),
+                h1=ops.dropout_mask((B, Sq, H), 0.1, 3 * seed + 1, DEV).cpu(),
+                h2=ops.dropout_mask((B, Sq, H), 0.1, 3 * seed + 2, DEV).cpu())
+    for k in ('attn', 'h1', 'h2'):
+        assert 0.87 <= float(drop[k].float().mean()) <= 0.93, k          # keep rate 1 - p
+    p = {'l.' + k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    ar, br = s1.clone().requires_grad_(True), s2.clone().requires_grad_(True)
+    ref = fusion_ref.cross_layer(ar, br, ext, p, 'l', nh, 1e-12, drop=drop)
+    (ref * wgt).sum().backward()
+    ftol = 1e-5 if mode == 'fp32' else 3e-2
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= ftol * max(1.0, float(ref.abs().max()))
+    assert float((a.grad.cpu() - ar.grad).abs().max()) <= tol * float(ar.grad.abs().max())
+    assert float((b.grad.cpu() - br.grad).abs().max()) <= tol * float(br.grad.abs().max())
+    for k, v in layer.named_parameters():
+        ref_k = p['l.' + k.replace('key.bias', 'query.bias')].grad      # d(key.bias) == 0 in exact arithmetic
+        assert float((v.grad.cpu() - p['l.' + k].grad).abs().max()) <= tol * float(ref_k.abs().max()) + 1e-7, k

@@ -47,10 +47,15 @@ def test_hidden_size_not_multiple_of_heads():
         icka_b200.BertCoAttention(icka_b200.FusionConfig(hidden_size=100, num_attention_heads=12))
 
 
-def test_training_mode_is_refused():
+def test_dropout_needs_the_recording_path():
+    """Training mode with p > 0: the graph-capable modules apply dropout only when autograd records (the masks are
+    regenerated in backward); forward-only use and the small forward-only blocks refuse rather than skip it."""
     enc = icka_b200.BertCrossEncoder(cfg(), 1).train()
-    with pytest.raises(NotImplementedError):
+    with torch.no_grad(), pytest.raises(NotImplementedError):
         enc(torch.zeros(1, 4, 128), torch.zeros(1, 3, 128), torch.zeros(1, 1, 1, 3))
+    so = icka_b200.BertSelfOutput(cfg()).train()
+    with pytest.raises(NotImplementedError):
+        so(torch.zeros(1, 4, 128), torch.zeros(1, 4, 128))
 
 
 def test_precision_switch():
