@@ -370,7 +370,7 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st);
 
 // 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel
-static int g_attn_mode = 0;
+int g_attn_mode = 0;   // shared with i2t_pool.cu
 extern "C" int icka_set_attn_mode(int mode) {
   if (mode < 0 || mode > 1) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..1", mode);
   g_attn_mode = mode;

@@ -244,6 +244,10 @@ int launch_pool(icka_handle* h, const void* U, const void* X, const float* mask_
 
 }  // namespace
 
+int icka_i2t_pool_tcgen05_launch(icka_handle* h, const void* U, const void* X, const float* mask_add, void* xbar, int B,
+                                 int S, int H, int nh, cudaStream_t st);
+extern int g_attn_mode;   // attention.cu: 0 = tcgen05 kernels where they apply, 1 = mma.sync kernels only
+
 extern "C" int icka_i2t_pool_fwd(icka_handle* h, const void* U, const void* X, const float* mask_add, void* xbar,
                                  int B, int S, int H, int nh, void* stream) {
   ICKA_CHECK_HANDLE(h);
@@ -252,6 +256,10 @@ extern "C" int icka_i2t_pool_fwd(icka_handle* h, const void* U, const void* X, c
   ICKA_REQUIRE(icka_aligned(U, 16) && icka_aligned(X, 16) && icka_aligned(xbar, 16), "i2t_pool: pointers must be 16-byte aligned");
   if (B == 0) return ICKA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_attn_mode == 0) {
+    const int rc = icka_i2t_pool_tcgen05_launch(h, U, X, mask_add, xbar, B, S, H, nh, st);
+    if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope
+  }
   if (H == 768) return launch_pool<768>(h, U, X, mask_add, xbar, B, S, nh, st);
   if (H == 1024) return launch_pool<1024>(h, U, X, mask_add, xbar, B, S, nh, st);
   ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "i2t_pool: hidden size %d not instantiated (768 and 1024 are)", H);

@@ -162,8 +162,9 @@ int icka_dropout_fwd(icka_handle* h, const void* x, int x_dtype, const float* re
 int icka_dropout_mask(icka_handle* h, uint8_t* mask, int64_t rows, int Skv, int kind, float p_drop, uint64_t seed,
                       void* stream);
 
-/* Kernel choice of the bf16 attention core (process-wide tuning/testing knob): 0 = per shape (tcgen05 / TMEM
- * kernel for Skv <= 64, mma.sync kernel otherwise; default), 1 = always the mma.sync kernel. */
+/* Kernel choice of the bf16 attention core and of icka_i2t_pool_fwd (process-wide tuning/testing knob): 0 = per
+ * shape (tcgen05 / TMEM kernels for Skv <= 64 resp. S <= 128, mma.sync kernels otherwise; default), 1 = always the
+ * mma.sync kernels. */
 int icka_set_attn_mode(int mode);
 
 /* Backward of icka_cross_attn_core_fwd: probabilities are recomputed from q, k, v (same layouts as the

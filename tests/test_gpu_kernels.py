@@ -134,13 +134,21 @@ def test_gate_fold_and_blend():
     assert rel(out.cpu(), g * tok + (1 - g) * fused) <= 2e-6
 
 
-@pytest.mark.parametrize('B,S,H,nh', [(3, 128, 768, 12), (2, 256, 768, 12), (2, 40, 1024, 16), (1, 7, 768, 12)])
-def test_i2t_pool(B, S, H, nh):
+@pytest.mark.parametrize('B,S,H,nh', [(3, 128, 768, 12), (2, 256, 768, 12), (2, 40, 1024, 16), (1, 7, 768, 12), (300, 128, 768, 12),
+                                      (5, 100, 768, 16)])
+@pytest.mark.parametrize('attn_mode', [0, 1], ids=['tcgen05', 'mma_sync'])
+def test_i2t_pool(B, S, H, nh, attn_mode):
+    from icka_b200 import _lib
     u = (rnd(B, nh * H, seed=1) / math.sqrt(H)).bfloat16()
     x = rnd(B * S, H, seed=2).bfloat16()
     mask = torch.zeros(B, S); mask[:, (S * 2) // 3:] = -10000.0; mask[0] = 0
     uf, xf = u.float().view(B, nh, H), x.float().view(B, S, H)
     sc = torch.einsum('bhd,bsd->bhs', uf, xf) / 8.0 + mask.view(B, 1, S)
     want = torch.einsum('bhs,bsd->bhd', torch.softmax(sc, -1), xf).reshape(B, nh * H)
-    got = ops.i2t_pool(u.to(DEV), x.to(DEV), mask.to(DEV), B, S, H, nh).float().cpu()
+    _lib.check(_lib.load().icka_set_attn_mode(attn_mode), 'icka_set_attn_mode')
+    try:
+        got = ops.i2t_pool(u.to(DEV), x.to(DEV), mask.to(DEV), B, S, H, nh).float().cpu()
+        torch.cuda.synchronize()
+    finally:
+        _lib.load().icka_set_attn_mode(0)
     assert rel(got, want) <= 2e-2

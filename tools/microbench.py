@@ -85,6 +85,8 @@ def main(B=1024, mode=0):
     tot += mem('gate blend', lambda: ops.gate_blend(fused, tok, g1, g1, 1e-5, wf, cf), B * S * H * 12)
     mem('ln + gate blend (fused)', lambda: ops.ln_gate_blend(fused, g1, g1, 1e-12, tok, g1, g1, 1e-5, wf, cf),
         B * S * H * 14)
+    u = (torch.randn(B, 12 * H, device=DEV) / math.sqrt(H)).bfloat16()
+    mem('i2t pool', lambda: ops.i2t_pool(u, xb, None, B, S, H, 12), B * (S * H * 2 + 2 * 12 * H * 2))
     print(f'sum of t2i-side kernels: {tot*1e3:.3f} ms for B={B} -> {B/tot:,.0f} sentences/s (excl. i2t)')
 
     sh = synth.STD
