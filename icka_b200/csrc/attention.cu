@@ -369,10 +369,11 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st);
 
-// 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel
-int g_attn_mode = 0;   // shared with i2t_pool.cu
+// 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel,
+// 2 = like 0 plus the wide tcgen05 variant for 64 < Skv <= 224
+int g_attn_mode = 0;   // shared with i2t_pool.cu and attention_sm100.cu
 extern "C" int icka_set_attn_mode(int mode) {
-  if (mode < 0 || mode > 1) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..1", mode);
+  if (mode < 0 || mode > 2) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..2", mode);
   g_attn_mode = mode;
   return ICKA_OK;
 }
@@ -404,7 +405,7 @@ extern "C" int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int6
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "cross_attn: Skv=%d needs %zu B shared memory (max %zu)", Skv, smem, h->smem_optin);
   dim3 grid((Sq + kRows - 1) / kRows, nh, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == ICKA_BF16 && g_attn_mode == 0) {
+  if (dtype == ICKA_BF16 && g_attn_mode != 1) {
     const int rc = icka_attn_tcgen05_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, B, Sq, Skv, nh, drop.thresh,
                                             drop.scale, drop.seed, st);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope

@@ -1,4 +1,5 @@
-// Cross-attention core on tcgen05 / TMEM for sm_100a (bf16, Skv <= 64: the 49-region text->image attention).
+// Cross-attention core on tcgen05 / TMEM for sm_100a (bf16; Skv <= 64: the 49-region text->image attention, and a
+// wide variant for Skv <= 224: the 196-region grid of the 448-px configuration).
 //
 // Same contract as cross_attn_mma_kernel (attention.cu; BertCoAttention, CMIM:598-623):
 //   P = softmax(Q_h K_h^T / 8 + mask),  ctx_h = P V_h,  heads merged in place.
@@ -285,6 +286,265 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Wide variant: 64 < Skv <= 224 keys (the 196-region grid of the 448-px configuration; 128-key problems).
+// Same structure with ONE {S, O} TMEM slot and one softmax group: S[128 x KEYS] is a single tcgen05.mma of
+// N = KEYS, the row softmax reads its TMEM row in 32-column pieces twice (max, then exp / sum / P), P is KEYS wide
+// (64-key K-major chunks), O = P V runs KEYS/16 k-steps over the in-place MN-major V tile.
+// ------------------------------------------------------------------------------------------------------------
+template <int KEYS>
+struct WideCfg {
+  static constexpr int kKVBytes = KEYS * 128;
+  static constexpr int kStageBytes = kQBytes + 2 * kKVBytes;
+  static constexpr int kStages = (KEYS <= 128) ? 3 : 2;
+  static constexpr int kPChunks = (KEYS + 63) / 64;
+  static constexpr int kPBytes = kPChunks * kRows * 128;
+  static constexpr int kThreads = 192;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kPBytes + 2 * KEYS * sizeof(float) + 1024 + 256;
+};
+
+template <int KEYS>
+__global__ void __launch_bounds__(WideCfg<KEYS>::kThreads, 1)
+cross_attn_tcgen05_wide_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                               const __grid_constant__ CUtensorMap tmap_v, const AttnArgs args) {
+  using Cfg = WideCfg<KEYS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint8_t* p_buf = smem + (size_t)Cfg::kStages * Cfg::kStageBytes;
+  float* mask_s = reinterpret_cast<float*>(p_buf + Cfg::kPBytes);                  // 2 buffers x [KEYS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 2 * KEYS);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* s_full = bars + 2 * Cfg::kStages;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_full = p_full + 1;
+  uint64_t* o_free = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+  constexpr uint32_t kOCol = 256;              // S at columns [0, KEYS), O at [256, 320)
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int items = args.B * args.nh * args.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+        const int h = bh % args.nh, b = bh / args.nh;
+        uint8_t* st = stage_base + (size_t)stage * Cfg::kStageBytes;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        tma_load_2d(st, &tmap_q, &full_bar[stage], h * kD, b * args.Sq + qt * kRows);
+        tma_load_2d(st + kQBytes, &tmap_k, &full_bar[stage], h * kD, b * args.Skv);
+        tma_load_2d(st + kQBytes + Cfg::kKVBytes, &tmap_v, &full_bar[stage], h * kD, b * args.Skv);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(kRows, KEYS);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(kRows, kD, false, true);
+      int stage = 0, prev_stage = 0;
+      uint32_t phase = 0;
+      int n = 0;
+      auto issue_pv = [&](int m, int st_idx) {
+        mbar_wait(p_full, m & 1);
+        if (m >= 1) mbar_wait(o_free, (m - 1) & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(p_buf);
+        const uint32_t v_addr = smem_u32(stage_base + (size_t)st_idx * Cfg::kStageBytes + kQBytes + Cfg::kKVBytes);
+#pragma unroll
+        for (int k = 0; k < KEYS / 16; ++k)
+          umma_bf16(tmem_base + kOCol, make_kmajor_sw128_desc(p_addr + (k >> 2) * (kRows * 128) + (k & 3) * 32),
+                    make_mnmajor_sw128_desc(v_addr + k * (16 * 128), Cfg::kKVBytes), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&empty_bar[st_idx]);
+        umma_commit(o_full);
+      };
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        mbar_wait(&full_bar[stage], phase);
+        if (n >= 1) issue_pv(n - 1, prev_stage);      // also guarantees S of item n-1 has been read (p_full)
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(stage_base + (size_t)stage * Cfg::kStageBytes);
+        const uint32_t k_addr = q_addr + kQBytes;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem_base, make_kmajor_sw128_desc(q_addr + k * 32), make_kmajor_sw128_desc(k_addr + k * 32), idesc_s,
+                    k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        prev_stage = stage;
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (n >= 1) issue_pv(n - 1, prev_stage);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int gtid = (warp - 2) * 32 + lane;
+    const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tmem_o = tmem_s + kOCol;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;
+    auto fetch_mask = [&](int item, float* dst) {
+      if (item < items) {
+        const int b = item / (args.q_tiles * args.nh);
+        for (int j = gtid; j < KEYS; j += 128)
+          dst[j] = (j < args.Skv) ? (args.mask_add ? args.mask_add[(size_t)b * args.Skv + j] * kLog2e : 0.0f) : -INFINITY;
+      }
+    };
+    fetch_mask((int)blockIdx.x, mask_s);
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const uint32_t par = n & 1;
+      const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+      const int h = bh % args.nh, b = bh / args.nh;
+      const float* mk = mask_s + (n & 1) * KEYS;
+      named_bar_sync(1, 128);
+      fetch_mask(it + (int)gridDim.x, mask_s + ((n & 1) ^ 1) * KEYS);
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      // ---- sweep 1: row maximum ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < KEYS; c0 += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tmem_s + (uint32_t)c0, sr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaf(__uint_as_float(sr[j]), kScale, mk[c0 + j]));
+      }
+      // ---- sweep 2: P = exp2(s - max) (bf16, dropped if training) into the K-major P tile; l = undropped row sum ----
+      float l = 0.0f;
+      const uint64_t drow = ((uint64_t)b * args.nh + h) * (uint64_t)args.Sq + (uint64_t)(qt * kRows + row);
+#pragma unroll 1
+      for (int c0 = 0; c0 < KEYS; c0 += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tmem_s + (uint32_t)c0, sr);
+        tmem_ld_wait();
+        uint8_t* prow = p_buf + (c0 >> 6) * (kRows * 128) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {      // 8 keys = one 16-byte chunk
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            p[j] = ex2(fmaf(__uint_as_float(sr[8 * c + j]), kScale, mk[c0 + 8 * c + j]) - mx);
+            l += p[j];
+          }
+          if (args.drop_thresh) {
+#pragma unroll
+            for (int g4 = 0; g4 < 2; ++g4) {
+              const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+                                                         icka_rng::attn_group(drow, args.Skv, c0 + 8 * c + 4 * g4), args.drop_thresh);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
+            }
+          }
+          uint4 u;
+          u.x = pack_bf16x2(p[0], p[1]);
+          u.y = pack_bf16x2(p[2], p[3]);
+          u.z = pack_bf16x2(p[4], p[5]);
+          u.w = pack_bf16x2(p[6], p[7]);
+          const int chunk = ((c0 & 63) >> 3) + c;
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ (row & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+
+      // ---- epilogue ----
+      mbar_wait(o_full, par);
+      tc_fence_after();
+      uint32_t orr[64];
+      tmem_ld_32x32b_x32(tmem_o, *reinterpret_cast<uint32_t(*)[32]>(&orr[0]));
+      tmem_ld_32x32b_x32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&orr[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      const float inv = 1.0f / l;
+      uint8_t* prow0 = p_buf + row * 128;      // first P chunk is free: P V has retired (o_full)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(prow0 + ((c ^ (row & 7)) << 4)) = u;
+      }
+      __syncwarp();
+      {
+        const int cch = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = quad * 32 + i * 4 + (lane >> 3);
+          const int q_row = qt * kRows + r;
+          if (q_row < args.Sq) {
+            const uint4 u = *reinterpret_cast<const uint4*>(p_buf + r * 128 + ((cch ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(args.ctx + ((size_t)b * args.Sq + q_row) * args.ldc + (size_t)h * kD + cch * 8) = u;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int KEYS>
+int launch_wide(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const AttnArgs& args,
+                cudaStream_t st) {
+  using Cfg = WideCfg<KEYS>;
+  if (h->smem_optin < Cfg::kSmemBytes) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc = icka_make_tmap_bf16(h, &tq, q, (int64_t)args.B * args.Sq, (int64_t)args.nh * kD, ldq, kRows);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tk, k, (int64_t)args.B * args.Skv, (int64_t)args.nh * kD, ldkv, KEYS);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tv, v, (int64_t)args.B * args.Skv, (int64_t)args.nh * kD, ldkv, KEYS);
+  if (rc) return rc;
+  const int items = args.B * args.nh * args.q_tiles;
+  ICKA_CUDA(cudaFuncSetAttribute(cross_attn_tcgen05_wide_kernel<KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg::kSmemBytes));
+  const int grid = items < h->sm_count ? items : h->sm_count;
+  cross_attn_tcgen05_wide_kernel<KEYS><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, args);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
 }  // namespace
 
 // Returns ICKA_OK after launching, or a positive value when the shape is outside this kernel's envelope
@@ -292,7 +552,16 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st) {
-  if (Skv > kKeys || h->smem_optin < kSmemBytes) return 1;
+  extern int g_attn_mode;
+  if (Skv > kKeys) {
+    // The wide variant is correct but, with one TMEM slot and one softmax group, no faster than the mma.sync kernel
+    // on the 196-region shape (0.47 ms vs 0.46 ms at B=512): it runs only when asked for (icka_set_attn_mode(2)).
+    if (Skv > 224 || g_attn_mode != 2) return 1;
+    AttnArgs wargs{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows,
+                   drop_thresh, drop_scale, seed};
+    return Skv <= 128 ? launch_wide<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide<224>(h, q, ldq, k, v, ldkv, wargs, st);
+  }
+  if (h->smem_optin < kSmemBytes) return 1;
   CUtensorMap tq, tk, tv;
   int rc = icka_make_tmap_bf16(h, &tq, q, (int64_t)B * Sq, (int64_t)nh * kD, ldq, kRows);
   if (rc) return rc;

@@ -256,7 +256,7 @@ extern "C" int icka_i2t_pool_fwd(icka_handle* h, const void* U, const void* X, c
   ICKA_REQUIRE(icka_aligned(U, 16) && icka_aligned(X, 16) && icka_aligned(xbar, 16), "i2t_pool: pointers must be 16-byte aligned");
   if (B == 0) return ICKA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g_attn_mode == 0) {
+  if (g_attn_mode != 1) {
     const int rc = icka_i2t_pool_tcgen05_launch(h, U, X, mask_add, xbar, B, S, H, nh, st);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope
   }

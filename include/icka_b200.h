@@ -164,7 +164,7 @@ int icka_dropout_mask(icka_handle* h, uint8_t* mask, int64_t rows, int Skv, int 
 
 /* Kernel choice of the bf16 attention core and of icka_i2t_pool_fwd (process-wide tuning/testing knob): 0 = per
  * shape (tcgen05 / TMEM kernels for Skv <= 64 resp. S <= 128, mma.sync kernels otherwise; default), 1 = always the
- * mma.sync kernels. */
+ * mma.sync kernels, 2 = like 0 plus the (not faster) wide tcgen05 attention variant for 64 < Skv <= 224. */
 int icka_set_attn_mode(int mode);
 
 /* Backward of icka_cross_attn_core_fwd: probabilities are recomputed from q, k, v (same layouts as the

@@ -92,8 +92,9 @@ def test_cross_attn_core_fp32_and_bf16():
 
 
 @pytest.mark.parametrize('B,Sq,Skv,nh', [(3, 128, 49, 12), (2, 16, 9, 2), (5, 128, 64, 1), (2, 300, 49, 3), (40, 128, 49, 12),
-                                          (1, 1, 1, 1)])
-@pytest.mark.parametrize('attn_mode', [0, 1], ids=['tcgen05', 'mma_sync'])
+                                          (1, 1, 1, 1), (2, 256, 196, 12), (30, 256, 196, 12), (3, 128, 128, 4), (3, 100, 100, 2),
+                                          (2, 128, 224, 1), (2, 64, 225, 2), (4, 1, 128, 12)])
+@pytest.mark.parametrize('attn_mode', [0, 1, 2], ids=['tcgen05', 'mma_sync', 'tcgen05_wide'])
 def test_cross_attn_core_bf16_kernels(B, Sq, Skv, nh, attn_mode):
     """Both bf16 attention kernels (tcgen05/TMEM for Skv <= 64, mma.sync) against the fp64 formula on the same
     bf16-rounded operands; ragged Sq (rows of the next sentence / zero fill inside the Q box) and key masks."""
@@ -152,3 +153,35 @@ def test_i2t_pool(B, S, H, nh, attn_mode):
     finally:
         _lib.load().icka_set_attn_mode(0)
     assert rel(got, want) <= 2e-2
+
+
+def test_tcgen05_kernels_long_pipelines_are_repeatable():
+    """Many work items per persistent CTA (the TMA rings wrap several times, both softmax groups and both TMEM slots
+    are re-used) -- results must match the mma.sync kernels' within bf16 noise and be bit-identical run to run."""
+    from icka_b200 import _lib
+    lib = _lib.load()
+    B, Sq, Skv, nh, H = 260, 128, 49, 12, 768
+    q = rnd(B * Sq, H, seed=21).bfloat16().to(DEV)
+    kv = rnd(B * Skv, 2 * H, seed=22).bfloat16().to(DEV)
+    mask = torch.zeros(B, Skv)
+    mask[1::2, 40:] = -10000.0
+    mask = mask.to(DEV)
+    a1 = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask, B, Sq, Skv, nh, 64)
+    a2 = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask, B, Sq, Skv, nh, 64)
+    u = (rnd(B * 3, nh * H, seed=23) / math.sqrt(H)).bfloat16().to(DEV)
+    x = rnd(B * 3 * 128, H, seed=24).bfloat16().to(DEV)
+    tm = torch.zeros(B * 3, 128)
+    tm[::3, 30:] = -10000.0
+    tm = tm.to(DEV)
+    p1 = ops.i2t_pool(u, x, tm, B * 3, 128, H, nh)
+    p2 = ops.i2t_pool(u, x, tm, B * 3, 128, H, nh)
+    _lib.check(lib.icka_set_attn_mode(1), 'icka_set_attn_mode')
+    try:
+        a_ref = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask, B, Sq, Skv, nh, 64)
+        p_ref = ops.i2t_pool(u, x, tm, B * 3, 128, H, nh)
+        torch.cuda.synchronize()
+    finally:
+        lib.icka_set_attn_mode(0)
+    assert torch.equal(a1, a2) and torch.equal(p1, p2)
+    assert float((a1.float() - a_ref.float()).abs().max()) <= 3e-2
+    assert float((p1.float() - p_ref.float()).abs().max()) <= 3e-2
