@@ -78,6 +78,8 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     'icka_crf_llh_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_void_p]),
+    'icka_ner_chunk_counts': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int, c_int, c_void_p]),
 }
 
 _lib = None

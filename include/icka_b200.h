@@ -244,6 +244,24 @@ int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const int64_t* tags
                      float* d_emissions, float* d_start, float* d_end, float* d_trans, int B, int S, int T,
                      void* stream);
 
+/* ---- tag post-processing + chunk-F1 ----------------------------------------- */
+
+/* Replaces the host loops that consume the decoded tags: My_cross_attention.py:879-903 / 1052-1077 (walk each
+ * sentence while its mask is on, keep positions whose GOLD label is not flagged ICKA_NER_SKIP) and
+ * ner_evaluate.py:4-48, 64-110 (get_chunks / evaluate) on the kept positions.
+ * pred [B,S] i32 (icka_viterbi_decode's tags_out), gold [B,S] i64 label ids, mask [B,S] u8 (NULL = all on).
+ * label_info [n_ids] u16 per label id: bits 0-7 = chunk-type id (name.split('-')[-1]), ICKA_NER_SKIP,
+ * ICKA_NER_OUTSIDE (the 'O' tag), ICKA_NER_BEGIN (name.split('-')[0] == 'B').
+ * totals [6] u64 are ADDED to: kept tokens, kept tokens with pred == gold, |gold & pred chunks|, |pred chunks|,
+ * |gold chunks|, positions with an id outside [0, n_ids) (must stay 0).  per_sentence [B,5] i32 (or NULL) gets
+ * the first five per sentence.  Exact integer arithmetic. */
+#define ICKA_NER_SKIP (1u << 8)
+#define ICKA_NER_OUTSIDE (1u << 9)
+#define ICKA_NER_BEGIN (1u << 10)
+int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* gold, const uint8_t* mask,
+                          const uint16_t* label_info, int n_ids, unsigned long long* totals,
+                          int32_t* per_sentence, int B, int S, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
