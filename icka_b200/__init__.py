@@ -4,6 +4,8 @@ Public surface (mirrors /root/reference/Cross_Modal_Interaction_Module.py and to
     modules.BertCrossEncoder, BertCrossAttentionLayer, BertCrossAttention, BertCoAttention,
     BertSelfOutput, BertIntermediate, BertOutput, BertLayerNorm, cls_layer_both, CrossModalFusion
     crf.CRF
+    emission.LSTM, emission.EmissionHead (the BiLSTM + classifier between fusion and CRF, CMIM:905-910, 1042-1043)
+    ner.ChunkF1 / ner.evaluate (tag post-processing + chunk-F1, My_cross_attention.py:879-903, ner_evaluate.py)
     set_precision('bf16' | 'fp32')
 Everything computes through libicka_b200.so (include/icka_b200.h); there is no CPU fallback.
 """
@@ -12,7 +14,8 @@ from .modules import (BertCoAttention, BertCrossAttention, BertCrossAttentionLay
                       BertIntermediate, BertLayerNorm, BertOutput, BertSelfOutput, CrossModalFusion,
                       cls_layer_both, get_precision, set_precision)
 from .crf import CRF  # noqa: F401
+from .emission import LSTM, EmissionHead  # noqa: F401
 
 __all__ = ['FusionConfig', 'BertCoAttention', 'BertCrossAttention', 'BertCrossAttentionLayer', 'BertCrossEncoder',
            'BertIntermediate', 'BertLayerNorm', 'BertOutput', 'BertSelfOutput', 'CrossModalFusion', 'cls_layer_both',
-           'CRF', 'get_precision', 'set_precision']
+           'CRF', 'LSTM', 'EmissionHead', 'get_precision', 'set_precision']

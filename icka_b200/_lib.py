@@ -78,6 +78,14 @@ SIGNATURES = {
                                     c_int, c_int, c_int, c_void_p]),
     'icka_crf_llh_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_void_p]),
+    'icka_lstm_rec_workspace_bytes': (c_int64, [c_int, c_int]),
+    'icka_lstm_rec_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_int, c_int, c_void_p]),
+    'icka_lstm_cell_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_void_p, c_int, c_int, c_int, c_void_p]),
+    'icka_emission_head_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,
+                                       c_int, c_void_p]),
+    'icka_add_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'icka_ner_chunk_counts': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_int, c_int, c_void_p]),
 }

@@ -1,0 +1,153 @@
+"""Emission head between the fusion stack and the CRF (SURVEY 8f "next" row 1): the reference's
+
+    self.lstm = nn.LSTM(input_size=H, hidden_size=H, batch_first=True, bidirectional=True)      CMIM:905-908
+    self.classifier = torch.nn.Linear(H * 2, num_labels)                                        CMIM:910
+    x, _ = self.lstm(result); emissions = self.classifier(x)                                    CMIM:1042-1043
+
+``LSTM`` keeps nn.LSTM's constructor arguments (the subset the reference uses), parameter names
+(``weight_ih_l0`` ... ``bias_hh_l0_reverse`` -> the same state_dict keys) and return value
+``(output, (h_n, c_n))``; ``EmissionHead`` owns ``lstm`` + ``classifier`` under the reference's attribute names.
+Inference only (no autograd nodes yet): parameters are used detached.
+
+bf16 mode, H = 768:  x -> [icka_linear_fwd: Gx = x . W_ih^T + b for both directions, slice-ordered columns, bf16]
+                       -> [icka_lstm_rec_fwd: ONE persistent weight-stationary tcgen05 kernel, all S steps]
+                       -> [icka_emission_head_fwd]
+otherwise (fp32 parity mode, other H): the per-step path  icka_linear_fwd (h . W_hh^T) + icka_lstm_cell_fwd.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import modules, ops
+from .modules import _OperandCache
+
+REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
+_SLICE_UNITS = 24
+_HALF_UNITS = 12
+
+
+def slice_order(H: int = REC_H) -> torch.Tensor:
+    """perm[8H]: row of the slice-ordered weights -> row of cat(weight_*_l0, weight_*_l0_reverse).
+    col = ((dir*32 + slice)*2 + half)*48 + gate*12 + j  <->  dir*4H + gate*H + slice*24 + half*12 + j."""
+    n_slices = H // _SLICE_UNITS
+    d = torch.arange(2).view(2, 1, 1, 1, 1)
+    s = torch.arange(n_slices).view(1, n_slices, 1, 1, 1)
+    hf = torch.arange(2).view(1, 1, 2, 1, 1)
+    g = torch.arange(4).view(1, 1, 1, 4, 1)
+    j = torch.arange(_HALF_UNITS).view(1, 1, 1, 1, _HALF_UNITS)
+    return (d * 4 * H + g * H + s * _SLICE_UNITS + hf * _HALF_UNITS + j).reshape(-1)
+
+
+class LSTM(nn.Module):
+    """Single-layer nn.LSTM mirror (CMIM:905-908).  ``forward(x) -> (output [B,S,2H] fp32, (h_n, c_n) [2,B,H])``."""
+
+    def __init__(self, input_size: int, hidden_size: int, num_layers: int = 1, bias: bool = True,
+                 batch_first: bool = False, dropout: float = 0.0, bidirectional: bool = False):
+        super().__init__()
+        if num_layers != 1 or not bias or dropout != 0.0 or not bidirectional:
+            raise NotImplementedError('icka_b200.LSTM covers the reference configuration: one bidirectional layer '
+                                      'with biases and no dropout (CMIM:905-908)')
+        self.input_size, self.hidden_size, self.batch_first = input_size, hidden_size, batch_first
+        self.num_layers, self.bidirectional = 1, True
+        k = 1.0 / math.sqrt(hidden_size)
+        for suffix in ('', '_reverse'):
+            for name, shape in (('weight_ih_l0', (4 * hidden_size, input_size)),
+                                ('weight_hh_l0', (4 * hidden_size, hidden_size)),
+                                ('bias_ih_l0', (4 * hidden_size,)), ('bias_hh_l0', (4 * hidden_size,))):
+                self.register_parameter(name + suffix, nn.Parameter(torch.empty(shape).uniform_(-k, k)))
+        self._cache = _OperandCache()
+
+    # ---- cached operands -------------------------------------------------------------------------
+    def _params(self):
+        return [getattr(self, n + s) for s in ('', '_reverse')
+                for n in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
+
+    def _prepared(self, persistent: bool):
+        """(W_ih [8H, I], bias [8H] = b_ih + b_hh, W_hh [8H, H]) for both directions, in the compute dtype; rows in
+        slice order for the persistent kernel, in PyTorch order otherwise."""
+        def build():
+            wi = torch.cat([self.weight_ih_l0.detach(), self.weight_ih_l0_reverse.detach()]).contiguous()
+            wh = torch.cat([self.weight_hh_l0.detach(), self.weight_hh_l0_reverse.detach()]).contiguous()
+            b = ops.add_f32(torch.cat([self.bias_ih_l0.detach(), self.bias_ih_l0_reverse.detach()]).contiguous(),
+                            torch.cat([self.bias_hh_l0.detach(), self.bias_hh_l0_reverse.detach()]).contiguous())
+            if persistent:
+                perm = slice_order(self.hidden_size).to(wi.device)
+                wi, wh, b = wi[perm].contiguous(), wh[perm].contiguous(), b[perm].contiguous()
+            if modules.get_precision() == 'bf16':
+                wi, wh = ops.cast_bf16(wi), ops.cast_bf16(wh)
+            return wi, b, wh
+        return self._cache.get('persistent' if persistent else 'step', self._params(), build)
+
+    def uses_persistent_kernel(self) -> bool:
+        return modules.get_precision() == 'bf16' and self.hidden_size == REC_H and self.input_size % 8 == 0
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def states(self, x: torch.Tensor, want_state: bool = False):
+        """x [B,S,I] (batch-first) -> (y [B,S,2H] in the compute dtype, h_n, c_n | None)."""
+        B, S, I = x.shape
+        H = self.hidden_size
+        lp = modules.get_precision() == 'bf16'
+        x2 = x.reshape(B * S, I)
+        if lp:
+            x2 = x2.contiguous() if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.float().contiguous())
+        else:
+            x2 = x2.float().contiguous()
+        if self.uses_persistent_kernel():
+            wi, b, wh = self._prepared(True)
+            gx = ops.linear(x2, wi, b, out_dtype=torch.bfloat16)
+            out = ops.lstm_rec(gx, wh, B, S, H, want_state=want_state)
+            return out if want_state else (out, None, None)
+        # per-step path
+        wi, b, wh = self._prepared(False)
+        cdt = torch.bfloat16 if lp else torch.float32
+        gx = ops.linear(x2, wi, b, out_dtype=cdt).view(B, S, 8 * H)
+        y = torch.empty(B, S, 2 * H, dtype=cdt, device=x.device)
+        h_n = torch.empty(2, B, H, dtype=torch.float32, device=x.device) if want_state else None
+        c_n = torch.zeros(2, B, H, dtype=torch.float32, device=x.device)
+        for d in range(2):
+            h_prev = torch.empty(B, H, dtype=cdt, device=x.device)
+            h_next = torch.empty(B, H, dtype=cdt, device=x.device)
+            c = c_n[d]
+            w = wh[d * 4 * H:(d + 1) * 4 * H]
+            for t in range(S):
+                pos = S - 1 - t if d else t
+                gates = None if t == 0 else ops.linear(h_prev, w, None, out_dtype=torch.float32)
+                ops.lstm_cell(gates, gx[:, pos, d * 4 * H:(d + 1) * 4 * H], c, h_next, y[:, pos, d * H:(d + 1) * H],
+                              h_n[d] if (want_state and t == S - 1) else None)
+                h_prev, h_next = h_next, h_prev
+        return y, h_n, (c_n if want_state else None)
+
+    def forward(self, input: torch.Tensor, hx=None) -> Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        if hx is not None:
+            raise NotImplementedError('initial states are not supported (the reference passes none, CMIM:1042)')
+        if input.dim() != 3:
+            raise ValueError(f'LSTM: Expected input to be 3D (batched), got {input.dim()}D instead')
+        if input.shape[-1] != self.input_size:
+            raise RuntimeError(f'input.size(-1) must be equal to input_size. Expected {self.input_size}, '
+                               f'got {input.shape[-1]}')
+        x = input if self.batch_first else input.transpose(0, 1)
+        y, h_n, c_n = self.states(x, want_state=True)
+        y = y.float()
+        return (y if self.batch_first else y.transpose(0, 1)), (h_n, c_n)
+
+
+class EmissionHead(nn.Module):
+    """``lstm`` + ``classifier`` of MTCCMBertForMMTokenClassificationCRF (CMIM:905-910) and their use at
+    CMIM:1042-1043: ``forward(result [B,S,H]) -> emissions [B,S,num_labels]`` fp32."""
+
+    def __init__(self, config, num_labels: int = 2):
+        super().__init__()
+        self.lstm = LSTM(input_size=config.hidden_size, hidden_size=config.hidden_size, batch_first=True,
+                         bidirectional=True)
+        self.classifier = nn.Linear(config.hidden_size * 2, num_labels)
+
+    def forward(self, result: torch.Tensor) -> torch.Tensor:
+        B, S, _ = result.shape
+        y, _, _ = self.lstm.states(result)
+        e = ops.emission_head(y.view(B * S, -1), self.classifier.weight.detach().float().contiguous(),
+                              self.classifier.bias.detach().float().contiguous())
+        return e.view(B, S, -1)

@@ -445,3 +445,84 @@ def dropout_mask(shape, p_drop: float, seed: int, device, attention: bool = Fals
     else:
         _lib.check(lib.icka_dropout_mask(h, m.data_ptr(), m.numel(), 1, 0, float(p_drop), int(seed), st), 'icka_dropout_mask')
     return m
+
+
+# ---- emission head (BiLSTM + classifier) -------------------------------------------------------
+
+def add_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _need(a, torch.float32, 'add_f32(a)')
+    _need(b, torch.float32, 'add_f32(b)')
+    if a.shape != b.shape:
+        raise RuntimeError('add_f32: shape mismatch')
+    lib, h, st = _ctx(a)
+    out = torch.empty_like(a)
+    _lib.check(lib.icka_add_f32(h, a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), st), 'icka_add_f32')
+    return out
+
+
+def lstm_rec_workspace_bytes(B: int, H: int) -> int:
+    n = int(_lib.load().icka_lstm_rec_workspace_bytes(int(B), int(H)))
+    if n < 0:
+        raise RuntimeError(f'lstm_rec: hidden size {H} is not supported by the persistent kernel')
+    return n
+
+
+def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, *, workspace: Optional[torch.Tensor] = None,
+             want_state: bool = False):
+    """gx [B*S, 8H] bf16 (slice order), w_hh_perm [8H, H] bf16 -> y [B,S,2H] bf16 (, h_n, c_n [2,B,H] fp32)."""
+    _need(gx, torch.bfloat16, 'lstm_rec(gx)')
+    _need(w_hh_perm, torch.bfloat16, 'lstm_rec(w_hh_perm)')
+    if gx.shape != (B * S, 8 * H) or w_hh_perm.shape != (8 * H, H):
+        raise RuntimeError(f'lstm_rec: bad shapes {tuple(gx.shape)} / {tuple(w_hh_perm.shape)} for B={B} S={S} H={H}')
+    lib, h, st = _ctx(gx)
+    need = lstm_rec_workspace_bytes(B, H)
+    if workspace is None:
+        workspace = torch.empty(need + 1024, dtype=torch.uint8, device=gx.device)
+    off = (-workspace.data_ptr()) % 1024
+    if workspace.numel() - off < need:
+        raise RuntimeError(f'lstm_rec: workspace of {workspace.numel()} B, need {need} + alignment')
+    y = torch.empty(B, S, 2 * H, dtype=torch.bfloat16, device=gx.device)
+    h_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
+    c_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
+    _lib.check(lib.icka_lstm_rec_fwd(h, gx.data_ptr(), w_hh_perm.data_ptr(), workspace.data_ptr() + off, need,
+                                     y.data_ptr(), _p(h_n), _p(c_n), B, S, H, st), 'icka_lstm_rec_fwd')
+    return (y, h_n, c_n) if want_state else y
+
+
+def lstm_cell(gates_h: Optional[torch.Tensor], gx: torch.Tensor, c: torch.Tensor, h_out: torch.Tensor,
+              y: Optional[torch.Tensor], h_f32: Optional[torch.Tensor] = None) -> None:
+    """One step of the per-step path.  gx [B,4H] / y [B,H] may be row-pitched views; c [B,H] fp32 in place."""
+    B, H = c.shape
+    _need(c, torch.float32, 'lstm_cell(c)')
+    if gx.dtype not in _DT or gx.shape != (B, 4 * H) or gx.stride(1) != 1:
+        raise RuntimeError('lstm_cell: bad gx')
+    _need(h_out, gx.dtype, 'lstm_cell(h_out)')
+    if gates_h is not None:
+        _need(gates_h, torch.float32, 'lstm_cell(gates_h)')
+        if gates_h.shape != (B, 4 * H):
+            raise RuntimeError('lstm_cell: bad gates_h')
+    if y is not None and (y.dtype != gx.dtype or y.shape != (B, H) or y.stride(1) != 1):
+        raise RuntimeError('lstm_cell: bad y')
+    if h_f32 is not None:
+        _need(h_f32, torch.float32, 'lstm_cell(h_f32)')
+    lib, h, st = _ctx(c)
+    _lib.check(lib.icka_lstm_cell_fwd(h, _p(gates_h), gx.data_ptr(), _ld(gx, 4 * H), c.data_ptr(), h_out.data_ptr(),
+                                      _p(y), 0 if y is None else _ld(y, H), _p(h_f32), _DT[gx.dtype], B, H, st),
+               'icka_lstm_cell_fwd')
+
+
+def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x [M,K] (fp32 or bf16, unit stride along K) . w[T,K]^T (fp32) + bias -> [M,T] fp32."""
+    if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:
+        raise RuntimeError('emission_head: bad x')
+    _need(w, torch.float32, 'emission_head(w)')
+    _need(bias, torch.float32, 'emission_head(bias)')
+    M, K = x.shape
+    T = w.shape[0]
+    if w.shape != (T, K) or bias.shape != (T,):
+        raise RuntimeError('emission_head: bad weight / bias shape')
+    lib, h, st = _ctx(x)
+    out = torch.empty(M, T, dtype=torch.float32, device=x.device)
+    _lib.check(lib.icka_emission_head_fwd(h, x.data_ptr(), _ld(x, K), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
+                                          _DT[x.dtype], M, K, T, st), 'icka_emission_head_fwd')
+    return out

@@ -262,6 +262,38 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
                           const uint16_t* label_info, int n_ids, unsigned long long* totals,
                           int32_t* per_sentence, int B, int S, void* stream);
 
+/* ---- emission head: BiLSTM + classifier -------------------------------------- */
+
+/* Recurrent half of `self.lstm = nn.LSTM(H, H, batch_first=True, bidirectional=True)` (CMIM:905-908, call :1042):
+ * one persistent, weight-stationary tcgen05 kernel walks all S steps of both directions (csrc/lstm_sm100.cu).
+ *   gx        [B*S, 2*4H] bf16 = x . W_ih^T + b_ih + b_hh for both directions (an icka_linear_fwd call), columns in the
+ *             kernel's slice order:  col = ((dir*32 + slice)*2 + half)*48 + gate*12 + j  <->  PyTorch row
+ *             gate*H + slice*24 + half*12 + j of direction `dir` (gate order i, f, g, o)
+ *   w_hh_perm [2*4H, H] bf16: weight_hh_l0 / weight_hh_l0_reverse with their rows in the same order
+ *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters, h ping-pong, cell state)
+ *   y         [B, S, 2H] bf16 (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
+ * H = 768 only (other sizes: the per-step path, icka_linear_fwd + icka_lstm_cell_fwd).  The launch is cooperative:
+ * 64 or 128 co-resident CTAs. */
+int64_t icka_lstm_rec_workspace_bytes(int B, int H);
+int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace, int64_t workspace_bytes,
+                      void* y, float* h_n, float* c_n, int B, int S, int H, void* stream);
+
+/* One LSTM step (per-step path: fp32 parity mode, or shapes icka_lstm_rec_fwd does not cover):
+ *   pre = gates_h[B,4H] (fp32, = h_{t-1} . W_hh^T; NULL at the first step) + gx[B, 4H] (`dtype`, row pitch ldgx)
+ *   c = sigmoid(pre_f) * c + sigmoid(pre_i) * tanh(pre_g);  h = sigmoid(pre_o) * tanh(c)      (gate order i, f, g, o)
+ * c [B,H] fp32 is updated in place; h goes to h_out [B,H] (`dtype`, the next step's GEMM operand), to y (`dtype`, row
+ * pitch ldy; may be NULL) and to h_f32 [B,H] (may be NULL). */
+int icka_lstm_cell_fwd(icka_handle* h, const float* gates_h, const void* gx, int64_t ldgx, float* c, void* h_out,
+                       void* y, int64_t ldy, float* h_f32, int dtype, int B, int H, void* stream);
+
+/* `self.classifier = nn.Linear(2H, num_labels)` (CMIM:910, :1043): out[M,T] fp32 = x[M,K] (`dtype`, pitch ldx) .
+ * W[T,K]^T (fp32) + bias[T].  T <= 16, K % 8 == 0.  fp32 accumulation in a fixed order. */
+int icka_emission_head_fwd(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias, float* out,
+                           int dtype, int64_t M, int K, int T, void* stream);
+
+/* out = a + b (fp32; weight preparation: b_ih + b_hh). */
+int icka_add_f32(icka_handle* h, const float* a, const float* b, float* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

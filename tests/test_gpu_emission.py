@@ -1,0 +1,128 @@
+"""GPU parity of the emission head (BiLSTM + classifier, CMIM:905-910, 1042-1043) against the
+oracle restatement (oracle/lstm_ref.py, pinned to torch.nn.LSTM in tests/test_oracle_lstm.py).
+
+Tolerances: fp32 mode max|a-b| / max(|b|,1) <= 1e-5 (the north star's fp32 bar); bf16 mode max|a-b| <= 2e-2 on the
+LSTM states (|h| < 1) and on the emissions (the north star's bf16 bar for activations)."""
+import pytest
+import torch
+from torch import nn
+
+import icka_b200
+from icka_b200 import ops
+from icka_b200.config import FusionConfig
+from oracle import lstm_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    prev = icka_b200.get_precision()
+    yield
+    icka_b200.set_precision(prev)
+
+
+def make(I, H, T, seed):
+    torch.manual_seed(seed)
+    ref_lstm = nn.LSTM(input_size=I, hidden_size=H, batch_first=True, bidirectional=True)
+    ref_cls = nn.Linear(2 * H, T)
+    ours = icka_b200.LSTM(input_size=I, hidden_size=H, batch_first=True, bidirectional=True)
+    ours.load_state_dict(ref_lstm.state_dict())                 # same keys as nn.LSTM
+    return ref_lstm, ref_cls, ours.cuda()
+
+
+def oracle(ref_lstm, ref_cls, x):
+    p = {k: v.detach().double() for k, v in ref_lstm.named_parameters()}
+    with torch.no_grad():
+        y, (hn, cn) = lstm_ref.bilstm(x.double(), p)
+        e = y @ ref_cls.weight.detach().double().t() + ref_cls.bias.detach().double()
+    return y, hn, cn, e
+
+
+def rel(a, b):
+    return ((a.double().cpu() - b).abs() / b.abs().clamp(min=1.0)).max().item()
+
+
+@pytest.mark.parametrize('B,S,I,H', [(3, 9, 32, 32), (2, 128, 24, 40), (2, 12, 768, 768)])
+def test_fp32_per_step_path(B, S, I, H):
+    icka_b200.set_precision('fp32')
+    ref_lstm, ref_cls, ours = make(I, H, 15, seed=B + S)
+    x = torch.randn(B, S, I)
+    y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
+    out, (h_n, c_n) = ours(x.cuda())
+    assert out.dtype == torch.float32 and out.shape == (B, S, 2 * H)
+    assert rel(out, y) <= 1e-5 and rel(h_n, hn) <= 1e-5 and rel(c_n, cn) <= 1e-5
+
+
+@pytest.mark.parametrize('B,S', [(5, 128), (300, 24), (128, 3), (1, 1)])
+def test_bf16_persistent_kernel(B, S):
+    icka_b200.set_precision('bf16')
+    H = 768
+    ref_lstm, ref_cls, ours = make(H, H, 15, seed=B * 7 + S)
+    assert ours.uses_persistent_kernel()
+    x = torch.randn(B, S, H)
+    y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
+    out, (h_n, c_n) = ours(x.cuda())
+    err_y = (out.double().cpu() - y).abs().max().item()
+    err_h = (h_n.double().cpu() - hn).abs().max().item()
+    err_c = (c_n.double().cpu() - cn).abs().max().item()
+    print(f'bf16 persistent B={B} S={S}: max|dy|={err_y:.2e} max|dh_n|={err_h:.2e} max|dc_n|={err_c:.2e}')
+    assert err_y <= 2e-2 and err_h <= 2e-2 and err_c <= 4e-2
+    out2, _ = ours(x.cuda())                                    # no atomics on the data path: reruns are identical
+    assert torch.equal(out, out2)
+
+
+def test_bf16_per_step_path_other_hidden_size():
+    icka_b200.set_precision('bf16')
+    ref_lstm, ref_cls, ours = make(64, 64, 15, seed=3)
+    assert not ours.uses_persistent_kernel()
+    x = torch.randn(4, 20, 64)
+    y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
+    out, (h_n, c_n) = ours(x.cuda())
+    assert (out.double().cpu() - y).abs().max().item() <= 2e-2
+    assert (h_n.double().cpu() - hn).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,K,T', [(1, 8, 1), (37, 1536, 15), (1000, 1536, 16), (9, 264, 7)])
+def test_emission_head_kernel(dtype, M, K, T):
+    torch.manual_seed(M + K + T)
+    x = torch.randn(M, K).to(dtype)
+    w = torch.randn(T, K) / K ** 0.5
+    b = torch.randn(T)
+    want = x.double() @ w.double().t() + b.double()
+    got = ops.emission_head(x.cuda(), w.cuda(), b.cuda())
+    assert got.shape == (M, T) and rel(got, want) <= 1e-5
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('bf16', 2e-2)])
+def test_emission_head_module(precision, tol):
+    icka_b200.set_precision(precision)
+    H, T, B, S = 768, 15, 6, 32
+    torch.manual_seed(42)
+    ref_lstm = nn.LSTM(input_size=H, hidden_size=H, batch_first=True, bidirectional=True)
+    ref_cls = nn.Linear(2 * H, T)
+    head = icka_b200.EmissionHead(FusionConfig(hidden_size=H), num_labels=T)
+    head.lstm.load_state_dict(ref_lstm.state_dict())
+    head.classifier.load_state_dict(ref_cls.state_dict())
+    head = head.cuda().eval()
+    x = torch.randn(B, S, H)
+    _, _, _, e = oracle(ref_lstm, ref_cls, x)
+    with torch.no_grad():
+        got = head(x.cuda())
+    assert got.shape == (B, S, T) and got.dtype == torch.float32
+    err = rel(got, e) if precision == 'fp32' else (got.double().cpu() - e).abs().max().item()
+    print(f'emission head {precision}: err {err:.2e}')
+    assert err <= tol
+
+
+def test_lstm_rejects_what_it_does_not_cover():
+    with pytest.raises(NotImplementedError):
+        icka_b200.LSTM(8, 8, batch_first=True, bidirectional=False)
+    m = icka_b200.LSTM(8, 8, batch_first=True, bidirectional=True).cuda()
+    with pytest.raises(ValueError):
+        m(torch.zeros(3, 8, device='cuda'))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3, 9, device='cuda'))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3, 8))                                 # CPU tensor: no fallback

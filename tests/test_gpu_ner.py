@@ -24,6 +24,11 @@ def test_evaluate_matches_reference_golden(case):
     assert list(map(float, got)) == case['evaluate']
 
 
+def same(a, b):
+    """tuple equality where nan == nan (np.mean([]) of the reference when no token is kept)"""
+    return all(x == y or (x != x and y != y) for x, y in zip(a, b)) and len(a) == len(b)
+
+
 def random_batch(rng, B, S, p_same, prefix=True):
     gold = torch.zeros(B, S, dtype=torch.int64)
     pred = torch.full((B, S), -1, dtype=torch.int32)
@@ -56,7 +61,7 @@ def test_counts_match_oracle(B, S, p_same, prefix):
         assert tuple(per[b].tolist()) == want, f'sentence {b}'
     want = ner_ref.counts(y_pred, y_true, tags)
     assert ev.counts() == want
-    assert ev.result() == ner_ref.scores(*want)
+    assert same(ev.result(), ner_ref.scores(*want))
     # accumulation over batches and bool / int64 masks
     ev.update(pred.cuda(), gold.cuda(), mask.cuda().bool())
     ev.update(pred.cuda(), gold.cuda(), mask.cuda().long())
