@@ -33,6 +33,13 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates_h, const T* __r
   if (h_f32) h_f32[idx] = hn;
 }
 
+// input rows may be time-major (row = t * B + b, tm_S = S > 0): the emissions are always written batch-major
+__device__ __forceinline__ int64_t out_row(int64_t r, int64_t M, int tm_S) {
+  if (tm_S <= 0) return r;
+  const int64_t B = M / tm_S;
+  return (r % B) * tm_S + r / B;
+}
+
 constexpr int kHeadThreads = 256;
 constexpr int kHeadRows = 4;      // rows per warp pass: every weight fetched from shared memory is used 4 times
 constexpr int kHeadMaxT = 16;
@@ -55,12 +62,30 @@ __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, flo
   }
 }
 
+// [B, S, H] (fp32 or bf16) -> [S, B, H] bf16: the recurrent kernel reads Gx and writes the states one TIME STEP at a
+// time, so time-major tensors make every step touch one contiguous block (DRAM-page and TLB friendly) instead of B
+// pieces scattered S rows apart.
+template <typename T>
+__global__ void cast_time_major_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int S, int H) {
+  const int64_t n8 = (int64_t)B * S * H / 8;
+  const int h8 = H / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % h8);
+    const int64_t r = i / h8;                 // output row t * B + b
+    const int b = (int)(r % B), t = (int)(r / B);
+    float v[8];
+    load8<T>(x + ((int64_t)b * S + t) * H + c * 8, v);
+    *reinterpret_cast<uint4*>(y + r * H + c * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 // out[r, t] = bias[t] + sum_k x[r, k] W[t, k].  Warp = 4 rows at a time, lane = 8 consecutive k per 256-wide sweep;
 // W (fp32) lives in shared memory for the life of the block; fp32 accumulation, fixed reduction order.
 template <typename T, int NT>
 __global__ void __launch_bounds__(kHeadThreads)
 emission_head_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ W, const float* __restrict__ bias,
-                     float* __restrict__ out, int64_t M, int K) {
+                     float* __restrict__ out, int64_t M, int K, int tm_S) {
   extern __shared__ float w_s[];   // [NT][K]
   for (int i = threadIdx.x * 4; i < NT * K; i += kHeadThreads * 4)
     *reinterpret_cast<float4*>(w_s + i) = __ldg(reinterpret_cast<const float4*>(W + i));
@@ -111,7 +136,96 @@ emission_head_kernel(const T* __restrict__ x, int64_t ldx, const float* __restri
 #pragma unroll
       for (int t = 0; t < NT; ++t)
         if (lane == t) mine = acc[r][t];
-      if (lane < NT && r0 + r < M) out[(r0 + r) * NT + lane] = mine + __ldg(bias + lane);
+      if (lane < NT && r0 + r < M) out[out_row(r0 + r, M, tm_S) * NT + lane] = mine + __ldg(bias + lane);
+    }
+  }
+}
+
+// bf16 states: the same product on mma.sync tensor cores.  The FFMA kernel above is bound by FMA issue + shared-memory
+// reads of W (measured 1.3 TB/s at T = 15); here the T x K weights are the M = 16 operand of m16n8k16 (tags padded to
+// 16), 8 state rows are the N operand, and W is split into hi + lo bf16 halves (two MMAs) so the weights keep ~16
+// mantissa bits -- the result matches the fp32-weight product to ~1e-6 while the kernel becomes a pure stream of the
+// states.  The contraction index is permuted so that every lane loads 16 contiguous bytes of its row (8 rows x 64 B per
+// warp request) and 16 contiguous bytes of two weight rows: logical k-pairs {2q, 2q+1} / {2q+8, 2q+9} of the two
+// MMAs of a 32-wide block are physical elements q*8 + {0,1} / {2,3} and q*8 + {4,5} / {6,7} for A and B alike.
+constexpr int kMmaHeadRows = 32;          // rows per warp pass (4 groups of 8)
+constexpr int kMmaHeadPad = 32;           // row pitch K + 32 bf16: the two rows of a quarter-warp hit disjoint banks
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kHeadThreads)
+emission_head_mma_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ W,
+                         const float* __restrict__ bias, float* __restrict__ out, int64_t M, int K, int T, int tm_S) {
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  const int ldw = K + kMmaHeadPad;
+  __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(head_smem);   // [16][ldw]
+  __nv_bfloat16* w_lo = w_hi + 16 * ldw;
+  for (int i = threadIdx.x; i < 16 * K; i += kHeadThreads) {
+    const int t = i / K, k = i % K;
+    const float w = t < T ? __ldg(W + (size_t)t * K + k) : 0.0f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    w_hi[t * ldw + k] = hi;
+    w_lo[t * ldw + k] = __float2bfloat16_rn(w - __bfloat162float(hi));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int g = lane >> 2, q = lane & 3;
+  const float bias_g = g < T ? __ldg(bias + g) : 0.0f, bias_g8 = g + 8 < T ? __ldg(bias + g + 8) : 0.0f;
+  const __nv_bfloat16* wh0 = w_hi + g * ldw + q * 8;
+  const __nv_bfloat16* wh1 = w_hi + (g + 8) * ldw + q * 8;
+  const __nv_bfloat16* wl0 = w_lo + g * ldw + q * 8;
+  const __nv_bfloat16* wl1 = w_lo + (g + 8) * ldw + q * 8;
+  const int64_t warps_total = (int64_t)gridDim.x * (kHeadThreads / 32);
+  for (int64_t r0 = ((int64_t)blockIdx.x * (kHeadThreads / 32) + warp) * kMmaHeadRows; r0 < M;
+       r0 += warps_total * kMmaHeadRows) {
+    float acc[4][4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[gi][i] = 0.0f;
+    const __nv_bfloat16* xp[4];
+    bool ok[4];
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+      const int64_t row = r0 + gi * 8 + g;
+      ok[gi] = row < M;
+      xp[gi] = x + (ok[gi] ? row : 0) * ldx + q * 8;
+    }
+#pragma unroll 4
+    for (int kb = 0; kb < K; kb += 32) {
+      uint4 xv[4];
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi)
+        xv[gi] = ok[gi] ? __ldg(reinterpret_cast<const uint4*>(xp[gi] + kb)) : make_uint4(0u, 0u, 0u, 0u);
+      const uint4 h0 = *reinterpret_cast<const uint4*>(wh0 + kb), h1 = *reinterpret_cast<const uint4*>(wh1 + kb);
+      const uint4 l0 = *reinterpret_cast<const uint4*>(wl0 + kb), l1 = *reinterpret_cast<const uint4*>(wl1 + kb);
+#pragma unroll
+      for (int gi = 0; gi < 4; ++gi) {
+        mma_bf16_16816(acc[gi], h0.x, h1.x, h0.y, h1.y, xv[gi].x, xv[gi].y);
+        mma_bf16_16816(acc[gi], h0.z, h1.z, h0.w, h1.w, xv[gi].z, xv[gi].w);
+        mma_bf16_16816(acc[gi], l0.x, l1.x, l0.y, l1.y, xv[gi].x, xv[gi].y);
+        mma_bf16_16816(acc[gi], l0.z, l1.z, l0.w, l1.w, xv[gi].z, xv[gi].w);
+      }
+    }
+    // d0, d1: tag g of rows 2q, 2q+1 of the group; d2, d3: tag g + 8
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t row = r0 + gi * 8 + 2 * q + i;
+        if (row < M) {
+          const int64_t orow = out_row(row, M, tm_S);
+          if (g < T) out[orow * T + g] = acc[gi][i] + bias_g;
+          if (g + 8 < T) out[orow * T + g + 8] = acc[gi][2 + i] + bias_g8;
+        }
+      }
     }
   }
 }
@@ -124,7 +238,7 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 
 template <typename T, int NT>
 int launch_head(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias, float* out, int64_t M,
-                int K, cudaStream_t st) {
+                int K, int tm_S, cudaStream_t st) {
   const size_t smem = (size_t)NT * K * sizeof(float);
   if (smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "emission_head: T=%d K=%d needs %zu B shared memory (max %zu)", NT, K, smem,
@@ -134,18 +248,18 @@ int launch_head(icka_handle* h, const void* x, int64_t ldx, const float* W, cons
   const int per_sm = smem > 100 * 1024 ? 1 : 2;
   const int64_t want = (M + (kHeadThreads / 32) * kHeadRows - 1) / ((kHeadThreads / 32) * kHeadRows);
   const int grid = (int)(want < (int64_t)h->sm_count * per_sm ? want : (int64_t)h->sm_count * per_sm);
-  kern<<<grid, kHeadThreads, smem, st>>>(static_cast<const T*>(x), ldx, W, bias, out, M, K);
+  kern<<<grid, kHeadThreads, smem, st>>>(static_cast<const T*>(x), ldx, W, bias, out, M, K, tm_S);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
 
 template <typename T>
 int dispatch_head(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias, float* out, int64_t M,
-                  int K, int T_, cudaStream_t st) {
+                  int K, int T_, int tm_S, cudaStream_t st) {
   switch (T_) {
 #define ICKA_HEAD_CASE(n) \
   case n:                 \
-    return launch_head<T, n>(h, x, ldx, W, bias, out, M, K, st);
+    return launch_head<T, n>(h, x, ldx, W, bias, out, M, K, tm_S, st);
     ICKA_HEAD_CASE(1) ICKA_HEAD_CASE(2) ICKA_HEAD_CASE(3) ICKA_HEAD_CASE(4) ICKA_HEAD_CASE(5) ICKA_HEAD_CASE(6)
     ICKA_HEAD_CASE(7) ICKA_HEAD_CASE(8) ICKA_HEAD_CASE(9) ICKA_HEAD_CASE(10) ICKA_HEAD_CASE(11) ICKA_HEAD_CASE(12)
     ICKA_HEAD_CASE(13) ICKA_HEAD_CASE(14) ICKA_HEAD_CASE(15) ICKA_HEAD_CASE(16)
@@ -180,17 +294,31 @@ extern "C" int icka_lstm_cell_fwd(icka_handle* h, const float* gates_h, const vo
 }
 
 extern "C" int icka_emission_head_fwd(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias,
-                                      float* out, int dtype, int64_t M, int K, int T, void* stream) {
+                                      float* out, int dtype, int64_t M, int K, int T, int time_major_S, void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(M >= 0 && K >= 8 && T >= 1, "emission_head: bad shape M=%lld K=%d T=%d", (long long)M, K, T);
   ICKA_REQUIRE(K % 8 == 0 && ldx >= K && ldx % 8 == 0, "emission_head: K and the row pitch must be multiples of 8");
   ICKA_REQUIRE(x && W && bias && out, "emission_head: null pointer");
   ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(W, 16), "emission_head: x and W must be 16-byte aligned");
   ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "emission_head: bad dtype %d", dtype);
+  ICKA_REQUIRE(time_major_S >= 0 && (time_major_S == 0 || M % time_major_S == 0),
+               "emission_head: M=%lld is not a multiple of the time-major S=%d", (long long)M, time_major_S);
   if (M == 0) return ICKA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == ICKA_F32) return dispatch_head<float>(h, x, ldx, W, bias, out, M, K, T, st);
-  return dispatch_head<__nv_bfloat16>(h, x, ldx, W, bias, out, M, K, T, st);
+  const int tm_S = time_major_S;
+  if (dtype == ICKA_F32) return dispatch_head<float>(h, x, ldx, W, bias, out, M, K, T, tm_S, st);
+  const size_t smem = (size_t)2 * 16 * (K + kMmaHeadPad) * sizeof(__nv_bfloat16);
+  if (T <= 16 && K % 32 == 0 && smem <= h->smem_optin) {   // tensor-core stream (hi/lo split weights)
+    ICKA_CUDA(cudaFuncSetAttribute(emission_head_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;
+    const int64_t want = (M + (kHeadThreads / 32) * kMmaHeadRows - 1) / ((kHeadThreads / 32) * kMmaHeadRows);
+    const int grid = (int)(want < (int64_t)h->sm_count * per_sm ? want : (int64_t)h->sm_count * per_sm);
+    emission_head_mma_kernel<<<grid, kHeadThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, W, bias, out,
+                                                               M, K, T, tm_S);
+    ICKA_LAUNCHED(h);
+    return ICKA_OK;
+  }
+  return dispatch_head<__nv_bfloat16>(h, x, ldx, W, bias, out, M, K, T, tm_S, st);
 }
 
 extern "C" int icka_add_f32(icka_handle* h, const float* a, const float* b, float* out, int64_t n, void* stream) {
@@ -198,6 +326,27 @@ extern "C" int icka_add_f32(icka_handle* h, const float* a, const float* b, floa
   ICKA_REQUIRE(n >= 0 && a && b && out, "add_f32: bad arguments");
   if (n == 0) return ICKA_OK;
   add_f32_kernel<<<(int)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_bf16, int in_dtype, int B, int S, int H,
+                                         void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && H >= 8 && H % 8 == 0, "cast_bf16_time_major: bad shape B=%d S=%d H=%d", B, S, H);
+  ICKA_REQUIRE(x && y_bf16 && icka_aligned(x, 16) && icka_aligned(y_bf16, 16), "cast_bf16_time_major: bad pointers");
+  ICKA_REQUIRE(in_dtype == ICKA_F32 || in_dtype == ICKA_BF16, "cast_bf16_time_major: bad dtype %d", in_dtype);
+  if (B == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n8 = (int64_t)B * S * H / 8;
+  const int64_t want = (n8 + 255) / 256;
+  const int grid = (int)(want < (int64_t)h->sm_count * 16 ? want : (int64_t)h->sm_count * 16);
+  if (in_dtype == ICKA_F32)
+    cast_time_major_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x),
+                                                         static_cast<__nv_bfloat16*>(y_bf16), B, S, H);
+  else
+    cast_time_major_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                                 static_cast<__nv_bfloat16*>(y_bf16), B, S, H);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -22,10 +22,14 @@
 // All CTAs must be co-resident (they wait on each other): the kernel is launched cooperatively.
 //
 // Column order inside a slice (chosen on the host when the weights are permuted once):
-//   column c = half * 48 + gate * 12 + j   <->   hidden unit  slice * 24 + half * 12 + j,  gate in (i, f, g, o)
-// so each epilogue thread reads one contiguous block of 48 TMEM columns and 96 contiguous bytes of Gx.
+//   column c = half * 48 + jg * 16 + gate * 4 + jj   <->   hidden unit  slice * 24 + half * 12 + jg * 4 + jj,
+//   gate in (i, f, g, o), jg in 0..2, jj in 0..3
+// so each epilogue thread reads one contiguous block of 48 TMEM columns (three 16-column groups, each holding the
+// four gates of four units) and 96 contiguous bytes of Gx.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -43,18 +47,23 @@ constexpr int kStages = 5;
 constexpr int kSlots = 4;                     // TMEM accumulator slots
 constexpr int kSlotCols = 128;                // column stride between slots (96 used)
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kPubWarp = 2 + kEpiWarps;       // warp 10: publishes finished items
+constexpr int kThreads = 32 * (kPubWarp + 1);
 constexpr size_t kSmemBytes = (size_t)kWBytes + (size_t)kStages * kABytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct LstmArgs {
-  const __nv_bfloat16* gx;   // [B*S, 2*4H] bf16, columns ordered [dir][slice][half][gate][12]
+  const __nv_bfloat16* gx;   // [S*Bn, 2*4H] bf16 TIME-MAJOR (row = t * Bn + sentence), columns ordered [dir][slice][half][jg][gate][4]
   int* cnt;                  // [2][MT] arrival counters (zeroed before launch)
   __nv_bfloat16* hbuf;       // [2 parity][2 dir][Bp][H] bf16, parity 0 zeroed (h_{-1} = 0)
-  float* cbuf;               // [2 dir][Bp][H] fp32, zeroed (c_{-1} = 0)
-  __nv_bfloat16* y;          // [B, S, 2H] bf16: forward states in [:H], backward in [H:]
-  float* h_n;                // [2, B, H] fp32 or null
-  float* c_n;                // [2, B, H] fp32 or null
+  __nv_bfloat16* y;          // [S, Bn, 2H] bf16 TIME-MAJOR: forward states in [:H], backward in [H:]
+  float* h_n;                // [2, Bn, H] fp32 or null (already offset to this launch's first sentence)
+  float* c_n;                // [2, Bn, H] fp32 or null
+  int Bn;                    // sentences of the whole call (pitch of the time planes of gx / y and of the direction
+                             // planes of h_n / c_n)
   int B, S, Bp, MT, TPG;     // sentences, steps, padded sentences (MT * 128), 128-row tiles, tiles per group
+  int debug;                 // developer probes (ICKA_LSTM_DEBUG): 1 = no dependency wait, 2 = no cell arithmetic /
+                             // state stores, 4 = publish without the gpu-scope release, 8 = no A loads, 16 = no MMAs
+                             // (results are WRONG)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -74,6 +83,140 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+// Cell epilogue of one CTA: NT sentence tiles, walked in (step, tile) order.  Thread = sentence row (TMEM lane) and 12
+// of the slice's 24 hidden units; the cell state of its NT rows lives in registers for the whole sequence.
+template <int NT>
+__device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* acc_full, uint64_t* acc_empty,
+                                              uint64_t* pub_bar, uint64_t* pub_free, uint32_t lane_taddr, int warp,
+                                              int lane, int dir, int slice, int tile0) {
+  const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+  const int half = (warp - 2) >> 2;          // which 12 of the slice's 24 units
+  const int unit0 = slice * kU + half * 12;
+  const size_t gx_col = (size_t)((dir * kNS + slice) * 2 + half) * 48;
+  const int S = args.S, Bp = args.Bp;
+  const int row0 = tile0 * 128 + quad * 32 + lane;
+  float c[NT][12];
+#pragma unroll
+  for (int ti = 0; ti < NT; ++ti)
+#pragma unroll
+    for (int q = 0; q < 12; ++q) c[ti][q] = 0.0f;
+  // Gx does not depend on the recurrence: it is fetched ONE ITEM AHEAD, off the step-to-step critical path
+  uint32_t gw_nxt[24];
+  auto fetch = [&](int t, int ti, uint32_t (&gw)[24]) {
+    const int pos = dir ? (S - 1 - t) : t;
+    const int row = row0 + ti * 128;
+    if (row < args.B) {
+      const uint4* gp = reinterpret_cast<const uint4*>(args.gx + ((size_t)pos * args.Bn + row) * (8 * kH) + gx_col);
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const uint4 v = __ldg(gp + q);
+        gw[4 * q] = v.x;
+        gw[4 * q + 1] = v.y;
+        gw[4 * q + 2] = v.z;
+        gw[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 24; ++q) gw[q] = 0u;
+    }
+  };
+  fetch(0, 0, gw_nxt);
+  int it = 0;
+  for (int t = 0; t < S; ++t) {
+    const int pos = dir ? (S - 1 - t) : t;
+#pragma unroll
+    for (int ti = 0; ti < NT; ++ti, ++it) {
+      const int slot = it % kSlots;
+      const uint32_t slot_phase = (it / kSlots) & 1;
+      const int row = row0 + ti * 128;
+      const bool valid = row < args.B;
+      uint32_t gw[24];
+#pragma unroll
+      for (int q = 0; q < 24; ++q) gw[q] = gw_nxt[q];
+      if (ti + 1 < NT) fetch(t, ti + 1, gw_nxt);
+      else if (t + 1 < S) fetch(t + 1, 0, gw_nxt);
+
+      mbar_wait(&acc_full[slot], slot_phase);
+      tc_fence_after();
+      // 48 accumulator columns = 3 groups of 4 units x (i, f, g, o): 16 columns are live at a time, the next group's
+      // tcgen05.ld is in flight while this one is being computed
+      const uint32_t taddr = lane_taddr + (uint32_t)(slot * kSlotCols + half * 48);
+      const bool probe = (args.debug & 2) != 0;      // probe: no cell arithmetic, no state stores
+      uint32_t ra[16], rb[16];
+      float hv[12];
+      auto cell4 = [&](const uint32_t (&r)[16], int jg) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float pre[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int e = jg * 16 + g * 4 + jj;
+            const uint32_t w = gw[e >> 1];
+            const float gxv = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+            pre[g] = __uint_as_float(r[g * 4 + jj]) + gxv;
+          }
+          const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]), gg = tanh_fast(pre[2]),
+                      og = sigmoid_fast(pre[3]);
+          const int j = jg * 4 + jj;
+          c[ti][j] = probe ? c[ti][j] : fmaf(fg, c[ti][j], ig * gg);
+          hv[j] = og * tanh_fast(c[ti][j]);
+        }
+      };
+      tmem_ld16(taddr, ra);
+      tmem_ld_wait();
+      tmem_ld16(taddr + 16, rb);
+      cell4(ra, 0);
+      tmem_ld_wait();
+      tmem_ld16(taddr + 32, ra);
+      cell4(rb, 1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);   // the MMA warp may reuse the slot
+      cell4(ra, 2);
+      if (valid && !(args.debug & 2)) {
+        uint32_t hw[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
+        // 24 bytes per row at byte offset 48 * slice + 24 * half: one 16-byte and one 8-byte store, ordered so the
+        // 16-byte one is aligned (half 0: 16 + 8, half 1: 8 + 16)
+        uint8_t* hp = reinterpret_cast<uint8_t*>(args.hbuf + ((size_t)(((t + 1) & 1) * 2 + dir) * Bp + row) * kH + unit0);
+        uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH + unit0);
+        if (half == 0) {
+          *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint2*>(hp + 16) = make_uint2(hw[4], hw[5]);
+          *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint2*>(yp + 16) = make_uint2(hw[4], hw[5]);
+        } else {
+          *reinterpret_cast<uint2*>(hp) = make_uint2(hw[0], hw[1]);
+          *reinterpret_cast<uint4*>(hp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
+          *reinterpret_cast<uint2*>(yp) = make_uint2(hw[0], hw[1]);
+          *reinterpret_cast<uint4*>(yp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
+        }
+        if (t == S - 1) {
+          if (args.h_n) {
+            float4* o = reinterpret_cast<float4*>(args.h_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) o[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
+          }
+          if (args.c_n) {
+            float4* o = reinterpret_cast<float4*>(args.c_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+              o[q] = make_float4(c[ti][4 * q], c[ti][4 * q + 1], c[ti][4 * q + 2], c[ti][4 * q + 3]);
+          }
+        }
+      }
+      // hand the item to the publisher warp: this warp's h stores are ordered before the arrival (release.cta)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_wait(&pub_free[slot], ((it / kSlots) & 1) ^ 1);   // the publisher is done with this slot's previous item
+        mbar_arrive(&pub_bar[slot]);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                         const LstmArgs args) {
@@ -86,7 +229,9 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
   uint64_t* empty_bar = bars + kStages;
   uint64_t* acc_full = bars + 2 * kStages;
   uint64_t* acc_empty = acc_full + kSlots;
-  uint64_t* w_bar = acc_empty + kSlots;
+  uint64_t* pub_bar = acc_empty + kSlots;
+  uint64_t* pub_free = pub_bar + kSlots;
+  uint64_t* w_bar = pub_free + kSlots;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -107,6 +252,8 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     for (int a = 0; a < kSlots; ++a) {
       mbar_init(&acc_full[a], 1);
       mbar_init(&acc_empty[a], kEpiWarps);
+      mbar_init(&pub_bar[a], kEpiWarps);
+      mbar_init(&pub_free[a], 1);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -133,7 +280,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         uint32_t phase = 0;
         for (int t = 0; t < S; ++t) {
           for (int m = tile0; m < tile1; ++m) {
-            if (t > 0) {
+            if (t > 0 && !(args.debug & 1)) {
               // h_{t-1} of this tile is complete once all slices of this direction have arrived t times
               const int* c = args.cnt + dir * args.MT + m;
               const int need = kNS * t;
@@ -153,8 +300,12 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             const int arow = ((t & 1) * 2 + dir) * Bp + m * 128;
             for (int kb = 0; kb < kKB; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-              tma_load_2d(smem_a + (size_t)stage * kABytes, &tmap_h, &full_bar[stage], kb * 64, arow);
+              if (args.debug & 8) {
+                mbar_arrive(&full_bar[stage]);           // probe: no A traffic
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], kABytes);
+                tma_load_2d(smem_a + (size_t)stage * kABytes, &tmap_h, &full_bar[stage], kb * 64, arow);
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -166,7 +317,11 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         constexpr uint32_t idesc = make_idesc_bf16_f32(128, kN);
         mbar_wait(w_bar, 0);
         tc_fence_after();
-        const uint32_t w_addr = smem_u32(smem_w);
+        // One thread issues ~50 short (N = 96) MMAs per item: the loop must cost less than the MMAs themselves, so
+        // the shared-memory descriptors are formed once and stepped by adding to their 14-bit address field.
+        const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem_a));
+        const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
+        const bool no_mma = (args.debug & 16) != 0;       // probe
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -177,15 +332,18 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             mbar_wait(&acc_empty[slot], slot_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(slot * kSlotCols);
-            for (int kb = 0; kb < kKB; ++kb) {
+            uint64_t b_desc = b_desc0;
+#pragma unroll 1
+            for (int kb = 0; kb < kKB; ++kb, b_desc += (kWChunkBytes >> 4)) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * kABytes);
-              const uint32_t b_addr = w_addr + (uint32_t)kb * kWChunkBytes;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d, make_kmajor_sw128_desc(a_addr + k * 32), make_kmajor_sw128_desc(b_addr + k * 32), idesc,
-                          (kb > 0 || k > 0) ? 1u : 0u);
+              const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kABytes >> 4));
+              if (!no_mma) {
+                umma_bf16(tmem_d, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+                umma_bf16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);
+                umma_bf16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
+                umma_bf16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
+              }
               umma_commit(&empty_bar[stage]);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -193,112 +351,35 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
           }
         }
       }
-    } else {
-      // ===================== cell epilogue: thread = sentence, 12 hidden units =====================
-      const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-      const int half = (warp - 2) >> 2;          // which 12 of the slice's 24 units
-      const int unit0 = slice * kU + half * 12;
-      const size_t gx_col = (size_t)((dir * kNS + slice) * 2 + half) * 48;
-      int it = 0;
-      for (int t = 0; t < S; ++t) {
-        const int pos = dir ? (S - 1 - t) : t;
-        for (int m = tile0; m < tile1; ++m, ++it) {
+    } else if (warp == kPubWarp) {
+      // ===================== publisher: one gpu-scope release per item, off the epilogue warps' path =====================
+      // The epilogue warps arrive on pub_bar[slot] (release.cta) after their h stores; this thread acquires the
+      // barrier and performs the ONE gpu-scope release of the CTA (cumulative over everything that happened-before
+      // it) -- so the ~1 us a MEMBAR.GPU takes never stalls the warps that do the cell arithmetic.
+      if (lane == 0) {
+        const int ntiles = tile1 - tile0;
+        const int items = S * ntiles;
+        for (int it = 0; it < items; ++it) {
+          const int m = tile0 + it % ntiles;
           const int slot = it % kSlots;
-          const uint32_t slot_phase = (it / kSlots) & 1;
-          const int row = m * 128 + quad * 32 + lane;
-          const bool valid = row < args.B;
-          // everything that does not depend on the recurrence is fetched before the accumulator is waited for
-          uint32_t gw[24];
-          float c[12];
-          float* cp = args.cbuf + ((size_t)dir * Bp + row) * kH + unit0;
-          if (valid) {
-            const uint4* gp = reinterpret_cast<const uint4*>(args.gx + ((size_t)row * S + pos) * (8 * kH) + gx_col);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              const uint4 v = __ldg(gp + q);
-              gw[4 * q] = v.x;
-              gw[4 * q + 1] = v.y;
-              gw[4 * q + 2] = v.z;
-              gw[4 * q + 3] = v.w;
-            }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const float4 v = *reinterpret_cast<const float4*>(cp + 4 * q);
-              c[4 * q] = v.x;
-              c[4 * q + 1] = v.y;
-              c[4 * q + 2] = v.z;
-              c[4 * q + 3] = v.w;
-            }
+          mbar_wait(&pub_bar[slot], (it / kSlots) & 1);
+          if (args.debug & 4) {
+            atomicAdd(args.cnt + dir * args.MT + m, 1);
           } else {
-#pragma unroll
-            for (int q = 0; q < 24; ++q) gw[q] = 0u;
-#pragma unroll
-            for (int q = 0; q < 12; ++q) c[q] = 0.0f;
-          }
-          mbar_wait(&acc_full[slot], slot_phase);
-          tc_fence_after();
-          uint32_t r[48];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * kSlotCols + half * 48);
-          tmem_ld16(taddr, &r[0]);
-          tmem_ld16(taddr + 16, &r[16]);
-          tmem_ld16(taddr + 32, &r[32]);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[slot]);   // the MMA warp may reuse the slot
-
-          float hv[12];
-#pragma unroll
-          for (int j = 0; j < 12; ++j) {
-            float pre[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int e = g * 12 + j;
-              const uint32_t w = gw[e >> 1];
-              const float gxv = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
-              pre[g] = __uint_as_float(r[e]) + gxv;
-            }
-            const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]), gg = tanh_fast(pre[2]),
-                        og = sigmoid_fast(pre[3]);
-            c[j] = fmaf(fg, c[j], ig * gg);
-            hv[j] = og * tanh_fast(c[j]);
-          }
-          if (valid) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-              *reinterpret_cast<float4*>(cp + 4 * q) = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-            uint2 hw[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-              hw[q] = make_uint2(pack_bf16x2(hv[4 * q], hv[4 * q + 1]), pack_bf16x2(hv[4 * q + 2], hv[4 * q + 3]));
-            uint2* hp = reinterpret_cast<uint2*>(args.hbuf + ((size_t)(((t + 1) & 1) * 2 + dir) * Bp + row) * kH + unit0);
-            uint2* yp = reinterpret_cast<uint2*>(args.y + ((size_t)row * S + pos) * (2 * kH) + dir * kH + unit0);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              hp[q] = hw[q];
-              yp[q] = hw[q];
-            }
-            if (t == S - 1) {
-              if (args.h_n) {
-                float4* o = reinterpret_cast<float4*>(args.h_n + ((size_t)dir * args.B + row) * kH + unit0);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) o[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
-              }
-              if (args.c_n) {
-                float4* o = reinterpret_cast<float4*>(args.c_n + ((size_t)dir * args.B + row) * kH + unit0);
-#pragma unroll
-                for (int q = 0; q < 3; ++q) o[q] = make_float4(c[4 * q], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
-              }
-            }
-          }
-          // publish: every epilogue thread's h stores are ordered before the one arrival of this CTA
-          __threadfence();
-          asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kEpiWarps) : "memory");
-          if (threadIdx.x == 64) {
             fence_proxy_async_all();
             red_release_gpu_add(args.cnt + dir * args.MT + m, 1);
           }
+          mbar_arrive(&pub_free[slot]);
         }
+      }
+    } else {
+      // ===================== cell epilogue: thread = sentence, 12 hidden units =====================
+      const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      switch (tile1 - tile0) {
+        case 1: lstm_epilogue<1>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
+        case 2: lstm_epilogue<2>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
+        case 3: lstm_epilogue<3>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
+        default: lstm_epilogue<4>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
       }
     }
   }
@@ -315,10 +396,18 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// sentences per launch: the cell state of a CTA's tiles lives in registers, at most 4 tiles of 128 per CTA
+static int lstm_chunk(int sm_count) { return 4 * 128 * (sm_count / (2 * kNS) > 0 ? sm_count / (2 * kNS) : 1); }
+
 extern "C" int64_t icka_lstm_rec_workspace_bytes(int B, int H) {
   if (B < 0 || H != kH) return -1;
-  const size_t MT = ((size_t)B + 127) / 128, Bp = MT * 128;
-  return (int64_t)(align_up(2 * MT * sizeof(int), 1024) + 4 * Bp * kH * 2 + 2 * Bp * kH * 4);
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = 2 * kNS;
+  const size_t chunk = (size_t)lstm_chunk(sms);
+  const size_t Bc = (size_t)B < chunk ? (size_t)B : chunk;
+  const size_t MT = (Bc + 127) / 128, Bp = MT * 128;
+  return (int64_t)(align_up(2 * MT * sizeof(int), 1024) + 4 * Bp * kH * 2);
 }
 
 extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
@@ -334,42 +423,50 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
   ICKA_REQUIRE(!h_n || icka_aligned(h_n, 16), "lstm_rec: h_n must be 16-byte aligned");
   ICKA_REQUIRE(!c_n || icka_aligned(c_n, 16), "lstm_rec: c_n must be 16-byte aligned");
   if (B == 0) return ICKA_OK;
-  ICKA_REQUIRE(workspace_bytes >= icka_lstm_rec_workspace_bytes(B, H), "lstm_rec: workspace of %lld B, need %lld",
-               (long long)workspace_bytes, (long long)icka_lstm_rec_workspace_bytes(B, H));
   ICKA_REQUIRE(h->sm_count >= 2 * kNS, "lstm_rec: needs %d co-resident CTAs, device has %d SMs", 2 * kNS, h->sm_count);
+  const int chunk = lstm_chunk(h->sm_count);
+  const int Bc_max = B < chunk ? B : chunk;
+  const size_t MT_max = ((size_t)Bc_max + 127) / 128;
+  const size_t cnt_bytes = align_up(2 * MT_max * sizeof(int), 1024);
+  const size_t need = cnt_bytes + 4 * MT_max * 128 * kH * 2;
+  ICKA_REQUIRE((size_t)workspace_bytes >= need, "lstm_rec: workspace of %lld B, need %lld", (long long)workspace_bytes,
+               (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-  LstmArgs args;
-  args.B = B;
-  args.S = S;
-  args.MT = (B + 127) / 128;
-  args.Bp = args.MT * 128;
-  int groups = h->sm_count / (2 * kNS);
-  if (groups > args.MT) groups = args.MT;
-  args.TPG = (args.MT + groups - 1) / groups;
-  groups = (args.MT + args.TPG - 1) / args.TPG;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const size_t cnt_bytes = align_up(2 * (size_t)args.MT * sizeof(int), 1024);
-  const size_t h_bytes = 4 * (size_t)args.Bp * kH * 2, c_bytes = 2 * (size_t)args.Bp * kH * 4;
-  args.cnt = reinterpret_cast<int*>(ws);
-  args.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + cnt_bytes);
-  args.cbuf = reinterpret_cast<float*>(ws + cnt_bytes + h_bytes);
-  args.gx = static_cast<const __nv_bfloat16*>(gx);
-  args.y = static_cast<__nv_bfloat16*>(y);
-  args.h_n = h_n;
-  args.c_n = c_n;
-  ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes + h_bytes + c_bytes, st));   // counters, h_{-1} = 0, c_{-1} = 0
-
-  CUtensorMap tw, th;
+  CUtensorMap tw;
   int rc = icka_make_tmap_bf16(h, &tw, w_hh_perm, 2 * 4 * kH, kH, kH, kN);
   if (rc) return rc;
-  rc = icka_make_tmap_bf16(h, &th, args.hbuf, 4 * (int64_t)args.Bp, kH, kH, 128);
-  if (rc) return rc;
-
   ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-  void* kargs[3] = {&tw, &th, &args};
-  ICKA_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_rec_tcgen05_kernel), dim3(groups * 2 * kNS),
-                                        dim3(kThreads), kargs, kSmemBytes, st));
-  ICKA_LAUNCHED(h);
+  const char* dbg = getenv("ICKA_LSTM_DEBUG");
+
+  // sentences are independent recurrences: launches of <= `chunk` sentences, one after the other on the stream
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    LstmArgs args;
+    args.B = (B - b0 < chunk) ? B - b0 : chunk;
+    args.S = S;
+    args.Bn = B;
+    args.MT = (args.B + 127) / 128;
+    args.Bp = args.MT * 128;
+    int groups = h->sm_count / (2 * kNS);
+    if (groups > args.MT) groups = args.MT;
+    args.TPG = (args.MT + groups - 1) / groups;
+    groups = (args.MT + args.TPG - 1) / args.TPG;
+    args.cnt = reinterpret_cast<int*>(ws);
+    args.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + cnt_bytes);
+    args.gx = static_cast<const __nv_bfloat16*>(gx) + (size_t)b0 * (8 * kH);     // time-major: row = t * B + b
+    args.y = static_cast<__nv_bfloat16*>(y) + (size_t)b0 * (2 * kH);
+    args.h_n = h_n ? h_n + (size_t)b0 * kH : nullptr;
+    args.c_n = c_n ? c_n + (size_t)b0 * kH : nullptr;
+    args.debug = dbg ? atoi(dbg) : 0;
+    const size_t h_bytes = 4 * (size_t)args.Bp * kH * 2;
+    ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes + h_bytes, st));   // arrival counters, h_{-1} = 0
+    CUtensorMap th;
+    rc = icka_make_tmap_bf16(h, &th, args.hbuf, 4 * (int64_t)args.Bp, kH, kH, 128);
+    if (rc) return rc;
+    void* kargs[3] = {&tw, &th, &args};
+    ICKA_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_rec_tcgen05_kernel), dim3(groups * 2 * kNS),
+                                          dim3(kThreads), kargs, kSmemBytes, st));
+    ICKA_LAUNCHED(h);
+  }
   return ICKA_OK;
 }

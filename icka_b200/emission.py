@@ -32,14 +32,15 @@ _HALF_UNITS = 12
 
 def slice_order(H: int = REC_H) -> torch.Tensor:
     """perm[8H]: row of the slice-ordered weights -> row of cat(weight_*_l0, weight_*_l0_reverse).
-    col = ((dir*32 + slice)*2 + half)*48 + gate*12 + j  <->  dir*4H + gate*H + slice*24 + half*12 + j."""
+    col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  dir*4H + gate*H + slice*24 + half*12 + jg*4 + jj."""
     n_slices = H // _SLICE_UNITS
-    d = torch.arange(2).view(2, 1, 1, 1, 1)
-    s = torch.arange(n_slices).view(1, n_slices, 1, 1, 1)
-    hf = torch.arange(2).view(1, 1, 2, 1, 1)
-    g = torch.arange(4).view(1, 1, 1, 4, 1)
-    j = torch.arange(_HALF_UNITS).view(1, 1, 1, 1, _HALF_UNITS)
-    return (d * 4 * H + g * H + s * _SLICE_UNITS + hf * _HALF_UNITS + j).reshape(-1)
+    d = torch.arange(2).view(2, 1, 1, 1, 1, 1)
+    s = torch.arange(n_slices).view(1, n_slices, 1, 1, 1, 1)
+    hf = torch.arange(2).view(1, 1, 2, 1, 1, 1)
+    jg = torch.arange(3).view(1, 1, 1, 3, 1, 1)
+    g = torch.arange(4).view(1, 1, 1, 1, 4, 1)
+    jj = torch.arange(4).view(1, 1, 1, 1, 1, 4)
+    return (d * 4 * H + g * H + s * _SLICE_UNITS + hf * _HALF_UNITS + jg * 4 + jj).reshape(-1)
 
 
 class LSTM(nn.Module):
@@ -87,20 +88,25 @@ class LSTM(nn.Module):
 
     # ---- forward -----------------------------------------------------------------------------------
     def states(self, x: torch.Tensor, want_state: bool = False):
-        """x [B,S,I] (batch-first) -> (y [B,S,2H] in the compute dtype, h_n, c_n | None)."""
+        """x [B,S,I] (batch-first) -> (y [B,S,2H] in the compute dtype, h_n, c_n | None).  On the persistent-kernel
+        path y is a batch-first VIEW of the time-major [S,B,2H] tensor the kernel writes."""
         B, S, I = x.shape
         H = self.hidden_size
         lp = modules.get_precision() == 'bf16'
+        if self.uses_persistent_kernel():
+            wi, b, wh = self._prepared(True)
+            xc = x.contiguous()
+            x_tm = ops.cast_bf16_time_major(xc if xc.dtype in (torch.float32, torch.bfloat16) else xc.float())
+            gx = ops.linear(x_tm.view(S * B, I), wi, b, out_dtype=torch.bfloat16)
+            out = ops.lstm_rec(gx, wh, B, S, H, want_state=want_state)
+            if want_state:
+                return out[0].transpose(0, 1), out[1], out[2]
+            return out.transpose(0, 1), None, None
         x2 = x.reshape(B * S, I)
         if lp:
             x2 = x2.contiguous() if x2.dtype == torch.bfloat16 else ops.cast_bf16(x2.float().contiguous())
         else:
             x2 = x2.float().contiguous()
-        if self.uses_persistent_kernel():
-            wi, b, wh = self._prepared(True)
-            gx = ops.linear(x2, wi, b, out_dtype=torch.bfloat16)
-            out = ops.lstm_rec(gx, wh, B, S, H, want_state=want_state)
-            return out if want_state else (out, None, None)
         # per-step path
         wi, b, wh = self._prepared(False)
         cdt = torch.bfloat16 if lp else torch.float32
@@ -148,6 +154,10 @@ class EmissionHead(nn.Module):
     def forward(self, result: torch.Tensor) -> torch.Tensor:
         B, S, _ = result.shape
         y, _, _ = self.lstm.states(result)
-        e = ops.emission_head(y.view(B * S, -1), self.classifier.weight.detach().float().contiguous(),
-                              self.classifier.bias.detach().float().contiguous())
+        w = self.classifier.weight.detach().float().contiguous()
+        b = self.classifier.bias.detach().float().contiguous()
+        if y.is_contiguous():
+            e = ops.emission_head(y.view(B * S, -1), w, b)
+        else:                                                   # time-major states of the persistent kernel
+            e = ops.emission_head(y.transpose(0, 1).view(S * B, -1), w, b, time_major_S=S)
         return e.view(B, S, -1)

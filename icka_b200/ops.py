@@ -469,7 +469,8 @@ def lstm_rec_workspace_bytes(B: int, H: int) -> int:
 
 def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, *, workspace: Optional[torch.Tensor] = None,
              want_state: bool = False):
-    """gx [B*S, 8H] bf16 (slice order), w_hh_perm [8H, H] bf16 -> y [B,S,2H] bf16 (, h_n, c_n [2,B,H] fp32)."""
+    """gx [S*B, 8H] bf16 (time-major rows, slice-ordered columns), w_hh_perm [8H, H] bf16 -> y [S,B,2H] bf16
+    time-major (, h_n, c_n [2,B,H] fp32)."""
     _need(gx, torch.bfloat16, 'lstm_rec(gx)')
     _need(w_hh_perm, torch.bfloat16, 'lstm_rec(w_hh_perm)')
     if gx.shape != (B * S, 8 * H) or w_hh_perm.shape != (8 * H, H):
@@ -481,7 +482,7 @@ def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, 
     off = (-workspace.data_ptr()) % 1024
     if workspace.numel() - off < need:
         raise RuntimeError(f'lstm_rec: workspace of {workspace.numel()} B, need {need} + alignment')
-    y = torch.empty(B, S, 2 * H, dtype=torch.bfloat16, device=gx.device)
+    y = torch.empty(S, B, 2 * H, dtype=torch.bfloat16, device=gx.device)
     h_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
     c_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
     _lib.check(lib.icka_lstm_rec_fwd(h, gx.data_ptr(), w_hh_perm.data_ptr(), workspace.data_ptr() + off, need,
@@ -511,8 +512,21 @@ def lstm_cell(gates_h: Optional[torch.Tensor], gx: torch.Tensor, c: torch.Tensor
                'icka_lstm_cell_fwd')
 
 
-def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """x [M,K] (fp32 or bf16, unit stride along K) . w[T,K]^T (fp32) + bias -> [M,T] fp32."""
+def cast_bf16_time_major(x: torch.Tensor) -> torch.Tensor:
+    """x [B,S,H] fp32 / bf16 contiguous -> [S,B,H] bf16."""
+    if x.dim() != 3 or x.dtype not in _DT or not x.is_contiguous():
+        raise RuntimeError('cast_bf16_time_major: x must be a contiguous [B,S,H] fp32 / bf16 tensor')
+    B, S, H = x.shape
+    lib, h, st = _ctx(x)
+    y = torch.empty(S, B, H, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.icka_cast_bf16_time_major(h, x.data_ptr(), y.data_ptr(), _DT[x.dtype], B, S, H, st),
+               'icka_cast_bf16_time_major')
+    return y
+
+
+def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, time_major_S: int = 0) -> torch.Tensor:
+    """x [M,K] (fp32 or bf16, unit stride along K) . w[T,K]^T (fp32) + bias -> [M,T] fp32.  ``time_major_S`` = S:
+    the rows of x are t*B + b and the output rows b*S + t."""
     if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:
         raise RuntimeError('emission_head: bad x')
     _need(w, torch.float32, 'emission_head(w)')
@@ -524,5 +538,5 @@ def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch
     lib, h, st = _ctx(x)
     out = torch.empty(M, T, dtype=torch.float32, device=x.device)
     _lib.check(lib.icka_emission_head_fwd(h, x.data_ptr(), _ld(x, K), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
-                                          _DT[x.dtype], M, K, T, st), 'icka_emission_head_fwd')
+                                          _DT[x.dtype], M, K, T, int(time_major_S), st), 'icka_emission_head_fwd')
     return out

@@ -266,12 +266,15 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
 
 /* Recurrent half of `self.lstm = nn.LSTM(H, H, batch_first=True, bidirectional=True)` (CMIM:905-908, call :1042):
  * one persistent, weight-stationary tcgen05 kernel walks all S steps of both directions (csrc/lstm_sm100.cu).
- *   gx        [B*S, 2*4H] bf16 = x . W_ih^T + b_ih + b_hh for both directions (an icka_linear_fwd call), columns in the
- *             kernel's slice order:  col = ((dir*32 + slice)*2 + half)*48 + gate*12 + j  <->  PyTorch row
- *             gate*H + slice*24 + half*12 + j of direction `dir` (gate order i, f, g, o)
+ *   gx        [S*B, 2*4H] bf16, TIME-MAJOR rows (row = t*B + sentence; x from icka_cast_bf16_time_major)
+ *             = x . W_ih^T + b_ih + b_hh for both directions (an icka_linear_fwd call), columns in the
+ *             kernel's slice order:  col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  PyTorch row
+ *             gate*H + slice*24 + half*12 + jg*4 + jj of direction `dir` (gate order i, f, g, o; jg < 3, jj < 4)
  *   w_hh_perm [2*4H, H] bf16: weight_hh_l0 / weight_hh_l0_reverse with their rows in the same order
  *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters, h ping-pong, cell state)
- *   y         [B, S, 2H] bf16 (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
+ *   y         [S, B, 2H] bf16 TIME-MAJOR (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
+ * Every step then reads / writes one contiguous block of gx / y.  More than 1024 sentences run as consecutive
+ * launches of <= 1024 (the cell state of a CTA's <= 4 sentence tiles lives in registers).
  * H = 768 only (other sizes: the per-step path, icka_linear_fwd + icka_lstm_cell_fwd).  The launch is cooperative:
  * 64 or 128 co-resident CTAs. */
 int64_t icka_lstm_rec_workspace_bytes(int B, int H);
@@ -287,9 +290,15 @@ int icka_lstm_cell_fwd(icka_handle* h, const float* gates_h, const void* gx, int
                        void* y, int64_t ldy, float* h_f32, int dtype, int B, int H, void* stream);
 
 /* `self.classifier = nn.Linear(2H, num_labels)` (CMIM:910, :1043): out[M,T] fp32 = x[M,K] (`dtype`, pitch ldx) .
- * W[T,K]^T (fp32) + bias[T].  T <= 16, K % 8 == 0.  fp32 accumulation in a fixed order. */
+ * W[T,K]^T (fp32) + bias[T].  T <= 16, K % 8 == 0.  fp32 accumulation in a fixed order.
+ * time_major_S = S > 0: the rows of x are time-major (row = t*B + b, B = M/S, as icka_lstm_rec_fwd writes them) and
+ * the emissions are written batch-major (row b*S + t), the layout the CRF entry points take; 0: same row order. */
 int icka_emission_head_fwd(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias, float* out,
-                           int dtype, int64_t M, int K, int T, void* stream);
+                           int dtype, int64_t M, int K, int T, int time_major_S, void* stream);
+
+/* x [B,S,H] (fp32 or bf16) -> y [S,B,H] bf16: the time-major operand of the input projection of icka_lstm_rec_fwd. */
+int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_bf16, int in_dtype, int B, int S, int H,
+                              void* stream);
 
 /* out = a + b (fp32; weight preparation: b_ih + b_hh). */
 int icka_add_f32(icka_handle* h, const float* a, const float* b, float* out, int64_t n, void* stream);

@@ -92,7 +92,8 @@ def test_emission_head_kernel(dtype, M, K, T):
     b = torch.randn(T)
     want = x.double() @ w.double().t() + b.double()
     got = ops.emission_head(x.cuda(), w.cuda(), b.cuda())
-    assert got.shape == (M, T) and rel(got, want) <= 1e-5
+    # bf16 states take the tensor-core kernel with hi + lo split weights (16 mantissa bits): 1e-4; fp32 stays 1e-5
+    assert got.shape == (M, T) and rel(got, want) <= (1e-5 if dtype == torch.float32 else 1e-4)
 
 
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('bf16', 2e-2)])
