@@ -11,10 +11,13 @@
 //     each slice stays in the shared memory of ONE CTA for the whole sequence (loaded once by TMA, SWIZZLE_128B,
 //     K-major B operand of tcgen05.mma);
 //   * a work item is (step t, 128-sentence tile m): the CTA streams h_{t-1}[tile m] (128 x 768 bf16, written by the
-//     32 slice CTAs of its direction) from L2 through a 5-stage TMA ring as the A operand, accumulates the
-//     128 x 96 gate pre-activations in TMEM (4 accumulator slots), and 8 epilogue warps (thread = sentence, two
-//     column halves) add Gx, apply the cell update out of TMEM and write h_t (bf16, next step's operand), c_t
-//     (fp32) and the output sequence;
+//     32 slice CTAs of its direction) from L2 through a 5-stage TMA ring as the A operand -- straight out of the
+//     time-major output sequence y[t-1], so h is written exactly once -- accumulates the 128 x 96 gate
+//     pre-activations in TMEM (4 accumulator slots), and 8 epilogue warps (thread = sentence, two column halves)
+//     add Gx (prefetched one item ahead), apply the cell update out of TMEM with the cell state in registers and
+//     write h_t (bf16) into y[t];
+//   * a publisher warp turns "all 8 epilogue warps stored their part of item (t, m)" into ONE gpu-scope release on
+//     the tile's arrival counter, so the ~4 us a MEMBAR.GPU takes on a busy SM never stalls the cell arithmetic;
 //   * sentence tiles are independent recurrences, so a CTA walks items in (t, m) order and only waits for
 //     "all 32 slices have published h_{t-1} of tile m" -- a per-(direction, tile) arrival counter in global memory
 //     (red.release / ld.acquire + fence.proxy.async before the TMA reads).  With several tiles per CTA the wait
@@ -54,13 +57,13 @@ constexpr size_t kSmemBytes = (size_t)kWBytes + (size_t)kStages * kABytes + 1024
 struct LstmArgs {
   const __nv_bfloat16* gx;   // [S*Bn, 2*4H] bf16 TIME-MAJOR (row = t * Bn + sentence), columns ordered [dir][slice][half][jg][gate][4]
   int* cnt;                  // [2][MT] arrival counters (zeroed before launch)
-  __nv_bfloat16* hbuf;       // [2 parity][2 dir][Bp][H] bf16, parity 0 zeroed (h_{-1} = 0)
   __nv_bfloat16* y;          // [S, Bn, 2H] bf16 TIME-MAJOR: forward states in [:H], backward in [H:]
   float* h_n;                // [2, Bn, H] fp32 or null (already offset to this launch's first sentence)
   float* c_n;                // [2, Bn, H] fp32 or null
   int Bn;                    // sentences of the whole call (pitch of the time planes of gx / y and of the direction
                              // planes of h_n / c_n)
-  int B, S, Bp, MT, TPG;     // sentences, steps, padded sentences (MT * 128), 128-row tiles, tiles per group
+  int B, S, b0, MT, TPG;     // sentences of this launch, steps, first sentence of this launch, 128-row tiles, tiles
+                             // per CTA group
   int debug;                 // developer probes (ICKA_LSTM_DEBUG): 1 = no dependency wait, 2 = no cell arithmetic /
                              // state stores, 4 = publish without the gpu-scope release, 8 = no A loads, 16 = no MMAs
                              // (results are WRONG)
@@ -93,7 +96,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
   const int half = (warp - 2) >> 2;          // which 12 of the slice's 24 units
   const int unit0 = slice * kU + half * 12;
   const size_t gx_col = (size_t)((dir * kNS + slice) * 2 + half) * 48;
-  const int S = args.S, Bp = args.Bp;
+  const int S = args.S;
   const int row0 = tile0 * 128 + quad * 32 + lane;
   float c[NT][12];
 #pragma unroll
@@ -180,16 +183,11 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
         // 24 bytes per row at byte offset 48 * slice + 24 * half: one 16-byte and one 8-byte store, ordered so the
         // 16-byte one is aligned (half 0: 16 + 8, half 1: 8 + 16)
-        uint8_t* hp = reinterpret_cast<uint8_t*>(args.hbuf + ((size_t)(((t + 1) & 1) * 2 + dir) * Bp + row) * kH + unit0);
         uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH + unit0);
         if (half == 0) {
-          *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint2*>(hp + 16) = make_uint2(hw[4], hw[5]);
           *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           *reinterpret_cast<uint2*>(yp + 16) = make_uint2(hw[4], hw[5]);
         } else {
-          *reinterpret_cast<uint2*>(hp) = make_uint2(hw[0], hw[1]);
-          *reinterpret_cast<uint4*>(hp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
           *reinterpret_cast<uint2*>(yp) = make_uint2(hw[0], hw[1]);
           *reinterpret_cast<uint4*>(yp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
         }
@@ -240,7 +238,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
   const int group = blockIdx.x / (2 * kNS);
   const int tile0 = group * args.TPG;
   const int tile1 = min(args.MT, tile0 + args.TPG);
-  const int S = args.S, Bp = args.Bp;
+  const int S = args.S;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -297,14 +295,17 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
               }
               fence_proxy_async_all();   // generic-proxy writes of the other CTAs -> visible to the TMA reads below
             }
-            const int arow = ((t & 1) * 2 + dir) * Bp + m * 128;
+            // A operand = h_{t-1} of this tile = the rows the previous step wrote into the (time-major) output
+            // sequence; at t = 0 an out-of-bounds row makes TMA deliver zeros (h_{-1} = 0)
+            const int prev = dir ? (S - t) : (t - 1);
+            const int arow = (t == 0) ? S * args.Bn : prev * args.Bn + args.b0 + m * 128;
             for (int kb = 0; kb < kKB; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
               if (args.debug & 8) {
                 mbar_arrive(&full_bar[stage]);           // probe: no A traffic
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-                tma_load_2d(smem_a + (size_t)stage * kABytes, &tmap_h, &full_bar[stage], kb * 64, arow);
+                tma_load_2d(smem_a + (size_t)stage * kABytes, &tmap_h, &full_bar[stage], dir * kH + kb * 64, arow);
               }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
@@ -366,8 +367,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
           if (args.debug & 4) {
             atomicAdd(args.cnt + dir * args.MT + m, 1);
           } else {
-            fence_proxy_async_all();
-            red_release_gpu_add(args.cnt + dir * args.MT + m, 1);
+            red_release_gpu_add(args.cnt + dir * args.MT + m, 1);   // the consumer's fence.proxy.async orders its TMA reads
           }
           mbar_arrive(&pub_free[slot]);
         }
@@ -406,8 +406,8 @@ extern "C" int64_t icka_lstm_rec_workspace_bytes(int B, int H) {
     sms = 2 * kNS;
   const size_t chunk = (size_t)lstm_chunk(sms);
   const size_t Bc = (size_t)B < chunk ? (size_t)B : chunk;
-  const size_t MT = (Bc + 127) / 128, Bp = MT * 128;
-  return (int64_t)(align_up(2 * MT * sizeof(int), 1024) + 4 * Bp * kH * 2);
+  const size_t MT = (Bc + 127) / 128;
+  return (int64_t)align_up(2 * MT * sizeof(int), 1024);
 }
 
 extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
@@ -428,13 +428,16 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
   const int Bc_max = B < chunk ? B : chunk;
   const size_t MT_max = ((size_t)Bc_max + 127) / 128;
   const size_t cnt_bytes = align_up(2 * MT_max * sizeof(int), 1024);
-  const size_t need = cnt_bytes + 4 * MT_max * 128 * kH * 2;
+  const size_t need = cnt_bytes;
   ICKA_REQUIRE((size_t)workspace_bytes >= need, "lstm_rec: workspace of %lld B, need %lld", (long long)workspace_bytes,
                (long long)need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  CUtensorMap tw;
+  CUtensorMap tw, th;
   int rc = icka_make_tmap_bf16(h, &tw, w_hh_perm, 2 * 4 * kH, kH, kH, kN);
+  if (rc) return rc;
+  // the A operand of step t is read straight out of the output sequence: [S*B rows, 2H columns], box 128 x 64
+  rc = icka_make_tmap_bf16(h, &th, y, (int64_t)S * B, 2 * kH, 2 * kH, 128);
   if (rc) return rc;
   ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* dbg = getenv("ICKA_LSTM_DEBUG");
@@ -446,23 +449,18 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
     args.S = S;
     args.Bn = B;
     args.MT = (args.B + 127) / 128;
-    args.Bp = args.MT * 128;
+    args.b0 = b0;
     int groups = h->sm_count / (2 * kNS);
     if (groups > args.MT) groups = args.MT;
     args.TPG = (args.MT + groups - 1) / groups;
     groups = (args.MT + args.TPG - 1) / args.TPG;
     args.cnt = reinterpret_cast<int*>(ws);
-    args.hbuf = reinterpret_cast<__nv_bfloat16*>(ws + cnt_bytes);
     args.gx = static_cast<const __nv_bfloat16*>(gx) + (size_t)b0 * (8 * kH);     // time-major: row = t * B + b
     args.y = static_cast<__nv_bfloat16*>(y) + (size_t)b0 * (2 * kH);
     args.h_n = h_n ? h_n + (size_t)b0 * kH : nullptr;
     args.c_n = c_n ? c_n + (size_t)b0 * kH : nullptr;
     args.debug = dbg ? atoi(dbg) : 0;
-    const size_t h_bytes = 4 * (size_t)args.Bp * kH * 2;
-    ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes + h_bytes, st));   // arrival counters, h_{-1} = 0
-    CUtensorMap th;
-    rc = icka_make_tmap_bf16(h, &th, args.hbuf, 4 * (int64_t)args.Bp, kH, kH, 128);
-    if (rc) return rc;
+    ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes, st));   // arrival counters
     void* kargs[3] = {&tw, &th, &args};
     ICKA_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_rec_tcgen05_kernel), dim3(groups * 2 * kNS),
                                           dim3(kThreads), kargs, kSmemBytes, st));

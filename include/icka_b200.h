@@ -271,7 +271,7 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
  *             kernel's slice order:  col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  PyTorch row
  *             gate*H + slice*24 + half*12 + jg*4 + jj of direction `dir` (gate order i, f, g, o; jg < 3, jj < 4)
  *   w_hh_perm [2*4H, H] bf16: weight_hh_l0 / weight_hh_l0_reverse with their rows in the same order
- *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters, h ping-pong, cell state)
+ *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters; zeroed by the call)
  *   y         [S, B, 2H] bf16 TIME-MAJOR (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
  * Every step then reads / writes one contiguous block of gx / y.  More than 1024 sentences run as consecutive
  * launches of <= 1024 (the cell state of a CTA's <= 4 sentence tiles lives in registers).
