@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=32, help='sentences in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-widened', action='store_true', help='skip the extra fusion -> BiLSTM+classifier -> Viterbi -> chunk-F1 measurement')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -321,6 +322,15 @@ def run_gpu_arm(args, shape):
                'api': 'icka_b200.pipeline.FusionViterbiPipeline.infer_host (pinned host fp32 inputs; H2D of batch i+1 '
                       'overlaps kernels of batch i; D2H of tags, lengths, gates)'}
 
+    # ---- widened path (SURVEY 8f rows 1 + 2; extra, not part of `value`) ----
+    widened = None
+    if not args.no_widened and args.precision == 'bf16' and shape.H == 768:
+        widened = run_widened(args, shape, dev, seed, d, barrier)
+        if widened is not None and world > 1:
+            widened['ms_per_step'] = shard.max_over_ranks(widened['ms_per_step'], device=dev)
+        if widened is not None:
+            widened['value'] = args.batch * world / (widened['ms_per_step'] * 1e-3)
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,13 +353,69 @@ def run_gpu_arm(args, shape):
                        'launch': 'CUDA graph replay of the captured step' if use_graph else 'eager host launches',
                        'l2_policy': 'inputs larger than L2 (>= 1.2 GB of inputs per step vs 126 MB L2); no flush needed'},
             'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
-            'cpu_baseline': cpu, 'kernels': kernel_table,
+            'cpu_baseline': cpu, 'widened': widened, 'kernels': kernel_table,
             'gemm_shapes': {k: {'launches_per_step': v['launches'] // args.steps, 'ms_per_launch': round(v['ms_per_launch'], 4),
                                 'tflops': round(v['tflops'], 1)} for k, v in gemm_shapes.items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_widened(args, shape, dev, seed, d, barrier):
+    """fusion -> emission head (BiLSTM + classifier) -> Viterbi of those emissions -> chunk-F1 counters, device-resident
+    inputs, CUDA-event timed per stage (eager launches; the recurrent kernel is one cooperative launch per <= 1024
+    sentences)."""
+    import torch
+    from icka_b200 import _lib
+    from icka_b200.pipeline import TaggingPipeline
+    from icka_b200 import synth
+    steps = max(3, min(args.steps, 10))
+    pipe = TaggingPipeline(shape, dev, args.precision, seed=seed)
+    labels = synth.crf_batch(args.batch, shape, seed=seed)['tags'].to(dev)
+    for _ in range(3):
+        pipe.step_tagging(d, labels)
+    barrier()
+    idx = torch.device(dev).index or 0
+    n0 = _lib.launch_count(idx)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(steps):
+        pipe.step_tagging(d, labels)
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    launches = (_lib.launch_count(idx) - n0) // steps
+    # stage split (same inputs, one stage at a time)
+    out = pipe.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'], d['img_mask'],
+                      d['text_mask'], return_dict=True, want_fused=False)
+    result = out['result']
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps
+
+    with torch.no_grad():
+        ms_head = timed(lambda: pipe.head(result))
+        em = pipe.head(result)
+        ms_vit = timed(lambda: pipe.crf.decode_tensors(em, d['crf_mask']))
+        tags, _ = pipe.crf.decode_tensors(em, d['crf_mask'])
+        ms_f1 = timed(lambda: pipe.f1.update(tags, labels, d['crf_mask']))
+    B, S, H = args.batch, shape.S, shape.H
+    rec_flops = 2.0 * B * S * 8 * H * H
+    return {'path': 'fusion -> BiLSTM + classifier (icka_lstm_rec_fwd, persistent tcgen05) -> Viterbi of those emissions -> '
+                    'chunk-F1 counters (icka_ner_chunk_counts)', 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+            'launches_per_step': int(launches),
+            'stage_ms': {'emission_head': round(ms_head, 4), 'viterbi': round(ms_vit, 4), 'chunk_f1': round(ms_f1, 4)},
+            'emission_head_tflops': round(2 * rec_flops / (ms_head * 1e-3) / 1e12, 1),
+            'note': 'extra measurement (SURVEY 8f rows 1-2), not included in `value`; eager launches'}
 
 
 def run_train_arm(args, shape):

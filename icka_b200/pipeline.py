@@ -17,6 +17,7 @@ import torch
 from . import _lib, synth
 from .config import FusionConfig
 from .crf import CRF
+from .emission import EmissionHead
 from .modules import CrossModalFusion, set_precision
 
 FUSION_KEYS = ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask', 'text_mask')
@@ -162,3 +163,29 @@ class FusionViterbiPipeline:
             results.append(out)
         end.record(main)
         return results, (start, end)
+
+
+class TaggingPipeline(FusionViterbiPipeline):
+    """The hot path widened by the SURVEY 8f "next" rows 1 and 2: fusion -> BiLSTM + classifier (CMIM:1042-1043) ->
+    CRF Viterbi decode of THOSE emissions (CMIM:1056) -> tag filtering + chunk-F1 counters (My_cross_attention.py:
+    1052-1077, ner_evaluate.py) -- everything between the encoders' outputs and the F1 integers stays on the device."""
+
+    def __init__(self, shape: synth.Shape = synth.STD, device: str = 'cuda:0', precision: str = 'bf16', seed: int = 0):
+        super().__init__(shape, device, precision, seed)
+        from . import ner
+        cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
+                           layer_norm_eps=shape.eps)
+        self.head = EmissionHead(cfg, num_labels=shape.T).to(self.device).eval()
+        self.f1 = ner.ChunkF1(device=self.device) if shape.T == 15 else None
+
+    @torch.no_grad()
+    def step_tagging(self, d: Dict[str, torch.Tensor], label_ids: Optional[torch.Tensor] = None):
+        """-> (emissions [B,S,T] fp32, tags [B,S] int32, lens [B] int32); updates ``self.f1`` when labels are given."""
+        set_precision(self.precision)
+        out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                          d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
+        emissions = self.head(out['result'])
+        tags, lens = self.crf.decode_tensors(emissions, d['crf_mask'])
+        if label_ids is not None and self.f1 is not None:
+            self.f1.update(tags, label_ids, d['crf_mask'])
+        return emissions, tags, lens
