@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libicka_b200.so')
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU_ERF, ACT_GELU_ERF_BWD = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_ERF_BWD, ACT_TANH = 0, 1, 2, 3
 
 # name -> (restype, argtypes); must list every symbol of include/icka_b200.h
 SIGNATURES = {

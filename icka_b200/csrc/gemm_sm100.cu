@@ -372,6 +372,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               x1 = gelu_erf(x1);
             }
           }
+          if (ACT == ICKA_ACT_TANH) {
+            if (OUT_BF16) {   // bf16 output: MUFU.TANH (2^-11 relative) is below the rounding of the store
+              asm("tanh.approx.f32 %0, %1;" : "=f"(x0) : "f"(x0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(x1) : "f"(x1));
+            } else {
+              x0 = tanhf(x0);
+              x1 = tanhf(x1);
+            }
+          }
           if (use_res) {
             x0 += res[i].x;
             x1 += res[i].y;
@@ -619,7 +628,7 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   const int BN = (N > 128) ? 256 : 128;
   // CTA pairs pay off once there are enough 256-row tiles to fill the machine
   bool pair = (BN == 256) && ((long long)((M + 255) / 256) * ((N + 255) / 256) >= h->sm_count / 2);
-  if (g_gemm_mode == 1) pair = false;
+  if (g_gemm_mode == 1 || act == ICKA_ACT_TANH) pair = false;
   if (g_gemm_mode == 2) pair = (BN == 256);
   CUtensorMap ta, tb;
   int rc = icka_make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
@@ -630,6 +639,14 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
                 (int64_t)N, 1, (K + kBK - 1) / kBK, 0};
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
+  if (act == ICKA_ACT_TANH) {   // prompt mapping networks (CMIM:914-930): M = batch, single-CTA tiles
+    if (BN == 256) {
+      if (bf) return launch_gemm<256, ICKA_ACT_TANH, true, 1, 0>(h, ta, tb, args, st);
+      return launch_gemm<256, ICKA_ACT_TANH, false, 1, 0>(h, ta, tb, args, st);
+    }
+    if (bf) return launch_gemm<128, ICKA_ACT_TANH, true, 1, 0>(h, ta, tb, args, st);
+    return launch_gemm<128, ICKA_ACT_TANH, false, 1, 0>(h, ta, tb, args, st);
+  }
   // Skinny problems (the single-query encoders: M = batch, N = 768, K = 3072 / 9216) have only a few dozen output
   // tiles for 148 SMs: split the contraction over CTAs into per-split slabs of the handle's workspace, then add the
   // slabs in split order (+ bias, residual) with a small reduce pass -- bit-reproducible, unlike atomics.

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kThreads) sgemm_tn_kernel(
         if (bias) v += bias[n];
         if (ACT == ICKA_ACT_GELU_ERF && pre_act_out) pre_act_out[(size_t)m * N + n] = v;
         if (ACT == ICKA_ACT_GELU_ERF) v = gelu_erf(v);
+        if (ACT == ICKA_ACT_TANH) v = tanhf(v);
         if (residual) v += residual[(size_t)m * N + n];
         if (OUT_BF16)
           static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = __float2bfloat16_rn(v);
@@ -175,7 +176,9 @@ int icka_sgemm_launch(icka_handle* h, const float* A, int64_t lda, const float* 
 #define ICKA_SGEMM(ACT_, BF_) \
   sgemm_tn_kernel<ACT_, BF_><<<grid, kThreads, 0, st>>>(A, lda, W, ldw, bias, residual, out, ldo, pre_act_out, M, N, K)
   const bool bf = out_dtype == ICKA_BF16;
-  if (act == ICKA_ACT_GELU_ERF) {
+  if (act == ICKA_ACT_TANH) {
+    if (bf) ICKA_SGEMM(ICKA_ACT_TANH, true); else ICKA_SGEMM(ICKA_ACT_TANH, false);
+  } else if (act == ICKA_ACT_GELU_ERF) {
     if (bf) ICKA_SGEMM(ICKA_ACT_GELU_ERF, true); else ICKA_SGEMM(ICKA_ACT_GELU_ERF, false);
   } else {
     if (bf) ICKA_SGEMM(ICKA_ACT_NONE, true); else ICKA_SGEMM(ICKA_ACT_NONE, false);

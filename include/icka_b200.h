@@ -40,7 +40,8 @@ enum icka_dtype { ICKA_F32 = 0, ICKA_BF16 = 1 };
 enum icka_act {
   ICKA_ACT_NONE = 0,
   ICKA_ACT_GELU_ERF = 1,     /* CMIM:31-37 */
-  ICKA_ACT_GELU_ERF_BWD = 2  /* internal: multiply by gelu'(pre-activation) (backward of CMIM:550) */
+  ICKA_ACT_GELU_ERF_BWD = 2, /* internal: multiply by gelu'(pre-activation) (backward of CMIM:550) */
+  ICKA_ACT_TANH = 3          /* torch.nn.Tanh of the prompt mapping networks, CMIM:917, :925 */
 };
 
 int icka_version(void);
