@@ -6,6 +6,7 @@ Public surface (mirrors /root/reference/Cross_Modal_Interaction_Module.py and to
     crf.CRF
     emission.LSTM, emission.EmissionHead (the BiLSTM + classifier between fusion and CRF, CMIM:905-910, 1042-1043)
     prompt.PromptMapping (prompt mapping networks + prefix assembly, CMIM:913-930, 995-1009)
+    resnet_tail.myResnet (region-producer tail: means, adaptive pooling, K-major region rows; resnet/resnet_utils.py)
     ner.ChunkF1 / ner.evaluate (tag post-processing + chunk-F1, My_cross_attention.py:879-903, ner_evaluate.py)
     set_precision('bf16' | 'fp32')
 Everything computes through libicka_b200.so (include/icka_b200.h); there is no CPU fallback.
@@ -17,7 +18,8 @@ from .modules import (BertCoAttention, BertCrossAttention, BertCrossAttentionLay
 from .crf import CRF  # noqa: F401
 from .emission import LSTM, EmissionHead  # noqa: F401
 from .prompt import PromptMapping  # noqa: F401
+from .resnet_tail import myResnet  # noqa: F401
 
 __all__ = ['FusionConfig', 'BertCoAttention', 'BertCrossAttention', 'BertCrossAttentionLayer', 'BertCrossEncoder',
            'BertIntermediate', 'BertLayerNorm', 'BertOutput', 'BertSelfOutput', 'CrossModalFusion', 'cls_layer_both',
-           'CRF', 'LSTM', 'EmissionHead', 'PromptMapping', 'get_precision', 'set_precision']
+           'CRF', 'LSTM', 'EmissionHead', 'PromptMapping', 'myResnet', 'get_precision', 'set_precision']

@@ -87,6 +87,8 @@ SIGNATURES = {
                                        c_int, c_int, c_void_p]),
     'icka_cast_bf16_time_major': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_add_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'icka_region_tail_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
     'icka_ner_chunk_counts': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_int, c_int, c_void_p]),
 }

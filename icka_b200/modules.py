@@ -443,19 +443,29 @@ class CrossModalFusion(nn.Module):
 
     def forward(self, sequence_output, visual_embeds_att, clip_features, token_embedding, added_attention_mask,
                 ori_input_mask, return_dict=False, want_fused=True):
-        """sequence_output [B,S,H] (CMIM:953), visual_embeds_att [B,2048,g,g], clip_features [B,1,512],
+        """sequence_output [B,S,H] (CMIM:953), visual_embeds_att [B,2048,g,g] (or region rows [B,R,2048]), clip_features [B,1,512],
         token_embedding [B,S,H] (CMIM:1024), added_attention_mask [B,>=R], ori_input_mask [B,S].
         Returns (result [B,S,H], clip_features [B,1,H]) -- CMIM:1036 and the loop result of CMIM:984-989."""
         for enc in (self.txt2img_attention, *self.cls_layer_Y):
             for l in enc.layer:
                 _check_inference(l, *l._dropouts(), graph_capable=True)
         B, S, H = sequence_output.shape
-        grid = visual_embeds_att.float().contiguous()
-        R = grid.numel() // (B * grid.shape[1])
+        # region rows [B, R, C] straight from the producer tail (icka_b200.myResnet.forward_rows): no relayout needed
+        rows_given = visual_embeds_att.dim() == 3 and visual_embeds_att.shape[-1] == self.vismap2text.in_features
+        if rows_given:
+            R = visual_embeds_att.shape[1]
+        else:
+            grid = visual_embeds_att.float().contiguous()
+            R = grid.numel() // (B * grid.shape[1])
 
         rec = _recording(sequence_output, token_embedding, module=self)
         # region projection, CMIM:956-958 (the ResNet grid carries no gradient: My_cross_attention.py:804-805)
-        rows = ops.region_rows(grid, _cdt())
+        if rows_given:
+            rows = visual_embeds_att.contiguous().view(B * R, -1)
+            if rows.dtype != _cdt():
+                rows = _to_lp(rows.float()) if _PRECISION == 'bf16' else rows.float()
+        else:
+            rows = ops.region_rows(grid, _cdt())
         w_vm2t = _operand(self._cache, 'vm2t', self.vismap2text.weight)
         if rec:
             regions32 = DenseFn.apply(rows, self.vismap2text.weight, self.vismap2text.bias, w_vm2t)

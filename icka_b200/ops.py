@@ -540,3 +540,21 @@ def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, time_maj
     _lib.check(lib.icka_emission_head_fwd(h, x.data_ptr(), _ld(x, K), w.data_ptr(), bias.data_ptr(), out.data_ptr(),
                                           _DT[x.dtype], M, K, T, int(time_major_S), st), 'icka_emission_head_fwd')
     return out
+
+
+def region_tail(x: torch.Tensor, att_size: int, *, want_fc: bool = True, want_att: bool = True,
+                rows_dtype: Optional[torch.dtype] = None):
+    """layer4 output x [B,C,g,g] fp32 -> (fc [B,C] | None, att [B,C,a,a] fp32 | None, rows [B, a*a, C] | None)."""
+    _need(x, torch.float32, 'region_tail(x)')
+    if x.dim() != 4 or x.shape[2] != x.shape[3]:
+        raise RuntimeError(f'region_tail: expected [B,C,g,g], got {tuple(x.shape)}')
+    B, C, g, _ = x.shape
+    a = int(att_size)
+    lib, h, st = _ctx(x)
+    fc = torch.empty(B, C, dtype=torch.float32, device=x.device) if want_fc else None
+    att = torch.empty(B, C, a, a, dtype=torch.float32, device=x.device) if want_att else None
+    rows = torch.empty(B, a * a, C, dtype=rows_dtype, device=x.device) if rows_dtype is not None else None
+    _lib.check(lib.icka_region_tail_fwd(h, x.data_ptr(), _p(fc), _p(att), _p(rows),
+                                        _DT[rows_dtype] if rows_dtype is not None else F32, B, C, g, a, st),
+               'icka_region_tail_fwd')
+    return fc, att, rows

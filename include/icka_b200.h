@@ -304,6 +304,16 @@ int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_bf16, int i
 /* out = a + b (fp32; weight preparation: b_ih + b_hh). */
 int icka_add_f32(icka_handle* h, const float* a, const float* b, float* out, int64_t n, void* stream);
 
+/* ---- region producer tail ---------------------------------------------------- */
+
+/* resnet/resnet_utils.py:36-43 on the layer4 output x [B, C, g, g] fp32, in ONE pass:
+ *   fc [B, C] = x.mean(3).mean(2);  att_f32 [B, C, a, a] = adaptive_avg_pool2d(x, [a, a]);
+ *   rows [B*a*a, C] (`rows_dtype`) = att.view(-1, C, a*a).permute(0, 2, 1) (CMIM:956) -- the K-major operand of the
+ *   region projection, which CrossModalFusion accepts directly (icka_region_rows is then skipped).
+ * Any of fc / att_f32 / rows may be NULL (at least one output). */
+int icka_region_tail_fwd(icka_handle* h, const float* x, float* fc, float* att_f32, void* rows, int rows_dtype,
+                         int B, int C, int g, int att_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
