@@ -364,8 +364,8 @@ def run_gpu_arm(args, shape):
 
 def run_widened(args, shape, dev, seed, d, barrier):
     """fusion -> emission head (BiLSTM + classifier) -> Viterbi of those emissions -> chunk-F1 counters, device-resident
-    inputs, CUDA-event timed per stage (eager launches; the recurrent kernel is one cooperative launch per <= 1024
-    sentences)."""
+    inputs, one CUDA-graph replay per step (the recurrent kernel is one cooperative launch per <= 1024 sentences);
+    then each stage on its own, CUDA-event timed."""
     import torch
     from icka_b200 import _lib
     from icka_b200.pipeline import TaggingPipeline
@@ -373,22 +373,42 @@ def run_widened(args, shape, dev, seed, d, barrier):
     steps = max(3, min(args.steps, 10))
     pipe = TaggingPipeline(shape, dev, args.precision, seed=seed)
     labels = synth.crf_batch(args.batch, shape, seed=seed)['tags'].to(dev)
-    for _ in range(3):
-        pipe.step_tagging(d, labels)
+    with torch.no_grad():
+        for _ in range(3):
+            pipe.step_tagging(d, labels)
     barrier()
     idx = torch.device(dev).index or 0
+    run, launch_mode = (lambda: pipe.step_tagging(d, labels)), 'eager launches'
+    launches = None
+    if not args.no_graph:                      # one graph replay per step, like the headline measurement
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count(idx)
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                pipe.step_tagging(d, labels)
+        launches = _lib.launch_count(idx) - n0
+        torch.cuda.current_stream().wait_stream(side)
+        run, launch_mode = graph.replay, 'CUDA graph replay'
+        pipe.f1.reset()
+    for _ in range(2):
+        run()
+    barrier()
     n0 = _lib.launch_count(idx)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for _ in range(steps):
-        pipe.step_tagging(d, labels)
+        run()
     ev[1].record()
     barrier()
     ms = ev[0].elapsed_time(ev[1]) / steps
-    launches = (_lib.launch_count(idx) - n0) // steps
+    if launches is None:
+        launches = (_lib.launch_count(idx) - n0) // steps
     # stage split (same inputs, one stage at a time)
-    out = pipe.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'], d['img_mask'],
-                      d['text_mask'], return_dict=True, want_fused=False)
+    with torch.no_grad():
+        out = pipe.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                          d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
     result = out['result']
 
     def timed(fn):
@@ -408,14 +428,23 @@ def run_widened(args, shape, dev, seed, d, barrier):
         ms_vit = timed(lambda: pipe.crf.decode_tensors(em, d['crf_mask']))
         tags, _ = pipe.crf.decode_tensors(em, d['crf_mask'])
         ms_f1 = timed(lambda: pipe.f1.update(tags, labels, d['crf_mask']))
+        # the two remaining 8f rows, on their own (they feed the encoders, which are outside the path)
+        from icka_b200 import FusionConfig, PromptMapping, ops
+        prompt = PromptMapping(FusionConfig(hidden_size=shape.H)).to(dev).eval()
+        vmean = d['visual_embeds_att'].mean(dim=(2, 3))
+        ms_prompt = timed(lambda: prompt(out['clip'], vmean, d['text_mask']))
+        ms_tail = timed(lambda: ops.region_tail(d['visual_embeds_att'], d['visual_embeds_att'].shape[-1],
+                                                want_att=False, rows_dtype=torch.bfloat16))
     B, S, H = args.batch, shape.S, shape.H
     rec_flops = 2.0 * B * S * 8 * H * H
     return {'path': 'fusion -> BiLSTM + classifier (icka_lstm_rec_fwd, persistent tcgen05) -> Viterbi of those emissions -> '
                     'chunk-F1 counters (icka_ner_chunk_counts)', 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
             'launches_per_step': int(launches),
             'stage_ms': {'emission_head': round(ms_head, 4), 'viterbi': round(ms_vit, 4), 'chunk_f1': round(ms_f1, 4)},
+            'other_rows_ms': {'prompt_mapping': round(ms_prompt, 4), 'region_tail_fc_rows': round(ms_tail, 4)},
+            'launch': launch_mode,
             'emission_head_tflops': round(2 * rec_flops / (ms_head * 1e-3) / 1e12, 1),
-            'note': 'extra measurement (SURVEY 8f rows 1-2), not included in `value`; eager launches'}
+            'note': 'extra measurement (SURVEY 8f rows), not included in `value`'}
 
 
 def run_train_arm(args, shape):
