@@ -7,28 +7,30 @@
 //
 // The recurrence is S serial steps of a [B, H] x [H, 4H] product per direction.  Launching a GEMM per step would
 // stream W_hh (4.7 MB bf16 per direction) from L2 S times per tile and pay a launch + pipeline fill per step; here
-//   * the 2 x 3072 x 768 weights are split into 2 x 32 slices of 24 hidden units (96 gate columns, 147 KB bf16) and
-//     each slice stays in the shared memory of ONE CTA for the whole sequence (loaded once by TMA, SWIZZLE_128B,
-//     K-major B operand of tcgen05.mma);
-//   * a work item is (step t, 128-sentence tile m): the CTA streams h_{t-1}[tile m] (128 x 768 bf16, written by the
-//     32 slice CTAs of its direction) from L2 through a 5-stage TMA ring as the A operand -- straight out of the
-//     time-major output sequence y[t-1], so h is written exactly once -- accumulates the 128 x 96 gate
-//     pre-activations in TMEM (4 accumulator slots), and 8 epilogue warps (thread = sentence, two column halves)
-//     add Gx (prefetched one item ahead), apply the cell update out of TMEM with the cell state in registers and
-//     write h_t (bf16) into y[t];
-//   * a publisher warp turns "all 8 epilogue warps stored their part of item (t, m)" into ONE gpu-scope release on
-//     the tile's arrival counter, so the ~4 us a MEMBAR.GPU takes on a busy SM never stalls the cell arithmetic;
-//   * sentence tiles are independent recurrences, so a CTA walks items in (t, m) order and only waits for
-//     "all 32 slices have published h_{t-1} of tile m" -- a per-(direction, tile) arrival counter in global memory
-//     (red.release / ld.acquire + fence.proxy.async before the TMA reads).  With several tiles per CTA the wait
-//     for tile m overlaps the work on the other tiles; no grid-wide barrier exists.
-// All CTAs must be co-resident (they wait on each other): the kernel is launched cooperatively.
+//   * weight-stationary CTA PAIRS: the 2 x 3072 x 768 weights are cut into 2 x 16 slices of 48 hidden units (192 gate
+//     columns); a slice belongs to a cluster of two CTAs, each keeping 96 of its columns (147 KB bf16) in shared
+//     memory for the whole sequence (loaded once by TMA, SWIZZLE_128B, K-major B operand).  The pair issues
+//     tcgen05.mma.cta_group::2 (M = 256: two sentence tiles, N = 192): every staged byte of A feeds twice the tensor
+//     work of a single-CTA N = 96 tile, which is what the kernel was short of -- with 5 x 16 KB of A in flight the
+//     N = 96 version kept only ~1000 cycles of MMA work queued against a ~2800-cycle issue -> commit -> refill loop
+//     (ncu: tensor pipe 32 % active);
+//   * a work item is (step t, PAIR of 128-sentence tiles): each CTA streams h_{t-1} of ITS tile (128 x 768 bf16) as
+//     the A operand through a 5-stage TMA ring straight out of the time-major output sequence y[t-1] (h is written
+//     exactly once; an out-of-bounds row coordinate delivers the zero state at t = 0), the leader CTA issues 48
+//     MMAs into one of 2 TMEM accumulator slots (128 lanes x 192 columns in each CTA), and 8 epilogue warps per CTA
+//     (thread = sentence = TMEM lane; two warp halves x two sequential blocks of 12 units) add Gx (prefetched one
+//     block ahead), apply the cell update with the cell state in registers, and store h_t (bf16) into y[t];
+//   * sentence tiles are independent recurrences: the only cross-CTA dependency is "the 16 CTAs that own tile m in my
+//     direction (one per slice pair) have published h_{t-1}" -- a per-(direction, tile) arrival counter in global memory (red.release /
+//     ld.acquire + fence.proxy.async before the TMA reads); no grid-wide barrier exists;
+//   * a publisher warp turns "all 8 epilogue warps stored their part of the item" into ONE gpu-scope release: a
+//     MEMBAR.GPU on a busy SM costs ~4 us and must not stall the warps that do the cell arithmetic.
+// All CTAs must be co-resident (they wait on each other): the kernel is launched cooperatively (clusters of 2).
 //
 // Column order inside a slice (chosen on the host when the weights are permuted once):
-//   column c = half * 48 + jg * 16 + gate * 4 + jj   <->   hidden unit  slice * 24 + half * 12 + jg * 4 + jj,
-//   gate in (i, f, g, o), jg in 0..2, jj in 0..3
-// so each epilogue thread reads one contiguous block of 48 TMEM columns (three 16-column groups, each holding the
-// four gates of four units) and 96 contiguous bytes of Gx.
+//   column c = blk * 48 + jg * 16 + gate * 4 + jj   <->   hidden unit  slice * 48 + blk * 12 + jg * 4 + jj,
+//   blk in 0..3 (= 2 * warp half + sequential block), gate in (i, f, g, o), jg in 0..2, jj in 0..3;
+//   columns 0..95 live in the pair's CTA 0, 96..191 in CTA 1.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -39,23 +41,26 @@ namespace {
 using namespace sm100;
 
 constexpr int kH = 768;                       // hidden size this kernel is built for
-constexpr int kU = 24;                        // hidden units per CTA
-constexpr int kNS = kH / kU;                  // 32 slices per direction
-constexpr int kN = 4 * kU;                    // 96 gate columns per CTA (UMMA N)
+constexpr int kU = 48;                        // hidden units per CTA pair
+constexpr int kNS = kH / kU;                  // 16 slices per direction
+constexpr int kN = 4 * kU;                    // 192 gate columns per pair (UMMA N)
+constexpr int kNHalf = kN / 2;                // 96 of them in each CTA's shared memory
 constexpr int kKB = kH / 64;                  // 12 k-chunks of 64 bf16 = 128 B
-constexpr int kWChunkBytes = kN * 128;        // 12,288
+constexpr int kWChunkBytes = kNHalf * 128;    // 12,288
 constexpr int kWBytes = kKB * kWChunkBytes;   // 147,456
 constexpr int kABytes = 128 * 128;            // one 128-row x 64-k A tile
 constexpr int kStages = 5;
-constexpr int kSlots = 4;                     // TMEM accumulator slots
-constexpr int kSlotCols = 128;                // column stride between slots (96 used)
+constexpr int kSlots = 2;                     // TMEM accumulator slots
+constexpr int kSlotCols = 256;                // column stride between slots (192 used)
 constexpr int kEpiWarps = 8;
 constexpr int kPubWarp = 2 + kEpiWarps;       // warp 10: publishes finished items
 constexpr int kThreads = 32 * (kPubWarp + 1);
+constexpr int kCtasPerGroup = 2 * kNS * 2;    // 2 directions x 16 slices x 2 CTAs = 64
 constexpr size_t kSmemBytes = (size_t)kWBytes + (size_t)kStages * kABytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct LstmArgs {
-  const __nv_bfloat16* gx;   // [S*Bn, 2*4H] bf16 TIME-MAJOR (row = t * Bn + sentence), columns ordered [dir][slice][half][jg][gate][4]
+  const __nv_bfloat16* gx;   // [S*Bn, 2*4H] bf16 TIME-MAJOR (row = t * Bn + sentence), columns ordered
+                             // [dir][slice][blk][jg][gate][4]
   int* cnt;                  // [2][MT] arrival counters (zeroed before launch)
   __nv_bfloat16* y;          // [S, Bn, 2H] bf16 TIME-MAJOR: forward states in [:H], backward in [H:]
   float* h_n;                // [2, Bn, H] fp32 or null (already offset to this launch's first sentence)
@@ -63,10 +68,9 @@ struct LstmArgs {
   int Bn;                    // sentences of the whole call (pitch of the time planes of gx / y and of the direction
                              // planes of h_n / c_n)
   int B, S, b0, MT, TPG;     // sentences of this launch, steps, first sentence of this launch, 128-row tiles, tiles
-                             // per CTA group
+                             // per CTA group (a pair walks them two at a time)
   int debug;                 // developer probes (ICKA_LSTM_DEBUG): 1 = no dependency wait, 2 = no cell arithmetic /
-                             // state stores, 4 = publish without the gpu-scope release, 8 = no A loads, 16 = no MMAs
-                             // (results are WRONG)
+                             // state stores, 4 = publish without the gpu-scope release, 16 = no MMAs (results are WRONG)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -86,30 +90,32 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-// Cell epilogue of one CTA: NT sentence tiles, walked in (step, tile) order.  Thread = sentence row (TMEM lane) and 12
-// of the slice's 24 hidden units; the cell state of its NT rows lives in registers for the whole sequence.
-template <int NT>
-__device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* acc_full, uint64_t* acc_empty,
+// Cell epilogue of one CTA: NP items (one sentence tile of this CTA each) per step, walked in (step, item) order.
+// Thread = sentence row (TMEM lane); per item it handles two blocks of 12 hidden units one after the other; the cell
+// state of its NP rows lives in registers for the whole sequence.
+template <int NP>
+__device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* acc_full, uint32_t acc_empty_leader0,
                                               uint64_t* pub_bar, uint64_t* pub_free, uint32_t lane_taddr, int warp,
-                                              int lane, int dir, int slice, int tile0) {
+                                              int lane, int dir, int slice, int tile_first) {
   const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-  const int half = (warp - 2) >> 2;          // which 12 of the slice's 24 units
-  const int unit0 = slice * kU + half * 12;
-  const size_t gx_col = (size_t)((dir * kNS + slice) * 2 + half) * 48;
+  const int half = (warp - 2) >> 2;          // which half of the slice's 48 units
   const int S = args.S;
-  const int row0 = tile0 * 128 + quad * 32 + lane;
-  float c[NT][12];
+  const int row0 = tile_first * 128 + quad * 32 + lane;   // item p: row0 + p * 256
+  float c[NP][2][12];
 #pragma unroll
-  for (int ti = 0; ti < NT; ++ti)
+  for (int p = 0; p < NP; ++p)
 #pragma unroll
-    for (int q = 0; q < 12; ++q) c[ti][q] = 0.0f;
-  // Gx does not depend on the recurrence: it is fetched ONE ITEM AHEAD, off the step-to-step critical path
+    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+      for (int q = 0; q < 12; ++q) c[p][hh][q] = 0.0f;
+  // Gx does not depend on the recurrence: it is fetched ONE BLOCK AHEAD, off the step-to-step critical path
   uint32_t gw_nxt[24];
-  auto fetch = [&](int t, int ti, uint32_t (&gw)[24]) {
+  auto fetch = [&](int t, int p, int hh, uint32_t (&gw)[24]) {
     const int pos = dir ? (S - 1 - t) : t;
-    const int row = row0 + ti * 128;
+    const int row = row0 + p * 256;
     if (row < args.B) {
-      const uint4* gp = reinterpret_cast<const uint4*>(args.gx + ((size_t)pos * args.Bn + row) * (8 * kH) + gx_col);
+      const size_t col = (size_t)((dir * kNS + slice) * 4 + half * 2 + hh) * 48;
+      const uint4* gp = reinterpret_cast<const uint4*>(args.gx + ((size_t)pos * args.Bn + row) * (8 * kH) + col);
 #pragma unroll
       for (int q = 0; q < 6; ++q) {
         const uint4 v = __ldg(gp + q);
@@ -123,85 +129,96 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
       for (int q = 0; q < 24; ++q) gw[q] = 0u;
     }
   };
-  fetch(0, 0, gw_nxt);
+  fetch(0, 0, 0, gw_nxt);
+  const bool probe = (args.debug & 2) != 0;      // probe: no cell arithmetic, no state stores
   int it = 0;
   for (int t = 0; t < S; ++t) {
     const int pos = dir ? (S - 1 - t) : t;
 #pragma unroll
-    for (int ti = 0; ti < NT; ++ti, ++it) {
+    for (int p = 0; p < NP; ++p, ++it) {
       const int slot = it % kSlots;
       const uint32_t slot_phase = (it / kSlots) & 1;
-      const int row = row0 + ti * 128;
+      const int row = row0 + p * 256;
       const bool valid = row < args.B;
-      uint32_t gw[24];
 #pragma unroll
-      for (int q = 0; q < 24; ++q) gw[q] = gw_nxt[q];
-      if (ti + 1 < NT) fetch(t, ti + 1, gw_nxt);
-      else if (t + 1 < S) fetch(t + 1, 0, gw_nxt);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int blk = half * 2 + hh;
+        uint32_t gw[24];
+#pragma unroll
+        for (int q = 0; q < 24; ++q) gw[q] = gw_nxt[q];
+        if (hh == 0) fetch(t, p, 1, gw_nxt);
+        else if (p + 1 < NP) fetch(t, p + 1, 0, gw_nxt);
+        else if (t + 1 < S) fetch(t + 1, 0, 0, gw_nxt);
 
-      mbar_wait(&acc_full[slot], slot_phase);
-      tc_fence_after();
-      // 48 accumulator columns = 3 groups of 4 units x (i, f, g, o): 16 columns are live at a time, the next group's
-      // tcgen05.ld is in flight while this one is being computed
-      const uint32_t taddr = lane_taddr + (uint32_t)(slot * kSlotCols + half * 48);
-      const bool probe = (args.debug & 2) != 0;      // probe: no cell arithmetic, no state stores
-      uint32_t ra[16], rb[16];
-      float hv[12];
-      auto cell4 = [&](const uint32_t (&r)[16], int jg) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float pre[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int e = jg * 16 + g * 4 + jj;
-            const uint32_t w = gw[e >> 1];
-            const float gxv = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
-            pre[g] = __uint_as_float(r[g * 4 + jj]) + gxv;
-          }
-          const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]), gg = tanh_fast(pre[2]),
-                      og = sigmoid_fast(pre[3]);
-          const int j = jg * 4 + jj;
-          c[ti][j] = probe ? c[ti][j] : fmaf(fg, c[ti][j], ig * gg);
-          hv[j] = og * tanh_fast(c[ti][j]);
+        if (hh == 0) {
+          mbar_wait(&acc_full[slot], slot_phase);
+          tc_fence_after();
         }
-      };
-      tmem_ld16(taddr, ra);
-      tmem_ld_wait();
-      tmem_ld16(taddr + 16, rb);
-      cell4(ra, 0);
-      tmem_ld_wait();
-      tmem_ld16(taddr + 32, ra);
-      cell4(rb, 1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[slot]);   // the MMA warp may reuse the slot
-      cell4(ra, 2);
-      if (valid && !(args.debug & 2)) {
-        uint32_t hw[6];
+        // 48 accumulator columns = 3 groups of 4 units x (i, f, g, o): 16 columns are live at a time, the next
+        // group's tcgen05.ld is in flight while this one is being computed
+        const uint32_t taddr = lane_taddr + (uint32_t)(slot * kSlotCols + blk * 48);
+        uint32_t ra[16], rb[16];
+        float hv[12];
+        auto cell4 = [&](const uint32_t (&r)[16], int jg) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
-        // 24 bytes per row at byte offset 48 * slice + 24 * half: one 16-byte and one 8-byte store, ordered so the
-        // 16-byte one is aligned (half 0: 16 + 8, half 1: 8 + 16)
-        uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH + unit0);
-        if (half == 0) {
-          *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint2*>(yp + 16) = make_uint2(hw[4], hw[5]);
-        } else {
-          *reinterpret_cast<uint2*>(yp) = make_uint2(hw[0], hw[1]);
-          *reinterpret_cast<uint4*>(yp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
-        }
-        if (t == S - 1) {
-          if (args.h_n) {
-            float4* o = reinterpret_cast<float4*>(args.h_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+          for (int jj = 0; jj < 4; ++jj) {
+            float pre[4];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) o[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
+            for (int g = 0; g < 4; ++g) {
+              const int e = jg * 16 + g * 4 + jj;
+              const uint32_t w = gw[e >> 1];
+              const float gxv = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+              pre[g] = __uint_as_float(r[g * 4 + jj]) + gxv;
+            }
+            const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]), gg = tanh_fast(pre[2]),
+                        og = sigmoid_fast(pre[3]);
+            const int j = jg * 4 + jj;
+            c[p][hh][j] = probe ? c[p][hh][j] : fmaf(fg, c[p][hh][j], ig * gg);
+            hv[j] = og * tanh_fast(c[p][hh][j]);
           }
-          if (args.c_n) {
-            float4* o = reinterpret_cast<float4*>(args.c_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+        };
+        tmem_ld16(taddr, ra);
+        tmem_ld_wait();
+        tmem_ld16(taddr + 16, rb);
+        cell4(ra, 0);
+        tmem_ld_wait();
+        tmem_ld16(taddr + 32, ra);
+        cell4(rb, 1);
+        tmem_ld_wait();
+        if (hh == 1) {   // this warp's last read of the slot: hand it back to the leader's MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + (uint32_t)slot * 8u);
+        }
+        cell4(ra, 2);
+
+        if (valid && !probe) {
+          const int unit0 = slice * kU + blk * 12;
+          uint32_t hw[6];
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-              o[q] = make_float4(c[ti][4 * q], c[ti][4 * q + 1], c[ti][4 * q + 2], c[ti][4 * q + 3]);
+          for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
+          // 24 bytes per row at byte offset 96 * slice + 24 * blk: one 16-byte and one 8-byte store, ordered so the
+          // 16-byte one is aligned (even blocks: 16 + 8, odd blocks: 8 + 16)
+          uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH + unit0);
+          if ((blk & 1) == 0) {
+            *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint2*>(yp + 16) = make_uint2(hw[4], hw[5]);
+          } else {
+            *reinterpret_cast<uint2*>(yp) = make_uint2(hw[0], hw[1]);
+            *reinterpret_cast<uint4*>(yp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
+          }
+          if (t == S - 1) {
+            if (args.h_n) {
+              float4* o = reinterpret_cast<float4*>(args.h_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+#pragma unroll
+              for (int q = 0; q < 3; ++q) o[q] = make_float4(hv[4 * q], hv[4 * q + 1], hv[4 * q + 2], hv[4 * q + 3]);
+            }
+            if (args.c_n) {
+              float4* o = reinterpret_cast<float4*>(args.c_n + ((size_t)dir * args.Bn + row) * kH + unit0);
+#pragma unroll
+              for (int q = 0; q < 3; ++q)
+                o[q] = make_float4(c[p][hh][4 * q], c[p][hh][4 * q + 1], c[p][hh][4 * q + 2], c[p][hh][4 * q + 3]);
+            }
           }
         }
       }
@@ -223,21 +240,24 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kWBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * kABytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* acc_full = bars + 2 * kStages;
-  uint64_t* acc_empty = acc_full + kSlots;
+  uint64_t* full_bar = bars;                 // leader's are used: both CTAs' TMA bytes are credited there
+  uint64_t* empty_bar = bars + kStages;      // own: the multicast commit arrives in both CTAs
+  uint64_t* acc_full = bars + 2 * kStages;   // own (multicast commit)
+  uint64_t* acc_empty = acc_full + kSlots;   // leader's: 2 x 8 epilogue warps arrive
   uint64_t* pub_bar = acc_empty + kSlots;
   uint64_t* pub_free = pub_bar + kSlots;
   uint64_t* w_bar = pub_free + kSlots;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int slice = blockIdx.x % kNS;
-  const int dir = (blockIdx.x / kNS) & 1;
-  const int group = blockIdx.x / (2 * kNS);
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int slice = pair % kNS;
+  const int dir = (pair / kNS) & 1;
+  const int group = pair / (2 * kNS);
   const int tile0 = group * args.TPG;
   const int tile1 = min(args.MT, tile0 + args.TPG);
+  const int npairs = (tile1 - tile0 + 1) / 2;      // items per step; item p: tiles tile0 + 2p (CTA 0), + 2p + 1 (CTA 1)
   const int S = args.S;
 
   if (warp == 0 && lane == 0) {
@@ -249,7 +269,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     }
     for (int a = 0; a < kSlots; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], kEpiWarps);
+      mbar_init(&acc_empty[a], 2 * kEpiWarps);
       mbar_init(&pub_bar[a], kEpiWarps);
       mbar_init(&pub_free[a], 1);
     }
@@ -258,28 +278,38 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, kSlots * kSlotCols);
-    tmem_relinquish();
+    tmem_alloc_pair(tmem_base_slot, kSlots * kSlotCols);
+    tmem_relinquish_pair();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                          // the peer's barriers are initialised before anyone uses them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  if (tile0 < tile1) {
+  // the weight half of this CTA: resident for the whole sequence
+  if (warp == 0 && lane == 0) {
+    mbar_arrive_expect_tx(w_bar, kWBytes);
+    const int wrow = (dir * kNS + slice) * kN + (int)rank * kNHalf;
+    for (int kb = 0; kb < kKB; ++kb) tma_load_2d(smem_w + (size_t)kb * kWChunkBytes, &tmap_w, w_bar, kb * 64, wrow);
+  }
+  if (warp == 1 && lane == 0) mbar_wait(w_bar, 0);
+  __syncwarp();
+  cluster_sync_all();                          // the leader's MMAs read BOTH halves: both have landed past this point
+
+  if (npairs > 0) {
     if (warp == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer (one per CTA) =====================
       if (lane == 0) {
-        // the weight slice: resident for the whole sequence
-        mbar_arrive_expect_tx(w_bar, kWBytes);
-        const int wrow = (dir * kNS + slice) * kN;
-        for (int kb = 0; kb < kKB; ++kb) tma_load_2d(smem_w + (size_t)kb * kWChunkBytes, &tmap_w, w_bar, kb * 64, wrow);
+        const uint32_t full_leader0 = map_to_cta(&full_bar[0], 0);
         int stage = 0;
         uint32_t phase = 0;
         for (int t = 0; t < S; ++t) {
-          for (int m = tile0; m < tile1; ++m) {
-            if (t > 0 && !(args.debug & 1)) {
-              // h_{t-1} of this tile is complete once all slices of this direction have arrived t times
+          for (int p = 0; p < npairs; ++p) {
+            const int m = tile0 + 2 * p + (int)rank;
+            const bool tile_ok = m < tile1;
+            if (t > 0 && tile_ok && !(args.debug & 1)) {
+              // h_{t-1} of this tile is complete once the 16 CTAs that own it (one per slice pair of this direction)
+              // have arrived t times
               const int* c = args.cnt + dir * args.MT + m;
               const int need = kNS * t;
               if (ld_acquire_gpu(c) < need) {
@@ -296,30 +326,25 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
               fence_proxy_async_all();   // generic-proxy writes of the other CTAs -> visible to the TMA reads below
             }
             // A operand = h_{t-1} of this tile = the rows the previous step wrote into the (time-major) output
-            // sequence; at t = 0 an out-of-bounds row makes TMA deliver zeros (h_{-1} = 0)
+            // sequence; at t = 0 (and for the missing tile of an odd count) an out-of-bounds row makes TMA deliver zeros
             const int prev = dir ? (S - t) : (t - 1);
-            const int arow = (t == 0) ? S * args.Bn : prev * args.Bn + args.b0 + m * 128;
+            const int arow = (t == 0 || !tile_ok) ? S * args.Bn : prev * args.Bn + args.b0 + m * 128;
             for (int kb = 0; kb < kKB; ++kb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              if (args.debug & 8) {
-                mbar_arrive(&full_bar[stage]);           // probe: no A traffic
-              } else {
-                mbar_arrive_expect_tx(&full_bar[stage], kABytes);
-                tma_load_2d(smem_a + (size_t)stage * kABytes, &tmap_h, &full_bar[stage], dir * kH + kb * 64, arow);
-              }
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kABytes);   // armed for the pair
+              tma_load_2d_pair(smem_a + (size_t)stage * kABytes, &tmap_h, full_leader0 + (uint32_t)stage * 8u,
+                               dir * kH + kb * 64, arow);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
     } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16_f32(128, kN);
-        mbar_wait(w_bar, 0);
-        tc_fence_after();
-        // One thread issues ~50 short (N = 96) MMAs per item: the loop must cost less than the MMAs themselves, so
-        // the shared-memory descriptors are formed once and stepped by adding to their 14-bit address field.
+      // ===================== MMA issuer (one thread of the leader CTA) =====================
+      if (lane == 0 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16_f32(256, kN);
+        // One thread issues ~50 MMAs per item: the loop must cost less than the MMAs themselves, so the
+        // shared-memory descriptors are formed once and stepped by adding to their 14-bit address field.
         const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem_a));
         const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(smem_w));
         const bool no_mma = (args.debug & 16) != 0;       // probe
@@ -327,7 +352,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         uint32_t phase = 0;
         int it = 0;
         for (int t = 0; t < S; ++t) {
-          for (int m = tile0; m < tile1; ++m, ++it) {
+          for (int p = 0; p < npairs; ++p, ++it) {
             const int slot = it % kSlots;
             const uint32_t slot_phase = (it / kSlots) & 1;
             mbar_wait(&acc_empty[slot], slot_phase ^ 1);
@@ -340,55 +365,55 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
               tc_fence_after();
               const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (kABytes >> 4));
               if (!no_mma) {
-                umma_bf16(tmem_d, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
-                umma_bf16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);
-                umma_bf16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
-                umma_bf16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
+                umma_bf16_pair(tmem_d, a_desc, b_desc, idesc, kb > 0 ? 1u : 0u);
+                umma_bf16_pair(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);
+                umma_bf16_pair(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
+                umma_bf16_pair(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
               }
-              umma_commit(&empty_bar[stage]);
+              umma_commit_pair(&empty_bar[stage], 3);     // the slot is free in both CTAs once these retire
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&acc_full[slot]);
+            umma_commit_pair(&acc_full[slot], 3);         // wake the epilogue warps of both CTAs
           }
         }
       }
     } else if (warp == kPubWarp) {
       // ===================== publisher: one gpu-scope release per item, off the epilogue warps' path =====================
       // The epilogue warps arrive on pub_bar[slot] (release.cta) after their h stores; this thread acquires the
-      // barrier and performs the ONE gpu-scope release of the CTA (cumulative over everything that happened-before
-      // it) -- so the ~1 us a MEMBAR.GPU takes never stalls the warps that do the cell arithmetic.
+      // barrier and performs the ONE gpu-scope release of the CTA (cumulative over everything that happened-before it).
       if (lane == 0) {
-        const int ntiles = tile1 - tile0;
-        const int items = S * ntiles;
+        const int items = S * npairs;
         for (int it = 0; it < items; ++it) {
-          const int m = tile0 + it % ntiles;
+          const int m = tile0 + 2 * (it % npairs) + (int)rank;
           const int slot = it % kSlots;
           mbar_wait(&pub_bar[slot], (it / kSlots) & 1);
-          if (args.debug & 4) {
-            atomicAdd(args.cnt + dir * args.MT + m, 1);
-          } else {
-            red_release_gpu_add(args.cnt + dir * args.MT + m, 1);   // the consumer's fence.proxy.async orders its TMA reads
+          if (m < tile1) {
+            if (args.debug & 4) {
+              atomicAdd(args.cnt + dir * args.MT + m, 1);
+            } else {
+              red_release_gpu_add(args.cnt + dir * args.MT + m, 1);   // the consumer's fence.proxy.async orders its TMA reads
+            }
           }
           mbar_arrive(&pub_free[slot]);
         }
       }
     } else {
-      // ===================== cell epilogue: thread = sentence, 12 hidden units =====================
+      // ===================== cell epilogue: thread = sentence, 2 x 12 hidden units per item =====================
       const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      switch (tile1 - tile0) {
-        case 1: lstm_epilogue<1>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
-        case 2: lstm_epilogue<2>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
-        case 3: lstm_epilogue<3>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
-        default: lstm_epilogue<4>(args, acc_full, acc_empty, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile0); break;
-      }
+      const uint32_t acc_empty_leader0 = map_to_cta(&acc_empty[0], 0);
+      const int tile_first = tile0 + (int)rank;
+      if (npairs == 1)
+        lstm_epilogue<1>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile_first);
+      else
+        lstm_epilogue<2>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile_first);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                          // the leader's MMAs read the peer's shared memory: nobody leaves early
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kSlots * kSlotCols);
+    tmem_dealloc_pair(tmem_base, kSlots * kSlotCols);
   }
 }
 
@@ -396,14 +421,15 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// sentences per launch: the cell state of a CTA's tiles lives in registers, at most 4 tiles of 128 per CTA
-static int lstm_chunk(int sm_count) { return 4 * 128 * (sm_count / (2 * kNS) > 0 ? sm_count / (2 * kNS) : 1); }
+// sentences per launch: the cell state of a CTA's tiles lives in registers, at most 2 tiles of 128 per CTA (= 4 per pair)
+static int lstm_groups(int sm_count) { return sm_count / kCtasPerGroup > 0 ? sm_count / kCtasPerGroup : 1; }
+static int lstm_chunk(int sm_count) { return 4 * 128 * lstm_groups(sm_count); }
 
 extern "C" int64_t icka_lstm_rec_workspace_bytes(int B, int H) {
   if (B < 0 || H != kH) return -1;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-    sms = 2 * kNS;
+    sms = kCtasPerGroup;
   const size_t chunk = (size_t)lstm_chunk(sms);
   const size_t Bc = (size_t)B < chunk ? (size_t)B : chunk;
   const size_t MT = (Bc + 127) / 128;
@@ -423,18 +449,18 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
   ICKA_REQUIRE(!h_n || icka_aligned(h_n, 16), "lstm_rec: h_n must be 16-byte aligned");
   ICKA_REQUIRE(!c_n || icka_aligned(c_n, 16), "lstm_rec: c_n must be 16-byte aligned");
   if (B == 0) return ICKA_OK;
-  ICKA_REQUIRE(h->sm_count >= 2 * kNS, "lstm_rec: needs %d co-resident CTAs, device has %d SMs", 2 * kNS, h->sm_count);
+  ICKA_REQUIRE(h->sm_count >= kCtasPerGroup, "lstm_rec: needs %d co-resident CTAs, device has %d SMs", kCtasPerGroup,
+               h->sm_count);
   const int chunk = lstm_chunk(h->sm_count);
   const int Bc_max = B < chunk ? B : chunk;
   const size_t MT_max = ((size_t)Bc_max + 127) / 128;
   const size_t cnt_bytes = align_up(2 * MT_max * sizeof(int), 1024);
-  const size_t need = cnt_bytes;
-  ICKA_REQUIRE((size_t)workspace_bytes >= need, "lstm_rec: workspace of %lld B, need %lld", (long long)workspace_bytes,
-               (long long)need);
+  ICKA_REQUIRE((size_t)workspace_bytes >= cnt_bytes, "lstm_rec: workspace of %lld B, need %lld", (long long)workspace_bytes,
+               (long long)cnt_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   CUtensorMap tw, th;
-  int rc = icka_make_tmap_bf16(h, &tw, w_hh_perm, 2 * 4 * kH, kH, kH, kN);
+  int rc = icka_make_tmap_bf16(h, &tw, w_hh_perm, 2 * 4 * kH, kH, kH, kNHalf);
   if (rc) return rc;
   // the A operand of step t is read straight out of the output sequence: [S*B rows, 2H columns], box 128 x 64
   rc = icka_make_tmap_bf16(h, &th, y, (int64_t)S * B, 2 * kH, 2 * kH, 128);
@@ -448,11 +474,12 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
     args.B = (B - b0 < chunk) ? B - b0 : chunk;
     args.S = S;
     args.Bn = B;
-    args.MT = (args.B + 127) / 128;
     args.b0 = b0;
-    int groups = h->sm_count / (2 * kNS);
-    if (groups > args.MT) groups = args.MT;
-    args.TPG = (args.MT + groups - 1) / groups;
+    args.MT = (args.B + 127) / 128;
+    int groups = lstm_groups(h->sm_count);
+    const int pair_tiles = (args.MT + 1) / 2;            // a pair walks two tiles at a time
+    if (groups > pair_tiles) groups = pair_tiles;
+    args.TPG = 2 * ((pair_tiles + groups - 1) / groups);
     groups = (args.MT + args.TPG - 1) / args.TPG;
     args.cnt = reinterpret_cast<int*>(ws);
     args.gx = static_cast<const __nv_bfloat16*>(gx) + (size_t)b0 * (8 * kH);     // time-major: row = t * B + b
@@ -461,9 +488,21 @@ extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_h
     args.c_n = c_n ? c_n + (size_t)b0 * kH : nullptr;
     args.debug = dbg ? atoi(dbg) : 0;
     ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes, st));   // arrival counters
-    void* kargs[3] = {&tw, &th, &args};
-    ICKA_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_rec_tcgen05_kernel), dim3(groups * 2 * kNS),
-                                          dim3(kThreads), kargs, kSmemBytes, st));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * kCtasPerGroup);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel, tw, th, args));
     ICKA_LAUNCHED(h);
   }
   return ICKA_OK;

@@ -26,21 +26,22 @@ from . import modules, ops
 from .modules import _OperandCache
 
 REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
-_SLICE_UNITS = 24
-_HALF_UNITS = 12
+_SLICE_UNITS = 48
+_BLOCK_UNITS = 12
 
 
 def slice_order(H: int = REC_H) -> torch.Tensor:
     """perm[8H]: row of the slice-ordered weights -> row of cat(weight_*_l0, weight_*_l0_reverse).
-    col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  dir*4H + gate*H + slice*24 + half*12 + jg*4 + jj."""
+    col = ((dir*16 + slice)*4 + blk)*48 + jg*16 + gate*4 + jj  <->  dir*4H + gate*H + slice*48 + blk*12 + jg*4 + jj
+    (a slice of 48 hidden units belongs to a CTA pair; columns 0..95 of it live in CTA 0, 96..191 in CTA 1)."""
     n_slices = H // _SLICE_UNITS
     d = torch.arange(2).view(2, 1, 1, 1, 1, 1)
     s = torch.arange(n_slices).view(1, n_slices, 1, 1, 1, 1)
-    hf = torch.arange(2).view(1, 1, 2, 1, 1, 1)
+    blk = torch.arange(4).view(1, 1, 4, 1, 1, 1)
     jg = torch.arange(3).view(1, 1, 1, 3, 1, 1)
     g = torch.arange(4).view(1, 1, 1, 1, 4, 1)
     jj = torch.arange(4).view(1, 1, 1, 1, 1, 4)
-    return (d * 4 * H + g * H + s * _SLICE_UNITS + hf * _HALF_UNITS + jg * 4 + jj).reshape(-1)
+    return (d * 4 * H + g * H + s * _SLICE_UNITS + blk * _BLOCK_UNITS + jg * 4 + jj).reshape(-1)
 
 
 class LSTM(nn.Module):

@@ -269,15 +269,15 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
  * one persistent, weight-stationary tcgen05 kernel walks all S steps of both directions (csrc/lstm_sm100.cu).
  *   gx        [S*B, 2*4H] bf16, TIME-MAJOR rows (row = t*B + sentence; x from icka_cast_bf16_time_major)
  *             = x . W_ih^T + b_ih + b_hh for both directions (an icka_linear_fwd call), columns in the
- *             kernel's slice order:  col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  PyTorch row
- *             gate*H + slice*24 + half*12 + jg*4 + jj of direction `dir` (gate order i, f, g, o; jg < 3, jj < 4)
+ *             kernel's slice order:  col = ((dir*16 + slice)*4 + blk)*48 + jg*16 + gate*4 + jj  <->  PyTorch row
+ *             gate*H + slice*48 + blk*12 + jg*4 + jj of direction `dir` (gate order i, f, g, o; blk < 4, jg < 3, jj < 4)
  *   w_hh_perm [2*4H, H] bf16: weight_hh_l0 / weight_hh_l0_reverse with their rows in the same order
  *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters; zeroed by the call)
  *   y         [S, B, 2H] bf16 TIME-MAJOR (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
  * Every step then reads / writes one contiguous block of gx / y.  More than 1024 sentences run as consecutive
  * launches of <= 1024 (the cell state of a CTA's <= 4 sentence tiles lives in registers).
  * H = 768 only (other sizes: the per-step path, icka_linear_fwd + icka_lstm_cell_fwd).  The launch is cooperative:
- * 64 or 128 co-resident CTAs. */
+ * 64 or 128 co-resident CTAs in clusters of 2 (tcgen05 cta_group::2 pairs sharing a 48-unit weight slice). */
 int64_t icka_lstm_rec_workspace_bytes(int B, int H);
 int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace, int64_t workspace_bytes,
                       void* y, float* h_n, float* c_n, int B, int S, int H, void* stream);
