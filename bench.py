@@ -325,7 +325,11 @@ def run_gpu_arm(args, shape):
     # ---- widened path (SURVEY 8f rows 1 + 2; extra, not part of `value`) ----
     widened = None
     if not args.no_widened and args.precision == 'bf16' and shape.H == 768:
-        widened = run_widened(args, shape, dev, seed, d, barrier)
+        try:
+            widened = run_widened(args, shape, dev, seed, d, barrier)
+        except RuntimeError as e:       # e.g. a profiler that cannot replay cooperative cluster launches; the headline is unaffected
+            widened = None
+            print(f'bench.py: widened measurement skipped: {e}', file=sys.stderr)
         if widened is not None and world > 1:
             widened['ms_per_step'] = shard.max_over_ranks(widened['ms_per_step'], device=dev)
         if widened is not None:

@@ -79,8 +79,9 @@ SIGNATURES = {
     'icka_crf_llh_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_void_p]),
     'icka_lstm_rec_workspace_bytes': (c_int64, [c_int, c_int]),
+    'icka_lstm_rec_variant': (c_int, [c_int]),
     'icka_lstm_rec_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int,
-                                  c_int, c_int, c_void_p]),
+                                  c_int, c_int, c_int, c_void_p]),
     'icka_lstm_cell_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_int, c_int, c_int, c_void_p]),
     'icka_emission_head_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,

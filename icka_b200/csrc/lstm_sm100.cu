@@ -436,9 +436,34 @@ extern "C" int64_t icka_lstm_rec_workspace_bytes(int B, int H) {
   return (int64_t)align_up(2 * MT * sizeof(int), 1024);
 }
 
+int icka_lstm_rec1_launch(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
+                          int64_t workspace_bytes, void* y, float* h_n, float* c_n, int B, int S, int H, void* stream);
+
+// Which kernel serves a batch of B sentences: 1 = single CTAs, 24-unit slices (lstm_sm100_single.cu: lower step
+// latency, one or two sentence tiles), 2 = CTA pairs, 48-unit slices (this file: twice the tensor work per staged
+// byte).  The two differ in the column order of gx / w_hh_perm, so the caller asks BEFORE preparing its operands.
+extern "C" int icka_lstm_rec_variant(int B) {
+  const char* force = getenv("ICKA_LSTM_VARIANT");
+  if (force && (atoi(force) == 1 || atoi(force) == 2)) return atoi(force);
+  return B <= 256 ? 1 : 2;
+}
+
+static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
+                            int64_t workspace_bytes, void* y, float* h_n, float* c_n, int B, int S, int H,
+                            void* stream);
+
 extern "C" int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
                                  int64_t workspace_bytes, void* y, float* h_n, float* c_n, int B, int S, int H,
-                                 void* stream) {
+                                 int variant, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(variant == 1 || variant == 2, "lstm_rec: variant %d (ask icka_lstm_rec_variant)", variant);
+  if (variant == 1) return icka_lstm_rec1_launch(h, gx, w_hh_perm, workspace, workspace_bytes, y, h_n, c_n, B, S, H, stream);
+  return lstm_rec2_launch(h, gx, w_hh_perm, workspace, workspace_bytes, y, h_n, c_n, B, S, H, stream);
+}
+
+static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace,
+                            int64_t workspace_bytes, void* y, float* h_n, float* c_n, int B, int S, int H,
+                            void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(H == kH, "lstm_rec: hidden size %d not supported by the persistent kernel (built for %d)", H, kH);
   ICKA_REQUIRE(B >= 0 && S >= 1, "lstm_rec: bad shape B=%d S=%d", B, S);

@@ -26,22 +26,22 @@ from . import modules, ops
 from .modules import _OperandCache
 
 REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
-_SLICE_UNITS = 48
-_BLOCK_UNITS = 12
 
 
-def slice_order(H: int = REC_H) -> torch.Tensor:
+def slice_order(H: int = REC_H, variant: int = 2) -> torch.Tensor:
     """perm[8H]: row of the slice-ordered weights -> row of cat(weight_*_l0, weight_*_l0_reverse).
-    col = ((dir*16 + slice)*4 + blk)*48 + jg*16 + gate*4 + jj  <->  dir*4H + gate*H + slice*48 + blk*12 + jg*4 + jj
-    (a slice of 48 hidden units belongs to a CTA pair; columns 0..95 of it live in CTA 0, 96..191 in CTA 1)."""
-    n_slices = H // _SLICE_UNITS
+    variant 2 (CTA pairs, 48-unit slices; columns 0..95 of a slice live in CTA 0, 96..191 in CTA 1):
+      col = ((dir*16 + slice)*4 + blk)*48 + jg*16 + gate*4 + jj  <->  dir*4H + gate*H + slice*48 + blk*12 + jg*4 + jj
+    variant 1 (single CTAs, 24-unit slices): the same with 32 slices of 2 blocks."""
+    units = 48 if variant == 2 else 24
+    n_slices, n_blk = H // units, units // 12
     d = torch.arange(2).view(2, 1, 1, 1, 1, 1)
     s = torch.arange(n_slices).view(1, n_slices, 1, 1, 1, 1)
-    blk = torch.arange(4).view(1, 1, 4, 1, 1, 1)
+    blk = torch.arange(n_blk).view(1, 1, n_blk, 1, 1, 1)
     jg = torch.arange(3).view(1, 1, 1, 3, 1, 1)
     g = torch.arange(4).view(1, 1, 1, 1, 4, 1)
     jj = torch.arange(4).view(1, 1, 1, 1, 1, 4)
-    return (d * 4 * H + g * H + s * _SLICE_UNITS + blk * _BLOCK_UNITS + jg * 4 + jj).reshape(-1)
+    return (d * 4 * H + g * H + s * units + blk * 12 + jg * 4 + jj).reshape(-1)
 
 
 class LSTM(nn.Module):
@@ -68,21 +68,21 @@ class LSTM(nn.Module):
         return [getattr(self, n + s) for s in ('', '_reverse')
                 for n in ('weight_ih_l0', 'weight_hh_l0', 'bias_ih_l0', 'bias_hh_l0')]
 
-    def _prepared(self, persistent: bool):
-        """(W_ih [8H, I], bias [8H] = b_ih + b_hh, W_hh [8H, H]) for both directions, in the compute dtype; rows in
-        slice order for the persistent kernel, in PyTorch order otherwise."""
+    def _prepared(self, variant: int):
+        """(W_ih [8H, I], bias [8H] = b_ih + b_hh, W_hh [8H, H]) for both directions, in the compute dtype; rows in the
+        slice order of persistent-kernel ``variant`` (1 or 2), in PyTorch order for 0 (the per-step path)."""
         def build():
             wi = torch.cat([self.weight_ih_l0.detach(), self.weight_ih_l0_reverse.detach()]).contiguous()
             wh = torch.cat([self.weight_hh_l0.detach(), self.weight_hh_l0_reverse.detach()]).contiguous()
             b = ops.add_f32(torch.cat([self.bias_ih_l0.detach(), self.bias_ih_l0_reverse.detach()]).contiguous(),
                             torch.cat([self.bias_hh_l0.detach(), self.bias_hh_l0_reverse.detach()]).contiguous())
-            if persistent:
-                perm = slice_order(self.hidden_size).to(wi.device)
+            if variant:
+                perm = slice_order(self.hidden_size, variant).to(wi.device)
                 wi, wh, b = wi[perm].contiguous(), wh[perm].contiguous(), b[perm].contiguous()
             if modules.get_precision() == 'bf16':
                 wi, wh = ops.cast_bf16(wi), ops.cast_bf16(wh)
             return wi, b, wh
-        return self._cache.get('persistent' if persistent else 'step', self._params(), build)
+        return self._cache.get(f'variant{variant}', self._params(), build)
 
     def uses_persistent_kernel(self) -> bool:
         return modules.get_precision() == 'bf16' and self.hidden_size == REC_H and self.input_size % 8 == 0
@@ -95,11 +95,12 @@ class LSTM(nn.Module):
         H = self.hidden_size
         lp = modules.get_precision() == 'bf16'
         if self.uses_persistent_kernel():
-            wi, b, wh = self._prepared(True)
+            variant = ops.lstm_rec_variant(B)
+            wi, b, wh = self._prepared(variant)
             xc = x.contiguous()
             x_tm = ops.cast_bf16_time_major(xc if xc.dtype in (torch.float32, torch.bfloat16) else xc.float())
             gx = ops.linear(x_tm.view(S * B, I), wi, b, out_dtype=torch.bfloat16)
-            out = ops.lstm_rec(gx, wh, B, S, H, want_state=want_state)
+            out = ops.lstm_rec(gx, wh, B, S, H, variant=variant, want_state=want_state)
             if want_state:
                 return out[0].transpose(0, 1), out[1], out[2]
             return out.transpose(0, 1), None, None
@@ -109,7 +110,7 @@ class LSTM(nn.Module):
         else:
             x2 = x2.float().contiguous()
         # per-step path
-        wi, b, wh = self._prepared(False)
+        wi, b, wh = self._prepared(0)
         cdt = torch.bfloat16 if lp else torch.float32
         gx = ops.linear(x2, wi, b, out_dtype=cdt).view(B, S, 8 * H)
         y = torch.empty(B, S, 2 * H, dtype=cdt, device=x.device)

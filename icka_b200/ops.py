@@ -467,8 +467,13 @@ def lstm_rec_workspace_bytes(B: int, H: int) -> int:
     return n
 
 
-def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, *, workspace: Optional[torch.Tensor] = None,
-             want_state: bool = False):
+def lstm_rec_variant(B: int) -> int:
+    """1 = single-CTA kernel (24-unit slices, small batches), 2 = CTA-pair kernel (48-unit slices)."""
+    return int(_lib.load().icka_lstm_rec_variant(int(B)))
+
+
+def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, *, variant: int,
+             workspace: Optional[torch.Tensor] = None, want_state: bool = False):
     """gx [S*B, 8H] bf16 (time-major rows, slice-ordered columns), w_hh_perm [8H, H] bf16 -> y [S,B,2H] bf16
     time-major (, h_n, c_n [2,B,H] fp32)."""
     _need(gx, torch.bfloat16, 'lstm_rec(gx)')
@@ -486,7 +491,8 @@ def lstm_rec(gx: torch.Tensor, w_hh_perm: torch.Tensor, B: int, S: int, H: int, 
     h_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
     c_n = torch.empty(2, B, H, dtype=torch.float32, device=gx.device) if want_state else None
     _lib.check(lib.icka_lstm_rec_fwd(h, gx.data_ptr(), w_hh_perm.data_ptr(), workspace.data_ptr() + off, need,
-                                     y.data_ptr(), _p(h_n), _p(c_n), B, S, H, st), 'icka_lstm_rec_fwd')
+                                     y.data_ptr(), _p(h_n), _p(c_n), B, S, H, int(variant), st),
+               'icka_lstm_rec_fwd')
     return (y, h_n, c_n) if want_state else y
 
 

@@ -279,8 +279,15 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
  * H = 768 only (other sizes: the per-step path, icka_linear_fwd + icka_lstm_cell_fwd).  The launch is cooperative:
  * 64 or 128 co-resident CTAs in clusters of 2 (tcgen05 cta_group::2 pairs sharing a 48-unit weight slice). */
 int64_t icka_lstm_rec_workspace_bytes(int B, int H);
+/* Two kernels serve the call; they differ in the slice width and therefore in the column order above:
+ *   variant 2 (B > 256): CTA pairs, 48-unit slices -- the order documented above;
+ *   variant 1 (B <= 256): single CTAs, 24-unit slices (lower step latency):
+ *             col = ((dir*32 + slice)*2 + half)*48 + jg*16 + gate*4 + jj  <->  gate*H + slice*24 + half*12 + jg*4 + jj.
+ * icka_lstm_rec_variant(B) says which one a batch of B sentences gets (ICKA_LSTM_VARIANT=1|2 overrides); the caller
+ * prepares gx / w_hh_perm for it and passes it back. */
+int icka_lstm_rec_variant(int B);
 int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, void* workspace, int64_t workspace_bytes,
-                      void* y, float* h_n, float* c_n, int B, int S, int H, void* stream);
+                      void* y, float* h_n, float* c_n, int B, int S, int H, int variant, void* stream);
 
 /* One LSTM step (per-step path: fp32 parity mode, or shapes icka_lstm_rec_fwd does not cover):
  *   pre = gates_h[B,4H] (fp32, = h_{t-1} . W_hh^T; NULL at the first step) + gx[B, 4H] (`dtype`, row pitch ldgx)

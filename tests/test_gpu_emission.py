@@ -54,8 +54,13 @@ def test_fp32_per_step_path(B, S, I, H):
     assert rel(out, y) <= 1e-5 and rel(h_n, hn) <= 1e-5 and rel(c_n, cn) <= 1e-5
 
 
-@pytest.mark.parametrize('B,S', [(5, 128), (300, 24), (128, 3), (1, 1)])
-def test_bf16_persistent_kernel(B, S):
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('B,S', [(5, 128), (300, 24), (128, 3), (1, 1), (640, 5)])
+def test_bf16_persistent_kernel(B, S, variant, monkeypatch):
+    """Both kernels behind icka_lstm_rec_fwd (1: single CTAs / 24-unit slices, 2: CTA pairs / 48-unit slices) at every
+    batch shape (the library picks 1 for B <= 256, 2 above; ICKA_LSTM_VARIANT forces one)."""
+    monkeypatch.setenv('ICKA_LSTM_VARIANT', str(variant))
+    assert ops.lstm_rec_variant(B) == variant
     icka_b200.set_precision('bf16')
     H = 768
     ref_lstm, ref_cls, ours = make(H, H, 15, seed=B * 7 + S)
@@ -66,10 +71,14 @@ def test_bf16_persistent_kernel(B, S):
     err_y = (out.double().cpu() - y).abs().max().item()
     err_h = (h_n.double().cpu() - hn).abs().max().item()
     err_c = (c_n.double().cpu() - cn).abs().max().item()
-    print(f'bf16 persistent B={B} S={S}: max|dy|={err_y:.2e} max|dh_n|={err_h:.2e} max|dc_n|={err_c:.2e}')
+    print(f'bf16 persistent variant {variant} B={B} S={S}: max|dy|={err_y:.2e} max|dh_n|={err_h:.2e} max|dc_n|={err_c:.2e}')
     assert err_y <= 2e-2 and err_h <= 2e-2 and err_c <= 4e-2
     out2, _ = ours(x.cuda())                                    # no atomics on the data path: reruns are identical
     assert torch.equal(out, out2)
+
+
+def test_variant_choice():
+    assert ops.lstm_rec_variant(1) == 1 and ops.lstm_rec_variant(256) == 1 and ops.lstm_rec_variant(257) == 2
 
 
 def test_bf16_per_step_path_other_hidden_size():

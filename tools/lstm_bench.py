@@ -18,7 +18,8 @@ torch.manual_seed(0)
 head = icka_b200.EmissionHead(FusionConfig(hidden_size=H), num_labels=T).cuda().eval()
 x = torch.randn(B, S, H, device='cuda')
 xb = ops.cast_bf16_time_major(x).view(S * B, H)
-wi, b, wh = head.lstm._prepared(True)
+variant = ops.lstm_rec_variant(B)
+wi, b, wh = head.lstm._prepared(variant)
 ws = torch.empty(ops.lstm_rec_workspace_bytes(B, H) + 1024, dtype=torch.uint8, device='cuda')
 
 
@@ -37,10 +38,10 @@ def timed(fn, n=10, warm=3):
 
 
 gx = ops.linear(xb, wi, b, out_dtype=torch.bfloat16)
-y = ops.lstm_rec(gx, wh, B, S, H, workspace=ws)
+y = ops.lstm_rec(gx, wh, B, S, H, variant=variant, workspace=ws)
 t_cast = timed(lambda: ops.cast_bf16_time_major(x))
 t_gx = timed(lambda: ops.linear(xb, wi, b, out_dtype=torch.bfloat16))
-t_rec = timed(lambda: ops.lstm_rec(gx, wh, B, S, H, workspace=ws))
+t_rec = timed(lambda: ops.lstm_rec(gx, wh, B, S, H, variant=variant, workspace=ws))
 w32, b32 = head.classifier.weight.detach().contiguous(), head.classifier.bias.detach().contiguous()
 t_head = timed(lambda: ops.emission_head(y.view(S * B, 2 * H), w32, b32, time_major_S=S))
 with torch.no_grad():
@@ -51,7 +52,7 @@ with torch.no_grad():
     t_cudnn = timed(lambda: ref(xr))
 flops_gx = 2.0 * B * S * 8 * H * H
 flops_rec = 2.0 * B * S * 8 * H * H
-print(f'B={B} S={S}: cast {t_cast:.3f} ms | gx GEMM {t_gx:.3f} ms ({flops_gx / t_gx / 1e9:.0f} TF/s) | '
+print(f'B={B} S={S} variant={variant}: cast {t_cast:.3f} ms | gx GEMM {t_gx:.3f} ms ({flops_gx / t_gx / 1e9:.0f} TF/s) | '
       f'recurrent {t_rec:.3f} ms ({flops_rec / t_rec / 1e9:.0f} TF/s, {t_rec / S * 1e3:.2f} us/step) | '
       f'classifier {t_head:.3f} ms ({B * S * 2 * H * 2 / t_head / 1e6:.0f} GB/s) | '
       f'module {t_all:.3f} ms = {B / t_all * 1e3:.0f} sentences/s | torch nn.LSTM (cuDNN, bf16) {t_cudnn:.3f} ms')
