@@ -70,7 +70,7 @@ struct LstmArgs {
   int B, S, b0, MT, TPG;     // sentences of this launch, steps, first sentence of this launch, 128-row tiles, tiles
                              // per CTA group (a pair walks them two at a time)
   int debug;                 // developer probes (ICKA_LSTM_DEBUG): 1 = no dependency wait, 2 = no cell arithmetic /
-                             // state stores, 4 = publish without the gpu-scope release, 16 = no MMAs (results are WRONG)
+                             // state stores, 4 = publish without the gpu-scope release, 16 = no MMAs, 32 = no state stores (results are WRONG)
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -192,7 +192,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         }
         cell4(ra, 2);
 
-        if (valid && !probe) {
+        if (valid && !probe && !(args.debug & 32)) {   // probe 32: cell arithmetic, no state stores
           const int unit0 = slice * kU + blk * 12;
           uint32_t hw[6];
 #pragma unroll
