@@ -83,6 +83,14 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
+// 256-bit store (sm_100: STG.E.ENL2.256), 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+               "r"(e), "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -140,6 +148,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
       const uint32_t slot_phase = (it / kSlots) & 1;
       const int row = row0 + p * 256;
       const bool valid = row < args.B;
+      uint32_t hw0[6];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int blk = half * 2 + hh;
@@ -192,20 +201,29 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         }
         cell4(ra, 2);
 
+        uint32_t hw[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
+        if (hh == 0) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) hw0[q] = hw[q];          // stored together with the second block
+        }
         if (valid && !probe && !(args.debug & 32)) {   // probe 32: cell arithmetic, no state stores
           const int unit0 = slice * kU + blk * 12;
-          uint32_t hw[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
-          // 24 bytes per row at byte offset 96 * slice + 24 * blk: one 16-byte and one 8-byte store, ordered so the
-          // 16-byte one is aligned (even blocks: 16 + 8, odd blocks: 8 + 16)
-          uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH + unit0);
-          if ((blk & 1) == 0) {
-            *reinterpret_cast<uint4*>(yp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint2*>(yp + 16) = make_uint2(hw[4], hw[5]);
-          } else {
-            *reinterpret_cast<uint2*>(yp) = make_uint2(hw[0], hw[1]);
-            *reinterpret_cast<uint4*>(yp + 8) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
+          if (hh == 1) {
+            // The thread's 24 units of the row = 48 contiguous bytes at byte offset 96 * slice + 48 * half.  Rows are 3 KB
+            // apart, so every store instruction is 32 separate L2 write transactions and the LSU is what bounds the kernel:
+            // one 256-bit + one 128-bit store per item (aligned: half 0 = 32 + 16 bytes, half 1 = 16 + 32) instead of four
+            // 16- / 8-byte pieces.
+            uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH +
+                                                     slice * kU + half * 24);
+            if (half == 0) {
+              st_global_v8(yp, hw0[0], hw0[1], hw0[2], hw0[3], hw0[4], hw0[5], hw[0], hw[1]);
+              *reinterpret_cast<uint4*>(yp + 32) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
+            } else {
+              *reinterpret_cast<uint4*>(yp) = make_uint4(hw0[0], hw0[1], hw0[2], hw0[3]);
+              st_global_v8(yp + 16, hw0[4], hw0[5], hw[0], hw[1], hw[2], hw[3], hw[4], hw[5]);
+            }
           }
           if (t == S - 1) {
             if (args.h_n) {
