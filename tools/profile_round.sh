@@ -16,6 +16,7 @@ ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_tcgen0
 tail -2 gpurun_out/ncu_gemm_${R}.log
 # emission head: stage timings, then one ncu --set full capture of the persistent recurrent kernel
 for b in 256 1024 2048; do python tools/lstm_bench.py $b 128 2>&1 | grep "B="; done > gpurun_out/lstm_bench_${R}.log
-ncu --set full --clock-control none --import-source on -k regex:lstm_rec --launch-skip 2 -c 1 -f \
+# (ncu cannot replay the cooperative launch of 2-CTA clusters of variant 2: the capture is of the single-CTA variant)
+ICKA_LSTM_VARIANT=1 ncu --set full --clock-control none --import-source on -k regex:lstm_rec --launch-skip 2 -c 1 -f \
     -o gpurun_out/lstm_${R} python tools/lstm_bench.py 1024 128 > gpurun_out/ncu_lstm_${R}.log 2>&1
 python bench.py --hires --batch 512 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_hires.json 2> gpurun_out/bench_${R}_hires.err
