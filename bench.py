@@ -30,9 +30,17 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-    os.environ['NCCL_DEBUG'] = 'WARN'
+# stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints its "NCCL version ..." banner to
+# stdout at NCCL_DEBUG=VERSION and =WARN; device-side printf of a watchdog): file descriptor 1 is pointed at stderr for the
+# whole run and the JSON line goes to the saved original descriptor (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
 
 METRIC = 'sentences/sec fusion+Viterbi'
 UNIT = 'sentences/s'
@@ -151,7 +159,7 @@ def run_reference_arm(args, shape):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -361,7 +369,7 @@ def run_gpu_arm(args, shape):
             'gemm_shapes': {k: {'launches_per_step': v['launches'] // args.steps, 'ms_per_launch': round(v['ms_per_launch'], 4),
                                 'tflops': round(v['tflops'], 1)} for k, v in gemm_shapes.items()},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -535,7 +543,7 @@ def run_train_arm(args, shape):
     peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
     tf = 3.0 * fwd * args.batch * args.steps / (ms * 1e-3) / 1e12
     if rank == 0:
-        print(json.dumps({
+        emit({
             'metric': 'sentences/sec fusion+CRF training step', 'value': args.batch * world * args.steps / (ms * 1e-3),
             'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32',
@@ -552,7 +560,7 @@ def run_train_arm(args, shape):
                          'note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, '
                                  'the all-reduce and the optimizer'},
             'kernels': kernel_table,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
