@@ -15,11 +15,12 @@
 //     N = 96 version kept only ~1000 cycles of MMA work queued against a ~2800-cycle issue -> commit -> refill loop
 //     (ncu: tensor pipe 32 % active);
 //   * a work item is (step t, PAIR of 128-sentence tiles): each CTA streams h_{t-1} of ITS tile (128 x 768 bf16) as
-//     the A operand through a 5-stage TMA ring straight out of the time-major output sequence y[t-1] (h is written
+//     the A operand through a 4-stage TMA ring straight out of the time-major output sequence y[t-1] (h is written
 //     exactly once; an out-of-bounds row coordinate delivers the zero state at t = 0), the leader CTA issues 48
 //     MMAs into one of 2 TMEM accumulator slots (128 lanes x 192 columns in each CTA), and 8 epilogue warps per CTA
 //     (thread = sentence = TMEM lane; two warp halves x two sequential blocks of 12 units) add Gx (prefetched one
-//     block ahead), apply the cell update with the cell state in registers, and store h_t (bf16) into y[t];
+//     block ahead), apply the cell update with the cell state in registers, and write h_t (bf16) into a shared-memory
+//     tile that the publisher warp stores into y[t] with one TMA instruction;
 //   * sentence tiles are independent recurrences: the only cross-CTA dependency is "the 16 CTAs that own tile m in my
 //     direction (one per slice pair) have published h_{t-1}" -- a per-(direction, tile) arrival counter in global memory (red.release /
 //     ld.acquire + fence.proxy.async before the TMA reads); no grid-wide barrier exists;
@@ -49,14 +50,16 @@ constexpr int kKB = kH / 64;                  // 12 k-chunks of 64 bf16 = 128 B
 constexpr int kWChunkBytes = kNHalf * 128;    // 12,288
 constexpr int kWBytes = kKB * kWChunkBytes;   // 147,456
 constexpr int kABytes = 128 * 128;            // one 128-row x 64-k A tile
-constexpr int kStages = 5;
+constexpr int kStages = 4;                    // (4 or 5 stages measure the same in pair mode; the 16 KB go to the h staging tile)
+constexpr int kStageTileBytes = 128 * kNHalf; // 128 rows x 48 units bf16 = 12,288: h_t of one item, stored by TMA
 constexpr int kSlots = 2;                     // TMEM accumulator slots
 constexpr int kSlotCols = 256;                // column stride between slots (192 used)
 constexpr int kEpiWarps = 8;
 constexpr int kPubWarp = 2 + kEpiWarps;       // warp 10: publishes finished items
 constexpr int kThreads = 32 * (kPubWarp + 1);
 constexpr int kCtasPerGroup = 2 * kNS * 2;    // 2 directions x 16 slices x 2 CTAs = 64
-constexpr size_t kSmemBytes = (size_t)kWBytes + (size_t)kStages * kABytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t kSmemBytes =
+    (size_t)kWBytes + (size_t)kStages * kABytes + kStageTileBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct LstmArgs {
   const __nv_bfloat16* gx;   // [S*Bn, 2*4H] bf16 TIME-MAJOR (row = t * Bn + sentence), columns ordered
@@ -83,6 +86,18 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
+// TMA store of a {48 units, 128 sentences, 1 step} box of the output sequence from shared memory (bulk async group)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait() {
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // writes performed, not only the source read
+}
+
 // 256-bit store (sm_100: STG.E.ENL2.256), 32-byte aligned
 __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
                                              uint32_t f, uint32_t g, uint32_t h) {
@@ -103,8 +118,8 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 // state of its NP rows lives in registers for the whole sequence.
 template <int NP>
 __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* acc_full, uint32_t acc_empty_leader0,
-                                              uint64_t* pub_bar, uint64_t* pub_free, uint32_t lane_taddr, int warp,
-                                              int lane, int dir, int slice, int tile_first) {
+                                              uint64_t* pub_bar, uint64_t* pub_free, uint8_t* h_tile, uint32_t lane_taddr,
+                                              int warp, int lane, int dir, int slice, int tile_first) {
   const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
   const int half = (warp - 2) >> 2;          // which half of the slice's 48 units
   const int S = args.S;
@@ -148,7 +163,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
       const uint32_t slot_phase = (it / kSlots) & 1;
       const int row = row0 + p * 256;
       const bool valid = row < args.B;
-      uint32_t hw0[6];
+      uint32_t hw0[6], hw1[6];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int blk = half * 2 + hh;
@@ -204,27 +219,13 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         uint32_t hw[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) hw[q] = pack_bf16x2(hv[2 * q], hv[2 * q + 1]);
-        if (hh == 0) {
 #pragma unroll
-          for (int q = 0; q < 6; ++q) hw0[q] = hw[q];          // stored together with the second block
+        for (int q = 0; q < 6; ++q) {
+          if (hh == 0) hw0[q] = hw[q];
+          else hw1[q] = hw[q];
         }
         if (valid && !probe && !(args.debug & 32)) {   // probe 32: cell arithmetic, no state stores
           const int unit0 = slice * kU + blk * 12;
-          if (hh == 1) {
-            // The thread's 24 units of the row = 48 contiguous bytes at byte offset 96 * slice + 48 * half.  Rows are 3 KB
-            // apart, so every store instruction is 32 separate L2 write transactions and the LSU is what bounds the kernel:
-            // one 256-bit + one 128-bit store per item (aligned: half 0 = 32 + 16 bytes, half 1 = 16 + 32) instead of four
-            // 16- / 8-byte pieces.
-            uint8_t* yp = reinterpret_cast<uint8_t*>(args.y + ((size_t)pos * args.Bn + row) * (2 * kH) + dir * kH +
-                                                     slice * kU + half * 24);
-            if (half == 0) {
-              st_global_v8(yp, hw0[0], hw0[1], hw0[2], hw0[3], hw0[4], hw0[5], hw[0], hw[1]);
-              *reinterpret_cast<uint4*>(yp + 32) = make_uint4(hw[2], hw[3], hw[4], hw[5]);
-            } else {
-              *reinterpret_cast<uint4*>(yp) = make_uint4(hw0[0], hw0[1], hw0[2], hw0[3]);
-              st_global_v8(yp + 16, hw0[4], hw0[5], hw[0], hw[1], hw[2], hw[3], hw[4], hw[5]);
-            }
-          }
           if (t == S - 1) {
             if (args.h_n) {
               float4* o = reinterpret_cast<float4*>(args.h_n + ((size_t)dir * args.Bn + row) * kH + unit0);
@@ -240,24 +241,34 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
           }
         }
       }
-      // hand the item to the publisher warp: this warp's h stores are ordered before the arrival (release.cta)
+      // h_t of the item goes through a [128 rows x 48 units] shared-memory tile that the publisher warp stores with ONE
+      // TMA instruction: with thread = row every global store instruction would be 32 separate L2 write transactions
+      // (rows are 3 KB apart) and the LSU, not the tensor pipe, would bound the kernel (measured: 3.8-4.9 us of a
+      // 12.6-13.4 us step).  The tile is free again once the previous item's store has read it (pub_free).
+      if (lane == 0) mbar_wait(&pub_free[0], (it & 1) ^ 1);
       __syncwarp();
-      if (lane == 0) {
-        mbar_wait(&pub_free[slot], ((it / kSlots) & 1) ^ 1);   // the publisher is done with this slot's previous item
-        mbar_arrive(&pub_bar[slot]);
+      if (!probe && !(args.debug & 32)) {
+        uint4* dst = reinterpret_cast<uint4*>(h_tile + (quad * 32 + lane) * kNHalf + half * 48);   // 96 B per row
+        dst[0] = make_uint4(hw0[0], hw0[1], hw0[2], hw0[3]);
+        dst[1] = make_uint4(hw0[4], hw0[5], hw1[0], hw1[1]);
+        dst[2] = make_uint4(hw1[2], hw1[3], hw1[4], hw1[5]);
       }
+      fence_proxy_async();                    // generic-proxy writes of the tile -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pub_bar[0]);
     }
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                        const LstmArgs args) {
+                        const __grid_constant__ CUtensorMap tmap_y, const LstmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_w = smem;
   uint8_t* smem_a = smem + kWBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * kABytes);
+  uint8_t* h_tile = smem_a + (size_t)kStages * kABytes;   // [128 rows][48 units] bf16, dense (the TMA store's box)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(h_tile + kStageTileBytes);
   uint64_t* full_bar = bars;                 // leader's are used: both CTAs' TMA bytes are credited there
   uint64_t* empty_bar = bars + kStages;      // own: the multicast commit arrives in both CTAs
   uint64_t* acc_full = bars + 2 * kStages;   // own (multicast commit)
@@ -281,6 +292,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_h);
+    tma_prefetch_desc(&tmap_y);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -402,17 +414,21 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       if (lane == 0) {
         const int items = S * npairs;
         for (int it = 0; it < items; ++it) {
+          const int t = it / npairs;
           const int m = tile0 + 2 * (it % npairs) + (int)rank;
-          const int slot = it % kSlots;
-          mbar_wait(&pub_bar[slot], (it / kSlots) & 1);
+          const int pos = dir ? (S - 1 - t) : t;
+          mbar_wait(&pub_bar[0], it & 1);                 // all 8 epilogue warps have written the tile
           if (m < tile1) {
+            if (!(args.debug & 34))
+              tma_store_3d(&tmap_y, h_tile, dir * kH + slice * kU, args.b0 + m * 128, pos);   // rows >= B are clipped
+            bulk_commit_and_wait();
             if (args.debug & 4) {
               atomicAdd(args.cnt + dir * args.MT + m, 1);
             } else {
               red_release_gpu_add(args.cnt + dir * args.MT + m, 1);   // the consumer's fence.proxy.async orders its TMA reads
             }
           }
-          mbar_arrive(&pub_free[slot]);
+          mbar_arrive(&pub_free[0]);                      // the tile may be overwritten
         }
       }
     } else {
@@ -421,9 +437,9 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       const uint32_t acc_empty_leader0 = map_to_cta(&acc_empty[0], 0);
       const int tile_first = tile0 + (int)rank;
       if (npairs == 1)
-        lstm_epilogue<1>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile_first);
+        lstm_epilogue<1>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
       else
-        lstm_epilogue<2>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, lane_taddr, warp, lane, dir, slice, tile_first);
+        lstm_epilogue<2>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
     }
   }
 
@@ -438,6 +454,23 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
 }  // namespace
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// output sequence as {2H columns, B sentences, S steps}; box {48 units, 128 sentences, 1 step}, no swizzle (dense tile)
+static int make_tmap_y_store(icka_handle* h, CUtensorMap* tm, void* y, int B, int S) {
+  const cuuint64_t gdim[3] = {(cuuint64_t)(2 * kH), (cuuint64_t)B, (cuuint64_t)S};
+  const cuuint64_t gstride[2] = {(cuuint64_t)(2 * kH) * 2, (cuuint64_t)B * (2 * kH) * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kU, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn3>(h->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, y, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ICKA_FAIL(ICKA_ERR_CUDA, "cuTensorMapEncodeTiled(y store) failed (%d) B=%d S=%d", (int)r, B, S);
+  return ICKA_OK;
+}
 
 // sentences per launch: the cell state of a CTA's tiles lives in registers, at most 2 tiles of 128 per CTA (= 4 per pair)
 static int lstm_groups(int sm_count) { return sm_count / kCtasPerGroup > 0 ? sm_count / kCtasPerGroup : 1; }
@@ -502,11 +535,13 @@ static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_per
                (long long)cnt_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  CUtensorMap tw, th;
+  CUtensorMap tw, th, ty;
   int rc = icka_make_tmap_bf16(h, &tw, w_hh_perm, 2 * 4 * kH, kH, kH, kNHalf);
   if (rc) return rc;
   // the A operand of step t is read straight out of the output sequence: [S*B rows, 2H columns], box 128 x 64
   rc = icka_make_tmap_bf16(h, &th, y, (int64_t)S * B, 2 * kH, 2 * kH, 128);
+  if (rc) return rc;
+  rc = make_tmap_y_store(h, &ty, y, B, S);
   if (rc) return rc;
   ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* dbg = getenv("ICKA_LSTM_DEBUG");
@@ -545,7 +580,7 @@ static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_per
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel, tw, th, args));
+    ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel, tw, th, ty, args));
     ICKA_LAUNCHED(h);
   }
   return ICKA_OK;
