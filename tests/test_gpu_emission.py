@@ -126,6 +126,23 @@ def test_emission_head_module(precision, tol):
     assert err <= tol
 
 
+def test_batches_above_one_launch_are_chunked():
+    """B > 1024: EmissionHead / LSTM walk 1024-sentence chunks; same result as the chunks on their own."""
+    icka_b200.set_precision('bf16')
+    H, T, B, S = 768, 15, 1100, 4
+    torch.manual_seed(2)
+    head = icka_b200.EmissionHead(FusionConfig(hidden_size=H), num_labels=T).cuda().eval()
+    x = torch.randn(B, S, H, device='cuda')
+    with torch.no_grad():
+        whole = head(x)
+        parts = torch.cat([head(x[:1024]), head(x[1024:])])
+        out, (h_n, c_n) = head.lstm(x)
+        out_a, (h_a, _) = head.lstm(x[:1024])
+    assert torch.equal(whole, parts)
+    assert out.shape == (B, S, 2 * H) and h_n.shape == (2, B, H) and c_n.shape == (2, B, H)
+    assert torch.equal(out[:1024], out_a) and torch.equal(h_n[:, :1024], h_a)
+
+
 def test_lstm_rejects_what_it_does_not_cover():
     with pytest.raises(NotImplementedError):
         icka_b200.LSTM(8, 8, batch_first=True, bidirectional=False)
