@@ -72,6 +72,7 @@ struct LstmArgs {
                              // planes of h_n / c_n)
   int B, S, b0, MT, TPG;     // sentences of this launch, steps, first sentence of this launch, 128-row tiles, tiles
                              // per CTA group (a pair walks them two at a time)
+  unsigned long long* trace; // developer timeline (ICKA_LSTM_TRACE): [item][8] globaltimer stamps of CTA 0, or null
   int debug;                 // developer probes (ICKA_LSTM_DEBUG): 1 = no dependency wait, 2 = no cell arithmetic /
                              // state stores, 4 = publish without the gpu-scope release, 16 = no MMAs, 32 = no state stores (results are WRONG)
 };
@@ -85,6 +86,18 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Developer timeline (tools/lstm_trace.py), slots per item: 0 dependency satisfied (producer), 1 last A chunk issued
+// (producer), 2 last MMA committed (MMA warp), 3 accumulator seen (epilogue warp 2), 4 tile written (epilogue warp 2),
+// 5 TMA store complete (publisher), 6 counter released (publisher)
+#define LSTM_TRACE(slot_, it_)                                                                      \
+  do {                                                                                              \
+    if (args.trace != nullptr && blockIdx.x == 0 && (it_) < 4096) args.trace[(size_t)(it_) * 8 + (slot_)] = globaltimer_ns(); \
+  } while (0)
 
 // TMA store of a {48 units, 128 sentences, 1 step} box of the output sequence from shared memory (bulk async group)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
@@ -106,6 +119,8 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
+// Activations: MUFU.TANH, sigmoid(x) = 0.5 tanh(x / 2) + 0.5 -- 5 MUFU per unit and sentence.  (ex2 + rcp forms, 10 MUFU, and
+// tanh.approx.f16x2, which splits into two MUFU.TANH.F16, both measured slower or equal.)
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -177,6 +192,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         if (hh == 0) {
           mbar_wait(&acc_full[slot], slot_phase);
           tc_fence_after();
+          if (warp == 2 && lane == 0) LSTM_TRACE(3, it);
         }
         // 48 accumulator columns = 3 groups of 4 units x (i, f, g, o): 16 columns are live at a time, the next
         // group's tcgen05.ld is in flight while this one is being computed
@@ -255,7 +271,10 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
       }
       fence_proxy_async();                    // generic-proxy writes of the tile -> visible to the TMA store
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pub_bar[0]);
+      if (lane == 0) {
+        if (warp == 2) LSTM_TRACE(4, it);
+        mbar_arrive(&pub_bar[0]);
+      }
     }
   }
 }
@@ -357,6 +376,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             }
             // A operand = h_{t-1} of this tile = the rows the previous step wrote into the (time-major) output
             // sequence; at t = 0 (and for the missing tile of an odd count) an out-of-bounds row makes TMA deliver zeros
+            LSTM_TRACE(0, t * npairs + p);
             const int prev = dir ? (S - t) : (t - 1);
             const int arow = (t == 0 || !tile_ok) ? S * args.Bn : prev * args.Bn + args.b0 + m * 128;
             for (int kb = 0; kb < kKB; ++kb) {
@@ -366,6 +386,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
                                dir * kH + kb * 64, arow);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            LSTM_TRACE(1, t * npairs + p);
           }
         }
       }
@@ -404,6 +425,7 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             umma_commit_pair(&acc_full[slot], 3);         // wake the epilogue warps of both CTAs
+            LSTM_TRACE(2, it);
           }
         }
       }
@@ -422,11 +444,13 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             if (!(args.debug & 34))
               tma_store_3d(&tmap_y, h_tile, dir * kH + slice * kU, args.b0 + m * 128, pos);   // rows >= B are clipped
             bulk_commit_and_wait();
+            LSTM_TRACE(5, it);
             if (args.debug & 4) {
               atomicAdd(args.cnt + dir * args.MT + m, 1);
             } else {
               red_release_gpu_add(args.cnt + dir * args.MT + m, 1);   // the consumer's fence.proxy.async orders its TMA reads
             }
+            LSTM_TRACE(6, it);
           }
           mbar_arrive(&pub_free[0]);                      // the tile may be overwritten
         }
@@ -565,6 +589,10 @@ static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_per
     args.h_n = h_n ? h_n + (size_t)b0 * kH : nullptr;
     args.c_n = c_n ? c_n + (size_t)b0 * kH : nullptr;
     args.debug = dbg ? atoi(dbg) : 0;
+    {
+      const char* tr = getenv("ICKA_LSTM_TRACE");   // developer timeline: device address of a >= 256 KB buffer
+      args.trace = tr ? reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0)) : nullptr;
+    }
     ICKA_CUDA(cudaMemsetAsync(ws, 0, cnt_bytes, st));   // arrival counters
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * kCtasPerGroup);
