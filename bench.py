@@ -63,6 +63,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-widened', action='store_true', help='skip the extra fusion -> BiLSTM+classifier -> Viterbi -> chunk-F1 measurement')
+    ap.add_argument('--inflight', type=int, default=2, choices=[1, 2],
+                    help='captured steps in flight: 2 = two batches (own device buffers, own library workspace) replayed on '
+                         'two streams, so the low-occupancy tail of one step overlaps the head of the next')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -253,22 +256,53 @@ def run_gpu_arm(args, shape):
     # region replays it (one driver call per step), so a slow host cannot starve the GPU.  gpu_launches counts the
     # kernels the graph contains (icka_launch_count over the capture) times the replays.
     use_graph = not args.no_graph
+    inflight = args.inflight if use_graph else 1
     if use_graph:
         graph, _outs = pipe.capture(d)
         per_step = pipe.graph_kernels
         run_step = graph.replay
+        if inflight == 2:
+            # a second batch with its own device buffers, graph and library handle slot (split-K workspace): steps i and
+            # i + 1 run on two streams, so the single-query encoders' small GEMMs at the end of a step (a few dozen CTAs)
+            # share the machine with the next step's region relayout / projections instead of leaving most SMs idle
+            d2 = pipe.to_device(pipe.make_host_batch(args.batch, shape, seed + 500))
+            torch.cuda.synchronize()
+            graph2, _outs2 = pipe.capture(d2, slot=1)
+            lanes = [(torch.cuda.Stream(), graph), (torch.cuda.Stream(), graph2)]
+            state = {'i': 0}
+
+            def run_step():
+                st, g = lanes[state['i'] & 1]
+                state['i'] += 1
+                with torch.cuda.stream(st):
+                    g.replay()
     else:
         per_step = None
         run_step = lambda: pipe.step_device(d)
+
+    def fork():
+        if inflight == 2:
+            for st, _ in lanes:
+                st.wait_stream(torch.cuda.current_stream())
+
+    def join():
+        if inflight == 2:
+            for st, _ in lanes:
+                torch.cuda.current_stream().wait_stream(st)
+
+    fork()
     for _ in range(max(args.warmup, 3)):
         run_step()
+    join()
     barrier()
     launches0 = _lib.launch_count(local_rank)
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         s_ev.record()
+        fork()
         for _ in range(args.steps):
             run_step()
+        join()
         e_ev.record()
         barrier()
     ms_total = s_ev.elapsed_time(e_ev)
@@ -362,7 +396,8 @@ def run_gpu_arm(args, shape):
                        'layers': shape.L, 'parallelism': f'batch-sharded x{world}, no collectives',
                        'precision': 'bf16 GEMM operands, fp32 accumulate/residual/LayerNorm/softmax' if args.precision == 'bf16' else 'fp32',
                        'weights': 'random init (nn.Linear default)',
-                       'launch': 'CUDA graph replay of the captured step' if use_graph else 'eager host launches',
+                       'launch': ('CUDA graph replay of the captured step' + (', two batches in flight on two streams' if inflight == 2 else ''))
+                                 if use_graph else 'eager host launches',
                        'l2_policy': 'inputs larger than L2 (>= 1.2 GB of inputs per step vs 126 MB L2); no flush needed'},
             'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu, 'widened': widened, 'kernels': kernel_table,

@@ -125,18 +125,41 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f'{what} failed ({rc}): {last_error()}')
 
 
+_slot = threading.local()
+
+
+class use_slot:
+    """Context manager: calls made inside use handle `slot` of each device (its own split-K workspace).  The C library's
+    rule is one stream at a time per handle; work that runs CONCURRENTLY on several streams (two captured steps in flight)
+    therefore takes one slot per stream.  Slot 0 is the default."""
+
+    def __init__(self, slot: int):
+        self.slot = int(slot)
+
+    def __enter__(self):
+        self.prev = getattr(_slot, 'value', 0)
+        _slot.value = self.slot
+        return self
+
+    def __exit__(self, *exc):
+        _slot.value = self.prev
+        return False
+
+
 def handle(device_index: int) -> c_void_p:
-    """Per-device library handle (created on first use, kept for the life of the process)."""
+    """Per-device library handle of the current slot (created on first use, kept for the life of the process)."""
+    key = (device_index, getattr(_slot, 'value', 0))
     with _lock:
-        h = _handles.get(device_index)
+        h = _handles.get(key)
         if h is None:
             lib = load()
             out = c_void_p()
             check(lib.icka_create(int(device_index), ctypes.byref(out)), 'icka_create')
-            h = _handles[device_index] = out
+            h = _handles[key] = out
         return h
 
 
 def launch_count(device_index: int = 0) -> int:
-    h = _handles.get(device_index)
-    return int(load().icka_launch_count(h)) if h is not None else 0
+    """Kernels launched so far on `device_index` through every slot's handle."""
+    lib = load()
+    return sum(int(lib.icka_launch_count(h)) for (d, _), h in list(_handles.items()) if d == device_index)

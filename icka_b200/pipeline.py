@@ -67,11 +67,18 @@ class FusionViterbiPipeline:
         return out['result'], out['clip'], tags, lens, out['gate']
 
     # ---- CUDA graph of the device-resident step -----------------------------------------------------
-    def capture(self, d: Dict[str, torch.Tensor]):
-        """Capture one ``step_device(d)`` -- ~40 kernel launches on two streams -- into a CUDA graph bound to the
+    def capture(self, d: Dict[str, torch.Tensor], slot: int = 0):
+        """``slot``: library handle slot (own split-K workspace) -- captures that will be replayed CONCURRENTLY on
+        different streams must use different slots.
+
+        Capture one ``step_device(d)`` -- ~40 kernel launches on two streams -- into a CUDA graph bound to the
         (static) device buffers ``d``.  Returns ``(graph, outputs)``; ``graph.replay()`` re-runs the step on new
         contents of ``d`` and refreshes ``outputs`` in place.  The step is launch-bound on a slow host (each
         launch goes Python -> ctypes -> cudaLaunchKernelEx); a replay is one driver call."""
+        with _lib.use_slot(slot):
+            return self._capture(d)
+
+    def _capture(self, d: Dict[str, torch.Tensor]):
         cur = torch.cuda.current_stream(self.device)
         warm = torch.cuda.Stream(self.device)
         warm.wait_stream(cur)
