@@ -57,19 +57,30 @@ __global__ void __launch_bounds__(256) region_rows_kernel(const float* __restric
   }
   __syncthreads();
   OutT* dst = rows + (size_t)b * R * C + c0;
-  // each thread writes two adjacent channels of one region row; a warp covers one 64-channel row segment
-  constexpr int pairs = kRegC / 2;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < R * pairs; i += 256) {
-    const int r = i / pairs, c = (i - r * pairs) * 2;
-    if (c + 1 < nc) {
-      const float v0 = tile[c * Rp + r], v1 = tile[(c + 1) * Rp + r];
+  // A warp writes one 64-channel segment of a region row per pass.  Reading the tile with lane = channel PAIR (stride
+  // 2 * Rp words) is a 2-way bank conflict for every odd or even pitch (ncu: 3.4 M conflicts, the kernel was issue /
+  // conflict bound at 60 % of HBM); lane = channel (and channel + 32) with the odd pitch is conflict-free, and two
+  // shuffles hand each lane the neighbouring channel it stores next to its own.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (nc == kRegC) {
+    const int src = 2 * (lane & 15);                 // lanes 0-15 store channels 0-31, lanes 16-31 channels 32-63
+    const bool upper = lane >= 16;
+#pragma unroll 2
+    for (int r = warp; r < R; r += 8) {
+      const float lo = tile[lane * Rp + r], hi = tile[(lane + 32) * Rp + r];
+      const float a0 = __shfl_sync(0xffffffffu, lo, src), a1 = __shfl_sync(0xffffffffu, lo, src + 1);
+      const float b0 = __shfl_sync(0xffffffffu, hi, src), b1 = __shfl_sync(0xffffffffu, hi, src + 1);
+      const float v0 = upper ? b0 : a0, v1 = upper ? b1 : a1;
+      const int c = (upper ? 32 : 0) + src;
       if constexpr (sizeof(OutT) == 2) {
         *reinterpret_cast<uint32_t*>(dst + (size_t)r * C + c) = pack_bf16x2(v0, v1);
       } else {
         *reinterpret_cast<float2*>(dst + (size_t)r * C + c) = make_float2(v0, v1);
       }
-    } else if (c < nc) {
+    }
+  } else {
+    for (int i = threadIdx.x; i < R * nc; i += 256) {
+      const int r = i / nc, c = i - r * nc;
       dst[(size_t)r * C + c] = from_f32<OutT>(tile[c * Rp + r]);
     }
   }
