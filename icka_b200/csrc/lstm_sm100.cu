@@ -19,8 +19,10 @@
 //     exactly once; an out-of-bounds row coordinate delivers the zero state at t = 0), the leader CTA issues 48
 //     MMAs into one of 2 TMEM accumulator slots (128 lanes x 192 columns in each CTA), and 8 epilogue warps per CTA
 //     (thread = sentence = TMEM lane; two warp halves x two sequential blocks of 12 units) add Gx (prefetched one
-//     block ahead), apply the cell update with the cell state in registers, and write h_t (bf16) into a shared-memory
-//     tile that the publisher warp stores into y[t] with one TMA instruction;
+//     block ahead), apply the cell update with the cell state in registers (first two tiles of a CTA) or in the spare
+//     TMEM columns next to the accumulators (tiles 3 and 4 at 2048 sentences per launch: four independent step chains
+//     per CTA hide the ~13 us chain latency of a tile), and write h_t (bf16) into a shared-memory tile that the
+//     publisher warp stores into y[t] with one TMA instruction;
 //   * sentence tiles are independent recurrences: the only cross-CTA dependency is "the 16 CTAs that own tile m in my
 //     direction (one per slice pair) have published h_{t-1}" -- a per-(direction, tile) arrival counter in global memory (red.release /
 //     ld.acquire + fence.proxy.async before the TMA reads); no grid-wide barrier exists;
@@ -139,9 +141,12 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
   const int half = (warp - 2) >> 2;          // which half of the slice's 48 units
   const int S = args.S;
   const int row0 = tile_first * 128 + quad * 32 + lane;   // item p: row0 + p * 256
-  float c[NP][2][12];
+  // cell state: items 0 and 1 of a step in registers; items 2 and 3 (2048 sentences per launch) in the 2 x 64 TMEM
+  // columns the two 192-column accumulator slots leave free (thread = lane owns its own 12 columns per block)
+  constexpr int NPR = NP < 2 ? NP : 2;
+  float c[NPR][2][12];
 #pragma unroll
-  for (int p = 0; p < NP; ++p)
+  for (int p = 0; p < NPR; ++p)
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -199,6 +204,25 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
         const uint32_t taddr = lane_taddr + (uint32_t)(slot * kSlotCols + blk * 48);
         uint32_t ra[16], rb[16];
         float hv[12];
+        // this block's cell state: registers (items 0, 1) or the spare TMEM columns of slot p - 2 (items 2, 3)
+        constexpr int kSpareCol = 192;
+        const int pr = p < NPR ? p : 0;
+        const uint32_t c_taddr = lane_taddr + (uint32_t)((p >= 2 ? p - 2 : 0) * kSlotCols + kSpareCol + blk * 12);
+        float cc[12];
+        if (p < 2) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q) cc[q] = c[pr][hh][q];
+        } else if (t > 0) {
+          uint32_t cw[12];
+          tmem_ld8(c_taddr, &cw[0]);
+          tmem_ld4(c_taddr + 8, &cw[8]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 12; ++q) cc[q] = __uint_as_float(cw[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 12; ++q) cc[q] = 0.0f;
+        }
         auto cell4 = [&](const uint32_t (&r)[16], int jg) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -213,8 +237,8 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
             const float ig = sigmoid_fast(pre[0]), fg = sigmoid_fast(pre[1]), gg = tanh_fast(pre[2]),
                         og = sigmoid_fast(pre[3]);
             const int j = jg * 4 + jj;
-            c[p][hh][j] = probe ? c[p][hh][j] : fmaf(fg, c[p][hh][j], ig * gg);
-            hv[j] = og * tanh_fast(c[p][hh][j]);
+            cc[j] = probe ? cc[j] : fmaf(fg, cc[j], ig * gg);
+            hv[j] = og * tanh_fast(cc[j]);
           }
         };
         tmem_ld16(taddr, ra);
@@ -231,6 +255,17 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
           if (lane == 0) mbar_arrive_cluster(acc_empty_leader0 + (uint32_t)slot * 8u);
         }
         cell4(ra, 2);
+        if (p < 2) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q) c[pr][hh][q] = cc[q];
+        } else {
+          uint32_t cw[12];
+#pragma unroll
+          for (int q = 0; q < 12; ++q) cw[q] = __float_as_uint(cc[q]);
+          tmem_st8(c_taddr, &cw[0]);
+          tmem_st4(c_taddr + 8, &cw[8]);
+          tmem_st_wait();
+        }
 
         uint32_t hw[6];
 #pragma unroll
@@ -252,7 +287,7 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
               float4* o = reinterpret_cast<float4*>(args.c_n + ((size_t)dir * args.Bn + row) * kH + unit0);
 #pragma unroll
               for (int q = 0; q < 3; ++q)
-                o[q] = make_float4(c[p][hh][4 * q], c[p][hh][4 * q + 1], c[p][hh][4 * q + 2], c[p][hh][4 * q + 3]);
+                o[q] = make_float4(cc[4 * q], cc[4 * q + 1], cc[4 * q + 2], cc[4 * q + 3]);
             }
           }
         }
@@ -279,6 +314,9 @@ __device__ __forceinline__ void lstm_epilogue(const LstmArgs& args, uint64_t* ac
   }
 }
 
+// MAXNP: most items per step a CTA of this instantiation walks (2: <= 1024 sentences per launch, cell state entirely in
+// registers; 4: <= 2048, two more tiles' state in TMEM) -- two kernels so the common case keeps its register allocation
+template <int MAXNP>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                         const __grid_constant__ CUtensorMap tmap_y, const LstmArgs args) {
@@ -460,10 +498,16 @@ lstm_rec_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       const uint32_t lane_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       const uint32_t acc_empty_leader0 = map_to_cta(&acc_empty[0], 0);
       const int tile_first = tile0 + (int)rank;
-      if (npairs == 1)
+      if (npairs == 1) {
         lstm_epilogue<1>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
-      else
+      } else if (npairs == 2) {
         lstm_epilogue<2>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
+      } else if constexpr (MAXNP >= 4) {
+        if (npairs == 3)
+          lstm_epilogue<3>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
+        else
+          lstm_epilogue<4>(args, acc_full, acc_empty_leader0, pub_bar, pub_free, h_tile, lane_taddr, warp, lane, dir, slice, tile_first);
+      }
     }
   }
 
@@ -496,9 +540,10 @@ static int make_tmap_y_store(icka_handle* h, CUtensorMap* tm, void* y, int B, in
   return ICKA_OK;
 }
 
-// sentences per launch: the cell state of a CTA's tiles lives in registers, at most 2 tiles of 128 per CTA (= 4 per pair)
+// sentences per launch: a CTA walks at most 4 tiles of 128 per step (cell state of two in registers, of two more in the
+// spare TMEM columns) = 8 per pair
 static int lstm_groups(int sm_count) { return sm_count / kCtasPerGroup > 0 ? sm_count / kCtasPerGroup : 1; }
-static int lstm_chunk(int sm_count) { return 4 * 128 * lstm_groups(sm_count); }
+static int lstm_chunk(int sm_count) { return 8 * 128 * lstm_groups(sm_count); }
 
 extern "C" int64_t icka_lstm_rec_workspace_bytes(int B, int H) {
   if (B < 0 || H != kH) return -1;
@@ -567,7 +612,8 @@ static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_per
   if (rc) return rc;
   rc = make_tmap_y_store(h, &ty, y, B, S);
   if (rc) return rc;
-  ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  ICKA_CUDA(cudaFuncSetAttribute(lstm_rec_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const char* dbg = getenv("ICKA_LSTM_DEBUG");
 
   // sentences are independent recurrences: launches of <= `chunk` sentences, one after the other on the stream
@@ -608,7 +654,8 @@ static int lstm_rec2_launch(icka_handle* h, const void* gx, const void* w_hh_per
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel, tw, th, ty, args));
+    if (args.TPG <= 4) ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel<2>, tw, th, ty, args));
+    else ICKA_CUDA(cudaLaunchKernelEx(&cfg, lstm_rec_tcgen05_kernel<4>, tw, th, ty, args));
     ICKA_LAUNCHED(h);
   }
   return ICKA_OK;

@@ -26,8 +26,8 @@ from . import modules, ops
 from .modules import _OperandCache
 
 REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
-REC_CHUNK = 1024     # sentences per persistent launch; larger batches are walked chunk by chunk so that the 1.6 GB Gx
-                     # buffer of a chunk is reused (measured: one 4096-sentence Gx costs the recurrence 27 % in TLB / L2 misses)
+REC_CHUNK = 2048     # sentences per persistent launch (4 sentence tiles per CTA); larger batches are walked chunk by chunk
+                     # so that the Gx buffer of a chunk (3.2 GB) is reused
 
 
 def slice_order(H: int = REC_H, variant: int = 2) -> torch.Tensor:

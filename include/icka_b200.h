@@ -274,8 +274,8 @@ int icka_ner_chunk_counts(icka_handle* h, const int32_t* pred, const int64_t* go
  *   w_hh_perm [2*4H, H] bf16: weight_hh_l0 / weight_hh_l0_reverse with their rows in the same order
  *   workspace icka_lstm_rec_workspace_bytes(B, H) bytes, 1024-byte aligned (arrival counters; zeroed by the call)
  *   y         [S, B, 2H] bf16 TIME-MAJOR (forward states in [:H], backward in [H:]); h_n, c_n [2, B, H] fp32 or NULL
- * Every step then reads / writes one contiguous block of gx / y.  More than 1024 sentences run as consecutive
- * launches of <= 1024 (the cell state of a CTA's <= 4 sentence tiles lives in registers).
+ * Every step then reads / writes one contiguous block of gx / y.  More than 2048 sentences run as consecutive
+ * launches of <= 2048 (a CTA keeps the cell state of <= 4 sentence tiles: two in registers, two in spare TMEM columns).
  * H = 768 only (other sizes: the per-step path, icka_linear_fwd + icka_lstm_cell_fwd).  The launch is cooperative:
  * 64 or 128 co-resident CTAs in clusters of 2 (tcgen05 cta_group::2 pairs sharing a 48-unit weight slice). */
 int64_t icka_lstm_rec_workspace_bytes(int B, int H);

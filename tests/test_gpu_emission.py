@@ -55,7 +55,7 @@ def test_fp32_per_step_path(B, S, I, H):
 
 
 @pytest.mark.parametrize('variant', [1, 2])
-@pytest.mark.parametrize('B,S', [(5, 128), (300, 24), (128, 3), (1, 1), (640, 5)])
+@pytest.mark.parametrize('B,S', [(5, 128), (300, 24), (128, 3), (1, 1), (640, 5), (1100, 3), (2048, 4), (1500, 2)])
 def test_bf16_persistent_kernel(B, S, variant, monkeypatch):
     """Both kernels behind icka_lstm_rec_fwd (1: single CTAs / 24-unit slices, 2: CTA pairs / 48-unit slices) at every
     batch shape (the library picks 1 for B <= 256, 2 above; ICKA_LSTM_VARIANT forces one)."""
@@ -127,20 +127,20 @@ def test_emission_head_module(precision, tol):
 
 
 def test_batches_above_one_launch_are_chunked():
-    """B > 1024: EmissionHead / LSTM walk 1024-sentence chunks; same result as the chunks on their own."""
+    """B > 2048: EmissionHead / LSTM walk 2048-sentence chunks; same result as the chunks on their own."""
     icka_b200.set_precision('bf16')
-    H, T, B, S = 768, 15, 1100, 4
+    H, T, B, S = 768, 15, 2100, 3
     torch.manual_seed(2)
     head = icka_b200.EmissionHead(FusionConfig(hidden_size=H), num_labels=T).cuda().eval()
     x = torch.randn(B, S, H, device='cuda')
     with torch.no_grad():
         whole = head(x)
-        parts = torch.cat([head(x[:1024]), head(x[1024:])])
+        parts = torch.cat([head(x[:2048]), head(x[2048:])])
         out, (h_n, c_n) = head.lstm(x)
-        out_a, (h_a, _) = head.lstm(x[:1024])
+        out_a, (h_a, _) = head.lstm(x[:2048])
     assert torch.equal(whole, parts)
     assert out.shape == (B, S, 2 * H) and h_n.shape == (2, B, H) and c_n.shape == (2, B, H)
-    assert torch.equal(out[:1024], out_a) and torch.equal(h_n[:, :1024], h_a)
+    assert torch.equal(out[:2048], out_a) and torch.equal(h_n[:, :2048], h_a)
 
 
 def test_lstm_rejects_what_it_does_not_cover():
