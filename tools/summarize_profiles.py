@@ -39,7 +39,7 @@ def launches(R):
         a[1] += float(r[vi].replace(',', '')) / 1e3
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, f'launches_{R}_summary.csv'), 'w') as f:
-        f.write(f'# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e` (B=1024, L=1)\n')
+        f.write(f'# ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e` (default batch, L=1)\n')
         f.write('# ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES\n')
         f.write(f'# {sum(v[0] for v in agg.values())} launches, total {tot / 1e3:.3f} ms\n')
         f.write('kernel,launches,total_us,share\n')
@@ -80,15 +80,19 @@ def gemm(R):
         out_rows.append(rec)
         traffic.append(rec['dram_bytes'])
     keys = list(out_rows[0].keys())
+    try:          # the batch of the bench line captured in the same round
+        batch = json.load(open(os.path.join(G, f'bench_{R}.json')))['config']['batch_per_gpu']
+    except Exception:
+        batch = 1024
     with open(os.path.join(P, f'ncu_gemm_{R}.csv'), 'w') as f:
         f.write('# ncu --set full --clock-control none -k regex:gemm_bf16_tcgen05 --launch-skip 45 -c 15 '
                 'python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e\n')
-        f.write('# = the 15 tcgen05 GEMM launches of one bench step (B=1024, L=1), in launch order\n')
+        f.write(f'# = the 15 tcgen05 GEMM launches of one bench step (B={batch}, L=1), in launch order\n')
         w = csv.DictWriter(f, fieldnames=keys)
         w.writeheader()
         for rec in out_rows:
             w.writerow(rec)
-    json.dump({'source': f'profiles/ncu_gemm_{R}.csv', 'workload': 'B1024_L1', 'launches': len(traffic),
+    json.dump({'source': f'profiles/ncu_gemm_{R}.csv', 'workload': f'B{batch}_L1', 'launches': len(traffic),
                'dram_bytes_per_launch_mean': sum(traffic) / len(traffic), 'dram_bytes_per_step': sum(traffic)},
               open(os.path.join(P, f'traffic_{R}.json'), 'w'), indent=1)
 
