@@ -7,7 +7,7 @@
 A "step" is one pass of the hot path over one batch of synthetic sentences per GPU: region relayout +
 projection, text->image cross encoder, image->text cross encoders, gated fusion, and CRF Viterbi decode
 of that batch's emission scores.  Workload = BASELINE.json configs[2] (Twitter-2017-shaped inference
-sweep, batch-sharded, no communication): --batch sentences per GPU (default 2048, inside the 256-4096
+sweep, batch-sharded, no communication): --batch sentences per GPU (default 1024, inside the 256-4096
 sweep), S=128, R=49, H=768, 12 heads, I=3072, T=15, --layers cross layers per encoder (default 1 = the
 reference constructor default, CMIM:888).
 
@@ -53,7 +53,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='icka', choices=['icka', 'reference'])
-    ap.add_argument('--batch', type=int, default=None, help='sentences per GPU per step (default 2048; 128 for --mode train)')
+    ap.add_argument('--batch', type=int, default=None, help='sentences per GPU per step (default 1024; 128 for --mode train)')
     ap.add_argument('--mode', default='infer', choices=['infer', 'train'],
                     help="'infer' (default, the BASELINE metric) or 'train' (configs[1]/[4]: fwd + bwd + all-reduce + AdamW)")
     ap.add_argument('--layers', type=int, default=1, help='cross layers per encoder (layer_num1)')
@@ -603,7 +603,7 @@ def run_train_arm(args, shape):
 def main():
     args = parse()
     if args.batch is None:
-        args.batch = 128 if args.mode == 'train' else 2048
+        args.batch = 128 if args.mode == 'train' else 1024
     from icka_b200 import synth
     shape = synth.Shape(L=args.layers, S=256 if args.hires else 128, R=196 if args.hires else 49)
     if args.impl == 'reference':
