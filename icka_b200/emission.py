@@ -90,9 +90,15 @@ class LSTM(nn.Module):
         return modules.get_precision() == 'bf16' and self.hidden_size == REC_H and self.input_size % 8 == 0
 
     # ---- forward -----------------------------------------------------------------------------------
+    def _check_inference(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError('icka_b200.LSTM is inference-only (no autograd nodes yet): call .eval() or run under '
+                                      'torch.no_grad() -- a silent forward without gradients would break training')
+
     def states(self, x: torch.Tensor, want_state: bool = False):
         """x [B,S,I] (batch-first) -> (y [B,S,2H] in the compute dtype, h_n, c_n | None).  On the persistent-kernel
         path y is a batch-first VIEW of the time-major [S,B,2H] tensor the kernel writes."""
+        self._check_inference()
         B, S, I = x.shape
         H = self.hidden_size
         lp = modules.get_precision() == 'bf16'

@@ -28,7 +28,7 @@ def make(I, H, T, seed):
     ref_cls = nn.Linear(2 * H, T)
     ours = icka_b200.LSTM(input_size=I, hidden_size=H, batch_first=True, bidirectional=True)
     ours.load_state_dict(ref_lstm.state_dict())                 # same keys as nn.LSTM
-    return ref_lstm, ref_cls, ours.cuda()
+    return ref_lstm, ref_cls, ours.cuda().eval()
 
 
 def oracle(ref_lstm, ref_cls, x):
@@ -147,6 +147,9 @@ def test_lstm_rejects_what_it_does_not_cover():
     with pytest.raises(NotImplementedError):
         icka_b200.LSTM(8, 8, batch_first=True, bidirectional=False)
     m = icka_b200.LSTM(8, 8, batch_first=True, bidirectional=True).cuda()
+    with pytest.raises(NotImplementedError):                    # training mode with autograd on: refused, not silent
+        m(torch.zeros(2, 3, 8, device='cuda'))
+    m.eval()
     with pytest.raises(ValueError):
         m(torch.zeros(3, 8, device='cuda'))
     with pytest.raises(RuntimeError):
