@@ -4,6 +4,7 @@ Public surface (mirrors /root/reference/Cross_Modal_Interaction_Module.py and to
     modules.BertCrossEncoder, BertCrossAttentionLayer, BertCrossAttention, BertCoAttention,
     BertSelfOutput, BertIntermediate, BertOutput, BertLayerNorm, cls_layer_both, CrossModalFusion
     crf.CRF
+    model.MTCCMBertForMMTokenClassificationCRF (the top-level class, CMIM:886-1057: same ctor / 19-argument forward, 'dev' / 'test')
     emission.LSTM, emission.EmissionHead (the BiLSTM + classifier between fusion and CRF, CMIM:905-910, 1042-1043)
     prompt.PromptMapping (prompt mapping networks + prefix assembly, CMIM:913-930, 995-1009)
     resnet_tail.myResnet (region-producer tail: means, adaptive pooling, K-major region rows; resnet/resnet_utils.py)
@@ -19,7 +20,8 @@ from .crf import CRF  # noqa: F401
 from .emission import LSTM, EmissionHead  # noqa: F401
 from .prompt import PromptMapping  # noqa: F401
 from .resnet_tail import myResnet  # noqa: F401
+from .model import MTCCMBertForMMTokenClassificationCRF  # noqa: F401
 
 __all__ = ['FusionConfig', 'BertCoAttention', 'BertCrossAttention', 'BertCrossAttentionLayer', 'BertCrossEncoder',
            'BertIntermediate', 'BertLayerNorm', 'BertOutput', 'BertSelfOutput', 'CrossModalFusion', 'cls_layer_both',
-           'CRF', 'LSTM', 'EmissionHead', 'PromptMapping', 'myResnet', 'get_precision', 'set_precision']
+           'CRF', 'LSTM', 'EmissionHead', 'PromptMapping', 'myResnet', 'MTCCMBertForMMTokenClassificationCRF', 'get_precision', 'set_precision']

@@ -526,3 +526,49 @@ class CrossModalFusion(nn.Module):
                 out['fused'] = fused32.view(B, S, H)
             return out
         return result, z32.view(B, 1, H)
+
+    # ---- the same segment in the two phases the full model needs (inference) -------------------------------------
+    # In MTCCMBertForMMTokenClassificationCRF.forward the gate's second operand, `token_embedding`, comes out of the
+    # RoBERTa `last_encoder`, which is fed prompts computed FROM the image->text result (CMIM:995-1024): the encoders
+    # (CMIM:954-989) and the gate + blend (CMIM:1029-1036) cannot be one call there.
+    @torch.no_grad()
+    def encode(self, sequence_output, visual_embeds_att, clip_features, added_attention_mask, ori_input_mask):
+        """CMIM:954-989 -> (cross_output_layer [B,S,H] fp32, clip_features [B,1,H] fp32)."""
+        B, S, H = sequence_output.shape
+        rows_given = visual_embeds_att.dim() == 3 and visual_embeds_att.shape[-1] == self.vismap2text.in_features
+        if rows_given:
+            R = visual_embeds_att.shape[1]
+            rows = visual_embeds_att.contiguous().view(B * R, -1)
+            if rows.dtype != _cdt():
+                rows = _to_lp(rows.float()) if _PRECISION == 'bf16' else rows.float()
+        else:
+            grid = visual_embeds_att.float().contiguous()
+            R = grid.numel() // (B * grid.shape[1])
+            rows = ops.region_rows(grid, _cdt())
+        regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
+                                self.vismap2text.bias.detach(), out_dtype=_cdt())
+        img_mask = ops.mask_additive(added_attention_mask, R)
+        txt_mask = ops.mask_additive(ori_input_mask, S)
+        x32 = _rows(sequence_output)
+        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R, keep_all=False)
+        fused32 = outs[-1]
+        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
+        z32 = ops.linear(clip_in, _operand(self._cache, 'vmap', self.vismapping.weight), self.vismapping.bias.detach(),
+                         out_dtype=torch.float32)
+        z_lp = _to_lp(z32)
+        for enc in self.cls_layer_Y:
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False)
+            z32 = zs[-1]
+        return fused32.view(B, S, H), z32.view(B, 1, H)
+
+    @torch.no_grad()
+    def blend(self, cross_output_layer, token_embedding):
+        """CMIM:1029-1036 -> result [B,S,H] fp32 = g * token_embedding + (1 - g) * cross_output_layer."""
+        ln = self.cls_layer.proj_norm
+        gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight, self.aux_head.bias)
+        w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
+            self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+            self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
+        result, _ = ops.gate_blend(cross_output_layer.float().contiguous(), token_embedding.float().contiguous(),
+                                   ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold)
+        return result

@@ -86,3 +86,37 @@ def test_crf_constructor_and_validation():
         crf(e, torch.zeros(2, 4, dtype=torch.long))
     with pytest.raises(ValueError, match='invalid reduction'):
         crf(e, torch.zeros(2, 3, dtype=torch.long), reduction='bogus')
+
+
+def test_full_model_state_dict_keys_are_the_reference_names():
+    """MTCCMBertForMMTokenClassificationCRF keeps the reference's flat parameter names (CMIM:886-935)."""
+    import icka_b200
+    from oracle import reference_shim
+    cfg = icka_b200.FusionConfig(hidden_size=768)
+    ours = icka_b200.MTCCMBertForMMTokenClassificationCRF(cfg, None, None, 1, 1, 1, num_labels=15)
+    keys = set(ours.state_dict())
+    for k in ('vismap2text.weight', 'txt2img_attention.layer.0.attention.self.query.weight', 'cls_layer_Y.1.layer.0.output.dense.bias',
+              'cls_layer.proj.weight', 'aux_head.bias', 'lstm.weight_hh_l0_reverse', 'classifier.weight', 'crf.transitions',
+              'mapping_network_alignment.1.weight', 'mapping_network_vision.4.bias', 'lastproj.weight'):
+        assert k in keys
+    assert not any(k.startswith(('_prompt', '_head', 'fusion.')) for k in keys)
+    if reference_shim.available():
+        import torch
+        cmim = reference_shim.load()
+
+        class _CRF(torch.nn.Module):
+            def __init__(self, num_tags, batch_first=False):
+                super().__init__()
+                self.start_transitions = torch.nn.Parameter(torch.zeros(num_tags))
+                self.end_transitions = torch.nn.Parameter(torch.zeros(num_tags))
+                self.transitions = torch.nn.Parameter(torch.zeros(num_tags, num_tags))
+        cmim.CRF = _CRF
+        rcfg = cmim.BertConfig(30522, hidden_size=768, num_hidden_layers=1, num_attention_heads=12, intermediate_size=3072)
+        ref = cmim.MTCCMBertForMMTokenClassificationCRF(rcfg, None, None, 1, 1, 1, num_labels=15)
+        ref_sd = ref.state_dict()
+        assert keys <= set(ref_sd), sorted(keys - set(ref_sd))
+        for k in keys:
+            assert tuple(ref_sd[k].shape) == tuple(ours.state_dict()[k].shape), k
+        # what the reference has and the drop-in leaves out: only the members its forward never touches
+        unused = {k.split('.')[0] for k in set(ref_sd) - keys}
+        assert unused <= {'self_attention', 'self_attention_v2', 'embedding_layer', 'LayerNorm'}, unused
