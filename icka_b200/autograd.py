@@ -171,3 +171,102 @@ class CrfLlhFn(torch.autograd.Function):
         mask_u8 = saved[5] if ctx.has_mask else None
         de, ds, dend, dtr = ops.crf_llh_bwd(emissions, tags, mask_u8, start, end, trans, dllh.float().contiguous())
         return de, ds, dend, dtr, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """out32[M,N] = x[M,K] . W^T + b with gradients for x, W and b (fp32 FFMA kernels): the 2H -> num_labels classifier
+    (CMIM:910, 1043), too narrow for a tensor-core tile."""
+
+    @staticmethod
+    def forward(ctx, x32, weight, bias):
+        x32 = x32.contiguous()
+        w = weight.detach().float().contiguous()
+        ctx.save_for_backward(x32, w)
+        return ops.linear(x32, w, bias.detach().float().contiguous(), out_dtype=F32)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x32, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        N = dout.shape[1]
+        if N % 2:                              # the column-sum kernel reads pairs: pad the odd label count with a zero column
+            padded = torch.zeros(dout.shape[0], N + 1, dtype=dout.dtype, device=dout.device)
+            padded[:, :N] = dout
+            db = ops.colsum(padded)[:N]
+        else:
+            db = ops.colsum(dout)
+        return ops.linear_dgrad(dout, w, out_dtype=F32), ops.linear_wgrad(dout, x32), db
+
+
+class BiLstmFn(torch.autograd.Function):
+    """Bidirectional single-layer LSTM (CMIM:905-908, 1042) with backpropagation through time, per-step kernels.
+
+    forward   Gx = x . [W_ih; W_ih_r]^T + (b_ih + b_hh) in one GEMM; per direction and step: gates = h_{t-1} . W_hh^T
+              (GEMM) and ``icka_lstm_cell_fwd_save`` (keeps the gate activations and the cell state, fp32)
+    backward  per direction, steps in reverse: ``icka_lstm_cell_bwd`` (gate pre-activation gradients straight into a
+              [B, S, 8H] buffer in position order) and dh_{t-1} = dpre_t . W_hh (dgrad GEMM); afterwards the weight,
+              bias and input gradients as FOUR big GEMMs over all B*S rows (dW_hh per direction against the shifted
+              output sequence, dW_ih, dx) and one column sum.
+    The persistent tcgen05 kernel serves inference; this first training path pays a GEMM launch per step.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r, bf16):
+        B, S, I = x.shape
+        H = w_hh.shape[1]
+        cdt = torch.bfloat16 if bf16 else F32
+        dev = x.device
+        op = (lambda t: ops.cast_bf16(t.detach().float().contiguous())) if bf16 else (lambda t: t.detach().float().contiguous())
+        x_op = op(x.reshape(B * S, I))
+        wi_op = op(torch.cat([w_ih, w_ih_r]))
+        wh_ops = (op(w_hh), op(w_hh_r))
+        bsum = ops.add_f32(torch.cat([b_ih, b_ih_r]).detach().float().contiguous(),
+                           torch.cat([b_hh, b_hh_r]).detach().float().contiguous())
+        gx = ops.linear(x_op, wi_op, bsum, out_dtype=cdt).view(B, S, 8 * H)
+        y32 = torch.empty(B, S, 2 * H, dtype=F32, device=dev)
+        y_op = torch.empty(B, S, 2 * H, dtype=cdt, device=dev)
+        acts = torch.empty(2, S, B, 4 * H, dtype=F32, device=dev)
+        c_all = torch.empty(2, S, B, H, dtype=F32, device=dev)
+        for d in range(2):
+            h_prev = torch.empty(B, H, dtype=cdt, device=dev)
+            h_next = torch.empty(B, H, dtype=cdt, device=dev)
+            for t in range(S):
+                pos = S - 1 - t if d else t
+                gates = None if t == 0 else ops.linear(h_prev, wh_ops[d], None, out_dtype=F32)
+                ops.lstm_cell_fwd_save(gates, gx[:, pos, d * 4 * H:(d + 1) * 4 * H], c_all[d, t - 1] if t else None,
+                                       c_all[d, t], acts[d, t], h_next, y_op[:, pos, d * H:(d + 1) * H],
+                                       y32[:, pos, d * H:(d + 1) * H])
+                h_prev, h_next = h_next, h_prev
+        ctx.save_for_backward(x_op, wi_op, wh_ops[0], wh_ops[1], y_op, acts, c_all)
+        ctx.dims = (B, S, I, H, bf16)
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_op, wi_op, wh0, wh1, y_op, acts, c_all = ctx.saved_tensors
+        B, S, I, H, bf16 = ctx.dims
+        cdt = torch.bfloat16 if bf16 else F32
+        dev = dy.device
+        dy = dy.contiguous()
+        dg = torch.empty(B, S, 8 * H, dtype=cdt, device=dev)           # gate pre-activation gradients, position order
+        for d, wh in ((0, wh0), (1, wh1)):
+            dc = torch.zeros(B, H, dtype=F32, device=dev)
+            dh_rec = None
+            for t in range(S - 1, -1, -1):
+                pos = S - 1 - t if d else t
+                dpre = dg[:, pos, d * 4 * H:(d + 1) * 4 * H]
+                ops.lstm_cell_bwd(dy[:, pos, d * H:(d + 1) * H], dh_rec, dc, acts[d, t], c_all[d, t - 1] if t else None,
+                                  c_all[d, t], dpre)
+                dh_rec = ops.linear_dgrad(dpre, wh, out_dtype=F32) if t else None
+        dg2 = dg.view(B * S, 8 * H)
+        # h_{t-1} of every step = the output sequence shifted by one position (zeros at the sequence ends)
+        hprev = torch.zeros(B, S, 2 * H, dtype=cdt, device=dev)
+        hprev[:, 1:, :H] = y_op[:, :-1, :H]
+        hprev[:, :-1, H:] = y_op[:, 1:, H:]
+        hp2 = hprev.view(B * S, 2 * H)
+        d_whh = ops.linear_wgrad(dg2[:, :4 * H], hp2[:, :H])
+        d_whh_r = ops.linear_wgrad(dg2[:, 4 * H:], hp2[:, H:])
+        d_wih = ops.linear_wgrad(dg2, x_op)
+        db = ops.colsum(dg2)
+        dx = ops.linear_dgrad(dg2, wi_op, out_dtype=F32).view(B, S, I)
+        return (dx, d_wih[:4 * H], d_whh, db[:4 * H], db[:4 * H], d_wih[4 * H:], d_whh_r, db[4 * H:], db[4 * H:], None)

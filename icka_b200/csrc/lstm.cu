@@ -33,6 +33,60 @@ __global__ void lstm_cell_kernel(const float* __restrict__ gates_h, const T* __r
   if (h_f32) h_f32[idx] = hn;
 }
 
+// ---- training (BPTT) of the per-step path ------------------------------------------------------------------------
+// Forward step that keeps what the backward pass needs: the gate activations (i, f, g, o after sigmoid / tanh) and
+// the new cell state, both fp32.
+template <typename T>
+__global__ void lstm_cell_fwd_save_kernel(const float* __restrict__ gates_h, const T* __restrict__ gx, int64_t ldgx,
+                                          const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                          float* __restrict__ acts, T* __restrict__ h_out, T* __restrict__ y_op,
+                                          int64_t ldyo, float* __restrict__ y32, int64_t ldy32, int B, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  float pre[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    pre[g] = to_f32<T>(gx[(int64_t)b * ldgx + g * H + j]);
+    if (gates_h) pre[g] = gates_h[(int64_t)b * 4 * H + g * H + j] + pre[g];
+  }
+  const float ig = sigmoid_exact(pre[0]), fg = sigmoid_exact(pre[1]), gg = tanhf(pre[2]), og = sigmoid_exact(pre[3]);
+  const float cn = fg * (c_prev ? c_prev[idx] : 0.0f) + ig * gg;
+  const float hn = og * tanhf(cn);
+  c_out[idx] = cn;
+  float* a = acts + (int64_t)b * 4 * H + j;
+  a[0] = ig;
+  a[H] = fg;
+  a[2 * H] = gg;
+  a[3 * H] = og;
+  h_out[idx] = from_f32<T>(hn);
+  y_op[(int64_t)b * ldyo + j] = from_f32<T>(hn);
+  y32[(int64_t)b * ldy32 + j] = hn;
+}
+
+// One BPTT step: dh = dy (gradient of the output slot) + dh_rec (from step t + 1 through W_hh); dc carries the cell
+// gradient from step t + 1 and leaves as the gradient for step t - 1; dpre = gradient of the gate pre-activations.
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ dh_rec,
+                                     float* __restrict__ dc, const float* __restrict__ acts,
+                                     const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                     T* __restrict__ dpre, int64_t lddp, int B, int H) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * H) return;
+  const int b = (int)(idx / H), j = (int)(idx % H);
+  const float* a = acts + (int64_t)b * 4 * H + j;
+  const float ig = a[0], fg = a[H], gg = a[2 * H], og = a[3 * H];
+  const float tc = tanhf(c_new[idx]);
+  const float dh = dy[(int64_t)b * lddy + j] + (dh_rec ? dh_rec[idx] : 0.0f);
+  const float dct = dc[idx] + dh * og * (1.0f - tc * tc);
+  T* d = dpre + (int64_t)b * lddp + j;
+  d[0] = from_f32<T>(dct * gg * ig * (1.0f - ig));
+  d[H] = from_f32<T>(dct * (c_prev ? c_prev[idx] : 0.0f) * fg * (1.0f - fg));
+  d[2 * H] = from_f32<T>(dct * ig * (1.0f - gg * gg));
+  d[3 * H] = from_f32<T>(dh * tc * og * (1.0f - og));
+  dc[idx] = dct * fg;
+}
+
 // input rows may be time-major (row = t * B + b, tm_S = S > 0): the emissions are always written batch-major
 __device__ __forceinline__ int64_t out_row(int64_t r, int64_t M, int tm_S) {
   if (tm_S <= 0) return r;
@@ -347,6 +401,50 @@ extern "C" int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_
   else
     cast_time_major_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                                  static_cast<__nv_bfloat16*>(y_bf16), B, S, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_lstm_cell_fwd_save(icka_handle* h, const float* gates_h, const void* gx, int64_t ldgx, const float* c_prev,
+                                       float* c_out, float* acts, void* h_out, void* y_op, int64_t ldyo, float* y32,
+                                       int64_t ldy32, int dtype, int B, int H, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && H >= 1, "lstm_cell_fwd_save: bad shape B=%d H=%d", B, H);
+  ICKA_REQUIRE(gx && c_out && acts && h_out && y_op && y32, "lstm_cell_fwd_save: null pointer");
+  ICKA_REQUIRE(ldgx >= 4 * (int64_t)H && ldyo >= H && ldy32 >= H, "lstm_cell_fwd_save: pitches smaller than the extents");
+  ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "lstm_cell_fwd_save: bad dtype %d", dtype);
+  if (B == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)(((int64_t)B * H + 255) / 256);
+  if (dtype == ICKA_F32)
+    lstm_cell_fwd_save_kernel<float><<<grid, 256, 0, st>>>(gates_h, static_cast<const float*>(gx), ldgx, c_prev, c_out, acts,
+                                                           static_cast<float*>(h_out), static_cast<float*>(y_op), ldyo, y32,
+                                                           ldy32, B, H);
+  else
+    lstm_cell_fwd_save_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        gates_h, static_cast<const __nv_bfloat16*>(gx), ldgx, c_prev, c_out, acts, static_cast<__nv_bfloat16*>(h_out),
+        static_cast<__nv_bfloat16*>(y_op), ldyo, y32, ldy32, B, H);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_lstm_cell_bwd(icka_handle* h, const float* dy, int64_t lddy, const float* dh_rec, float* dc,
+                                  const float* acts, const float* c_prev, const float* c_new, void* dpre, int64_t lddp,
+                                  int dtype, int B, int H, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && H >= 1, "lstm_cell_bwd: bad shape B=%d H=%d", B, H);
+  ICKA_REQUIRE(dy && dc && acts && c_new && dpre, "lstm_cell_bwd: null pointer");
+  ICKA_REQUIRE(lddy >= H && lddp >= 4 * (int64_t)H, "lstm_cell_bwd: pitches smaller than the extents");
+  ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "lstm_cell_bwd: bad dtype %d", dtype);
+  if (B == 0) return ICKA_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = (int)(((int64_t)B * H + 255) / 256);
+  if (dtype == ICKA_F32)
+    lstm_cell_bwd_kernel<float><<<grid, 256, 0, st>>>(dy, lddy, dh_rec, dc, acts, c_prev, c_new, static_cast<float*>(dpre),
+                                                      lddp, B, H);
+  else
+    lstm_cell_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dy, lddy, dh_rec, dc, acts, c_prev, c_new,
+                                                              static_cast<__nv_bfloat16*>(dpre), lddp, B, H);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -7,7 +7,8 @@
 ``LSTM`` keeps nn.LSTM's constructor arguments (the subset the reference uses), parameter names
 (``weight_ih_l0`` ... ``bias_hh_l0_reverse`` -> the same state_dict keys) and return value
 ``(output, (h_n, c_n))``; ``EmissionHead`` owns ``lstm`` + ``classifier`` under the reference's attribute names.
-Inference only (no autograd nodes yet): parameters are used detached.
+Inference runs on the persistent kernel (parameters detached); when autograd is recording, ``autograd.BiLstmFn`` /
+``LinearFn`` take over (per-step kernels with backpropagation through time).
 
 bf16 mode, H = 768:  x -> [icka_linear_fwd: Gx = x . W_ih^T + b for both directions, slice-ordered columns, bf16]
                        -> [icka_lstm_rec_fwd: ONE persistent weight-stationary tcgen05 kernel, all S steps]
@@ -23,6 +24,7 @@ import torch
 from torch import nn
 
 from . import modules, ops
+from .autograd import BiLstmFn, LinearFn
 from .modules import _OperandCache
 
 REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
@@ -90,10 +92,17 @@ class LSTM(nn.Module):
         return modules.get_precision() == 'bf16' and self.hidden_size == REC_H and self.input_size % 8 == 0
 
     # ---- forward -----------------------------------------------------------------------------------
+    def _recording(self, x: torch.Tensor) -> bool:
+        """True when this call must build an autograd graph (BiLstmFn: per-step kernels with BPTT)."""
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def _check_inference(self):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('icka_b200.LSTM is inference-only (no autograd nodes yet): call .eval() or run under '
-                                      'torch.no_grad() -- a silent forward without gradients would break training')
+        pass
+
+    def _train_forward(self, x: torch.Tensor) -> torch.Tensor:
+        return BiLstmFn.apply(x, self.weight_ih_l0, self.weight_hh_l0, self.bias_ih_l0, self.bias_hh_l0,
+                              self.weight_ih_l0_reverse, self.weight_hh_l0_reverse, self.bias_ih_l0_reverse,
+                              self.bias_hh_l0_reverse, modules.get_precision() == 'bf16')
 
     def states(self, x: torch.Tensor, want_state: bool = False):
         """x [B,S,I] (batch-first) -> (y [B,S,2H] in the compute dtype, h_n, c_n | None).  On the persistent-kernel
@@ -147,6 +156,11 @@ class LSTM(nn.Module):
                                f'got {input.shape[-1]}')
         x = input if self.batch_first else input.transpose(0, 1)
         B = x.shape[0]
+        if self._recording(x):                                  # training: autograd node, final states not tracked
+            y = self._train_forward(x.float())
+            H = self.hidden_size
+            h_n = torch.stack([y[:, -1, :H], y[:, 0, H:]]).detach()
+            return (y if self.batch_first else y.transpose(0, 1)), (h_n, None)
         if B > REC_CHUNK and self.uses_persistent_kernel():
             parts = [self.states(x[b0:b0 + REC_CHUNK], want_state=True) for b0 in range(0, B, REC_CHUNK)]
             y = torch.cat([p[0].float() for p in parts], dim=0)
@@ -170,6 +184,9 @@ class EmissionHead(nn.Module):
 
     def forward(self, result: torch.Tensor) -> torch.Tensor:
         B, S, _ = result.shape
+        if self.lstm._recording(result) or (torch.is_grad_enabled() and self.classifier.weight.requires_grad):
+            y = self.lstm._train_forward(result.float())                     # [B,S,2H] fp32, autograd node (BPTT)
+            return LinearFn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
         if B > REC_CHUNK and self.lstm.uses_persistent_kernel():
             out = torch.empty(B, S, self.classifier.out_features, dtype=torch.float32, device=result.device)
             for b0 in range(0, B, REC_CHUNK):

@@ -564,3 +564,22 @@ def region_tail(x: torch.Tensor, att_size: int, *, want_fc: bool = True, want_at
                                         _DT[rows_dtype] if rows_dtype is not None else F32, B, C, g, a, st),
                'icka_region_tail_fwd')
     return fc, att, rows
+
+
+def lstm_cell_fwd_save(gates_h, gx, c_prev, c_out, acts, h_out, y_op, y32) -> None:
+    """Training forward step (keeps activations); gx [B,4H], y_op / y32 [B,H] may be row-pitched views."""
+    B, H = c_out.shape
+    lib, h, st = _ctx(c_out)
+    _lib.check(lib.icka_lstm_cell_fwd_save(h, _p(gates_h), gx.data_ptr(), _ld(gx, 4 * H), _p(c_prev), c_out.data_ptr(),
+                                           acts.data_ptr(), h_out.data_ptr(), y_op.data_ptr(), _ld(y_op, H),
+                                           y32.data_ptr(), _ld(y32, H), _DT[gx.dtype], B, H, st),
+               'icka_lstm_cell_fwd_save')
+
+
+def lstm_cell_bwd(dy, dh_rec, dc, acts, c_prev, c_new, dpre) -> None:
+    """One BPTT step; dy [B,H] fp32 and dpre [B,4H] may be row-pitched views, dc is updated in place."""
+    B, H = dc.shape
+    lib, h, st = _ctx(dc)
+    _lib.check(lib.icka_lstm_cell_bwd(h, dy.data_ptr(), _ld(dy, H), _p(dh_rec), dc.data_ptr(), acts.data_ptr(), _p(c_prev),
+                                      c_new.data_ptr(), dpre.data_ptr(), _ld(dpre, 4 * H), _DT[dpre.dtype], B, H, st),
+               'icka_lstm_cell_bwd')

@@ -297,6 +297,20 @@ int icka_lstm_rec_fwd(icka_handle* h, const void* gx, const void* w_hh_perm, voi
 int icka_lstm_cell_fwd(icka_handle* h, const float* gates_h, const void* gx, int64_t ldgx, float* c, void* h_out,
                        void* y, int64_t ldy, float* h_f32, int dtype, int B, int H, void* stream);
 
+/* Training (BPTT through the per-step path; autograd of CMIM:1042).  Forward step like icka_lstm_cell_fwd that also keeps
+ * the gate activations `acts` [B,4H] fp32 (i, f, g, o after sigmoid / tanh) and writes the new cell state to c_out
+ * (c_prev may be NULL = zeros); h goes to h_out [B,H] (`dtype`), y_op (`dtype`, pitch ldyo) and y32 (fp32, pitch ldy32). */
+int icka_lstm_cell_fwd_save(icka_handle* h, const float* gates_h, const void* gx, int64_t ldgx, const float* c_prev,
+                            float* c_out, float* acts, void* h_out, void* y_op, int64_t ldyo, float* y32, int64_t ldy32,
+                            int dtype, int B, int H, void* stream);
+
+/* One backward step: dh = dy[B,H] (pitch lddy, gradient of this step's output) + dh_rec[B,H] (from the next step through
+ * W_hh; NULL at the last step); dc [B,H] in: cell gradient from the next step, out: for the previous step;
+ * dpre [B,4H] (`dtype`, pitch lddp) = gradient of the gate pre-activations (operand of the dgrad / wgrad GEMMs). */
+int icka_lstm_cell_bwd(icka_handle* h, const float* dy, int64_t lddy, const float* dh_rec, float* dc, const float* acts,
+                       const float* c_prev, const float* c_new, void* dpre, int64_t lddp, int dtype, int B, int H,
+                       void* stream);
+
 /* `self.classifier = nn.Linear(2H, num_labels)` (CMIM:910, :1043): out[M,T] fp32 = x[M,K] (`dtype`, pitch ldx) .
  * W[T,K]^T (fp32) + bias[T].  T <= 16, K % 8 == 0.  fp32 accumulation in a fixed order.
  * time_major_S = S > 0: the rows of x are time-major (row = t*B + b, B = M/S, as icka_lstm_rec_fwd writes them) and

@@ -49,7 +49,8 @@ def test_fp32_per_step_path(B, S, I, H):
     ref_lstm, ref_cls, ours = make(I, H, 15, seed=B + S)
     x = torch.randn(B, S, I)
     y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
-    out, (h_n, c_n) = ours(x.cuda())
+    with torch.no_grad():
+        out, (h_n, c_n) = ours(x.cuda())
     assert out.dtype == torch.float32 and out.shape == (B, S, 2 * H)
     assert rel(out, y) <= 1e-5 and rel(h_n, hn) <= 1e-5 and rel(c_n, cn) <= 1e-5
 
@@ -67,13 +68,15 @@ def test_bf16_persistent_kernel(B, S, variant, monkeypatch):
     assert ours.uses_persistent_kernel()
     x = torch.randn(B, S, H)
     y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
-    out, (h_n, c_n) = ours(x.cuda())
+    with torch.no_grad():
+        out, (h_n, c_n) = ours(x.cuda())
     err_y = (out.double().cpu() - y).abs().max().item()
     err_h = (h_n.double().cpu() - hn).abs().max().item()
     err_c = (c_n.double().cpu() - cn).abs().max().item()
     print(f'bf16 persistent variant {variant} B={B} S={S}: max|dy|={err_y:.2e} max|dh_n|={err_h:.2e} max|dc_n|={err_c:.2e}')
     assert err_y <= 2e-2 and err_h <= 2e-2 and err_c <= 4e-2
-    out2, _ = ours(x.cuda())                                    # no atomics on the data path: reruns are identical
+    with torch.no_grad():
+        out2, _ = ours(x.cuda())                                # no atomics on the data path: reruns are identical
     assert torch.equal(out, out2)
 
 
@@ -87,7 +90,8 @@ def test_bf16_per_step_path_other_hidden_size():
     assert not ours.uses_persistent_kernel()
     x = torch.randn(4, 20, 64)
     y, hn, cn, _ = oracle(ref_lstm, ref_cls, x)
-    out, (h_n, c_n) = ours(x.cuda())
+    with torch.no_grad():
+        out, (h_n, c_n) = ours(x.cuda())
     assert (out.double().cpu() - y).abs().max().item() <= 2e-2
     assert (h_n.double().cpu() - hn).abs().max().item() <= 2e-2
 
@@ -146,13 +150,53 @@ def test_batches_above_one_launch_are_chunked():
 def test_lstm_rejects_what_it_does_not_cover():
     with pytest.raises(NotImplementedError):
         icka_b200.LSTM(8, 8, batch_first=True, bidirectional=False)
-    m = icka_b200.LSTM(8, 8, batch_first=True, bidirectional=True).cuda()
-    with pytest.raises(NotImplementedError):                    # training mode with autograd on: refused, not silent
-        m(torch.zeros(2, 3, 8, device='cuda'))
-    m.eval()
+    m = icka_b200.LSTM(8, 8, batch_first=True, bidirectional=True).cuda().eval()
     with pytest.raises(ValueError):
         m(torch.zeros(3, 8, device='cuda'))
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 3, 9, device='cuda'))
     with pytest.raises(RuntimeError):
         m(torch.zeros(2, 3, 8))                                 # CPU tensor: no fallback
+
+
+def _grad_case(precision, B, S, H, T, seed):
+    icka_b200.set_precision(precision)
+    torch.manual_seed(seed)
+    ref_lstm = nn.LSTM(input_size=H, hidden_size=H, batch_first=True, bidirectional=True)
+    ref_cls = nn.Linear(2 * H, T)
+    head = icka_b200.EmissionHead(FusionConfig(hidden_size=H), num_labels=T)
+    head.lstm.load_state_dict(ref_lstm.state_dict())
+    head.classifier.load_state_dict(ref_cls.state_dict())
+    head = head.cuda().train()
+    x = torch.randn(B, S, H)
+    w_out = torch.randn(B, S, T)                                 # fixed upstream gradient
+    # oracle: autograd through the restatement (fp64)
+    xo = x.double().requires_grad_(True)
+    po = {k: v.detach().double().requires_grad_(True) for k, v in ref_lstm.named_parameters()}
+    wc, bc = ref_cls.weight.detach().double().requires_grad_(True), ref_cls.bias.detach().double().requires_grad_(True)
+    e = lstm_ref.emission_head(xo, po, wc, bc)
+    (e * w_out.double()).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    got = head(xg)
+    (got * w_out.cuda()).sum().backward()
+    return head, xg, got, e.detach(), xo, po, wc, bc
+
+
+@pytest.mark.parametrize('precision,B,S,H,tol', [('fp32', 3, 7, 32, 2e-4), ('fp32', 2, 5, 768, 2e-4), ('bf16', 4, 12, 64, 4e-2),
+                                                 ('bf16', 3, 6, 768, 4e-2)])
+def test_training_gradients_match_oracle_autograd(precision, B, S, H, tol):
+    """BiLstmFn / LinearFn (BPTT on per-step kernels) against autograd through the oracle: every gradient within `tol`
+    of its own scale (max |g|), as in tests/test_gpu_training.py."""
+    head, xg, got, want_e, xo, po, wc, bc = _grad_case(precision, B, S, H, 15, seed=B * 10 + S)
+    assert (got.detach().double().cpu() - want_e).abs().max().item() <= (1e-5 if precision == 'fp32' else 2e-2)
+
+    def close(name, g, w):
+        scale = w.abs().max().item()
+        err = (g.double().cpu() - w).abs().max().item()
+        assert err <= tol * max(scale, 1e-6), f'{name}: err {err:.3e} vs scale {scale:.3e}'
+
+    close('dx', xg.grad, xo.grad)
+    for k, v in head.lstm.named_parameters():
+        close(k, v.grad, po[k].grad)
+    close('classifier.weight', head.classifier.weight.grad, wc.grad)
+    close('classifier.bias', head.classifier.bias.grad, bc.grad)
