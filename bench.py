@@ -66,6 +66,9 @@ def parse():
     ap.add_argument('--inflight', type=int, default=2, choices=[1, 2],
                     help='captured steps in flight: 2 = two batches (own device buffers, own library workspace) replayed on '
                          'two streams, so the low-occupancy tail of one step overlaps the head of the next')
+    ap.add_argument('--real-head', action='store_true',
+                    help="--mode train: the reference's BiLSTM + classifier emission head (BPTT on per-step kernels) instead of the "
+                         'nn.Linear(H,T) stand-in')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -519,7 +522,11 @@ def run_train_arm(args, shape):
     cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
                        layer_norm_eps=shape.eps)
     fusion = CrossModalFusion(cfg, layer_num1=shape.L).to(dev).train()      # dropout p = 0.1 on all three sites
-    head = torch.nn.Linear(shape.H, shape.T).to(dev)
+    if args.real_head:
+        from icka_b200 import EmissionHead
+        head = EmissionHead(cfg, num_labels=shape.T).to(dev).train()
+    else:
+        head = torch.nn.Linear(shape.H, shape.T).to(dev)
     crf = CRF(shape.T, batch_first=True).to(dev)
     params = list(fusion.parameters()) + list(head.parameters()) + list(crf.parameters())
     for m in (fusion, head, crf):
@@ -587,7 +594,8 @@ def run_train_arm(args, shape):
                        'global_batch': args.batch * world, 'parallelism': f'data-parallel x{world}, bucketed NCCL gradient all-reduce',
                        'params_allreduced': n_param, 'buckets': len(reducer.buckets),
                        'buckets_launched_inside_backward_per_step': reducer.launched_early // (args.steps + max(args.warmup, 3)),
-                       'outside_hot_path': 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier; optimizer = torch AdamW(fused)',
+                       'outside_hot_path': ('emission head = icka_b200.EmissionHead (BiLSTM + classifier, BPTT on per-step kernels)' if args.real_head
+                                            else 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier') + '; optimizer = torch AdamW(fused)',
                        'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)'},
             'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
             'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor', 'achieved': tf,

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import ACT_GELU_ERF
 
 F32 = torch.float32
@@ -198,6 +198,23 @@ class LinearFn(torch.autograd.Function):
         return ops.linear_dgrad(dout, w, out_dtype=F32), ops.linear_wgrad(dout, x32), db
 
 
+_side_streams = {}
+
+
+def _two_streams(dev, run_direction):
+    """The two directions of the BiLSTM are independent chains of small kernels: direction 1 runs on a side stream with
+    its own library handle slot (workspace), direction 0 on the current stream."""
+    main = torch.cuda.current_stream(dev)
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side), _lib.use_slot(1):
+        run_direction(1)
+    run_direction(0)
+    main.wait_stream(side)
+
+
 class BiLstmFn(torch.autograd.Function):
     """Bidirectional single-layer LSTM (CMIM:905-908, 1042) with backpropagation through time, per-step kernels.
 
@@ -227,16 +244,22 @@ class BiLstmFn(torch.autograd.Function):
         y_op = torch.empty(B, S, 2 * H, dtype=cdt, device=dev)
         acts = torch.empty(2, S, B, 4 * H, dtype=F32, device=dev)
         c_all = torch.empty(2, S, B, H, dtype=F32, device=dev)
-        for d in range(2):
-            h_prev = torch.empty(B, H, dtype=cdt, device=dev)
-            h_next = torch.empty(B, H, dtype=cdt, device=dev)
-            for t in range(S):
-                pos = S - 1 - t if d else t
-                gates = None if t == 0 else ops.linear(h_prev, wh_ops[d], None, out_dtype=F32)
-                ops.lstm_cell_fwd_save(gates, gx[:, pos, d * 4 * H:(d + 1) * 4 * H], c_all[d, t - 1] if t else None,
-                                       c_all[d, t], acts[d, t], h_next, y_op[:, pos, d * H:(d + 1) * H],
-                                       y32[:, pos, d * H:(d + 1) * H])
-                h_prev, h_next = h_next, h_prev
+        lib = _lib.load()
+        esz_dt = _lib.BF16 if bf16 else _lib.F32
+
+        def run_direction(d):
+            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            gates = torch.empty(B, 4 * H, dtype=F32, device=dev)
+            h_scr = torch.empty(2, B, H, dtype=cdt, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.icka_lstm_dir_fwd_save(
+                h_dev, gx[:, :, d * 4 * H:].data_ptr(), S * 8 * H, 8 * H, wh_ops[d].data_ptr(), acts[d].data_ptr(),
+                c_all[d].data_ptr(), y_op[:, :, d * H:].data_ptr(), y32[:, :, d * H:].data_ptr(), S * 2 * H, 2 * H,
+                gates.data_ptr(), h_scr.data_ptr(), esz_dt, B, S, H, d, st), 'icka_lstm_dir_fwd_save')
+            gates.record_stream(torch.cuda.current_stream(dev))
+            h_scr.record_stream(torch.cuda.current_stream(dev))
+
+        _two_streams(dev, run_direction)
         ctx.save_for_backward(x_op, wi_op, wh_ops[0], wh_ops[1], y_op, acts, c_all)
         ctx.dims = (B, S, I, H, bf16)
         return y32
@@ -249,15 +272,23 @@ class BiLstmFn(torch.autograd.Function):
         dev = dy.device
         dy = dy.contiguous()
         dg = torch.empty(B, S, 8 * H, dtype=cdt, device=dev)           # gate pre-activation gradients, position order
-        for d, wh in ((0, wh0), (1, wh1)):
-            dc = torch.zeros(B, H, dtype=F32, device=dev)
-            dh_rec = None
-            for t in range(S - 1, -1, -1):
-                pos = S - 1 - t if d else t
-                dpre = dg[:, pos, d * 4 * H:(d + 1) * 4 * H]
-                ops.lstm_cell_bwd(dy[:, pos, d * H:(d + 1) * H], dh_rec, dc, acts[d, t], c_all[d, t - 1] if t else None,
-                                  c_all[d, t], dpre)
-                dh_rec = ops.linear_dgrad(dpre, wh, out_dtype=F32) if t else None
+        lib = _lib.load()
+        esz_dt = _lib.BF16 if bf16 else _lib.F32
+
+        def run_direction(d):
+            wh = wh1 if d else wh0
+            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            dc = torch.empty(B, H, dtype=F32, device=dev)
+            dh = torch.empty(B, H, dtype=F32, device=dev)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.icka_lstm_dir_bwd(
+                h_dev, dy[:, :, d * H:].data_ptr(), S * 2 * H, 2 * H, wh.data_ptr(), acts[d].data_ptr(), c_all[d].data_ptr(),
+                dg[:, :, d * 4 * H:].data_ptr(), S * 8 * H, 8 * H, dc.data_ptr(), dh.data_ptr(), esz_dt, B, S, H, d, st),
+                'icka_lstm_dir_bwd')
+            dc.record_stream(torch.cuda.current_stream(dev))
+            dh.record_stream(torch.cuda.current_stream(dev))
+
+        _two_streams(dev, run_direction)
         dg2 = dg.view(B * S, 8 * H)
         # h_{t-1} of every step = the output sequence shifted by one position (zeros at the sequence ends)
         hprev = torch.zeros(B, S, 2 * H, dtype=cdt, device=dev)

@@ -448,3 +448,65 @@ extern "C" int icka_lstm_cell_bwd(icka_handle* h, const float* dy, int64_t lddy,
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
+
+// ---- one direction of the training recurrence as ONE host call ---------------------------------------------------
+// The per-step kernels are tiny; issued from Python (ctypes per launch) the training step was bound by the host
+// (23 ms for 128 steps x 2 directions x 4 launches).  These loops issue the same launches from C.
+extern "C" int icka_lstm_dir_fwd_save(icka_handle* h, const void* gx_dir, int64_t ld_gx_row, int64_t gx_pos_stride,
+                                      const void* w_hh, float* acts, float* c_all, void* y_op_dir, float* y32_dir,
+                                      int64_t ld_y_row, int64_t y_pos_stride, float* gates_scratch, void* h_scratch,
+                                      int dtype, int B, int S, int H, int reverse, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && H >= 1, "lstm_dir_fwd_save: bad shape B=%d S=%d H=%d", B, S, H);
+  ICKA_REQUIRE(gx_dir && w_hh && acts && c_all && y_op_dir && y32_dir && gates_scratch && h_scratch,
+               "lstm_dir_fwd_save: null pointer");
+  ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "lstm_dir_fwd_save: bad dtype %d", dtype);
+  if (B == 0) return ICKA_OK;
+  const size_t esz = dtype == ICKA_BF16 ? 2 : 4;
+  uint8_t* hbuf = static_cast<uint8_t*>(h_scratch);
+  const size_t hbytes = (size_t)B * H * esz;
+  for (int t = 0; t < S; ++t) {
+    const int pos = reverse ? S - 1 - t : t;
+    void* h_prev = hbuf + (size_t)((t + 1) & 1) * hbytes;
+    void* h_next = hbuf + (size_t)(t & 1) * hbytes;
+    if (t > 0) {
+      int rc = icka_linear_fwd(h, h_prev, H, w_hh, H, nullptr, nullptr, gates_scratch, 4 * (int64_t)H, dtype, ICKA_F32, B,
+                               4 * H, H, ICKA_ACT_NONE, stream);
+      if (rc) return rc;
+    }
+    int rc = icka_lstm_cell_fwd_save(
+        h, t > 0 ? gates_scratch : nullptr, static_cast<const uint8_t*>(gx_dir) + (size_t)pos * gx_pos_stride * esz,
+        ld_gx_row, t > 0 ? c_all + (size_t)(t - 1) * B * H : nullptr, c_all + (size_t)t * B * H,
+        acts + (size_t)t * B * 4 * H, h_next, static_cast<uint8_t*>(y_op_dir) + (size_t)pos * y_pos_stride * esz, ld_y_row,
+        y32_dir + (size_t)pos * y_pos_stride, ld_y_row, dtype, B, H, stream);
+    if (rc) return rc;
+  }
+  return ICKA_OK;
+}
+
+extern "C" int icka_lstm_dir_bwd(icka_handle* h, const float* dy_dir, int64_t ld_dy_row, int64_t dy_pos_stride,
+                                 const void* w_hh, const float* acts, const float* c_all, void* dg_dir, int64_t ld_dg_row,
+                                 int64_t dg_pos_stride, float* dc_scratch, float* dh_scratch, int dtype, int B, int S,
+                                 int H, int reverse, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(B >= 0 && S >= 1 && H >= 1, "lstm_dir_bwd: bad shape B=%d S=%d H=%d", B, S, H);
+  ICKA_REQUIRE(dy_dir && w_hh && acts && c_all && dg_dir && dc_scratch && dh_scratch, "lstm_dir_bwd: null pointer");
+  ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "lstm_dir_bwd: bad dtype %d", dtype);
+  if (B == 0) return ICKA_OK;
+  const size_t esz = dtype == ICKA_BF16 ? 2 : 4;
+  ICKA_CUDA(cudaMemsetAsync(dc_scratch, 0, (size_t)B * H * sizeof(float), static_cast<cudaStream_t>(stream)));
+  for (int t = S - 1; t >= 0; --t) {
+    const int pos = reverse ? S - 1 - t : t;
+    void* dpre = static_cast<uint8_t*>(dg_dir) + (size_t)pos * dg_pos_stride * esz;
+    int rc = icka_lstm_cell_bwd(h, dy_dir + (size_t)pos * dy_pos_stride, ld_dy_row, t < S - 1 ? dh_scratch : nullptr,
+                                dc_scratch, acts + (size_t)t * B * 4 * H, t > 0 ? c_all + (size_t)(t - 1) * B * H : nullptr,
+                                c_all + (size_t)t * B * H, dpre, ld_dg_row, dtype, B, H, stream);
+    if (rc) return rc;
+    if (t > 0) {
+      rc = icka_linear_dgrad(h, dpre, ld_dg_row, w_hh, H, nullptr, nullptr, 0, dh_scratch, H, dtype, ICKA_F32, B, 4 * H, H,
+                             stream);
+      if (rc) return rc;
+    }
+  }
+  return ICKA_OK;
+}

@@ -16,7 +16,8 @@ Parameter names are the reference's (``vismap2text.*``, ``txt2img_attention.*``,
 ``lastproj.*``), so ``model.load_state_dict(torch.load(path)['net'], False)`` (My_cross_attention.py:997-998) works.  The
 members the reference constructs but never uses (``self_attention``, ``self_attention_v2``, ``embedding_layer``,
 ``LayerNorm``; CMIM:894-895, 903, 935) are not created -- their checkpoint keys are ignored by the non-strict load.
-``mode='train'`` is refused: the BiLSTM has no autograd nodes yet (the fusion stack and the CRF do).
+``mode='train'`` is refused: the prompt mapping networks have no autograd nodes yet (the fusion stack, the BiLSTM +
+classifier and the CRF do).
 """
 from __future__ import annotations
 
@@ -65,7 +66,7 @@ class MTCCMBertForMMTokenClassificationCRF(CrossModalFusion):
                 rela_score, temp=None, temp_lamb=None, lamb=None, labels=None, negative_rate=None, mode=None):
         if mode not in ('dev', 'test'):
             raise NotImplementedError("icka_b200.MTCCMBertForMMTokenClassificationCRF runs mode='dev' and mode='test'; "
-                                      "mode='train' needs autograd through the BiLSTM, which is not built yet")
+                                      "mode='train' needs autograd through the prompt mapping networks, which is not built yet")
         with torch.no_grad():
             offset = offsets.tolist()[0]                                                        # CMIM:948
             sequence_output = self.bert(ori_input_ids, token_type_ids=ori_segment_ids,

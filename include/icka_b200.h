@@ -311,6 +311,18 @@ int icka_lstm_cell_bwd(icka_handle* h, const float* dy, int64_t lddy, const floa
                        const float* c_prev, const float* c_new, void* dpre, int64_t lddp, int dtype, int B, int H,
                        void* stream);
 
+/* One direction of the training recurrence as ONE host call (the per-step launches of icka_linear_fwd /
+ * icka_lstm_cell_fwd_save, resp. icka_lstm_cell_bwd / icka_linear_dgrad, issued from C: from Python the step was host-bound).
+ * Strides in ELEMENTS: row (sentence) pitch and position (time) stride of the [B, S, .] tensors; `*_dir` pointers are
+ * already offset to this direction's column block.  acts [S,B,4H], c_all [S,B,H] fp32 are indexed by STEP.  Scratch:
+ * gates [B,4H] fp32 and h [2,B,H] (`dtype`) for the forward; dc, dh [B,H] fp32 for the backward. */
+int icka_lstm_dir_fwd_save(icka_handle* h, const void* gx_dir, int64_t ld_gx_row, int64_t gx_pos_stride, const void* w_hh,
+                           float* acts, float* c_all, void* y_op_dir, float* y32_dir, int64_t ld_y_row, int64_t y_pos_stride,
+                           float* gates_scratch, void* h_scratch, int dtype, int B, int S, int H, int reverse, void* stream);
+int icka_lstm_dir_bwd(icka_handle* h, const float* dy_dir, int64_t ld_dy_row, int64_t dy_pos_stride, const void* w_hh,
+                      const float* acts, const float* c_all, void* dg_dir, int64_t ld_dg_row, int64_t dg_pos_stride,
+                      float* dc_scratch, float* dh_scratch, int dtype, int B, int S, int H, int reverse, void* stream);
+
 /* `self.classifier = nn.Linear(2H, num_labels)` (CMIM:910, :1043): out[M,T] fp32 = x[M,K] (`dtype`, pitch ldx) .
  * W[T,K]^T (fp32) + bias[T].  T <= 16, K % 8 == 0.  fp32 accumulation in a fixed order.
  * time_major_S = S > 0: the rows of x are time-major (row = t*B + b, B = M/S, as icka_lstm_rec_fwd writes them) and
