@@ -367,6 +367,22 @@ def run_gpu_arm(args, shape):
                'api': 'icka_b200.pipeline.FusionViterbiPipeline.infer_host (pinned host fp32 inputs; H2D of batch i+1 '
                       'overlaps kernels of batch i; D2H of tags, lengths, gates)'}
 
+        # the same call with the inputs a bf16 caller holds (half the PCIe bytes; extra, the headline `e2e` stays fp32)
+        if args.precision == 'bf16':
+            hosts16 = [pipe.make_host_batch(args.batch, shape, seed + 2000 + i, bf16_states=True) for i in range(2)]
+            seq16 = [hosts16[i & 1] for i in range(n_e2e)]
+            pipe.infer_host(seq16[:2], use_graphs=use_graph)
+            barrier()
+            _, (s3, e3) = pipe.infer_host(seq16, use_graphs=use_graph)
+            barrier()
+            ms16 = shard.max_over_ranks(s3.elapsed_time(e3), device=dev)
+            e2e['bf16_host_inputs'] = {
+                'value': args.batch * world * n_e2e / (ms16 * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': pipe.h2d_bytes(hosts16[0]),
+                'inputs': 'text states + token embedding bf16, regions as bf16 K-major rows [B,R,2048] '
+                          '(producer-tail layout), clip fp32, emissions fp32'}
+            del hosts16, seq16
+
     # ---- widened path (SURVEY 8f rows 1 + 2; extra, not part of `value`) ----
     widened = None
     if not args.no_widened and args.precision == 'bf16' and shape.H == 768:

@@ -28,6 +28,29 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// bf16 -> fp32 widening (exact): a caller that already holds bf16 text states / token embeddings (the
+// encoders ran in bf16) hands them over as the GEMM operand directly; this builds the fp32 residual stream.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            float* __restrict__ y, int64_t n) {
+  const int64_t nvec = n / 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+    const uint4 a = reinterpret_cast<const uint4*>(x)[v];
+    float4 lo, hi;      // a bf16 is the upper half of the fp32 with the same value
+    lo.x = __uint_as_float(a.x << 16); lo.y = __uint_as_float(a.x & 0xffff0000u);
+    lo.z = __uint_as_float(a.y << 16); lo.w = __uint_as_float(a.y & 0xffff0000u);
+    hi.x = __uint_as_float(a.z << 16); hi.y = __uint_as_float(a.z & 0xffff0000u);
+    hi.z = __uint_as_float(a.w << 16); hi.w = __uint_as_float(a.w & 0xffff0000u);
+    reinterpret_cast<float4*>(y)[2 * v] = lo;
+    reinterpret_cast<float4*>(y)[2 * v + 1] = hi;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = nvec * 8 + threadIdx.x; i < n; i += blockDim.x) y[i] = __bfloat162float(x[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Region relayout: grid [B, C, R] fp32 (R contiguous)  ->  rows [B*R, C] (C contiguous), CMIM:956.
 // One block moves a [64 channels x R] slab through shared memory (coalesced on both sides).
 // ------------------------------------------------------------------------------------------------
@@ -452,6 +475,21 @@ extern "C" int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y, in
   if (blocks < 1) blocks = 1;
   cast_f32_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(y), n);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_cast_bf16_to_f32(icka_handle* h, const void* x, float* y, int64_t n, void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(n >= 0 && x && y, "cast: bad arguments");
+  ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(y, 16), "cast: pointers must be 16-byte aligned");
+  if (n == 0) return ICKA_OK;
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_bf16_f32_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, n);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -85,11 +85,30 @@ def _to_lp(x32: torch.Tensor) -> torch.Tensor:
     return ops.cast_bf16(x32) if _PRECISION == 'bf16' else x32
 
 
+def _widen(x: torch.Tensor) -> torch.Tensor:
+    """-> fp32.  A bf16 CUDA tensor outside autograd goes through the library's exact widening kernel."""
+    if x.dtype == torch.float32:
+        return x
+    if x.dtype == torch.bfloat16 and x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad):
+        return ops.cast_f32(x.contiguous())
+    return x.float()
+
+
 def _rows(x: torch.Tensor) -> torch.Tensor:
     """[B, S, H] (any float dtype / strides) -> contiguous fp32 [B*S, H] view."""
-    if x.dtype != torch.float32:
-        x = x.float()
+    x = _widen(x)
     return x.contiguous().view(-1, x.shape[-1])
+
+
+def _rows_and_operand(x: torch.Tensor):
+    """[B, S, H] -> (fp32 residual rows, GEMM operand rows in the compute dtype).  States that arrive in bf16 on the
+    bf16 path (the caller's encoders ran in bf16) ARE the operand: no rounding pass, only the exact widening."""
+    if (_PRECISION == 'bf16' and x.dtype == torch.bfloat16 and x.is_cuda
+            and not (torch.is_grad_enabled() and x.requires_grad)):
+        x_lp = x.contiguous().view(-1, x.shape[-1])
+        return ops.cast_f32(x_lp), x_lp
+    x32 = _rows(x)
+    return x32, _to_lp(x32.detach())
 
 
 def _mask2d(mask: Optional[torch.Tensor], B: int, Skv: int) -> Optional[torch.Tensor]:
@@ -455,7 +474,7 @@ class CrossModalFusion(nn.Module):
         if rows_given:
             R = visual_embeds_att.shape[1]
         else:
-            grid = visual_embeds_att.float().contiguous()
+            grid = _widen(visual_embeds_att).contiguous()
             R = grid.numel() // (B * grid.shape[1])
 
         rec = _recording(sequence_output, token_embedding, module=self)
@@ -478,17 +497,17 @@ class CrossModalFusion(nn.Module):
         txt_mask = ops.mask_additive(ori_input_mask, S)
 
         # text -> image, CMIM:968-969
-        x32 = _rows(sequence_output)
+        x32, x_lp = _rows_and_operand(sequence_output)
         tok32 = _rows(token_embedding).view(B, S, H)
         ln = self.cls_layer.proj_norm
         if rec:
-            outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32.detach()), regions_lp, img_mask, B, S, R,
+            outs, fused_lp = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R,
                                                          keep_all=False, y32=regions32)
             fused32 = outs[-1]
         else:
             # inference: the encoder's last LayerNorm is fused with the gate + blend (CMIM:1029-1036), which also
             # emits the operand copy of `fused` the image->text encoders read
-            outs, _ = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R, keep_all=False,
+            outs, _ = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R, keep_all=False,
                                                   defer_last_ln=True)
             ln2 = self.txt2img_attention.layer[-1].output.LayerNorm
             gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight,
@@ -542,15 +561,15 @@ class CrossModalFusion(nn.Module):
             if rows.dtype != _cdt():
                 rows = _to_lp(rows.float()) if _PRECISION == 'bf16' else rows.float()
         else:
-            grid = visual_embeds_att.float().contiguous()
+            grid = _widen(visual_embeds_att).contiguous()
             R = grid.numel() // (B * grid.shape[1])
             rows = ops.region_rows(grid, _cdt())
         regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
                                 self.vismap2text.bias.detach(), out_dtype=_cdt())
         img_mask = ops.mask_additive(added_attention_mask, R)
         txt_mask = ops.mask_additive(ori_input_mask, S)
-        x32 = _rows(sequence_output)
-        outs, fused_lp = self.txt2img_attention._run(x32, _to_lp(x32), regions_lp, img_mask, B, S, R, keep_all=False)
+        x32, x_lp = _rows_and_operand(sequence_output)
+        outs, fused_lp = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R, keep_all=False)
         fused32 = outs[-1]
         clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
         z32 = ops.linear(clip_in, _operand(self._cache, 'vmap', self.vismapping.weight), self.vismapping.bias.detach(),
@@ -569,6 +588,6 @@ class CrossModalFusion(nn.Module):
         w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
             self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
             self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
-        result, _ = ops.gate_blend(cross_output_layer.float().contiguous(), token_embedding.float().contiguous(),
+        result, _ = ops.gate_blend(_widen(cross_output_layer).contiguous(), _widen(token_embedding).contiguous(),
                                    ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold)
         return result

@@ -46,6 +46,17 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    """bf16 -> fp32 (exact widening): the fp32 residual stream of a caller-supplied bf16 tensor."""
+    _need(x, torch.bfloat16, 'cast_f32(x)')
+    lib, h, st = _ctx(x)
+    y = torch.empty_like(x, dtype=torch.float32)
+    if x.numel() == 0:
+        return y
+    _lib.check(lib.icka_cast_bf16_to_f32(h, x.data_ptr(), y.data_ptr(), x.numel(), st), 'icka_cast_bf16_to_f32')
+    return y
+
+
 def region_rows(grid: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     """[B, C, g, g] (or [B, C, R]) fp32 ResNet grid -> [B*R, C] rows (CMIM:956)."""
     _need(grid, torch.float32, 'region_rows(grid)')

@@ -101,10 +101,19 @@ class FusionViterbiPipeline:
 
     # ---- host batches ---------------------------------------------------------------------------
     @staticmethod
-    def make_host_batch(B: int, shape: synth.Shape, seed: int, pin: bool = True) -> Dict[str, torch.Tensor]:
+    def make_host_batch(B: int, shape: synth.Shape, seed: int, pin: bool = True,
+                        bf16_states: bool = False) -> Dict[str, torch.Tensor]:
+        """Synthetic host batch.  ``bf16_states``: what a caller whose encoders run in bf16 holds -- text states and
+        token embedding in bf16, the regions as the producer tail's bf16 K-major rows [B, R, 2048]
+        (icka_region_tail_fwd / myResnet.forward_rows; CMIM:956 applied at the source) -- half the bytes per sentence."""
         f = synth.fusion_inputs(B, shape, seed=seed)
         c = synth.crf_batch(B, shape, seed=seed)
         host = {k: f[k] for k in FUSION_KEYS}
+        if bf16_states:
+            g = host['visual_embeds_att']
+            host['visual_embeds_att'] = g.reshape(B, g.shape[1], -1).permute(0, 2, 1).to(torch.bfloat16).contiguous()
+            host['text_states'] = host['text_states'].to(torch.bfloat16)
+            host['token_embedding'] = host['token_embedding'].to(torch.bfloat16)
         host['emissions'] = c['emissions']
         host['crf_mask'] = c['mask'].to(torch.uint8)
         if pin:
@@ -140,9 +149,14 @@ class FusionViterbiPipeline:
         start.record(cs)
         for i, host in enumerate(batches):
             slot = i & 1
-            if dev_bufs[slot] is None:
-                dev_bufs[slot] = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
             with torch.cuda.stream(cs):
+                if dev_bufs[slot] is None:
+                    # Allocated from the COPY stream's pool: a block the main stream's pool hands out may still be read
+                    # by the previous batch's in-flight kernels (eager launches free their temporaries in host order),
+                    # and the copy stream would overwrite it without waiting for them.
+                    dev_bufs[slot] = {k: torch.empty_like(v, device=self.device) for k, v in host.items()}
+                    for t in dev_bufs[slot].values():
+                        t.record_stream(main)
                 if compute_done[slot] is not None:
                     cs.wait_event(compute_done[slot])          # buffer set is free again
                 for k, v in host.items():

@@ -56,6 +56,11 @@ int64_t icka_launch_count(const icka_handle* h);
 /* fp32 -> bf16 copy of a GEMM operand (the residual stream itself stays fp32). */
 int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y_bf16, int64_t n, void* stream);
 
+/* bf16 -> fp32 widening (exact).  For callers whose encoders already produce bf16 states (the "bf16 path" of the
+ * north star): the bf16 tensor is used as the GEMM operand as is, this builds the fp32 residual stream
+ * (`+ input_tensor` of CMIM:564) / the fp32 `token_embedding` operand of the gate + blend (CMIM:1036). */
+int icka_cast_bf16_to_f32(icka_handle* h, const void* x_bf16, float* y, int64_t n, void* stream);
+
 /* CMIM:956  `visual_embeds_att.view(-1, 2048, 49).permute(0, 2, 1)`:
  * grid [B, C, R] fp32 (R contiguous) -> rows [B*R, C] in `out_dtype` (C contiguous, the K-major GEMM
  * operand the region projection wants). */

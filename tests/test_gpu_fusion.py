@@ -111,3 +111,48 @@ def test_weight_update_refreshes_operand_cache():
         enc.layer[0].output.dense.weight.mul_(0.5)
         b = enc(x, y, m)[-1]
     assert (a - b).abs().max() > 1e-3
+
+
+def test_cast_f32_exact():
+    """icka_cast_bf16_to_f32 is an exact widening, tails and odd sizes included."""
+    from icka_b200 import ops
+    for n in (0, 1, 7, 8, 4096 + 5, 128 * 768 * 3):
+        x = torch.randn(n, device=DEV).to(torch.bfloat16)
+        y = ops.cast_f32(x)
+        assert y.dtype == torch.float32 and torch.equal(y, x.float())
+
+
+@pytest.mark.parametrize('name', ['std_L1', 'hires_L1'])
+@pytest.mark.parametrize('rows', [False, True])
+def test_fusion_bf16_resident_inputs(name, rows):
+    """bf16 path with inputs that ARRIVE in bf16 (the caller's encoders ran in bf16; `rows`: regions as the producer
+    tail's K-major bf16 rows [B,R,2048] instead of the fp32 grid).  The bf16 states are the GEMM operand as is and the
+    residual stream is their exact widening, so the result must (a) equal, bit for bit, the run on the same values
+    handed over as fp32, and (b) stay within the bf16 gate (2e-2) of the fp32 oracle on those values."""
+    B, shape, params, inp, stride = build_case(name)
+    cfg = icka_b200.FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads,
+                                 intermediate_size=shape.inter, layer_norm_eps=shape.eps)
+    model = icka_b200.CrossModalFusion(cfg, layer_num1=shape.L, region_dim=shape.region_dim,
+                                       clip_dim=shape.clip_dim).to(DEV).eval()
+    model.load_state_dict(params, strict=True)
+    icka_b200.set_precision('bf16')
+    lp = dict(inp)
+    for k in ('text_states', 'token_embedding', 'visual_embeds_att'):
+        lp[k] = inp[k].to(torch.bfloat16)
+    grid = lp['visual_embeds_att']
+    R = grid.shape[2] * grid.shape[3]
+    regions = grid.view(B, grid.shape[1], R).permute(0, 2, 1).contiguous() if rows else grid     # CMIM:956
+    keys = ('clip_features', 'token_embedding', 'img_mask', 'text_mask')
+    with torch.no_grad():
+        got = model(lp['text_states'].to(DEV), regions.to(DEV), *[lp[k].to(DEV) for k in keys], return_dict=True)
+        same = model(lp['text_states'].float().to(DEV), grid.float().to(DEV),
+                     *[lp[k].float().to(DEV) if lp[k].is_floating_point() else lp[k].to(DEV) for k in keys],
+                     return_dict=True)
+    torch.cuda.synchronize()
+    for k in ('result', 'fused', 'clip', 'gate'):
+        assert torch.equal(got[k], same[k]), k
+    widened = {k: (v.float() if v.is_floating_point() else v) for k, v in lp.items()}
+    want = oracle(shape, params, widened)
+    for k in ('result', 'fused', 'clip', 'gate'):
+        err = float((got[k].float().cpu().reshape(want[k].shape) - want[k]).abs().max())
+        assert err <= 2e-2, (k, err)

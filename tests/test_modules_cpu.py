@@ -120,3 +120,20 @@ def test_full_model_state_dict_keys_are_the_reference_names():
         # what the reference has and the drop-in leaves out: only the members its forward never touches
         unused = {k.split('.')[0] for k in set(ref_sd) - keys}
         assert unused <= {'self_attention', 'self_attention_v2', 'embedding_layer', 'LayerNorm'}, unused
+
+
+def test_host_batch_bf16_states_layout():
+    """make_host_batch(bf16_states=True): the same values, bf16, regions as CMIM:956 rows [B, R, 2048]."""
+    import torch
+    from icka_b200 import synth
+    from icka_b200.pipeline import FusionViterbiPipeline as P
+    a = P.make_host_batch(3, synth.STD, 9, pin=False)
+    b = P.make_host_batch(3, synth.STD, 9, pin=False, bf16_states=True)
+    assert b['text_states'].dtype == b['token_embedding'].dtype == b['visual_embeds_att'].dtype == torch.bfloat16
+    assert torch.equal(b['text_states'], a['text_states'].to(torch.bfloat16))
+    rows = a['visual_embeds_att'].view(-1, 2048, 49).permute(0, 2, 1)
+    assert b['visual_embeds_att'].shape == (3, 49, 2048) and b['visual_embeds_att'].is_contiguous()
+    assert torch.equal(b['visual_embeds_att'], rows.to(torch.bfloat16))
+    for k in ('clip_features', 'img_mask', 'text_mask', 'emissions', 'crf_mask'):
+        assert torch.equal(a[k], b[k])
+    assert P.h2d_bytes(b) < 0.51 * P.h2d_bytes(a)
