@@ -104,3 +104,11 @@ def crf_batch(B: int, shape: Shape = STD, seed: int = BASE_SEED, kind: str = 'no
     tags = (torch.randint(1, shape.T, (B, shape.S), generator=g) if shape.T > 1
             else torch.zeros(B, shape.S, dtype=torch.long)) * mask.long()
     return dict(emissions=e, mask=mask, tags=tags, lens=lens)
+
+
+def forbid_cells(emissions: torch.Tensor, seed: int, frac: float = 0.3, value: float = float('-inf')) -> torch.Tensor:
+    """Constrained decoding as callers do it: a random subset of (step, tag) cells is forbidden (-inf or -10000)."""
+    g = torch.Generator().manual_seed(seed)
+    e = emissions.clone()
+    e[torch.rand(e.shape, generator=g) < frac] = value
+    return e

@@ -111,3 +111,18 @@ def test_crf_llh(reduction):
     want = crf_ref.log_likelihood(batch['emissions'], batch['tags'], batch['mask'], cp['start_transitions'],
                                   cp['end_transitions'], cp['transitions'], reduction)
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-4), float((got - want).abs().max())
+
+
+@pytest.mark.parametrize('value', [float('-inf'), -10000.0])
+@pytest.mark.parametrize('T', [15, 20])
+def test_viterbi_forbidden_cells(value, T):
+    """Constrained decoding: -inf / -10000 emissions on a random 30 % of the (step, tag) cells, one step with no allowed
+    tag at all.  Tags stay bit-exact (both the T <= 16 lock-step kernel and the generic one).  NaN emissions are outside
+    the contract (the kernels' max is fmaxf-based; torch.max would propagate the NaN)."""
+    sh = synth.Shape(S=128, T=T)
+    batch = synth.crf_batch(130, sh, seed=21, kind='ties')
+    e = synth.forbid_cells(batch['emissions'], 4, value=value)
+    e[0, 2, :] = value
+    crf, cp = make_crf(T, 13, 'normal')
+    got = crf.decode(e.to(DEV), batch['mask'].to(DEV))
+    assert got == oracle_c(e, batch['mask'], cp)

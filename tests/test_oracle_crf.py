@@ -118,3 +118,17 @@ def test_validate_errors():
     m = torch.ones(2, 3, dtype=torch.bool); m[1, 0] = False
     with pytest.raises(ValueError):
         crf_ref.validate(e, 4, mask=m)
+
+
+@pytest.mark.parametrize('value', [float('-inf'), -10000.0])
+def test_c_port_forbidden_cells(value):
+    """-inf / -10000 emissions (forbidden tags; whole steps can be all -inf): every comparison is still ordered, the
+    first maximal index wins, and the C port follows the torch restatement (torch.max) exactly."""
+    sh = synth.Shape(S=30, T=15)
+    batch = synth.crf_batch(41, sh, seed=8, kind='ties', median_len=14)
+    e = synth.forbid_cells(batch['emissions'], 3, value=value)
+    e[0, 2, :] = value                      # a step with no allowed tag
+    st, en, tr = P(sh.T, 6, 'normal')
+    want = crf_ref.viterbi_decode(e, batch['mask'], st, en, tr)
+    tags, lens = viterbi_c.viterbi(e.numpy(), batch['mask'].numpy(), st.numpy(), en.numpy(), tr.numpy())
+    assert viterbi_c.to_lists(tags, lens) == want
