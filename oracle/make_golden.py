@@ -30,6 +30,7 @@ CASES = {
     'std_L1': (1, dict(L=1), 21, 22, 4, 28.0),
     'std_L2_eps5': (2, dict(L=2, eps=1e-5), 31, 32, 8, 28.0),
     'hires_L1': (1, dict(S=256, R=196, L=1), 41, 42, 8, 60.0),
+    'std_L5': (1, dict(L=5), 51, 52, 8, 28.0),      # the training script's default depth (MCA:603)
 }
 
 
@@ -50,7 +51,7 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):      # optional: only the named cases
         B, shape, params, inp, stride = build_case(name)
         mods = reference_shim.build_reference_modules(
             params, hidden=shape.H, heads=shape.heads, inter=shape.inter, num_layers=shape.L,
