@@ -18,7 +18,7 @@ from oracle.make_golden import CASES, build_case
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
-PENDING = {'std_L5'}      # golden cases not yet confirmed on a B200 (tools/parity_case.py prints their errors)
+PENDING = set()           # golden cases not yet confirmed on a B200 (tools/parity_case.py prints their errors)
 GPU_CASES = [c for c in CASES if c not in PENDING]
 
 
