@@ -1,0 +1,109 @@
+"""Property tests (hypothesis) that widen the anchors of the oracles on the CPU:
+
+* Viterbi: torch restatement == plain-C port == brute-force optimum, over random tag counts, lengths, masks (prefix and
+  with holes), tie-heavy / forbidden-cell emissions -- the CRF oracle is parity-unpinned (no pytorch-crf here), so the
+  enumerated optimum is the independent witness;
+* chunk extraction / F1: oracle/ner_ref.py == the reference's own ner_evaluate.py on random label sequences (skipped
+  where /root/reference is absent; the committed golden file covers that case).
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import crf_ref, ner_ref, viterbi_c
+
+SET = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+
+
+@st.composite
+def crf_problem(draw):
+    T = draw(st.integers(1, 5))
+    S = draw(st.integers(1, 6))
+    B = draw(st.integers(1, 4))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    kind = draw(st.sampled_from(['normal', 'ties', 'forbidden']))
+    holes = draw(st.booleans())
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(B, S, T, generator=g) * 2
+    if kind != 'normal':
+        e = torch.round(e * 2) / 2                       # multiples of 0.5: many exact ties
+    if kind == 'forbidden':
+        e[torch.rand(B, S, T, generator=g) < 0.25] = float('-inf')
+    start, end = torch.round(torch.randn(T, generator=g) * 4) / 4, torch.round(torch.randn(T, generator=g) * 4) / 4
+    trans = torch.round(torch.randn(T, T, generator=g) * 4) / 4
+    if holes:
+        mask = torch.rand(B, S, generator=g) > 0.35
+    else:
+        lens = torch.randint(1, S + 1, (B,), generator=g)
+        mask = torch.arange(S)[None, :] < lens[:, None]
+    mask[:, 0] = True
+    return e, mask, start, end, trans, holes
+
+
+@settings(max_examples=120, **SET)
+@given(crf_problem())
+def test_viterbi_restatement_c_port_and_enumeration_agree(p):
+    e, mask, start, end, trans, holes = p
+    want = crf_ref.viterbi_decode(e, mask, start, end, trans)
+    tags, lens = viterbi_c.viterbi(e.numpy(), mask.numpy(), start.numpy(), end.numpy(), trans.numpy())
+    assert viterbi_c.to_lists(tags, lens) == want
+    assert [len(w) for w in want] == mask.sum(1).tolist()
+    if holes:
+        return                      # with holes upstream's procedure is not the optimum of any simple model
+    for b, path in enumerate(want):
+        L = len(path)
+        best, arg = crf_ref.brute_force_best(e[b, :L], L, start, end, trans)
+        got = crf_ref._seq_score(e[b].double(), path, start.double(), end.double(), trans.double())
+        if np.isinf(best):          # every path crosses a forbidden cell
+            assert np.isinf(got) and got < 0
+            continue
+        assert abs(got - best) < 1e-6                 # quarter / half grid: scores are exact in fp32
+        assert path in arg                            # one of the enumerated optima ...
+        assert path == min(arg, key=lambda q: q[::-1])    # ... the one first-index tie-breaking selects, back to front
+
+
+REF = '/root/reference'
+
+
+@pytest.fixture(scope='module')
+def ref_eval():
+    if not os.path.isfile(os.path.join(REF, 'ner_evaluate.py')):
+        pytest.skip('/root/reference absent (GPU box): the committed golden file covers this')
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    try:
+        import ner_evaluate
+    finally:
+        sys.path.remove(REF)
+    return ner_evaluate
+
+
+labels = st.lists(st.integers(0, 14), min_size=1, max_size=24)
+
+
+@settings(max_examples=150, **SET)
+@given(st.lists(st.tuples(labels, st.integers(0, 2 ** 31 - 1)), min_size=1, max_size=6))
+def test_chunks_and_f1_match_the_reference_evaluator(ref_eval, rows):
+    tags = ner_ref.tag_dict()
+    gold = [g for g, _ in rows]
+    pred = []
+    for g, seed in rows:
+        r = np.random.RandomState(seed)
+        pred.append([x if r.rand() < 0.7 else int(r.randint(0, 15)) for x in g])
+    for seq in gold + pred:
+        assert ner_ref.get_chunks(seq, tags) == ref_eval.get_chunks(seq, tags)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:          # the reference's evaluate() writes ./test_results.txt
+        os.chdir(tmp)
+        try:
+            words = [['w'] * len(g) for g in gold]
+            want = ref_eval.evaluate(pred, gold, [[str(x) for x in s] for s in pred],
+                                     [[str(x) for x in s] for s in gold], words, tags)
+        finally:
+            os.chdir(cwd)
+    assert list(map(float, ner_ref.evaluate(pred, gold, tags))) == list(map(float, want))
