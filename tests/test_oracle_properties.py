@@ -107,3 +107,26 @@ def test_chunks_and_f1_match_the_reference_evaluator(ref_eval, rows):
         finally:
             os.chdir(cwd)
     assert list(map(float, ner_ref.evaluate(pred, gold, tags))) == list(map(float, want))
+
+
+@settings(max_examples=80, **SET)
+@given(crf_problem(), st.integers(0, 2 ** 31 - 1))
+def test_log_likelihood_is_a_normalised_distribution(p, seed):
+    """Prefix masks, finite emissions: llh(gold) = score(gold) - log sum over ALL enumerated paths, so the probabilities
+    of all T^L paths of a sentence sum to one and every reduction is the stated function of the per-sentence values."""
+    e, mask, start, end, trans, holes = p
+    if holes or not torch.isfinite(e).all():
+        return
+    B, S, T = e.shape
+    g = torch.Generator().manual_seed(seed)
+    tags = torch.randint(0, T, (B, S), generator=g)
+    llh = crf_ref.log_likelihood(e, tags, mask, start, end, trans, reduction='none')
+    for b in range(B):
+        L = int(mask[b].sum())
+        want = crf_ref._seq_score(e[b].double(), tags[b, :L].tolist(), start.double(), end.double(), trans.double()) \
+            - crf_ref.brute_force_logZ(e[b, :L], L, start, end, trans)
+        assert abs(float(llh[b]) - want) < 1e-4 * max(1.0, abs(want))
+    assert torch.allclose(crf_ref.log_likelihood(e, tags, mask, start, end, trans, 'sum'), llh.sum())
+    assert torch.allclose(crf_ref.log_likelihood(e, tags, mask, start, end, trans, 'mean'), llh.mean())
+    assert torch.allclose(crf_ref.log_likelihood(e, tags, mask, start, end, trans, 'token_mean'),
+                          llh.sum() / mask.sum())
