@@ -130,3 +130,43 @@ def test_log_likelihood_is_a_normalised_distribution(p, seed):
     assert torch.allclose(crf_ref.log_likelihood(e, tags, mask, start, end, trans, 'mean'), llh.mean())
     assert torch.allclose(crf_ref.log_likelihood(e, tags, mask, start, end, trans, 'token_mean'),
                           llh.sum() / mask.sum())
+
+
+@st.composite
+def fusion_problem(draw):
+    heads = draw(st.sampled_from([1, 2, 4]))
+    H = heads * draw(st.sampled_from([8, 16]))
+    g = draw(st.integers(1, 4))                       # region grid g x g
+    return dict(B=draw(st.integers(1, 3)), S=draw(st.integers(1, 12)), R=g * g, H=H, heads=heads,
+                inter=draw(st.sampled_from([16, 48])), region_dim=draw(st.sampled_from([8, 24])),
+                clip_dim=draw(st.sampled_from([4, 12])), L=draw(st.integers(1, 3)),
+                eps=draw(st.sampled_from([1e-12, 1e-5])), seed=draw(st.integers(0, 2 ** 31 - 1)),
+                mask_regions=draw(st.booleans()))
+
+
+@settings(max_examples=25, **SET)
+@given(fusion_problem())
+def test_fusion_restatement_matches_reference_classes_on_random_shapes(q):
+    """oracle/fusion_ref.py vs the reference's own BertCrossEncoder / cls_layer_both / Linear members (CMIM:509-667,
+    873-884) over random widths, head counts, depths, grid sizes, sentence lengths and region masks."""
+    from icka_b200 import synth
+    from oracle import fusion_ref, reference_shim
+    if not reference_shim.available():
+        pytest.skip('/root/reference absent (GPU box): the committed golden files cover this')
+    shape = synth.Shape(S=q['S'], R=q['R'], H=q['H'], heads=q['heads'], inter=q['inter'], region_dim=q['region_dim'],
+                        clip_dim=q['clip_dim'], L=q['L'], eps=q['eps'])
+    params = fusion_ref.make_params(shape.H, shape.heads, shape.inter, shape.L, seed=q['seed'] % 1000,
+                                    region_dim=shape.region_dim, clip_dim=shape.clip_dim)
+    inp = synth.fusion_inputs(q['B'], shape, seed=q['seed'], median_len=max(1.0, q['S'] / 2))
+    if q['mask_regions']:
+        inp['img_mask'][:, ::2] = 0
+    args = (inp['text_states'], inp['visual_embeds_att'], inp['clip_features'], inp['token_embedding'],
+            inp['img_mask'], inp['text_mask'])
+    out = fusion_ref.fusion_segment(*args, params, num_layers=shape.L, num_heads=shape.heads,
+                                    layer_norm_eps=shape.eps)
+    mods = reference_shim.build_reference_modules(params, hidden=shape.H, heads=shape.heads, inter=shape.inter,
+                                                  num_layers=shape.L, layer_norm_eps=shape.eps)
+    ref = reference_shim.reference_fusion_segment(mods, *args)
+    for k in ('regions', 'fused', 'clip', 'result', 'gate'):
+        err = float(((out[k] - ref[k]).abs() / ref[k].abs().clamp(min=1.0)).max())
+        assert err <= 1e-5, (k, err)
