@@ -17,7 +17,9 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 
 from oracle import crf_ref, ner_ref, viterbi_c
 
-SET = dict(deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+# derandomize: the same examples on every run (the driver runs this suite with -x; no flaky counterexample hunting)
+SET = dict(deadline=None, derandomize=True, database=None,
+           suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 
 
 @st.composite
@@ -42,13 +44,13 @@ def crf_problem(draw):
         lens = torch.randint(1, S + 1, (B,), generator=g)
         mask = torch.arange(S)[None, :] < lens[:, None]
     mask[:, 0] = True
-    return e, mask, start, end, trans, holes
+    return e, mask, start, end, trans, holes, kind != 'normal'
 
 
 @settings(max_examples=120, **SET)
 @given(crf_problem())
 def test_viterbi_restatement_c_port_and_enumeration_agree(p):
-    e, mask, start, end, trans, holes = p
+    e, mask, start, end, trans, holes, on_grid = p
     want = crf_ref.viterbi_decode(e, mask, start, end, trans)
     tags, lens = viterbi_c.viterbi(e.numpy(), mask.numpy(), start.numpy(), end.numpy(), trans.numpy())
     assert viterbi_c.to_lists(tags, lens) == want
@@ -61,6 +63,9 @@ def test_viterbi_restatement_c_port_and_enumeration_agree(p):
         got = crf_ref._seq_score(e[b].double(), path, start.double(), end.double(), trans.double())
         if np.isinf(best):          # every path crosses a forbidden cell
             assert np.isinf(got) and got < 0
+            continue
+        if not on_grid:             # generic floats: the fp32 DP may pick a path within rounding of the fp64 optimum
+            assert abs(got - best) < 1e-4
             continue
         assert abs(got - best) < 1e-6                 # quarter / half grid: scores are exact in fp32
         assert path in arg                            # one of the enumerated optima ...
@@ -114,7 +119,7 @@ def test_chunks_and_f1_match_the_reference_evaluator(ref_eval, rows):
 def test_log_likelihood_is_a_normalised_distribution(p, seed):
     """Prefix masks, finite emissions: llh(gold) = score(gold) - log sum over ALL enumerated paths, so the probabilities
     of all T^L paths of a sentence sum to one and every reduction is the stated function of the per-sentence values."""
-    e, mask, start, end, trans, holes = p
+    e, mask, start, end, trans, holes, _ = p
     if holes or not torch.isfinite(e).all():
         return
     B, S, T = e.shape
