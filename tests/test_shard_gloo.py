@@ -102,7 +102,10 @@ def _dp_worker(rank, world, port, q):
             reducer.finish()
             grads.append([p.grad.clone() for p in model.parameters()])
         if rank == 0:
-            q.put((grads, len(reducer.buckets), reducer.launched_early, extra.grad))
+            # by value (numpy): a torch tensor on a multiprocessing queue travels as a file descriptor that the parent
+            # must fetch from THIS process while it is still alive -- a race once the worker exits right after the put
+            q.put(([[t.numpy() for t in step] for step in grads], len(reducer.buckets), reducer.launched_early,
+                   None if extra.grad is None else extra.grad.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -124,7 +127,7 @@ def test_two_rank_gradient_allreduce_matches_full_batch():
     ((model(x) - y) ** 2).mean().backward()                 # equal shards: mean of shard means == full-batch mean
     for step in range(2):
         for got, p in zip(grads[step], model.parameters()):
-            assert torch.allclose(got, p.grad, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(torch.from_numpy(got), p.grad, rtol=1e-5, atol=1e-6)
     assert n_buckets >= 3                                   # 1 KiB buckets split this model
     assert early >= 2 * (n_buckets - 1)                     # all but the unused-parameter bucket start inside backward
-    assert extra_grad is not None and float(extra_grad.abs().max()) == 0.0
+    assert extra_grad is not None and float(abs(extra_grad).max()) == 0.0
