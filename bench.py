@@ -59,7 +59,9 @@ def parse():
     ap.add_argument('--layers', type=int, default=1, help='cross layers per encoder (layer_num1)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--hires', action='store_true', help='S=256, R=196 variant (BASELINE configs[3])')
-    ap.add_argument('--cpu-sample', type=int, default=32, help='sentences in the CPU-baseline sample')
+    ap.add_argument('--cpu-sample', type=int, default=256,
+                    help='sentences per pass of the CPU baseline / reference arm (torch-CPU throughput still grows with the '
+                         'batch up to a few hundred sentences: 32 under-reports the reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-widened', action='store_true', help='skip the extra fusion -> BiLSTM+classifier -> Viterbi -> chunk-F1 measurement')
@@ -400,7 +402,7 @@ def run_gpu_arm(args, shape):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         base = CpuBaseline(shape, args.cpu_sample, seed=19260817)
-        reps = 3 if shape.L == 1 else 2
+        reps = 8 if shape.L == 1 and not args.hires else 3      # a few seconds of CPU work on the box's cores
         v, sec = base.run(reps, 1)
         cpu = {'value': v, 'unit': UNIT, 'cores': base.cores, 'kind': 'port',
                'sample': f'{args.cpu_sample} sentences x {reps} passes (fusion fwd fp32 + Viterbi), oracle port on host CPU, '
