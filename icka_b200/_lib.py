@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libicka_b200.so')
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU_ERF, ACT_GELU_ERF_BWD, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_ERF_BWD, ACT_TANH, ACT_RELU, ACT_SWISH = 0, 1, 2, 3, 4, 5
 
 # name -> (restype, argtypes); must list every symbol of include/icka_b200.h
 SIGNATURES = {
@@ -38,6 +38,7 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_linear_wgrad': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_void_p]),
+    'icka_act_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     'icka_colsum': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     'icka_layernorm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int, c_int, c_void_p]),

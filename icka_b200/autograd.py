@@ -21,7 +21,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
-from ._lib import ACT_GELU_ERF
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_TANH
 
 F32 = torch.float32
 
@@ -54,7 +54,7 @@ class CrossLayerFn(torch.autograd.Function):
     def forward(ctx, x32, y32, x_op, y_op, mask2d, meta,
                 wq, bq, wk, bk, wv, bv, wo, bo, g1, b1, wi, bi, wd, bd, g2, b2,
                 wq_op, wkv_op, bkv, wo_op, wi_op, wd_op):
-        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed = meta
+        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed, act = meta
         H = nh * d
         dt = x_op.dtype
         bf = dt == torch.bfloat16
@@ -68,7 +68,7 @@ class CrossLayerFn(torch.autograd.Function):
         a32, a16 = ops.layernorm(pre1, g1, b1, eps, want_f32=True, want_bf16=bf)
         a_op = _op(a32, a16)
         u = torch.empty(a_op.shape[0], wi_op.shape[0], dtype=dt, device=a_op.device)
-        f = ops.linear(a_op, wi_op, bi, act=ACT_GELU_ERF, out_dtype=dt, pre_act_out=u)
+        f = ops.linear(a_op, wi_op, bi, act=act, out_dtype=dt, pre_act_out=u)
         if p_hid > 0:     # CMIM:533-535
             pre2 = ops.dropout(ops.linear(f, wd_op, bd, out_dtype=F32), p_hid, 3 * seed + 2, residual=a32)
         else:
@@ -84,7 +84,7 @@ class CrossLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, do32, _unused):
-        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed = ctx.meta
+        B, Sq, Skv, nh, d, eps, p_attn, p_hid, seed, act = ctx.meta
         H = nh * d
         saved = ctx.saved_tensors
         x_op, y_op, q, kv, att, pre1, a_op, u, f, pre2, g1, g2, wq_op, wkv_op, wo_op, wi_op, wd_op = saved[:17]
@@ -103,7 +103,11 @@ class CrossLayerFn(torch.autograd.Function):
         else:
             dpre2_op = _op(dpre2, dpre2_16)
         dwd = ops.linear_wgrad(dpre2_op, f)
-        dgl = ops.linear_dgrad(dpre2_op, wd_op, gelu_pre=u, out_dtype=dt)          # d(pre-activation) [M, I]
+        if act == ACT_GELU_ERF:   # the default: gelu' fused into the dgrad epilogue
+            dgl = ops.linear_dgrad(dpre2_op, wd_op, gelu_pre=u, out_dtype=dt)      # d(pre-activation) [M, I]
+        else:                     # config.hidden_act = 'relu' / 'swish' (CMIM:43): one extra element-wise pass
+            dgl = ops.linear_dgrad(dpre2_op, wd_op, out_dtype=dt)
+            ops.act_bwd(dgl, u, act, out=dgl)
         dwi = ops.linear_wgrad(dgl, a_op)
         dbi = ops.colsum(dgl)
         da1 = ops.linear_dgrad(dgl, wi_op, residual=dpre2, out_dtype=F32)          # + the residual branch
@@ -130,6 +134,148 @@ class CrossLayerFn(torch.autograd.Function):
         return (dx32, dy32, None, None, None, None,
                 dwq, dbq, dwkv[:H], dbkv[:H], dwkv[H:], dbkv[H:], dwo, dbo, dg1, db1, dwi, dbi, dwd, dbd, dg2, db2,
                 None, None, None, None, None, None)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """BertLayerNorm / nn.LayerNorm over the last dimension of x32 [M, N] (CMIM:509-522, :876) as a node of its own --
+    the building blocks (BertLayerNorm, BertSelfOutput, BertOutput, cls_layer_both) called outside a cross layer."""
+
+    @staticmethod
+    def forward(ctx, x32, gamma, beta, eps):
+        x32 = x32.contiguous()
+        g = gamma.detach().float().contiguous()
+        y32, _ = ops.layernorm(x32, g, beta.detach().float().contiguous(), eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x32, g)
+        return y32
+
+    @staticmethod
+    def backward(ctx, dy):
+        x32, g = ctx.saved_tensors
+        dx32, _, dg, db, _ = ops.layernorm_bwd(dy.contiguous(), x32, g, ctx.eps, want_f32=True, want_bf16=False,
+                                               want_dbias=False)
+        return dx32, dg, db, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """y = x * keep / (1 - p) with the Philox keep-mask of ``seed`` (regenerated, not stored, in backward):
+    nn.Dropout of the prompt mapping networks (CMIM:915, :918, :923, :926)."""
+
+    @staticmethod
+    def forward(ctx, x32, p, seed):
+        ctx.p, ctx.seed = p, seed
+        return ops.dropout(x32.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy.contiguous(), ctx.p, ctx.seed), None, None
+
+
+class DenseActFn(torch.autograd.Function):
+    """out32[M,N] = act(x32[M,K] . W[N,K]^T + b) (+ residual32) with gradients for x, W, b and the residual: a dense layer
+    as a node of its own (the prompt mapping networks CMIM:914-930, and BertIntermediate / BertSelfOutput / BertOutput /
+    cls_layer_both.proj / the projections of BertCoAttention when they are called outside a cross layer).
+    ``bf16``: tcgen05 operands (x and W rounded to bf16, as on the inference path); otherwise the fp32 FFMA kernels.
+    bf16 needs N % 64 == 0 and K % 64 == 0 (the backward GEMMs read both operands MN-major)."""
+
+    @staticmethod
+    def forward(ctx, x32, weight, bias, residual, act, bf16):
+        x32 = x32.contiguous()
+        w = weight.detach().float().contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        x_op, w_op = (ops.cast_bf16(x32), ops.cast_bf16(w)) if bf16 else (x32, w)
+        u = None
+        if act not in (ACT_NONE, ACT_TANH):
+            u = torch.empty(x_op.shape[0], w_op.shape[0], dtype=x_op.dtype, device=x_op.device)
+        res = residual.contiguous() if residual is not None else None
+        if act == ACT_NONE or res is None:
+            out = ops.linear(x_op, w_op, b, residual=res, act=act, out_dtype=F32, pre_act_out=u)
+        else:
+            raise RuntimeError('DenseActFn: an activation and a residual do not occur together on this path')
+        ctx.act, ctx.has_bias, ctx.has_res = act, bias is not None, residual is not None
+        ref = out if act == ACT_TANH else u
+        ctx.save_for_backward(x_op, w_op, *([ref] if ref is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        x_op, w_op = saved[:2]
+        dout = dout.contiguous()
+        bf = x_op.dtype == torch.bfloat16
+        if ctx.act != ACT_NONE:
+            ref = saved[2]
+            if ctx.act == ACT_TANH:            # ref = the fp32 output
+                dpre32 = ops.act_bwd(dout, ref, ctx.act)
+                d_op = ops.cast_bf16(dpre32) if bf else dpre32
+            else:                              # ref = the pre-activation in the operand dtype
+                d_op = ops.act_bwd(ops.cast_bf16(dout) if bf else dout, ref, ctx.act)
+        else:
+            d_op = ops.cast_bf16(dout) if bf else dout
+        dx = ops.linear_dgrad(d_op, w_op, out_dtype=F32) if ctx.needs_input_grad[0] else None
+        dw = ops.linear_wgrad(d_op, x_op) if ctx.needs_input_grad[1] else None
+        db = _colsum_any(d_op) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dres = dout if (ctx.has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None
+
+
+def _colsum_any(x):
+    """Column sums for any column count (the kernel reads column pairs: an odd count gets a zero column)."""
+    N = x.shape[1]
+    if N % 2 == 0:
+        return ops.colsum(x)
+    padded = torch.zeros(x.shape[0], N + 1, dtype=x.dtype, device=x.device)
+    padded[:, :N] = x
+    return ops.colsum(padded)[:N]
+
+
+class AttnCoreFn(torch.autograd.Function):
+    """ctx = softmax(Q K^T / sqrt(d) + mask) V per head (CMIM:605-623) as a node of its own: BertCoAttention called
+    outside a cross layer.  q [B*Sq, H], kv [B*Skv, 2H] in the operand dtype; the core's output in the same dtype."""
+
+    @staticmethod
+    def forward(ctx, q, kv, mask2d, dims, p_drop, seed):
+        B, Sq, Skv, nh, d = dims
+        H = nh * d
+        out = ops.cross_attn_core(q, kv[:, :H], kv[:, H:], mask2d, B, Sq, Skv, nh, d, p_drop=p_drop, seed=seed)
+        ctx.dims, ctx.p_drop, ctx.seed, ctx.has_mask = dims, p_drop, seed, mask2d is not None
+        ctx.save_for_backward(q, kv, out, *([mask2d] if mask2d is not None else []))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        q, kv, out = saved[:3]
+        mask2d = saved[3] if ctx.has_mask else None
+        B, Sq, Skv, nh, d = ctx.dims
+        H = nh * d
+        dq, dkv = ops.cross_attn_core_bwd(q, kv[:, :H], kv[:, H:], mask2d, dout.contiguous().to(q.dtype), B, Sq, Skv, nh, d,
+                                          ctx=out, p_drop=ctx.p_drop, seed=ctx.seed)
+        return dq, dkv, None, None, None, None
+
+
+class AddFn(torch.autograd.Function):
+    """a + b (fp32, same shape) on the library's kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add_f32(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, d):
+        return d, d
+
+
+class CastFn(torch.autograd.Function):
+    """fp32 -> operand dtype (bf16 rounding / identity) whose backward widens the gradient again."""
+
+    @staticmethod
+    def forward(ctx, x32, bf16):
+        return ops.cast_bf16(x32.contiguous()) if bf16 else x32
+
+    @staticmethod
+    def backward(ctx, d):
+        return (ops.cast_f32(d.contiguous()) if d.dtype == torch.bfloat16 else d), None
 
 
 class GateBlendFn(torch.autograd.Function):

@@ -63,6 +63,11 @@ class CRF(nn.Module):
             first = mask[:, 0] if self.batch_first else mask[0]
             if not bool(first.all()):
                 raise ValueError('mask of the first timestep must all be on')
+        if tags is not None and tags.numel() and bool(((tags < 0) | (tags >= self.num_tags)).any()):
+            # pytorch-crf indexes start_transitions / transitions / emissions with every tag id (masked positions too):
+            # an id outside [0, num_tags) -- e.g. an ignore-index of -100 on padding -- is an IndexError there
+            raise IndexError(f'tags must lie in [0, {self.num_tags}); got values in '
+                             f'[{int(tags.min())}, {int(tags.max())}]')
 
     def _batch_first(self, emissions, tags, mask):
         if not self.batch_first:

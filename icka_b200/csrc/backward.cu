@@ -983,3 +983,44 @@ extern "C" int icka_gate_fold_bwd(icka_handle* h, const float* Wp, const float* 
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
+
+// ---- element-wise activation backward: dx = dy * act'(ref) -----------------------------------------------------------
+// ref = the PRE-activation for gelu / relu / swish (BertIntermediate, CMIM:549-550 with config.hidden_act, CMIM:43) and the
+// OUTPUT y for tanh (tanh' = 1 - y^2: the prompt mapping networks keep only the activated tensor, CMIM:917, :925).
+// The default GELU layer never comes here inside a cross layer (its derivative is fused into the FFN-down dgrad epilogue).
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ ref, T* __restrict__ dx,
+                                                      int64_t n, int act) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float g = to_f32<T>(dy[i]), r = to_f32<T>(ref[i]);
+    float d;
+    if (act == ICKA_ACT_TANH) d = 1.0f - r * r;
+    else if (act == ICKA_ACT_RELU) d = act_relu_grad(r);
+    else if (act == ICKA_ACT_SWISH) d = act_swish_grad(r);
+    else d = gelu_erf_grad(r);
+    dx[i] = from_f32<T>(g * d);
+  }
+}
+
+extern "C" int icka_act_bwd(icka_handle* h, const void* dy, const void* ref, void* dx, int dtype, int64_t n, int act,
+                            void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(dy && ref && dx && n >= 0, "act_bwd: bad arguments");
+  ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "act_bwd: bad dtype %d", dtype);
+  ICKA_REQUIRE(act == ICKA_ACT_GELU_ERF || act == ICKA_ACT_TANH || act == ICKA_ACT_RELU || act == ICKA_ACT_SWISH,
+               "act_bwd: bad activation %d", act);
+  if (n == 0) return ICKA_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == ICKA_F32)
+    act_bwd_kernel<float><<<(int)blocks, 256, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(ref),
+                                                       static_cast<float*>(dx), n, act);
+  else
+    act_bwd_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                               static_cast<const __nv_bfloat16*>(ref),
+                                                               static_cast<__nv_bfloat16*>(dx), n, act);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}

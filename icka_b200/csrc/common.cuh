@@ -55,7 +55,25 @@ int icka_make_tmap_bf16(icka_handle* h, CUtensorMap* tm, const void* ptr, int64_
     (h)->launches.fetch_add(1);          \
   } while (0)
 
-#define ICKA_CHECK_HANDLE(h) ICKA_REQUIRE((h) != nullptr, "null handle")
+// Every entry point runs against the HANDLE's device, whatever the caller's current device is (a caller that holds
+// tensors on cuda:1 while cuda:0 is current, e.g. one nn.DataParallel worker thread per GPU): set it for the duration of
+// the call and restore it, as a PyTorch op's device guard would.
+struct icka_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit icka_device_guard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~icka_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  icka_device_guard(const icka_device_guard&) = delete;
+  icka_device_guard& operator=(const icka_device_guard&) = delete;
+};
+
+#define ICKA_CHECK_HANDLE(h)                       \
+  ICKA_REQUIRE((h) != nullptr, "null handle");     \
+  icka_device_guard icka_guard_((h)->device)
 
 static inline bool icka_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -76,6 +94,16 @@ __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { retu
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// The other two entries of the reference's ACT2FN table (CMIM:39-43): relu, and swish(x) = x * sigmoid(x).
+__device__ __forceinline__ float act_relu(float x) { return fmaxf(x, 0.0f); }
+__device__ __forceinline__ float act_swish(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float act_swish_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // bf16 outputs
+__device__ __forceinline__ float act_relu_grad(float x) { return x > 0.0f ? 1.0f : 0.0f; }
+__device__ __forceinline__ float act_swish_grad(float x) {
+  const float s = 1.0f / (1.0f + expf(-x));
+  return s * fmaf(x, 1.0f - s, 1.0f);
 }
 
 // erf-GELU exactly as the reference writes it (CMIM:31-37): x * 0.5 * (1 + erf(x / sqrt(2)))

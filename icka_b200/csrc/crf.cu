@@ -18,6 +18,11 @@ namespace {
 
 constexpr int kThreads = 128;
 
+// Gold tag ids index start[], trans[][], e[t][] and shared-memory accumulators: ids outside [0, T) (e.g. an ignore-index
+// of -100 on padding) are clamped so no access leaves its array.  pytorch-crf raises IndexError for them; the Python
+// mirror (icka_b200/crf.py) checks the range before the launch, so a clamped id never reaches a result.
+__device__ __forceinline__ int gold_tag(int64_t y, int T) { return (int)(y < 0 ? 0 : (y >= T ? T - 1 : y)); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -208,8 +213,7 @@ __device__ __forceinline__ Cand take_first_max(const Cand a, const Cand b) {   /
   return r;
 }
 
-constexpr int kV16Threads = 128;
-constexpr int kV16Seqs = kV16Threads / 16;
+constexpr int kV16Threads = 128;   // maximum; long sequences launch fewer warps per block so the per-sentence slabs fit
 
 __global__ void __launch_bounds__(kV16Threads) viterbi16_kernel(
     const float* __restrict__ emissions, const uint8_t* __restrict__ mask, const float* __restrict__ start,
@@ -220,8 +224,9 @@ __global__ void __launch_bounds__(kV16Threads) viterbi16_kernel(
   const int g_in_block = threadIdx.x >> 4;
   const int gl = threadIdx.x & 15;
   const int gshift = threadIdx.x & 16;
-  const int b_raw = blockIdx.x * kV16Seqs + g_in_block;
-  if (blockIdx.x * kV16Seqs + (g_in_block & ~1) >= B) return;   // whole warp out of range
+  const int seqs_per_block = blockDim.x >> 4;
+  const int b_raw = blockIdx.x * seqs_per_block + g_in_block;
+  if (blockIdx.x * seqs_per_block + (g_in_block & ~1) >= B) return;   // whole warp out of range
   const bool seq_ok = b_raw < B;
   const int b = seq_ok ? b_raw : B - 1;   // an odd tail half shadows the last sentence and stores nothing
 
@@ -427,13 +432,13 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
   float s = 0.0f;
   int len = 0;
   for (int t = gl; t < S; t += LPS) {
-    const int y = (int)y_g[t];
+    const int y = gold_tag(y_g[t], T);
     const bool on = m_g ? (m_g[t] != 0) : true;
     if (t == 0) {
       s += start[y] + e_g[y];
       len += on;
     } else if (on) {
-      s += trans[(int)y_g[t - 1] * T + y] + e_g[t * T + y];
+      s += trans[gold_tag(y_g[t - 1], T) * T + y] + e_g[t * T + y];
       len += 1;
     }
   }
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_kernel(
     len += __shfl_xor_sync(gmask, len, off, LPS);
   }
   if (gl == 0) {
-    const int last = (int)y_g[max(len - 1, 0)];
+    const int last = gold_tag(y_g[max(len - 1, 0)], T);
     llh_out[b] = (s + end[last]) - logz;
   }
 }
@@ -498,7 +503,7 @@ __global__ void __launch_bounds__(kThreads) crf_llh_bwd_kernel(
       len += __popc(bits_m);
     }
     for (int i = gl; i < S * T; i += LPS) de_g[i] = 0.0f;
-    for (int t = gl; t < S; t += LPS) y_s[t] = (int)y_g[t];   // the sweeps below must not wait on HBM per step
+    for (int t = gl; t < S; t += LPS) y_s[t] = gold_tag(y_g[t], T);   // the sweeps below must not wait on HBM per step
     __syncwarp(gmask);
 
     float tr[LPS], trr[LPS];   // column gl and row gl of the transition matrix
@@ -649,8 +654,7 @@ __device__ __forceinline__ float group16_lse(float v, bool active) {   // over t
   return mx + fast_log(ex);
 }
 
-constexpr int kL16Threads = 128;
-constexpr int kL16Seqs = kL16Threads / 16;
+constexpr int kL16Threads = 128;   // maximum; long sequences launch fewer warps per block so the per-sentence slabs fit
 
 // shared memory per sentence (16-byte aligned pieces): alpha[S][16] | e[S*T] | on_idx[S] | y[S] | xch[2][16]
 __host__ __device__ inline size_t llh16_seq_bytes(int S, int T, bool with_alpha) {
@@ -677,11 +681,12 @@ __global__ void __launch_bounds__(kL16Threads) crf_llh16_kernel(
   const int gl = threadIdx.x & 15;
   const int gshift = threadIdx.x & 16;
   if (kBackward) {
-    for (int i = threadIdx.x; i < T * T + 2 * T; i += kL16Threads) s_dtrans[i] = 0.0f;
+    for (int i = threadIdx.x; i < T * T + 2 * T; i += blockDim.x) s_dtrans[i] = 0.0f;
     __syncthreads();
   }
-  const int b_raw = blockIdx.x * kL16Seqs + g_in_block;
-  const bool warp_ok = blockIdx.x * kL16Seqs + (g_in_block & ~1) < B;
+  const int seqs_per_block = blockDim.x >> 4;
+  const int b_raw = blockIdx.x * seqs_per_block + g_in_block;
+  const bool warp_ok = blockIdx.x * seqs_per_block + (g_in_block & ~1) < B;
   if (warp_ok) {
     const bool seq_ok = b_raw < B;
     const int b = seq_ok ? b_raw : B - 1;   // an odd tail half shadows the last sentence and stores nothing
@@ -696,7 +701,7 @@ __global__ void __launch_bounds__(kL16Threads) crf_llh16_kernel(
     const bool active = gl < T;
 
     stage_slab<16>(emissions + (size_t)b * S * T, e_s, S * T, gl);
-    for (int t = gl; t < S; t += 16) y_s[t] = (int)y_g[t];
+    for (int t = gl; t < S; t += 16) y_s[t] = gold_tag(y_g[t], T);
     // on-steps (t = 0 always counts, as in _compute_normalizer); len = sum(mask) as pytorch-crf counts it
     int n_on = 0, len = 0;
     for (int t0 = 0; t0 < S; t0 += 16) {
@@ -812,8 +817,8 @@ __global__ void __launch_bounds__(kL16Threads) crf_llh16_kernel(
   }
   if (kBackward) {
     __syncthreads();
-    for (int i = threadIdx.x; i < T * T; i += kL16Threads) atomicAdd(d_trans + i, s_dtrans[i]);
-    for (int i = threadIdx.x; i < T; i += kL16Threads) {
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) atomicAdd(d_trans + i, s_dtrans[i]);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
       atomicAdd(d_start + i, s_dstart[i]);
       atomicAdd(d_end + i, s_dend[i]);
     }
@@ -833,7 +838,10 @@ extern "C" int icka_viterbi_decode(icka_handle* h, const float* emissions, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int LPS = (T <= 16) ? 16 : 32;
   const size_t per_seq = seq_smem_bytes(S, T, LPS);
-  const int spb = kThreads / LPS;
+  int spb = kThreads / LPS;
+  // long sequences (S >~ 470 at T = 15): fewer sentences per block (whole warps: 2 sentences each) until the slabs fit
+  if (LPS == 16)
+    while (spb > 2 && per_seq * spb > h->smem_optin) spb >>= 1;
   const size_t smem = per_seq * spb;
   if (smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "viterbi: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T,
@@ -841,8 +849,8 @@ extern "C" int icka_viterbi_decode(icka_handle* h, const float* emissions, const
   const int grid = (B + spb - 1) / spb;
   if (LPS == 16) {
     ICKA_CUDA(cudaFuncSetAttribute(viterbi16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    viterbi16_kernel<<<grid, kV16Threads, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B, S,
-                                                      T, per_seq);
+    viterbi16_kernel<<<grid, spb * 16, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B, S,
+                                                   T, per_seq);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(viterbi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     viterbi_kernel<32><<<grid, kThreads, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B,
@@ -865,15 +873,17 @@ extern "C" int icka_crf_llh_fwd(icka_handle* h, const float* emissions, const in
   const int spb = kThreads / LPS;
   const int grid = (B + spb - 1) / spb;
   const size_t smem = ((((size_t)S * T + 3) / 4 * 4) * sizeof(float) + ((size_t)S + 15) / 16 * 16) * spb;
-  if (smem > h->smem_optin)
+  if (LPS != 16 && smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,
               h->smem_optin);
   if (LPS == 16) {
-    const size_t smem16 = llh16_seq_bytes(S, T, false) * kL16Seqs;
+    int seqs = kL16Threads / 16;
+    while (seqs > 2 && llh16_seq_bytes(S, T, false) * seqs > h->smem_optin) seqs >>= 1;
+    const size_t smem16 = llh16_seq_bytes(S, T, false) * seqs;
     if (smem16 > h->smem_optin)
       ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh: S=%d T=%d needs %zu B shared memory per block", S, T, smem16);
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-    crf_llh16_kernel<false><<<(B + kL16Seqs - 1) / kL16Seqs, kL16Threads, smem16, st>>>(
+    crf_llh16_kernel<false><<<(B + seqs - 1) / seqs, seqs * 16, smem16, st>>>(
         emissions, tags, mask, start, end, trans, nullptr, llh_out, nullptr, nullptr, nullptr, nullptr, B, S, T);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -901,16 +911,19 @@ extern "C" int icka_crf_llh_bwd(icka_handle* h, const float* emissions, const in
       ((size_t)S * LPS * sizeof(float) + 2 * (size_t)S * sizeof(int) + (((size_t)S * T + 3) / 4 * 4) * sizeof(float) + 15) /
       16 * 16;
   const size_t smem = head + per_seq * spb;
-  if (smem > h->smem_optin)
+  if (LPS != 16 && smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh_bwd: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T, smem,
               h->smem_optin);
   const int grid = (B + spb - 1) / spb;
   if (LPS == 16) {
-    const size_t smem16 = head + llh16_seq_bytes(S, T, true) * kL16Seqs;
+    // S = 256 (the hi-res shape) at 8 sentences per block needs ~271 KB: halve the sentences per block until it fits
+    int seqs = kL16Threads / 16;
+    while (seqs > 2 && head + llh16_seq_bytes(S, T, true) * seqs > h->smem_optin) seqs >>= 1;
+    const size_t smem16 = head + llh16_seq_bytes(S, T, true) * seqs;
     if (smem16 > h->smem_optin)
       ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "crf_llh_bwd: S=%d T=%d needs %zu B shared memory per block", S, T, smem16);
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
-    crf_llh16_kernel<true><<<(B + kL16Seqs - 1) / kL16Seqs, kL16Threads, smem16, st>>>(
+    crf_llh16_kernel<true><<<(B + seqs - 1) / seqs, seqs * 16, smem16, st>>>(
         emissions, tags, mask, start, end, trans, w, nullptr, d_emissions, d_start, d_end, d_trans, B, S, T);
   } else {
     ICKA_CUDA(cudaFuncSetAttribute(crf_llh_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -45,6 +45,7 @@ constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant; they split the column blocks
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kActRuntime = 100;   // template ACT value: relu / swish (config.hidden_act, CMIM:43) chosen by GemmArgs::act_rt
 
 // CTAS == 1: one CTA computes a 128 x BN tile.  CTAS == 2: a CTA pair (cluster of 2, tcgen05 cta_group::2)
 // computes a 256 x BN tile; each CTA stages its own 128 rows of A and HALF of the weight tile (BN/2 rows),
@@ -80,6 +81,7 @@ struct GemmArgs {
   const float* ln_beta;
   float ln_eps;
   __nv_bfloat16* out16;          // [M, N] bf16 copy of the normalised rows (pitch N) or null
+  int act_rt;                    // ACT == kActRuntime: ICKA_ACT_RELU or ICKA_ACT_SWISH
 };
 
 constexpr int kChunkBytes = kBK * 128;   // one 64-element-wide MN-major chunk of a stage: 64 contraction rows x 128 B
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmArgs args) {
   static_assert(!LNF || (MAJOR == 0 && CTAS == 1 && !OUT_BF16 && ACT == ICKA_ACT_NONE), "LNF: plain fp32 forward only");
+  static_assert(ACT != kActRuntime || MAJOR == 0, "runtime activations are forward-only");
   static_assert(MAJOR == 0 || CTAS == 1, "MN-major operands are built for single-CTA tiles only");
   static_assert(MAJOR != 2 || (!OUT_BF16 && ACT == ICKA_ACT_NONE), "wgrad accumulates plain fp32");
   using Cfg = GemmCfg<BN, CTAS>;
@@ -347,7 +350,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[i] = *reinterpret_cast<const float2*>(rd_base[i & 3] + i * 256);
         __syncwarp();   // staging tile may be rewritten (next column block) once every lane has read it
-        if (ACT == ICKA_ACT_GELU_ERF && args.aux_out != nullptr) {   // training: keep the pre-activation
+        if ((ACT == ICKA_ACT_GELU_ERF || ACT == kActRuntime) && args.aux_out != nullptr) {   // training: keep the pre-activation
           __nv_bfloat16* up = args.aux_out + row0 * args.ld_aux + col;
           const size_t ustep = (size_t)2 * args.ld_aux;
 #pragma unroll
@@ -370,6 +373,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             } else {
               x0 = gelu_erf(x0);
               x1 = gelu_erf(x1);
+            }
+          }
+          if (ACT == kActRuntime) {
+            if (args.act_rt == ICKA_ACT_RELU) {
+              x0 = act_relu(x0);
+              x1 = act_relu(x1);
+            } else if (OUT_BF16) {
+              x0 = act_swish_fast(x0);
+              x1 = act_swish_fast(x1);
+            } else {
+              x0 = act_swish(x0);
+              x1 = act_swish(x1);
             }
           }
           if (ACT == ICKA_ACT_TANH) {
@@ -621,8 +636,9 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
                "linear(bf16): A, W, out must be 16-byte aligned");
   ICKA_REQUIRE(N % 8 == 0 && ldo % 8 == 0, "linear(bf16): N=%d and ldo=%lld must be multiples of 8", N, (long long)ldo);
   ICKA_REQUIRE(!residual || icka_aligned(residual, 16), "linear(bf16): residual must be 16-byte aligned");
-  ICKA_REQUIRE(!aux_out || (act == ICKA_ACT_GELU_ERF && icka_aligned(aux_out, 16)),
-               "linear(bf16): aux_out needs act = gelu and 16-byte alignment");
+  const bool rt = act == ICKA_ACT_RELU || act == ICKA_ACT_SWISH;
+  ICKA_REQUIRE(!aux_out || ((act == ICKA_ACT_GELU_ERF || rt) && icka_aligned(aux_out, 16)),
+               "linear(bf16): aux_out needs an FFN activation (gelu / relu / swish) and 16-byte alignment");
   constexpr size_t kNeedSmem = GemmCfg<256, 1>::kSmemBytes;
   ICKA_REQUIRE(h->smem_optin >= kNeedSmem, "linear(bf16): device offers too little shared memory");
   const int BN = (N > 128) ? 256 : 128;
@@ -637,6 +653,7 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   if (rc) return rc;
   GemmArgs args{bias, residual, out, ldo, M, N, K, g_gemm_debug, nullptr, static_cast<__nv_bfloat16*>(aux_out),
                 (int64_t)N, 1, (K + kBK - 1) / kBK, 0};
+  args.act_rt = act;
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
   if (act == ICKA_ACT_TANH) {   // prompt mapping networks (CMIM:914-930): M = batch, single-CTA tiles
@@ -650,7 +667,7 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   // Skinny problems (the single-query encoders: M = batch, N = 768, K = 3072 / 9216) have only a few dozen output
   // tiles for 148 SMs: split the contraction over CTAs into per-split slabs of the handle's workspace, then add the
   // slabs in split order (+ bias, residual) with a small reduce pass -- bit-reproducible, unlike atomics.
-  if (!bf && !gelu && !pair && ldo == N) {
+  if (!bf && !gelu && !rt && !pair && ldo == N) {
     const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
     const int num_kb = (K + kBK - 1) / kBK;
     int splits = h->sm_count / tiles;
@@ -675,6 +692,11 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
     }
   }
 #define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_, 0>(h, ta, tb, args, st)
+  if (rt) {   // non-default config.hidden_act
+    if (pair)           { if (bf) ICKA_GEMM(256, kActRuntime, true, 2); else ICKA_GEMM(256, kActRuntime, false, 2); }
+    else if (BN == 256) { if (bf) ICKA_GEMM(256, kActRuntime, true, 1); else ICKA_GEMM(256, kActRuntime, false, 1); }
+    else                { if (bf) ICKA_GEMM(128, kActRuntime, true, 1); else ICKA_GEMM(128, kActRuntime, false, 1); }
+  }
   if (pair) {
     if (gelu) { if (bf) ICKA_GEMM(256, ICKA_ACT_GELU_ERF, true, 2); else ICKA_GEMM(256, ICKA_ACT_GELU_ERF, false, 2); }
     else      { if (bf) ICKA_GEMM(256, ICKA_ACT_NONE, true, 2);     else ICKA_GEMM(256, ICKA_ACT_NONE, false, 2); }

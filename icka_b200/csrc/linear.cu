@@ -50,8 +50,10 @@ extern "C" int icka_linear_fwd_ex(icka_handle* h, const void* A, int64_t lda, co
   ICKA_REQUIRE(lda >= K && ldw >= K && ldo >= N, "linear: pitches smaller than the logical extents");
   ICKA_REQUIRE(in_dtype == ICKA_F32 || in_dtype == ICKA_BF16, "linear: bad in_dtype %d", in_dtype);
   ICKA_REQUIRE(out_dtype == ICKA_F32 || out_dtype == ICKA_BF16, "linear: bad out_dtype %d", out_dtype);
-  ICKA_REQUIRE(act == ICKA_ACT_NONE || act == ICKA_ACT_GELU_ERF || act == ICKA_ACT_TANH, "linear: bad activation %d", act);
-  ICKA_REQUIRE(!pre_act_out || act == ICKA_ACT_GELU_ERF, "linear: pre_act_out is only defined for the GELU layer");
+  ICKA_REQUIRE(act == ICKA_ACT_NONE || act == ICKA_ACT_GELU_ERF || act == ICKA_ACT_TANH || act == ICKA_ACT_RELU ||
+                   act == ICKA_ACT_SWISH, "linear: bad activation %d", act);
+  ICKA_REQUIRE(!pre_act_out || act == ICKA_ACT_GELU_ERF || act == ICKA_ACT_RELU || act == ICKA_ACT_SWISH,
+               "linear: pre_act_out is only defined for the FFN activations (gelu / relu / swish)");
   if (M == 0) return ICKA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (in_dtype == ICKA_BF16)

@@ -89,9 +89,11 @@ __global__ void __launch_bounds__(kThreads) sgemm_tn_kernel(
         if (n >= N) continue;
         float v = acc[i][jh * 4 + j];
         if (bias) v += bias[n];
-        if (ACT == ICKA_ACT_GELU_ERF && pre_act_out) pre_act_out[(size_t)m * N + n] = v;
+        if (ACT != ICKA_ACT_NONE && ACT != ICKA_ACT_TANH && pre_act_out) pre_act_out[(size_t)m * N + n] = v;
         if (ACT == ICKA_ACT_GELU_ERF) v = gelu_erf(v);
         if (ACT == ICKA_ACT_TANH) v = tanhf(v);
+        if (ACT == ICKA_ACT_RELU) v = act_relu(v);
+        if (ACT == ICKA_ACT_SWISH) v = act_swish(v);
         if (residual) v += residual[(size_t)m * N + n];
         if (OUT_BF16)
           static_cast<__nv_bfloat16*>(out)[(size_t)m * ldo + n] = __float2bfloat16_rn(v);
@@ -180,6 +182,10 @@ int icka_sgemm_launch(icka_handle* h, const float* A, int64_t lda, const float* 
     if (bf) ICKA_SGEMM(ICKA_ACT_TANH, true); else ICKA_SGEMM(ICKA_ACT_TANH, false);
   } else if (act == ICKA_ACT_GELU_ERF) {
     if (bf) ICKA_SGEMM(ICKA_ACT_GELU_ERF, true); else ICKA_SGEMM(ICKA_ACT_GELU_ERF, false);
+  } else if (act == ICKA_ACT_RELU) {
+    if (bf) ICKA_SGEMM(ICKA_ACT_RELU, true); else ICKA_SGEMM(ICKA_ACT_RELU, false);
+  } else if (act == ICKA_ACT_SWISH) {
+    if (bf) ICKA_SGEMM(ICKA_ACT_SWISH, true); else ICKA_SGEMM(ICKA_ACT_SWISH, false);
   } else {
     if (bf) ICKA_SGEMM(ICKA_ACT_NONE, true); else ICKA_SGEMM(ICKA_ACT_NONE, false);
   }

@@ -1,7 +1,8 @@
 """Top-level drop-in: ``MTCCMBertForMMTokenClassificationCRF`` (Cross_Modal_Interaction_Module.py:886-1057).
 
 Same constructor ``(config, embedding, last_encoder, layer_num1=1, layer_num2=1, layer_num3=1, num_labels=2)`` and the
-same 19-argument ``forward`` with ``mode`` in {'dev', 'test'} (returns ``(pred_tags, loss)`` / ``pred_tags``).  The two
+same 19-argument ``forward`` with ``mode`` in {'train', 'dev', 'test'} (returns ``loss`` / ``(pred_tags, loss)`` /
+``pred_tags``, CMIM:1046-1057).  The two
 transformer encoders are the caller's own torch modules (``embedding`` = ``self.bert``, ``last_encoder``; outside the
 hot path); everything between them and the tag lists runs on libicka_b200.so:
 
@@ -16,8 +17,9 @@ Parameter names are the reference's (``vismap2text.*``, ``txt2img_attention.*``,
 ``lastproj.*``), so ``model.load_state_dict(torch.load(path)['net'], False)`` (My_cross_attention.py:997-998) works.  The
 members the reference constructs but never uses (``self_attention``, ``self_attention_v2``, ``embedding_layer``,
 ``LayerNorm``; CMIM:894-895, 903, 935) are not created -- their checkpoint keys are ignored by the non-strict load.
-``mode='train'`` is refused: the prompt mapping networks have no autograd nodes yet (the fusion stack, the BiLSTM +
-classifier and the CRF do).
+``mode='train'`` (the reference's main call, My_cross_attention.py:814-817) builds the autograd graph out of the
+kernel-backed nodes of ``icka_b200.autograd`` (cross layers, dense layers of the prompt networks, gate + blend, BiLSTM with
+BPTT, classifier, CRF log-likelihood); gradients flow through the caller's two encoders by ordinary PyTorch autograd.
 """
 from __future__ import annotations
 
@@ -64,10 +66,12 @@ class MTCCMBertForMMTokenClassificationCRF(CrossModalFusion):
     def forward(self, input_ids, segment_ids, input_mask, ori_input_ids, ori_input_mask, ori_segment_ids,
                 added_attention_mask, clip_features, visual_embeds_mean, visual_embeds_att, offsets, output_mask,
                 rela_score, temp=None, temp_lamb=None, lamb=None, labels=None, negative_rate=None, mode=None):
-        if mode not in ('dev', 'test'):
-            raise NotImplementedError("icka_b200.MTCCMBertForMMTokenClassificationCRF runs mode='dev' and mode='test'; "
-                                      "mode='train' needs autograd through the prompt mapping networks, which is not built yet")
-        with torch.no_grad():
+        if mode not in ('train', 'dev', 'test'):
+            return None             # the reference's if / elif chain falls through (CMIM:1046-1057)
+        from .precision import precision
+        # 'train' records the autograd graph (when autograd is enabled); 'dev' / 'test' never do (the reference wraps them
+        # in torch.no_grad(), My_cross_attention.py:870, :1045)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and mode == 'train'), precision(self.precision):
             offset = offsets.tolist()[0]                                                        # CMIM:948
             sequence_output = self.bert(ori_input_ids, token_type_ids=ori_segment_ids,
                                         attention_mask=ori_input_mask)[0].float()               # CMIM:949-950
@@ -83,6 +87,8 @@ class MTCCMBertForMMTokenClassificationCRF(CrossModalFusion):
             result = self.blend(cross_output_layer, token_embedding)                            # CMIM:1029-1036
             emissions = self._head(result)                                                      # CMIM:1042-1043
             output_mask = (output_mask != 0)                                                    # CMIM:1045
+            if mode == 'train':
+                return -self.crf(emissions, tags=labels, mask=output_mask, reduction='token_mean')   # CMIM:1047-1048
             pred_tags = self.crf.decode(emissions, mask=output_mask)                            # CMIM:1051 / 1056
             if mode == 'test':
                 return pred_tags

@@ -21,10 +21,13 @@ sequence of C-ABI kernel launches (icka_b200.ops).  Two precision modes (``set_p
 
 Training: when autograd is recording (``torch.is_grad_enabled()``), ``BertCrossAttentionLayer``,
 ``BertCrossEncoder``, ``CrossModalFusion`` and ``CRF.forward`` build their graph out of the nodes in
-``icka_b200.autograd`` (kernel-backed forward and backward); the small building blocks below them
-(``BertSelfOutput`` ... called on their own) stay forward-only.  Dropout (attention probabilities CMIM:616,
-dense outputs CMIM:563 / 534) is applied on that recording path when the module is in training mode: a
-per-call seed expands into Philox keep-masks inside the kernels and backward regenerates them.
+``icka_b200.autograd`` (kernel-backed forward and backward): one fused ``CrossLayerFn`` node per cross layer; the small
+building blocks below them (``BertLayerNorm``, ``BertSelfOutput``, ``BertIntermediate``, ``BertOutput``,
+``BertCoAttention``, ``BertCrossAttention``, ``cls_layer_both`` called on their own) compose the generic nodes
+(``DenseActFn``, ``LayerNormFn``, ``AttnCoreFn``, ``DropoutFn``), so a stack assembled from them trains with the same
+gradients.  Dropout (attention probabilities CMIM:616, dense outputs CMIM:563 / 534) is applied on the recording path when
+the module is in training mode: a per-call seed expands into Philox keep-masks inside the kernels and backward
+regenerates them.  The precision mode is never mutated inside a forward (``icka_b200.precision``).
 """
 from __future__ import annotations
 
@@ -35,28 +38,18 @@ import torch
 from torch import nn
 
 from . import ops
-from ._lib import ACT_GELU_ERF, ACT_NONE
-from .autograd import CrossLayerFn, DenseFn, GateBlendFn
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_RELU, ACT_SWISH
+from .autograd import (AddFn, AttnCoreFn, CastFn, CrossLayerFn, DenseActFn, DenseFn, DropoutFn, GateBlendFn,
+                       LayerNormFn)
+from .precision import compute_dtype, get_precision, precision, set_precision  # noqa: F401  (re-exported)
 
-_PRECISION = 'bf16'
 _FUSE_LN = False     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
                      # B200 the second (normalising) pass re-reads rows that have left L2 and is latency-bound:
                      # 511 us fused vs 227 + 152 us unfused at B=1024, so it stays off
 
 
-def set_precision(mode: str) -> None:
-    global _PRECISION
-    if mode not in ('bf16', 'fp32'):
-        raise ValueError(f"precision must be 'bf16' or 'fp32', got {mode!r}")
-    _PRECISION = mode
-
-
-def get_precision() -> str:
-    return _PRECISION
-
-
 def _cdt() -> torch.dtype:
-    return torch.bfloat16 if _PRECISION == 'bf16' else torch.float32
+    return compute_dtype()
 
 
 class _OperandCache:
@@ -66,7 +59,7 @@ class _OperandCache:
         self._store = {}
 
     def get(self, key: str, params, build):
-        sig = (_PRECISION,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        sig = (get_precision(),) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         hit = self._store.get(key)
         if hit is None or hit[0] != sig:
             with torch.no_grad():
@@ -76,13 +69,13 @@ class _OperandCache:
 
 
 def _operand(cache: _OperandCache, key: str, w: torch.Tensor) -> torch.Tensor:
-    if _PRECISION == 'fp32':
+    if get_precision() == 'fp32':
         return w.detach()
     return cache.get(key, (w,), lambda: ops.cast_bf16(w.detach().contiguous()))
 
 
 def _to_lp(x32: torch.Tensor) -> torch.Tensor:
-    return ops.cast_bf16(x32) if _PRECISION == 'bf16' else x32
+    return ops.cast_bf16(x32) if get_precision() == 'bf16' else x32
 
 
 def _widen(x: torch.Tensor) -> torch.Tensor:
@@ -103,7 +96,7 @@ def _rows(x: torch.Tensor) -> torch.Tensor:
 def _rows_and_operand(x: torch.Tensor):
     """[B, S, H] -> (fp32 residual rows, GEMM operand rows in the compute dtype).  States that arrive in bf16 on the
     bf16 path (the caller's encoders ran in bf16) ARE the operand: no rounding pass, only the exact widening."""
-    if (_PRECISION == 'bf16' and x.dtype == torch.bfloat16 and x.is_cuda
+    if (get_precision() == 'bf16' and x.dtype == torch.bfloat16 and x.is_cuda
             and not (torch.is_grad_enabled() and x.requires_grad)):
         x_lp = x.contiguous().view(-1, x.shape[-1])
         return ops.cast_f32(x_lp), x_lp
@@ -120,14 +113,21 @@ def _mask2d(mask: Optional[torch.Tensor], B: int, Skv: int) -> Optional[torch.Te
     return mask.reshape(B, Skv).float().contiguous()
 
 
-def _check_inference(module: nn.Module, *ps: float, graph_capable: bool = False) -> None:
-    """Dropout (CMIM:616, 563, 534) lives in the autograd-recording path only (Philox masks regenerated in backward).
-    A module in training mode with p > 0 must therefore be one of the graph-capable ones (cross layer / encoder /
-    CrossModalFusion) called with autograd enabled; the small forward-only blocks refuse instead of silently
-    skipping dropout."""
+def _check_inference(module: nn.Module, *ps: float, graph_capable: bool = True) -> None:
+    """Dropout (CMIM:616, 563, 534) lives in the autograd-recording path only (Philox masks regenerated in backward): a
+    module in training mode with p > 0 called with autograd disabled refuses instead of silently skipping dropout."""
     if module.training and any(p > 0 for p in ps) and not (graph_capable and torch.is_grad_enabled()):
-        raise NotImplementedError('dropout is applied on the autograd-recording path of BertCrossAttentionLayer / '
-                                  'BertCrossEncoder / CrossModalFusion only: call .eval() for forward-only use')
+        raise NotImplementedError('dropout is applied on the autograd-recording path only: call .eval() for '
+                                  'forward-only use (or leave autograd enabled in training mode)')
+
+
+def _seed() -> int:
+    """One host-side draw per call (torch's CPU generator: reproducible under torch.manual_seed); the kernels expand it
+    into per-element Philox masks and backward regenerates them from the same number."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+_ACT_CODES = {'gelu': ACT_GELU_ERF, 'relu': ACT_RELU, 'swish': ACT_SWISH}
 
 
 def _recording(*tensors, module: Optional[nn.Module] = None) -> bool:
@@ -150,6 +150,8 @@ class BertLayerNorm(nn.Module):
 
     def forward(self, x):
         shape = x.shape
+        if _recording(x, module=self):
+            return LayerNormFn.apply(_rows(x), self.weight, self.bias, self.variance_epsilon).view(shape)
         y, _ = ops.layernorm(_rows(x), self.weight.detach(), self.bias.detach(), self.variance_epsilon)
         return y.view(shape)
 
@@ -173,14 +175,24 @@ class _DenseResidualNorm(nn.Module):
             # per 128-row block leaves most SMs idle, so skinny problems keep the split-K GEMM + row kernel
             return ops.linear_ln(h_lp, w, self.dense.bias.detach(), res32, self.LayerNorm.weight.detach(),
                                  self.LayerNorm.bias.detach(), self.LayerNorm.variance_epsilon,
-                                 want_bf16=_PRECISION == 'bf16')
+                                 want_bf16=get_precision() == 'bf16')
         pre = ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32)
         return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
-                             self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=_PRECISION == 'bf16')
+                             self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=get_precision() == 'bf16')
 
     def forward(self, hidden_states, input_tensor):
         _check_inference(self, self.dropout.p)
         shape = input_tensor.shape
+        if _recording(hidden_states, input_tensor, module=self):
+            bf = get_precision() == 'bf16'
+            ln = self.LayerNorm
+            if self.training and self.dropout.p > 0:      # LN(dropout(dense(h)) + input), CMIM:562-565 / 533-536
+                dense = DenseActFn.apply(_rows(hidden_states), self.dense.weight, self.dense.bias, None, ACT_NONE, bf)
+                pre = AddFn.apply(DropoutFn.apply(dense, self.dropout.p, _seed()), _rows(input_tensor))
+            else:
+                pre = DenseActFn.apply(_rows(hidden_states), self.dense.weight, self.dense.bias, _rows(input_tensor),
+                                       ACT_NONE, bf)
+            return LayerNormFn.apply(pre, ln.weight, ln.bias, ln.variance_epsilon).view(shape)
         y32, _ = self._run(_to_lp(_rows(hidden_states)), _rows(input_tensor))
         return y32.view(shape)
 
@@ -196,21 +208,31 @@ class BertOutput(_DenseResidualNorm):
 
 
 class BertIntermediate(nn.Module):
-    """CMIM:539-551; only the reference's default activation 'gelu' (erf form, CMIM:31-37) is built."""
+    """CMIM:539-551.  ``config.hidden_act`` names an entry of the reference's ACT2FN table (CMIM:43): 'gelu' (erf form,
+    CMIM:31-37, the default), 'relu' or 'swish' (CMIM:38-39) -- each fused into the GEMM epilogue.  The reference also
+    accepts a callable there (CMIM:543-546); an arbitrary Python function cannot be fused into a kernel, so only the
+    three table entries (by name) are accepted."""
 
     def __init__(self, config):
         super().__init__()
         self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
-        if config.hidden_act != 'gelu':
-            raise NotImplementedError(f"hidden_act={config.hidden_act!r}: only 'gelu' (erf) is implemented")
+        if not isinstance(config.hidden_act, str):
+            raise NotImplementedError('hidden_act must name an ACT2FN entry (gelu / relu / swish): a callable cannot be '
+                                      'fused into the GEMM epilogue')
+        if config.hidden_act not in _ACT_CODES:
+            raise KeyError(config.hidden_act)           # ACT2FN[config.hidden_act] raises the same (CMIM:544)
+        self.act = _ACT_CODES[config.hidden_act]
         self._cache = _OperandCache()
 
     def _run(self, x_lp: torch.Tensor) -> torch.Tensor:
         w = _operand(self._cache, 'w', self.dense.weight)
-        return ops.linear(x_lp, w, self.dense.bias.detach(), act=ACT_GELU_ERF, out_dtype=_cdt())
+        return ops.linear(x_lp, w, self.dense.bias.detach(), act=self.act, out_dtype=_cdt())
 
     def forward(self, hidden_states):
         shape = hidden_states.shape[:-1]
+        if _recording(hidden_states, module=self):
+            return DenseActFn.apply(_rows(hidden_states), self.dense.weight, self.dense.bias, None, self.act,
+                                    get_precision() == 'bf16').view(*shape, -1)
         return self._run(_to_lp(_rows(hidden_states))).float().view(*shape, -1)
 
 
@@ -239,7 +261,7 @@ class BertCoAttention(nn.Module):
         def build():
             w = torch.cat([self.key.weight.detach(), self.value.weight.detach()], dim=0).contiguous()
             b = torch.cat([self.key.bias.detach(), self.value.bias.detach()], dim=0).contiguous()
-            return (ops.cast_bf16(w) if _PRECISION == 'bf16' else w), b
+            return (ops.cast_bf16(w) if get_precision() == 'bf16' else w), b
 
         return self._cache.get('kv', ps, build)
 
@@ -256,8 +278,18 @@ class BertCoAttention(nn.Module):
         _check_inference(self, self.dropout.p)
         B, Sq, H = s1_hidden_states.shape
         Skv = s2_hidden_states.shape[1]
-        ctx = self._run(_to_lp(_rows(s1_hidden_states)), _to_lp(_rows(s2_hidden_states)),
-                        _mask2d(s2_attention_mask, B, Skv), B, Sq, Skv)
+        mask2d = _mask2d(s2_attention_mask, B, Skv)
+        if _recording(s1_hidden_states, s2_hidden_states, module=self):
+            bf = get_precision() == 'bf16'
+            q32 = DenseActFn.apply(_rows(s1_hidden_states), self.query.weight, self.query.bias, None, ACT_NONE, bf)
+            kv32 = DenseActFn.apply(_rows(s2_hidden_states), torch.cat([self.key.weight, self.value.weight], dim=0),
+                                    torch.cat([self.key.bias, self.value.bias], dim=0), None, ACT_NONE, bf)
+            p = self.dropout.p if self.training else 0.0
+            ctx = AttnCoreFn.apply(CastFn.apply(q32, bf), CastFn.apply(kv32, bf), mask2d,
+                                   (B, Sq, Skv, self.num_attention_heads, self.attention_head_size), float(p),
+                                   _seed() if p > 0 else 0)
+            return ctx.float().view(B, Sq, H)
+        ctx = self._run(_to_lp(_rows(s1_hidden_states)), _to_lp(_rows(s2_hidden_states)), mask2d, B, Sq, Skv)
         return ctx.float().view(B, Sq, H)
 
 
@@ -279,7 +311,7 @@ class BertCrossAttention(nn.Module):
     # -- single-query fold (image->text encoders, CMIM:984-989) ------------------------
     def _can_fold(self) -> bool:
         att = self.self
-        return (_PRECISION == 'bf16' and att.attention_head_size == 64 and att.num_attention_heads <= 16
+        return (get_precision() == 'bf16' and att.attention_head_size == 64 and att.num_attention_heads <= 16
                 and att.all_head_size in (768, 1024))
 
     def _folded_operands(self):
@@ -326,6 +358,8 @@ class BertCrossAttention(nn.Module):
         _check_inference(self, self.self.dropout.p, self.output.dropout.p)
         B, Sq, H = s1_input_tensor.shape
         Skv = s2_input_tensor.shape[1]
+        if _recording(s1_input_tensor, s2_input_tensor, module=self):      # CMIM:633-636, node by node
+            return self.output(self.self(s1_input_tensor, s2_input_tensor, s2_attention_mask), s1_input_tensor)
         x32 = _rows(s1_input_tensor)
         y32, _ = self._run(x32, _to_lp(x32), _to_lp(_rows(s2_input_tensor)), _mask2d(s2_attention_mask, B, Skv),
                            B, Sq, Skv)
@@ -361,11 +395,9 @@ class BertCrossAttentionLayer(nn.Module):
         p_hid = so.dropout.p if self.training else 0.0
         if self.training and so.dropout.p != out.dropout.p:
             raise RuntimeError('the two hidden dropouts of a cross layer must share hidden_dropout_prob')
-        # one host-side draw per call (torch's CPU generator: reproducible under torch.manual_seed); the kernels expand
-        # it into per-element Philox masks and backward regenerates them from the same number
-        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if (p_attn > 0 or p_hid > 0) else 0
+        seed = _seed() if (p_attn > 0 or p_hid > 0) else 0
         meta = (B, Sq, Skv, att.num_attention_heads, att.attention_head_size, so.LayerNorm.variance_epsilon,
-                float(p_attn), float(p_hid), seed)
+                float(p_attn), float(p_hid), seed, self.intermediate.act)
         o32, o16 = CrossLayerFn.apply(
             x32, y32, x_lp.detach(), y_lp.detach(), mask2d, meta,
             att.query.weight, att.query.bias, att.key.weight, att.key.bias, att.value.weight, att.value.bias,
@@ -431,26 +463,30 @@ class cls_layer_both(nn.Module):  # noqa: N801  (reference class name, CMIM:873)
         self.proj = nn.Linear(input_dim, output_dim)
 
     def forward(self, lang_feat, img_feat):
-        saved = get_precision()
-        set_precision('fp32')          # a [B, H] x [H, H] product: run it on the fp32 kernel
-        try:
-            x = (lang_feat + img_feat).float().contiguous()
-            n, _ = ops.layernorm(x, self.proj_norm.weight.detach(), self.proj_norm.bias.detach(), self.proj_norm.eps)
-            return ops.linear(n, self.proj.weight.detach(), self.proj.bias.detach())
-        finally:
-            set_precision(saved)
+        # a [B, H] x [H, H] product: always on the fp32 kernels (ops dispatch on the operand dtype; no mode switch)
+        ln = self.proj_norm
+        a, b = _widen(lang_feat).contiguous(), _widen(img_feat).contiguous()
+        shape = a.shape[:-1]
+        a, b = a.view(-1, a.shape[-1]), b.view(-1, b.shape[-1])
+        if _recording(lang_feat, img_feat, module=self):
+            n = LayerNormFn.apply(AddFn.apply(a, b), ln.weight, ln.bias, ln.eps)
+            return DenseActFn.apply(n, self.proj.weight, self.proj.bias, None, ACT_NONE, False).view(*shape, -1)
+        n, _ = ops.layernorm(ops.add_f32(a, b), ln.weight.detach(), ln.bias.detach(), ln.eps)
+        return ops.linear(n, self.proj.weight.detach(), self.proj.bias.detach()).view(*shape, -1)
 
 
 class CrossModalFusion(nn.Module):
     """Hot-path slice of MTCCMBertForMMTokenClassificationCRF (CMIM:887-1057).
 
     Constructor mirrors the reference's use of ``config`` and ``layer_num1`` (CMIM:888-901, 933-934);
-    ``num_i2t_encoders`` is 2 in the live model and 5 in the ``_bert`` clone (CMIM:1075).
+    ``num_i2t_encoders`` is 2 in the live model and 5 in the ``_bert`` clone (CMIM:1075).  ``precision``: None = follow
+    ``icka_b200.get_precision()``, or 'bf16' / 'fp32' for this module's forwards (thread-safe, see icka_b200.precision).
     """
 
-    def __init__(self, config, layer_num1=1, region_dim=2048, clip_dim=512, num_i2t_encoders=2):
+    def __init__(self, config, layer_num1=1, region_dim=2048, clip_dim=512, num_i2t_encoders=2, precision=None):
         super().__init__()
         self.hidden_size = config.hidden_size
+        self.precision = precision
         self.vismap2text = nn.Linear(region_dim, config.hidden_size)                 # CMIM:897
         self.vismapping = nn.Linear(clip_dim, config.hidden_size)                    # CMIM:899
         self.txt2img_attention = BertCrossEncoder(config, layer_num1)                # CMIM:900
@@ -460,38 +496,71 @@ class CrossModalFusion(nn.Module):
         self.aux_head = nn.Linear(config.hidden_size, 1)                             # CMIM:934
         self._cache = _OperandCache()
 
+    # ---- pieces shared by forward / encode / blend ----------------------------------------------------------------
+    def _check_layers(self):
+        for enc in (self.txt2img_attention, *self.cls_layer_Y):
+            for l in enc.layer:
+                _check_inference(l, *l._dropouts(), graph_capable=True)
+
+    def _region_operand(self, visual_embeds_att, B):
+        """-> (rows [B*R, C] in the compute dtype, R): the K-major operand of the region projection (CMIM:956).  Region
+        rows [B, R, C] straight from the producer tail (icka_b200.myResnet.forward_rows) need no relayout."""
+        if visual_embeds_att.dim() == 3 and visual_embeds_att.shape[-1] == self.vismap2text.in_features:
+            R = visual_embeds_att.shape[1]
+            rows = visual_embeds_att.detach().contiguous().view(B * R, -1)
+            if rows.dtype != _cdt():
+                rows = _to_lp(rows.float()) if get_precision() == 'bf16' else rows.float()
+            return rows, R
+        grid = _widen(visual_embeds_att.detach()).contiguous()
+        R = grid.numel() // (B * grid.shape[1])
+        return ops.region_rows(grid, _cdt()), R
+
+    def _regions(self, rows, rec):
+        """Region projection, CMIM:956-958 (the ResNet grid carries no gradient: My_cross_attention.py:804-805)
+        -> (regions32 | None, regions operand)."""
+        w_vm2t = _operand(self._cache, 'vm2t', self.vismap2text.weight)
+        if rec:
+            regions32 = DenseFn.apply(rows, self.vismap2text.weight, self.vismap2text.bias, w_vm2t)
+            return regions32, _to_lp(regions32.detach())
+        return None, ops.linear(rows, w_vm2t, self.vismap2text.bias.detach(), out_dtype=_cdt())
+
+    def _image_to_text(self, clip_features, fused32, fused_lp, txt_mask, B, S, rec):
+        """CMIM:954, 981-989: the single CLIP token queries the fused text states through every encoder of
+        ``cls_layer_Y`` -> z32 [B, H]."""
+        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
+        w_vmap = _operand(self._cache, 'vmap', self.vismapping.weight)
+        if rec:
+            z32 = DenseFn.apply(clip_in, self.vismapping.weight, self.vismapping.bias, w_vmap)
+        else:
+            z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
+        z_lp = _to_lp(z32.detach())
+        for enc in self.cls_layer_Y:
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None)
+            z32 = zs[-1]
+        return z32
+
+    def _gate_fold(self):
+        gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight, self.aux_head.bias)
+        return self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
+            self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
+            self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
+
     def forward(self, sequence_output, visual_embeds_att, clip_features, token_embedding, added_attention_mask,
                 ori_input_mask, return_dict=False, want_fused=True):
         """sequence_output [B,S,H] (CMIM:953), visual_embeds_att [B,2048,g,g] (or region rows [B,R,2048]), clip_features [B,1,512],
         token_embedding [B,S,H] (CMIM:1024), added_attention_mask [B,>=R], ori_input_mask [B,S].
         Returns (result [B,S,H], clip_features [B,1,H]) -- CMIM:1036 and the loop result of CMIM:984-989."""
-        for enc in (self.txt2img_attention, *self.cls_layer_Y):
-            for l in enc.layer:
-                _check_inference(l, *l._dropouts(), graph_capable=True)
-        B, S, H = sequence_output.shape
-        # region rows [B, R, C] straight from the producer tail (icka_b200.myResnet.forward_rows): no relayout needed
-        rows_given = visual_embeds_att.dim() == 3 and visual_embeds_att.shape[-1] == self.vismap2text.in_features
-        if rows_given:
-            R = visual_embeds_att.shape[1]
-        else:
-            grid = _widen(visual_embeds_att).contiguous()
-            R = grid.numel() // (B * grid.shape[1])
+        with precision(self.precision):
+            return self._forward(sequence_output, visual_embeds_att, clip_features, token_embedding,
+                                 added_attention_mask, ori_input_mask, return_dict, want_fused)
 
+    def _forward(self, sequence_output, visual_embeds_att, clip_features, token_embedding, added_attention_mask,
+                 ori_input_mask, return_dict, want_fused):
+        self._check_layers()
+        B, S, H = sequence_output.shape
         rec = _recording(sequence_output, token_embedding, module=self)
-        # region projection, CMIM:956-958 (the ResNet grid carries no gradient: My_cross_attention.py:804-805)
-        if rows_given:
-            rows = visual_embeds_att.contiguous().view(B * R, -1)
-            if rows.dtype != _cdt():
-                rows = _to_lp(rows.float()) if _PRECISION == 'bf16' else rows.float()
-        else:
-            rows = ops.region_rows(grid, _cdt())
-        w_vm2t = _operand(self._cache, 'vm2t', self.vismap2text.weight)
-        if rec:
-            regions32 = DenseFn.apply(rows, self.vismap2text.weight, self.vismap2text.bias, w_vm2t)
-            regions_lp = _to_lp(regions32.detach())
-        else:
-            regions32 = None
-            regions_lp = ops.linear(rows, w_vm2t, self.vismap2text.bias.detach(), out_dtype=_cdt())
+        rows, R = self._region_operand(visual_embeds_att, B)
+        regions32, regions_lp = self._regions(rows, rec)
         # masks, CMIM:962-965 and 976-982
         img_mask = ops.mask_additive(added_attention_mask, R)
         txt_mask = ops.mask_additive(ori_input_mask, S)
@@ -510,12 +579,8 @@ class CrossModalFusion(nn.Module):
             outs, _ = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R, keep_all=False,
                                                   defer_last_ln=True)
             ln2 = self.txt2img_attention.layer[-1].output.LayerNorm
-            gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight,
-                           self.aux_head.bias)
-            w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
-                self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
-                self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
-            bf = _PRECISION == 'bf16'
+            w_fold, c_fold = self._gate_fold()
+            bf = get_precision() == 'bf16'
             result, gate, fused32, fused16 = ops.ln_gate_blend(
                 outs[-1].view(B, S, H), ln2.weight.detach(), ln2.bias.detach(), ln2.variance_epsilon, tok32,
                 ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold,
@@ -523,16 +588,7 @@ class CrossModalFusion(nn.Module):
             fused_lp = fused16 if bf else fused32.view(B * S, H)
 
         # image -> text, CMIM:954, 981-989 (single CLIP token as the query)
-        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
-        w_vmap = _operand(self._cache, 'vmap', self.vismapping.weight)
-        if rec:
-            z32 = DenseFn.apply(clip_in, self.vismapping.weight, self.vismapping.bias, w_vmap)
-        else:
-            z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
-        z_lp = _to_lp(z32.detach())
-        for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None)
-            z32 = zs[-1]
+        z32 = self._image_to_text(clip_features, fused32, fused_lp, txt_mask, B, S, rec)
 
         # gated fusion, CMIM:1029-1036 (recording pass; the inference pass did it above)
         if rec:
@@ -546,48 +602,40 @@ class CrossModalFusion(nn.Module):
             return out
         return result, z32.view(B, 1, H)
 
-    # ---- the same segment in the two phases the full model needs (inference) -------------------------------------
+    # ---- the same segment in the two phases the full model needs --------------------------------------------------
     # In MTCCMBertForMMTokenClassificationCRF.forward the gate's second operand, `token_embedding`, comes out of the
     # RoBERTa `last_encoder`, which is fed prompts computed FROM the image->text result (CMIM:995-1024): the encoders
-    # (CMIM:954-989) and the gate + blend (CMIM:1029-1036) cannot be one call there.
-    @torch.no_grad()
+    # (CMIM:954-989) and the gate + blend (CMIM:1029-1036) cannot be one call there.  Both phases build the autograd
+    # graph when autograd is recording (mode='train', CMIM:1046-1048) and run the plain kernels otherwise.
     def encode(self, sequence_output, visual_embeds_att, clip_features, added_attention_mask, ori_input_mask):
         """CMIM:954-989 -> (cross_output_layer [B,S,H] fp32, clip_features [B,1,H] fp32)."""
-        B, S, H = sequence_output.shape
-        rows_given = visual_embeds_att.dim() == 3 and visual_embeds_att.shape[-1] == self.vismap2text.in_features
-        if rows_given:
-            R = visual_embeds_att.shape[1]
-            rows = visual_embeds_att.contiguous().view(B * R, -1)
-            if rows.dtype != _cdt():
-                rows = _to_lp(rows.float()) if _PRECISION == 'bf16' else rows.float()
-        else:
-            grid = _widen(visual_embeds_att).contiguous()
-            R = grid.numel() // (B * grid.shape[1])
-            rows = ops.region_rows(grid, _cdt())
-        regions_lp = ops.linear(rows, _operand(self._cache, 'vm2t', self.vismap2text.weight),
-                                self.vismap2text.bias.detach(), out_dtype=_cdt())
-        img_mask = ops.mask_additive(added_attention_mask, R)
-        txt_mask = ops.mask_additive(ori_input_mask, S)
-        x32, x_lp = _rows_and_operand(sequence_output)
-        outs, fused_lp = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R, keep_all=False)
-        fused32 = outs[-1]
-        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
-        z32 = ops.linear(clip_in, _operand(self._cache, 'vmap', self.vismapping.weight), self.vismapping.bias.detach(),
-                         out_dtype=torch.float32)
-        z_lp = _to_lp(z32)
-        for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False)
-            z32 = zs[-1]
-        return fused32.view(B, S, H), z32.view(B, 1, H)
+        with precision(self.precision):
+            self._check_layers()
+            B, S, H = sequence_output.shape
+            rec = _recording(sequence_output, module=self)
+            with torch.set_grad_enabled(rec):
+                rows, R = self._region_operand(visual_embeds_att, B)
+                regions32, regions_lp = self._regions(rows, rec)
+                img_mask = ops.mask_additive(added_attention_mask, R)
+                txt_mask = ops.mask_additive(ori_input_mask, S)
+                x32, x_lp = _rows_and_operand(sequence_output)
+                outs, fused_lp = self.txt2img_attention._run(x32, x_lp, regions_lp, img_mask, B, S, R, keep_all=False,
+                                                             y32=regions32)
+                fused32 = outs[-1]
+                z32 = self._image_to_text(clip_features, fused32, fused_lp, txt_mask, B, S, rec)
+            return fused32.view(B, S, H), z32.view(B, 1, H)
 
-    @torch.no_grad()
     def blend(self, cross_output_layer, token_embedding):
         """CMIM:1029-1036 -> result [B,S,H] fp32 = g * token_embedding + (1 - g) * cross_output_layer."""
-        ln = self.cls_layer.proj_norm
-        gate_params = (self.cls_layer.proj.weight, self.cls_layer.proj.bias, self.aux_head.weight, self.aux_head.bias)
-        w_fold, c_fold = self._cache.get('gate_fold', gate_params, lambda: ops.gate_fold(
-            self.cls_layer.proj.weight.detach(), self.cls_layer.proj.bias.detach(),
-            self.aux_head.weight.detach().view(-1), self.aux_head.bias.detach()))
-        result, _ = ops.gate_blend(_widen(cross_output_layer).contiguous(), _widen(token_embedding).contiguous(),
-                                   ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold)
-        return result
+        with precision(self.precision):
+            ln = self.cls_layer.proj_norm
+            if _recording(cross_output_layer, token_embedding, module=self):
+                result, _ = GateBlendFn.apply(_widen(cross_output_layer).contiguous(), _widen(token_embedding).contiguous(),
+                                              ln.weight, ln.bias, self.cls_layer.proj.weight, self.cls_layer.proj.bias,
+                                              self.aux_head.weight, self.aux_head.bias, ln.eps)
+                return result
+            with torch.no_grad():
+                w_fold, c_fold = self._gate_fold()
+                result, _ = ops.gate_blend(_widen(cross_output_layer).contiguous(), _widen(token_embedding).contiguous(),
+                                           ln.weight.detach(), ln.bias.detach(), ln.eps, w_fold, c_fold)
+            return result

@@ -200,6 +200,20 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] 
     return out
 
 
+def act_bwd(dy: torch.Tensor, ref: torch.Tensor, act: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = dy * act'(ref) element-wise; ref = pre-activation (gelu / relu / swish) or the output (tanh).  ``out`` may be dy."""
+    if dy.dtype not in _DT or ref.dtype != dy.dtype or dy.shape != ref.shape or not dy.is_contiguous() or not ref.is_contiguous():
+        raise RuntimeError('act_bwd: dy / ref must be contiguous tensors of one shape and dtype (fp32 or bf16)')
+    if out is None:
+        out = torch.empty_like(dy)
+    elif out.dtype != dy.dtype or out.shape != dy.shape or not out.is_contiguous():
+        raise RuntimeError('act_bwd: bad `out`')
+    lib, h, st = _ctx(dy)
+    _lib.check(lib.icka_act_bwd(h, dy.data_ptr(), ref.data_ptr(), out.data_ptr(), _DT[dy.dtype], dy.numel(), int(act), st),
+               'icka_act_bwd')
+    return out
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     """Column sums of a 2-D fp32/bf16 view -> fp32 [N] (bias gradient)."""
     if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:

@@ -18,7 +18,8 @@ from . import _lib, synth
 from .config import FusionConfig
 from .crf import CRF
 from .emission import EmissionHead
-from .modules import CrossModalFusion, set_precision
+from .modules import CrossModalFusion
+from .precision import precision as precision_ctx
 
 FUSION_KEYS = ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask', 'text_mask')
 CRF_KEYS = ('emissions', 'crf_mask')
@@ -44,7 +45,10 @@ class FusionViterbiPipeline:
     @torch.no_grad()
     def step_device(self, d: Dict[str, torch.Tensor]):
         """One pass of the hot path over a device-resident batch; returns (result, clip, tags, lens, gate)."""
-        set_precision(self.precision)
+        with precision_ctx(self.precision):
+            return self._step_device(d)
+
+    def _step_device(self, d: Dict[str, torch.Tensor]):
         if not self.overlap_decode:
             tags, lens = self.crf.decode_tensors(d['emissions'], d['crf_mask'])
             out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
@@ -202,7 +206,10 @@ class TaggingPipeline(FusionViterbiPipeline):
     @torch.no_grad()
     def step_tagging(self, d: Dict[str, torch.Tensor], label_ids: Optional[torch.Tensor] = None):
         """-> (emissions [B,S,T] fp32, tags [B,S] int32, lens [B] int32); updates ``self.f1`` when labels are given."""
-        set_precision(self.precision)
+        with precision_ctx(self.precision):
+            return self._step_tagging(d, label_ids)
+
+    def _step_tagging(self, d: Dict[str, torch.Tensor], label_ids: Optional[torch.Tensor] = None):
         out = self.fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
                           d['img_mask'], d['text_mask'], return_dict=True, want_fused=False)
         emissions = self.head(out['result'])

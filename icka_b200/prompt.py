@@ -5,8 +5,11 @@ image->text encoders and the gate of ``MTCCMBertForMMTokenClassificationCRF``:
     Alignment_prompt, prefix_vision, prefix_emb (cat + lastproj), prompt_mask               CMIM:995-1009
 
 ``PromptMapping`` keeps the reference's attribute names and ``nn.Sequential`` indices, so the checkpoint keys
-(``mapping_network_alignment.1.weight`` ... ``lastproj.bias``) load unchanged.  Inference only (the two Dropout(0.3)
-layers are the identity in eval mode; a module left in training mode raises instead of silently skipping them).
+(``mapping_network_alignment.1.weight`` ... ``lastproj.bias``) load unchanged.  When autograd is recording (mode='train',
+CMIM:1046-1048) the same five layers are ``autograd.DenseActFn`` nodes (tcgen05 forward, dgrad and wgrad GEMMs; tanh'
+through ``icka_act_bwd``) and the Dropout(0.3) layers (CMIM:915, :918, :923, :926) are Philox ``DropoutFn`` nodes whose
+masks backward regenerates; a module in training mode called with autograd disabled raises instead of silently skipping
+the dropout.
 
 Five tensor-core GEMMs (``icka_linear_fwd``), the Tanh fused into the epilogue of the first layer of each network
 (ICKA_ACT_TANH).  756 * 5 = 3780 is not a multiple of 8 (16-byte bf16 rows for TMA): the bf16 operand copies are
@@ -22,7 +25,8 @@ from torch import nn
 
 from . import modules, ops
 from ._lib import ACT_NONE, ACT_TANH
-from .modules import _OperandCache
+from .autograd import DenseActFn, DropoutFn
+from .modules import _OperandCache, _seed
 
 
 def _pad8(n: int) -> int:
@@ -65,8 +69,13 @@ class PromptMapping(nn.Module):
                 input_mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """clip_features [B,1,H] or [B,H], visual_embeds_mean [B,vision_dim], input_mask [B,L]
         -> (prefix_emb [B, 2*prompt_len, out_dim] fp32, prompt_mask [B, 2*prompt_len])."""
+        rec = torch.is_grad_enabled() and (clip_features.requires_grad or visual_embeds_mean.requires_grad
+                                           or any(p.requires_grad for p in self.parameters()))
+        if rec:
+            return self._forward_recorded(clip_features, visual_embeds_mean, input_mask)
         if self.training:
-            raise NotImplementedError('PromptMapping is inference-only (Dropout(0.3) of CMIM:915, 918): call .eval()')
+            raise NotImplementedError('PromptMapping in training mode (Dropout(0.3) of CMIM:915, 918) runs on the '
+                                      'autograd-recording path only: call .eval() for forward-only use')
         B, H, P = clip_features.shape[0], self.hidden_size, self.prompt_len
         lp = modules.get_precision() == 'bf16'
         cdt = torch.bfloat16 if lp else torch.float32
@@ -90,6 +99,40 @@ class PromptMapping(nn.Module):
             prefix = prefix.view(B, 2 * P, self.out_dim)
         else:
             prefix = prefix.float().view(B, 2 * P, H)
+        return prefix, self._prompt_mask(input_mask)
+
+    def _prompt_mask(self, input_mask: torch.Tensor) -> torch.Tensor:
         first = input_mask[:, :1]
-        prompt_mask = torch.cat([first.repeat(1, P), first.repeat(1, P)], dim=1)      # CMIM:1007-1009
-        return prefix, prompt_mask
+        return torch.cat([first.repeat(1, self.prompt_len), first.repeat(1, self.prompt_len)], dim=1)   # CMIM:1007-1009
+
+    def _forward_recorded(self, clip_features, visual_embeds_mean, input_mask):
+        """Training pass (autograd recording).  bf16: the hidden width 3780 is zero-padded to 3840 -- the backward GEMMs read
+        both operands MN-major in 64-element chunks; tanh(0) = 0 meets zero weight columns, so the padding is exact and its
+        gradient rows are sliced away by autograd's view of the pad."""
+        B, H, P = clip_features.shape[0], self.hidden_size, self.prompt_len
+        bf = modules.get_precision() == 'bf16'
+        pad = torch.nn.functional.pad
+
+        def run(x, net):
+            l1, l2 = net[1], net[4]
+            p1, p2 = (net[0].p, net[3].p) if self.training else (0.0, 0.0)
+            x32 = x.reshape(B, -1).float().contiguous()
+            if p1 > 0:
+                x32 = DropoutFn.apply(x32, p1, _seed())
+            inner = l1.out_features
+            extra = ((inner + 63) // 64 * 64 - inner) if bf else 0
+            w1 = pad(l1.weight, (0, 0, 0, extra)) if extra else l1.weight
+            b1 = pad(l1.bias, (0, extra)) if extra else l1.bias
+            w2 = pad(l2.weight, (0, extra)) if extra else l2.weight
+            hidden = DenseActFn.apply(x32, w1, b1, None, ACT_TANH, bf)
+            if p2 > 0:
+                hidden = DropoutFn.apply(hidden, p2, _seed())
+            return DenseActFn.apply(hidden, w2, l2.bias, None, ACT_NONE, bf)
+
+        prefix_vision = run(visual_embeds_mean, self.mapping_network_vision).view(B, P, H)          # CMIM:998-999
+        alignment = run(clip_features, self.mapping_network_alignment).view(B, P, H)                 # CMIM:995
+        prefix = torch.cat([prefix_vision, alignment], dim=1)                                        # CMIM:1002
+        if H != 1024:                                                                                # CMIM:1003-1004
+            prefix = DenseActFn.apply(prefix.reshape(B * 2 * P, H), self.lastproj.weight, self.lastproj.bias, None,
+                                      ACT_NONE, bf).view(B, 2 * P, self.out_dim)
+        return prefix, self._prompt_mask(input_mask)

@@ -5,6 +5,7 @@ the only distributed logic: shard bounds, and gathering ragged per-rank tag list
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List, Sequence, Tuple
 
 import torch
@@ -85,6 +86,12 @@ class GradientAllReducer:
     transfers and averages over the ranks -- ranks hold equal shards, so this is the global-batch mean the
     reference's DDP produces; ``p.grad`` becomes a view of its bucket (no unpack copy, like DDP's
     ``gradient_as_bucket_view``).
+
+    Gradient accumulation (the reference's ``--gradient_accumulation_steps``, My_cross_attention.py:821-831): run every
+    micro-batch but the last under ``with reducer.no_sync():`` -- their ``backward()`` only accumulates into ``p.grad``,
+    nothing is counted or sent -- and the last one normally; its hooks see the ACCUMULATED gradients, so the buckets
+    carry the sum.  A second ``backward()`` outside ``no_sync()`` before ``finish()`` would accumulate into a buffer an
+    asynchronous all-reduce is still reading: it raises instead.
     """
 
     def __init__(self, params, bucket_bytes: int = 25 << 20, group=None):
@@ -114,6 +121,16 @@ class GradientAllReducer:
                 self._where[id(p)] = b
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.launched_early = 0      # buckets whose all-reduce started from inside backward (diagnostics)
+        self._sync = True
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Micro-batches whose gradients are only accumulated locally (all but the last of an accumulation window)."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
 
     def remove_hooks(self) -> None:
         for h in self._handles:
@@ -122,7 +139,13 @@ class GradientAllReducer:
 
     # -- internals -------------------------------------------------------------------------------------
     def _on_grad(self, p: torch.Tensor) -> None:
+        if not self._sync:
+            return
         b = self._where[id(p)]
+        if b.pending <= 0 or b.work is not None:
+            raise RuntimeError('GradientAllReducer: a gradient arrived for a bucket that was already handed to the '
+                               'all-reduce -- a second backward() before finish(); wrap all micro-batches but the last '
+                               'in `with reducer.no_sync():`')
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
             self._launch(b)

@@ -41,7 +41,9 @@ enum icka_act {
   ICKA_ACT_NONE = 0,
   ICKA_ACT_GELU_ERF = 1,     /* CMIM:31-37 */
   ICKA_ACT_GELU_ERF_BWD = 2, /* internal: multiply by gelu'(pre-activation) (backward of CMIM:550) */
-  ICKA_ACT_TANH = 3          /* torch.nn.Tanh of the prompt mapping networks, CMIM:917, :925 */
+  ICKA_ACT_TANH = 3,         /* torch.nn.Tanh of the prompt mapping networks, CMIM:917, :925 */
+  ICKA_ACT_RELU = 4,         /* ACT2FN["relu"], CMIM:43 (config.hidden_act) */
+  ICKA_ACT_SWISH = 5         /* ACT2FN["swish"] = x * sigmoid(x), CMIM:38-39, :43 */
 };
 
 int icka_version(void);
@@ -114,6 +116,12 @@ int icka_linear_dgrad(icka_handle* h, const void* dY, int64_t ldd, const void* W
  * bf16 path: N % 64 == 0 and K % 64 == 0; token range split over CTAs, partial sums added with red.global. */
 int icka_linear_wgrad(icka_handle* h, const void* dY, int64_t ldd, const void* X, int64_t ldx, float* dW,
                       int in_dtype, int M, int N, int K, int accumulate, void* stream);
+
+/* Backward of an element-wise activation (autograd of CMIM:550 with config.hidden_act != 'gelu' -- ACT2FN, CMIM:43 -- and
+ * of the torch.nn.Tanh of the prompt mapping networks, CMIM:917, :925):  dx[i] = dy[i] * act'(ref[i]), all three tensors
+ * in `dtype`.  ref is the PRE-activation for ICKA_ACT_GELU_ERF / _RELU / _SWISH and the activation's OUTPUT for
+ * ICKA_ACT_TANH (1 - y^2).  dx may alias dy. */
+int icka_act_bwd(icka_handle* h, const void* dy, const void* ref, void* dx, int dtype, int64_t n, int act, void* stream);
 
 /* Column sums of x[M,N] (pitch ld, fp32 or bf16) -> out[N] fp32: the bias gradient of a dense layer. */
 int icka_colsum(icka_handle* h, const void* x, int64_t ld, int dtype, float* out, int M, int N, int accumulate,

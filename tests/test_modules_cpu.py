@@ -48,14 +48,55 @@ def test_hidden_size_not_multiple_of_heads():
 
 
 def test_dropout_needs_the_recording_path():
-    """Training mode with p > 0: the graph-capable modules apply dropout only when autograd records (the masks are
-    regenerated in backward); forward-only use and the small forward-only blocks refuse rather than skip it."""
+    """Training mode with p > 0: dropout is applied only when autograd records (the masks are regenerated in backward);
+    forward-only use refuses rather than skip it."""
     enc = icka_b200.BertCrossEncoder(cfg(), 1).train()
     with torch.no_grad(), pytest.raises(NotImplementedError):
         enc(torch.zeros(1, 4, 128), torch.zeros(1, 3, 128), torch.zeros(1, 1, 1, 3))
     so = icka_b200.BertSelfOutput(cfg()).train()
-    with pytest.raises(NotImplementedError):
+    with torch.no_grad(), pytest.raises(NotImplementedError):
         so(torch.zeros(1, 4, 128), torch.zeros(1, 4, 128))
+    pm = icka_b200.PromptMapping(cfg()).train()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        pm(torch.zeros(1, 1, 128), torch.zeros(1, 2048), torch.ones(1, 8, dtype=torch.long))
+
+
+def test_hidden_act_follows_act2fn():
+    """config.hidden_act names an ACT2FN entry (CMIM:43); an unknown name is the reference's KeyError (CMIM:544)."""
+    for name in ('gelu', 'relu', 'swish'):
+        c = cfg()
+        c.hidden_act = name
+        icka_b200.BertIntermediate(c)
+    c = cfg()
+    c.hidden_act = 'mish'
+    with pytest.raises(KeyError):
+        icka_b200.BertIntermediate(c)
+
+
+def test_precision_override_is_thread_local():
+    import threading
+    icka_b200.set_precision('bf16')
+    seen = []
+    with icka_b200.precision('fp32'):
+        assert icka_b200.get_precision() == 'fp32'
+        t = threading.Thread(target=lambda: seen.append(icka_b200.get_precision()))
+        t.start()
+        t.join()
+        with icka_b200.precision(None):
+            assert icka_b200.get_precision() == 'fp32'
+    assert seen == ['bf16'] and icka_b200.get_precision() == 'bf16'
+    with pytest.raises(ValueError):
+        icka_b200.precision('fp8')
+
+
+def test_crf_tag_range_is_an_index_error():
+    crf = icka_b200.CRF(4, batch_first=True)
+    e = torch.zeros(2, 3, 4)
+    for bad in (-100, 4):
+        tags = torch.zeros(2, 3, dtype=torch.long)
+        tags[1, 2] = bad
+        with pytest.raises(IndexError):
+            crf(e, tags)
 
 
 def test_precision_switch():

@@ -131,3 +131,59 @@ def test_two_rank_gradient_allreduce_matches_full_batch():
     assert n_buckets >= 3                                   # 1 KiB buckets split this model
     assert early >= 2 * (n_buckets - 1)                     # all but the unused-parameter bucket start inside backward
     assert extra_grad is not None and float(abs(extra_grad).max()) == 0.0
+
+
+# ---- gradient accumulation: several backward() calls per finish() (My_cross_attention.py:821-831) ---------------------
+def _accum_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model = _make_model()
+        reducer = shard.GradientAllReducer(list(model.parameters()), bucket_bytes=1024)
+        g = torch.Generator().manual_seed(13)
+        x, y = torch.randn(12, 12, generator=g), torch.randn(12, 3, generator=g)
+        mine = shard.shard_batch({'x': x, 'y': y}, world, rank)        # 6 rows per rank = 2 micro-batches of 3
+        grads = []
+        for step in range(2):                                           # second window: p.grad are bucket views by then
+            model.zero_grad(set_to_none=(step == 0))                    # both zero_grad flavours
+            micro = [(mine['x'][i:i + 3], mine['y'][i:i + 3]) for i in (0, 3)]
+            with reducer.no_sync():
+                (((model(micro[0][0]) - micro[0][1]) ** 2).mean() / 2).backward()
+            (((model(micro[1][0]) - micro[1][1]) ** 2).mean() / 2).backward()
+            reducer.finish()
+            grads.append([p.grad.clone().numpy() for p in model.parameters()])
+        # a second synchronising backward() before finish() must raise, not race
+        raised = False
+        model.zero_grad(set_to_none=True)
+        ((model(mine['x']) - mine['y']) ** 2).mean().backward()
+        try:
+            ((model(mine['x']) - mine['y']) ** 2).mean().backward()
+        except RuntimeError as e:
+            raised = 'no_sync' in str(e)
+        reducer.finish()
+        if rank == 0:
+            q.put((grads, raised))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_accumulation_matches_full_batch():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_accum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads, raised = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = _make_model()
+    g = torch.Generator().manual_seed(13)
+    x, y = torch.randn(12, 12, generator=g), torch.randn(12, 3, generator=g)
+    ((model(x) - y) ** 2).mean().backward()        # equal micro-batches: mean of means == full-batch mean
+    for step in range(2):
+        for got, p in zip(grads[step], model.parameters()):
+            assert torch.allclose(torch.from_numpy(got), p.grad, rtol=1e-5, atol=1e-6)
+    assert raised
