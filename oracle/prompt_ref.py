@@ -38,14 +38,22 @@ def make_params(H: int = 768, vision_dim: int = 2048, seed: int = 0, prompt_len:
 
 
 def prompt_prefix(clip_features: torch.Tensor, visual_embeds_mean: torch.Tensor, input_mask: torch.Tensor,
-                  p: Dict[str, torch.Tensor], prompt_len: int = PROMPT_LEN):
+                  p: Dict[str, torch.Tensor], prompt_len: int = PROMPT_LEN, drop=None):
     """clip_features [B,1,H] (output of the image->text encoders), visual_embeds_mean [B,2048], input_mask [B,L]
-    -> (prefix_emb [B, 2*prompt_len, 1024], prompt_mask [B, 2*prompt_len])."""
+    -> (prefix_emb [B, 2*prompt_len, 1024], prompt_mask [B, 2*prompt_len]).
+    ``drop`` (training mode, CMIM:915, :918, :923, :926): dict(p=0.3, masks={'<network>.0': keep [B,in], '<network>.3':
+    keep [B,inner]}) -- 0/1 keep masks applied as nn.Dropout would (x * keep / (1 - p)), so a test can replay the masks
+    the CUDA kernels drew."""
     B = clip_features.shape[0]
 
+    def dropped(x, key):
+        if drop is None:
+            return x
+        return x * drop['masks'][key].to(x.dtype).view(x.shape) / (1.0 - drop['p'])
+
     def mlp(x, name):
-        h = torch.tanh(x @ p[f'{name}.1.weight'].t() + p[f'{name}.1.bias'])
-        return h @ p[f'{name}.4.weight'].t() + p[f'{name}.4.bias']
+        h = torch.tanh(dropped(x, f'{name}.0') @ p[f'{name}.1.weight'].t() + p[f'{name}.1.bias'])
+        return dropped(h, f'{name}.3') @ p[f'{name}.4.weight'].t() + p[f'{name}.4.bias']
 
     alignment = mlp(clip_features, 'mapping_network_alignment').unsqueeze(1).view(B, prompt_len, -1)   # CMIM:995
     vision = mlp(visual_embeds_mean, 'mapping_network_vision').reshape(B, prompt_len, -1)               # CMIM:998-999

@@ -42,12 +42,12 @@ def load():
 
 
 def build_reference_modules(params, *, hidden, heads, inter, num_layers, layer_norm_eps,
-                            num_i2t_encoders=2):
+                            num_i2t_encoders=2, hidden_act='gelu'):
     """Instantiate the reference's classes and load ``params`` (reference key names) into them."""
     import torch
     cmim = load()
     cfg = cmim.BertConfig(30522, hidden_size=hidden, num_hidden_layers=12, num_attention_heads=heads,
-                          intermediate_size=inter, hidden_dropout_prob=0.0,
+                          intermediate_size=inter, hidden_act=hidden_act, hidden_dropout_prob=0.0,
                           attention_probs_dropout_prob=0.0, layer_norm_eps=layer_norm_eps)
     mods = torch.nn.ModuleDict({
         'vismap2text': torch.nn.Linear(params['vismap2text.weight'].shape[1], hidden),   # CMIM:897

@@ -126,3 +126,68 @@ def test_viterbi_forbidden_cells(value, T):
     crf, cp = make_crf(T, 13, 'normal')
     got = crf.decode(e.to(DEV), batch['mask'].to(DEV))
     assert got == oracle_c(e, batch['mask'], cp)
+
+
+# ---- long sequences: fewer sentences per block so the per-sentence shared-memory slabs fit -----------
+@pytest.mark.parametrize('S', [256, 600, 900])
+def test_viterbi_long_sequences(S):
+    """S = 256 is the hi-res shape (BASELINE configs[3]); from S ~ 470 the 8-sentence layout no longer fits 227 KB."""
+    sh = synth.Shape(S=S, T=15)
+    batch = synth.crf_batch(37, sh, seed=S, kind='ties', median_len=S * 0.6)
+    crf, cp = make_crf(15, 41, 'normal')
+    got = crf.decode(batch['emissions'].to(DEV), batch['mask'].to(DEV))
+    assert got == oracle_c(batch['emissions'], batch['mask'], cp)
+
+
+@pytest.mark.parametrize('S', [256, 400])
+def test_crf_llh_forward_and_backward_long_sequences(S):
+    """The CRF loss of the hi-res training shape (S = 256, `bench.py --mode train --hires`): the backward kept alpha[S][16]
+    for 8 sentences per block (271 KB) and was refused; now 4 (or 2) sentences per block."""
+    sh = synth.Shape(S=S, T=15)
+    batch = synth.crf_batch(21, sh, seed=S + 1, median_len=S * 0.5)
+    crf, cp = make_crf(15, 43, 'uniform')
+    e = batch['emissions'].to(DEV).requires_grad_(True)
+    loss = -crf(e, batch['tags'].to(DEV), batch['mask'].to(DEV), reduction='token_mean')
+    loss.backward()
+    ed = batch['emissions'].double().requires_grad_(True)
+    pd = {k: v.double().requires_grad_(True) for k, v in cp.items()}
+    want = -crf_ref.log_likelihood(ed, batch['tags'], batch['mask'], pd['start_transitions'], pd['end_transitions'],
+                                   pd['transitions'], 'token_mean')
+    want.backward()
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    assert float((e.grad.cpu().double() - ed.grad).abs().max()) <= 1e-6
+    for name, p in crf.named_parameters():
+        assert float((p.grad.cpu().double() - pd[name].grad).abs().max()) <= 2e-5, name
+
+
+def test_crf_tags_outside_the_label_range_raise_index_error():
+    """pytorch-crf indexes its parameter tensors with every tag id: -100 (ignore-index padding) or T is an IndexError."""
+    sh = synth.Shape(S=12, T=15)
+    batch = synth.crf_batch(4, sh, seed=3)
+    crf, _ = make_crf(15, 5, 'uniform')
+    for bad in (-100, 15):
+        tags = batch['tags'].clone()
+        tags[2, 11] = bad                     # a masked (padding) position counts too
+        with pytest.raises(IndexError):
+            crf(batch['emissions'].to(DEV), tags.to(DEV), batch['mask'].to(DEV))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_entry_points_run_on_the_tensor_device_not_the_current_one():
+    """Tensors on cuda:1 while cuda:0 is the current device (one nn.DataParallel worker thread per GPU,
+    My_cross_attention.py:777-779): every C entry point sets the handle's device for the call and restores it."""
+    sh = synth.STD
+    batch = synth.crf_batch(64, sh, seed=5, kind='ties')
+    cp = synth.crf_params(sh.T, 6, 'normal')
+    crf = icka_b200.CRF(sh.T, batch_first=True).to('cuda:1')
+    crf.load_state_dict(cp)
+    assert torch.cuda.current_device() == 0
+    got = crf.decode(batch['emissions'].to('cuda:1'), batch['mask'].to('cuda:1'))
+    assert torch.cuda.current_device() == 0
+    assert got == oracle_c(batch['emissions'], batch['mask'], cp)
+    from icka_b200 import ops
+    a = torch.randn(256, 768, device='cuda:1').bfloat16()
+    w = torch.randn(768, 768, device='cuda:1').bfloat16()
+    out = ops.linear(a, w, None, out_dtype=torch.float32)          # tcgen05 path: cudaFuncSetAttribute + TMA descriptors
+    torch.cuda.synchronize('cuda:1')
+    assert float((out.double() - a.double() @ w.double().t()).abs().max()) <= 1e-3

@@ -13,7 +13,7 @@ import torch
 
 import icka_b200
 from oracle import fusion_ref
-from oracle.make_golden import CASES, build_case
+from oracle.make_golden import CASES, build_case, case_extras
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -28,34 +28,33 @@ def rel(a, b):
 
 def run_ours(name, precision):
     B, shape, params, inp, stride = build_case(name)
+    extras = case_extras(name)
     cfg = icka_b200.FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads,
-                                 intermediate_size=shape.inter, layer_norm_eps=shape.eps)
-    model = icka_b200.CrossModalFusion(cfg, layer_num1=shape.L, region_dim=shape.region_dim,
-                                       clip_dim=shape.clip_dim).to(DEV).eval()
+                                 intermediate_size=shape.inter, layer_norm_eps=shape.eps,
+                                 hidden_act=extras.get('hidden_act', 'gelu'))
+    model = icka_b200.CrossModalFusion(cfg, layer_num1=shape.L, region_dim=shape.region_dim, clip_dim=shape.clip_dim,
+                                       num_i2t_encoders=extras.get('num_i2t_encoders', 2), precision=precision).to(DEV).eval()
     model.load_state_dict(params, strict=True)
-    icka_b200.set_precision(precision)
-    try:
-        with torch.no_grad():
-            out = model(inp['text_states'].to(DEV), inp['visual_embeds_att'].to(DEV), inp['clip_features'].to(DEV),
-                        inp['token_embedding'].to(DEV), inp['img_mask'].to(DEV), inp['text_mask'].to(DEV),
-                        return_dict=True)
-        torch.cuda.synchronize()
-    finally:
-        icka_b200.set_precision('bf16')
+    with torch.no_grad():
+        out = model(inp['text_states'].to(DEV), inp['visual_embeds_att'].to(DEV), inp['clip_features'].to(DEV),
+                    inp['token_embedding'].to(DEV), inp['img_mask'].to(DEV), inp['text_mask'].to(DEV),
+                    return_dict=True)
+    torch.cuda.synchronize()
     out = {k: v.float().cpu() for k, v in out.items()}
     return B, shape, params, inp, stride, out
 
 
-def oracle(shape, params, inp):
+def oracle(shape, params, inp, name=None):
     return fusion_ref.fusion_segment(inp['text_states'], inp['visual_embeds_att'], inp['clip_features'],
                                      inp['token_embedding'], inp['img_mask'], inp['text_mask'], params,
-                                     num_layers=shape.L, num_heads=shape.heads, layer_norm_eps=shape.eps)
+                                     num_layers=shape.L, num_heads=shape.heads, layer_norm_eps=shape.eps,
+                                     **(case_extras(name) if name else {}))
 
 
 @pytest.mark.parametrize('name', GPU_CASES)
 def test_fusion_fp32_parity(name):
     B, shape, params, inp, stride, out = run_ours(name, 'fp32')
-    want = oracle(shape, params, inp)
+    want = oracle(shape, params, inp, name)
     for k in ('regions', 'fused', 'clip', 'result', 'gate'):
         assert rel(out[k].reshape(want[k].shape), want[k]) <= 1e-5, k
     g = np.load(os.path.join(GOLDEN, f'fusion_{name}.npz'))

@@ -115,5 +115,79 @@ def test_full_model_dev_and_test_modes():
     want_loss = -crf_ref.log_likelihood(em.cpu(), labels, mask, cp['start_transitions'], cp['end_transitions'],
                                             cp['transitions'], reduction='token_mean')
     assert abs(float(loss) - float(want_loss)) <= 1e-4 * max(1.0, abs(float(want_loss)))
-    with pytest.raises(NotImplementedError):
-        model(*args, labels=dev(labels), mode='train')
+    assert model(*args, labels=dev(labels), mode='predict') is None          # the reference's if/elif chain falls through
+
+
+def test_full_model_train_mode_loss_and_gradients():
+    """mode='train' (the reference's main call, My_cross_attention.py:814-817; CMIM:1046-1048): the loss and the gradient
+    of EVERY parameter -- fusion stack, prompt networks, gate, BiLSTM, classifier, CRF and, through ordinary autograd, the
+    caller's two encoders -- against autograd through the fp64 oracle chain.  fp32 kernels, dropout off (p = 0 / eval)."""
+    icka_b200.set_precision('fp32')
+    torch.manual_seed(11)
+    B = 2
+    shape = synth.Shape(L=1)
+    cfg = icka_b200.FusionConfig(hidden_size=H, num_attention_heads=12, intermediate_size=3072, hidden_dropout_prob=0.0,
+                                 attention_probs_dropout_prob=0.0)
+    model = icka_b200.MTCCMBertForMMTokenClassificationCRF(cfg, StubEmbedding(), StubLastEncoder(), 1, 1, 1, num_labels=T)
+    model = model.eval()                                   # Dropout(0.3) of the prompt networks off; autograd stays on
+    inp = synth.fusion_inputs(B, shape, seed=12)
+    crf_b = synth.crf_batch(B, shape, seed=12)
+    g = torch.Generator().manual_seed(13)
+    input_ids = torch.randint(0, 50, (B, L), generator=g)
+    ori_input_ids = torch.randint(0, 50, (B, S), generator=g)
+    input_mask = torch.ones(B, L, dtype=torch.long)
+    segment_ids = torch.zeros(B, L, dtype=torch.long)
+    ori_segment_ids = torch.zeros(B, S, dtype=torch.long)
+    vmean = inp['visual_embeds_att'].mean(3).mean(2)
+    offsets = torch.full((B,), OFFSET, dtype=torch.long)
+    output_mask, labels = crf_b['mask'].long(), crf_b['tags']
+
+    # ---- fp64 oracle chain with autograd, parameters under the model's own state_dict names
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    ln = lambda x: nn.functional.layer_norm(x, (H,))
+    seq = ln(sd['bert.emb.weight'][ori_input_ids])
+    fparams = {k: v for k, v in sd.items() if k.split('.')[0] in ('vismap2text', 'vismapping', 'txt2img_attention',
+                                                                  'cls_layer_Y', 'cls_layer', 'aux_head')}
+    grid64, clip64 = inp['visual_embeds_att'].double(), inp['clip_features'].double()
+    seg = lambda tok: fusion_ref.fusion_segment(seq, grid64, clip64, tok, inp['img_mask'], inp['text_mask'], fparams,
+                                                num_layers=1, num_heads=12, layer_norm_eps=cfg.layer_norm_eps)
+    first = seg(torch.zeros(B, S, H, dtype=torch.float64))
+    pparams = {k: v for k, v in sd.items() if k.split('.')[0] in ('mapping_network_alignment', 'mapping_network_vision',
+                                                                  'lastproj')}
+    prefix, pmask = prompt_ref.prompt_prefix(first['clip'], vmean.double(), input_mask, pparams)
+    e = sd['last_encoder.emb.weight'][input_ids]
+    pr = prefix @ sd['last_encoder.proj.weight'].t() + sd['last_encoder.proj.bias']
+    enc = ln(torch.cat([e[:, :OFFSET], pr, e[:, OFFSET + 2:]], dim=1) + 0.05 * pr.mean(dim=1, keepdim=True))
+    off = OFFSET - 2 + prefix.size(1)
+    result = fusion_ref.gate_blend(first['fused'], enc[:, off:off + 128, :], fparams)[0]
+    lp = {k[5:]: v for k, v in sd.items() if k.startswith('lstm.')}
+    em = lstm_ref.emission_head(result, lp, sd['classifier.weight'], sd['classifier.bias'])
+    want_loss = -crf_ref.log_likelihood(em, labels, crf_b['mask'].bool(), sd['crf.start_transitions'],
+                                        sd['crf.end_transitions'], sd['crf.transitions'], reduction='token_mean')
+    want_loss.backward()
+
+    # ---- the drop-in on the GPU
+    model = model.cuda()
+    dev = lambda t: t.cuda()
+    args = [dev(input_ids), dev(segment_ids), dev(input_mask), dev(ori_input_ids), dev(inp['text_mask']), dev(ori_segment_ids),
+            dev(inp['img_mask']), dev(inp['clip_features']), dev(vmean), dev(inp['visual_embeds_att']), dev(offsets),
+            dev(output_mask), None]
+    loss = model(*args, labels=dev(labels), mode='train')
+    assert loss.dim() == 0 and loss.grad_fn is not None
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(want_loss)) <= 1e-4 * max(1.0, abs(float(want_loss)))
+    bad = {}
+    for k, v in model.named_parameters():
+        want = sd[k].grad
+        assert want is not None and v.grad is not None, k
+        scale = float(want.abs().max())
+        if k.endswith('key.bias'):
+            scale = float(sd[k.replace('key.bias', 'query.bias')].grad.abs().max())
+        err = float((v.grad.double().cpu() - want).abs().max())
+        if not err <= 1e-3 * scale + 1e-9:
+            bad[k] = (err, scale)
+    assert not bad, bad
+    # 'dev' right after must not record a graph (the reference calls it under torch.no_grad())
+    _, dev_loss = model(*args, labels=dev(labels), mode='dev')
+    assert dev_loss.grad_fn is None

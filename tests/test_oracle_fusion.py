@@ -7,7 +7,7 @@ import torch
 
 from icka_b200 import synth
 from oracle import fusion_ref, reference_shim
-from oracle.make_golden import CASES, build_case, checksum
+from oracle.make_golden import CASES, build_case, case_extras, checksum
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 
@@ -22,7 +22,7 @@ def run_oracle(name):
     out = fusion_ref.fusion_segment(
         inp['text_states'], inp['visual_embeds_att'], inp['clip_features'], inp['token_embedding'],
         inp['img_mask'], inp['text_mask'], params, num_layers=shape.L, num_heads=shape.heads,
-        layer_norm_eps=shape.eps)
+        layer_norm_eps=shape.eps, **case_extras(name))
     return B, shape, params, inp, stride, out
 
 
@@ -42,12 +42,12 @@ def test_oracle_matches_golden(name):
 
 
 @pytest.mark.skipif(not reference_shim.available(), reason='/root/reference not present (GPU box)')
-@pytest.mark.parametrize('name', ['tiny', 'std_L1'])
+@pytest.mark.parametrize('name', ['tiny', 'std_L1', 'tiny_relu', 'tiny_swish'])
 def test_oracle_matches_reference_classes(name):
     B, shape, params, inp, stride, out = run_oracle(name)
     mods = reference_shim.build_reference_modules(
         params, hidden=shape.H, heads=shape.heads, inter=shape.inter, num_layers=shape.L,
-        layer_norm_eps=shape.eps)
+        layer_norm_eps=shape.eps, **case_extras(name))
     ref = reference_shim.reference_fusion_segment(
         mods, inp['text_states'], inp['visual_embeds_att'], inp['clip_features'],
         inp['token_embedding'], inp['img_mask'], inp['text_mask'])
