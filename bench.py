@@ -71,6 +71,7 @@ def parse():
     ap.add_argument('--real-head', action='store_true',
                     help="--mode train: the reference's BiLSTM + classifier emission head (BPTT on per-step kernels) instead of the "
                          'nn.Linear(H,T) stand-in')
+    ap.add_argument('--no-configs', action='store_true', help='skip the extra BASELINE.json configurations (`configs` block of the line)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying a CUDA graph')
     return ap.parse_args()
 
@@ -113,13 +114,13 @@ class CpuBaseline:
     """The reference's modules restated on torch-CPU (oracle/fusion_ref.py; the reference itself is Python
     and /root/reference does not exist on the GPU box) + the C restatement of pytorch-crf's Viterbi."""
 
-    def __init__(self, shape, sample, seed):
+    def __init__(self, shape, sample, seed, threads=None):
         import torch
         from icka_b200 import synth
         from oracle import fusion_ref, viterbi_c
         self.torch, self.fusion_ref, self.viterbi_c = torch, fusion_ref, viterbi_c
         self.shape, self.sample = shape, sample
-        self.cores = os.cpu_count() or 1
+        self.cores = threads or os.cpu_count() or 1
         torch.set_num_threads(self.cores)
         self.params = fusion_ref.make_params(shape.H, shape.heads, shape.inter, shape.L, seed=seed,
                                              distinct_layers=True, perturb_ln=False)
@@ -225,43 +226,53 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def run_gpu_arm(args, shape):
-    import torch
-    import torch.distributed as dist
-    from icka_b200 import _lib, shard
+class Env:
+    """Process-wide context of one bench run: rank / world, device, barrier, peaks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit('launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...')
+        torch.cuda.set_device(self.local_rank)
+        self.dev = f'cuda:{self.local_rank}'
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            dist.init_process_group('nccl', device_id=torch.device(self.dev))
+        self.peaks = load_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        from icka_b200 import shard
+        return shard.max_over_ranks(v, device=self.dev)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def bench_inference(env, args, shape, batch, steps, seed, precision='bf16', inflight=2, use_graph=True, sample_clocks=False):
+    """Device-resident timing of `steps` passes of the hot path over `batch` sentences per GPU + the per-kernel roofline pass.
+    One step = ~40 kernel launches on two streams; by default it is captured once into a CUDA graph and the timed region
+    replays it (one driver call per step), two captured batches in flight on two streams."""
+    torch = env.torch
+    from icka_b200 import _lib
     from icka_b200.pipeline import FusionViterbiPipeline
     from icka_b200.profiler import KernelTimer
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit('launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...')
-    torch.cuda.set_device(local_rank)
-    dev = f'cuda:{local_rank}'
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device(dev))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    peaks = load_peaks()
-    seed = 19260817 + rank
-    pipe = FusionViterbiPipeline(shape, dev, args.precision, seed=seed)
-    host = pipe.make_host_batch(args.batch, shape, seed)
+    pipe = FusionViterbiPipeline(shape, env.dev, precision, seed=seed)
+    host = pipe.make_host_batch(batch, shape, seed)
     d = pipe.to_device(host)
     torch.cuda.synchronize()
-
-    # ---- device-resident timing ----
-    # One step = ~40 kernel launches on two streams; by default it is captured once into a CUDA graph and the timed
-    # region replays it (one driver call per step), so a slow host cannot starve the GPU.  gpu_launches counts the
-    # kernels the graph contains (icka_launch_count over the capture) times the replays.
-    use_graph = not args.no_graph
-    inflight = args.inflight if use_graph else 1
+    inflight = inflight if use_graph else 1
+    lanes = []
     if use_graph:
         graph, _outs = pipe.capture(d)
         per_step = pipe.graph_kernels
@@ -270,7 +281,7 @@ def run_gpu_arm(args, shape):
             # a second batch with its own device buffers, graph and library handle slot (split-K workspace): steps i and
             # i + 1 run on two streams, so the single-query encoders' small GEMMs at the end of a step (a few dozen CTAs)
             # share the machine with the next step's region relayout / projections instead of leaving most SMs idle
-            d2 = pipe.to_device(pipe.make_host_batch(args.batch, shape, seed + 500))
+            d2 = pipe.to_device(pipe.make_host_batch(batch, shape, seed + 500, pin=False))
             torch.cuda.synchronize()
             graph2, _outs2 = pipe.capture(d2, slot=1)
             lanes = [(torch.cuda.Stream(), graph), (torch.cuda.Stream(), graph2)]
@@ -286,42 +297,46 @@ def run_gpu_arm(args, shape):
         run_step = lambda: pipe.step_device(d)
 
     def fork():
-        if inflight == 2:
-            for st, _ in lanes:
-                st.wait_stream(torch.cuda.current_stream())
+        for st, _ in lanes:
+            st.wait_stream(torch.cuda.current_stream())
 
     def join():
-        if inflight == 2:
-            for st, _ in lanes:
-                torch.cuda.current_stream().wait_stream(st)
+        for st, _ in lanes:
+            torch.cuda.current_stream().wait_stream(st)
 
+    warm = max(args.warmup, 3)
     fork()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         run_step()
     join()
-    barrier()
-    launches0 = _lib.launch_count(local_rank)
+    env.barrier()
+    launches0 = _lib.launch_count(env.local_rank)
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        s_ev.record()
-        fork()
-        for _ in range(args.steps):
-            run_step()
-        join()
-        e_ev.record()
-        barrier()
-    ms_total = s_ev.elapsed_time(e_ev)
-    launches = per_step * args.steps if use_graph else _lib.launch_count(local_rank) - launches0
-    ms_total = shard.max_over_ranks(ms_total, device=dev)
-    value = args.batch * world * args.steps / (ms_total * 1e-3)
+    clk = ClockSampler(env.local_rank) if sample_clocks else None
+    if clk is not None:
+        clk.__enter__()
+    s_ev.record()
+    fork()
+    for _ in range(steps):
+        run_step()
+    join()
+    e_ev.record()
+    env.barrier()
+    if clk is not None:
+        clk.__exit__(None, None, None)
+    ms_total = env.max_over_ranks(s_ev.elapsed_time(e_ev))
+    launches = per_step * steps if use_graph else _lib.launch_count(env.local_rank) - launches0
+    value = batch * env.world * steps / (ms_total * 1e-3)
 
     # ---- per-kernel roofline pass (same step, CUDA events around every C-ABI launch) ----
+    peaks = env.peaks
     pipe.overlap_decode = False          # events on one stream: the decode must not be timed while it waits
     for _ in range(2):                   # eager warm-up: the caching allocator must not cudaMalloc inside the events
         pipe.step_device(d)
     torch.cuda.synchronize()
+    n_prof = min(steps, 10)
     with KernelTimer() as kt:
-        for _ in range(args.steps):
+        for _ in range(n_prof):
             pipe.step_device(d)
         kernels = kt.summary()
         gemm_shapes = kt.gemm_shapes()
@@ -334,11 +349,12 @@ def run_gpu_arm(args, shape):
         'frac': gemm['tflops'] / peak_tf, 'traffic': None,
         'peak_source': peaks['_source'] + ', bf16_tflops_sustained (kernel timed inside a long step)',
         'frac_of_burst_peak': gemm['tflops'] / peaks.get('bf16_tflops', FALLBACK_PEAKS['bf16_tflops']),
-        'launches_per_step': gemm['launches'] // args.steps, 'ms_per_launch': gemm['ms_per_launch'],
+        'launches_per_step': gemm['launches'] // n_prof, 'ms_per_launch': gemm['ms_per_launch'],
         'flops_per_launch': gemm['flops_per_launch'],
+        'gemm_ms_per_step': gemm['ms_total'] / n_prof,
     }
-    if args.precision == 'bf16' and not args.hires:
-        cap = measured_traffic(f'B{args.batch}_L{shape.L}')
+    if precision == 'bf16':
+        cap = measured_traffic(f'B{batch}_L{shape.L}' + ('_hires' if shape.S != 128 else ''))
         if cap is not None:
             roofline['traffic'] = cap[0]['dram_bytes_per_launch_mean']
             roofline['traffic_source'] = (f'profiles/{cap[1]}: dram__bytes_read.sum + dram__bytes_write.sum, mean over the '
@@ -347,71 +363,129 @@ def run_gpu_arm(args, shape):
     hbm = peaks.get('hbm_gbs', FALLBACK_PEAKS['hbm_gbs'])
     kernel_table = {}
     for name, k in kernels.items():
-        kernel_table[name] = {'launches_per_step': k['launches'] // args.steps, 'ms_per_step': k['ms_total'] / args.steps,
+        kernel_table[name] = {'launches_per_step': k['launches'] // n_prof, 'ms_per_step': round(k['ms_total'] / n_prof, 5),
                               'tflops': round(k['tflops'], 2), 'gbs': round(k['gbs'], 1),
                               'frac_tensor': round(k['tflops'] / peak_tf, 4), 'frac_hbm': round(k['gbs'] / hbm, 4)}
+    # whole-step fraction of the tensor peak: the reference formulation's FLOPs per sentence / step time
+    S, R, H, I, L = shape.S, shape.R, shape.H, shape.inter, shape.L
+    layer = lambda sq, skv: 2.0 * (2 * sq * H * H + 2 * skv * H * H + 2 * sq * H * I) + 4.0 * sq * skv * H
+    ref_flops = 2.0 * R * shape.region_dim * H + L * layer(S, R) + 2 * L * layer(1, S)
+    step_frac = ref_flops * batch * env.world * steps / (ms_total * 1e-3) / 1e12 / (peak_tf * env.world)
+    return dict(value=value, ms_per_step=ms_total / steps, launches=int(launches), roofline=roofline, kernels=kernel_table,
+                gemm_shapes={k: {'launches_per_step': v['launches'] // n_prof, 'ms_per_launch': round(v['ms_per_launch'], 4),
+                                 'tflops': round(v['tflops'], 1)} for k, v in gemm_shapes.items()},
+                clocks=clk.report() if clk is not None else None, pipe=pipe, host=host, d=d, inflight=inflight,
+                step_frac_of_tensor_peak=step_frac, reference_formulation_gflop_per_sentence=ref_flops / 1e9)
+
+
+def pcie_probe(env, nbytes=1 << 30, reps=4):
+    """Raw pinned host -> device copy bandwidth of THIS rank while every rank copies at once: the ceiling of `e2e`."""
+    torch = env.torch
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
+    dst.copy_(src, non_blocking=True)
+    env.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    b.record()
+    env.barrier()
+    ms = env.max_over_ranks(a.elapsed_time(b))
+    return nbytes * reps / (ms * 1e-3) / 1e9
+
+
+def bench_e2e(env, args, shape, batch, seed, steps, use_graph=True):
+    """The same metric end to end through the public API with HOST buffers: TaggingPipeline.infer_host -- pinned host
+    inputs -> H2D -> fusion -> BiLSTM + classifier -> Viterbi of THOSE emissions -> chunk-F1 counters -> D2H of tags,
+    lengths and counters, all inside the timed region (copies of batch i+1 overlap the kernels of batch i)."""
+    torch = env.torch
+    from icka_b200.pipeline import TaggingPipeline
+    pipe = TaggingPipeline(shape, env.dev, args.precision, seed=seed)
+    n_e2e = max(4, min(steps, 10))
+    out = None
+    variants = [('fp32', False)] + ([('bf16', True)] if args.precision == 'bf16' else [])
+    for tag, bf16_states in variants:
+        hosts = [pipe.make_host_batch(batch, shape, seed + 1000 + i, bf16_states=bf16_states) for i in range(2)]
+        seq = [hosts[i & 1] for i in range(n_e2e)]
+        pipe.infer_host(seq[:2], use_graphs=use_graph)
+        env.barrier()
+        results, (s2, e2) = pipe.infer_host(seq, use_graphs=use_graph)
+        env.barrier()
+        ms = env.max_over_ranks(s2.elapsed_time(e2))
+        h2d = pipe.h2d_bytes(hosts[0])
+        d2h = sum(x.numel() * x.element_size() for x in results[0])
+        entry = {'value': batch * env.world * n_e2e / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                 'd2h_bytes_per_step': d2h, 'steps': n_e2e, 'h2d_gbs_per_rank': h2d * n_e2e / (ms * 1e-3) / 1e9}
+        if tag == 'fp32':
+            out = entry
+            out['api'] = ('icka_b200.pipeline.TaggingPipeline.infer_host: pinned host fp32 inputs (text states, ResNet grid, CLIP '
+                          'feature, token embedding, masks, gold labels) -> H2D -> fusion -> BiLSTM + classifier -> Viterbi of those '
+                          'emissions -> chunk-F1 counters -> D2H of tags, lengths, counters; H2D of batch i+1 overlaps kernels of batch i')
+            counters = [int(x) for x in results[-1][2].tolist()]
+            out['chunk_f1_counters_last_batch'] = counters[:5]
+        else:
+            entry['inputs'] = ('text states + token embedding bf16, regions as bf16 K-major rows [B,R,2048] (producer-tail layout), '
+                               'clip fp32: what a caller whose encoders run in bf16 holds')
+            out['bf16_host_inputs'] = entry
+        del hosts, seq, results
+    out['pcie_h2d_gbs_per_rank_all_ranks_copying'] = round(pcie_probe(env), 2)
+    out['bound'] = ('PCIe: h2d_gbs_per_rank vs the raw pinned-copy rate measured in the same run; aggregate H2D over N ranks is '
+                    'limited by the host (one NUMA node, shared PCIe uplinks), not by the kernels')
+    del pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_arm(args, shape):
+    env = Env(args)
+    torch = env.torch
+    rank, world, dev = env.rank, env.world, env.dev
+    seed = 19260817 + rank
+    use_graph = not args.no_graph
+    head = bench_inference(env, args, shape, args.batch, args.steps, seed, precision=args.precision, inflight=args.inflight,
+                           use_graph=use_graph, sample_clocks=True)
+    value, roofline = head['value'], head['roofline']
 
     # ---- end to end from pinned host memory ----
     e2e = None
     if not args.no_e2e:
-        hosts = [host, pipe.make_host_batch(args.batch, shape, seed + 1000)]
-        n_e2e = max(4, min(args.steps, 10))
-        seq = [hosts[i & 1] for i in range(n_e2e)]
-        pipe.infer_host(seq[:2], use_graphs=use_graph)
-        barrier()
-        results, (s2, e2) = pipe.infer_host(seq, use_graphs=use_graph)
-        barrier()
-        ms_e2e = s2.elapsed_time(e2)
-        ms_e2e = shard.max_over_ranks(ms_e2e, device=dev)
-        d2h = sum(x.numel() * x.element_size() for x in results[0])
-        e2e = {'value': args.batch * world * n_e2e / (ms_e2e * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': pipe.h2d_bytes(host), 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
-               'api': 'icka_b200.pipeline.FusionViterbiPipeline.infer_host (pinned host fp32 inputs; H2D of batch i+1 '
-                      'overlaps kernels of batch i; D2H of tags, lengths, gates)'}
-
-        # the same call with the inputs a bf16 caller holds (half the PCIe bytes; extra, the headline `e2e` stays fp32)
-        if args.precision == 'bf16':
-            hosts16 = [pipe.make_host_batch(args.batch, shape, seed + 2000 + i, bf16_states=True) for i in range(2)]
-            seq16 = [hosts16[i & 1] for i in range(n_e2e)]
-            pipe.infer_host(seq16[:2], use_graphs=use_graph)
-            barrier()
-            _, (s3, e3) = pipe.infer_host(seq16, use_graphs=use_graph)
-            barrier()
-            ms16 = shard.max_over_ranks(s3.elapsed_time(e3), device=dev)
-            e2e['bf16_host_inputs'] = {
-                'value': args.batch * world * n_e2e / (ms16 * 1e-3), 'unit': UNIT,
-                'h2d_bytes_per_step': pipe.h2d_bytes(hosts16[0]),
-                'inputs': 'text states + token embedding bf16, regions as bf16 K-major rows [B,R,2048] '
-                          '(producer-tail layout), clip fp32, emissions fp32'}
-            del hosts16, seq16
+        if args.precision == 'bf16' and shape.H == 768 and shape.T == 15:
+            e2e = bench_e2e(env, args, shape, args.batch, seed, args.steps, use_graph)
+        else:
+            e2e = bench_e2e_fusion_viterbi(env, args, head['pipe'], head['host'], shape, seed, use_graph)
 
     # ---- widened path (SURVEY 8f rows 1 + 2; extra, not part of `value`) ----
     widened = None
     if not args.no_widened and args.precision == 'bf16' and shape.H == 768:
         try:
-            widened = run_widened(args, shape, dev, seed, d, barrier)
+            widened = run_widened(args, shape, dev, seed, head['d'], env.barrier)
         except RuntimeError as e:       # e.g. a profiler that cannot replay cooperative cluster launches; the headline is unaffected
             widened = None
             print(f'bench.py: widened measurement skipped: {e}', file=sys.stderr)
         if widened is not None and world > 1:
-            widened['ms_per_step'] = shard.max_over_ranks(widened['ms_per_step'], device=dev)
+            widened['ms_per_step'] = env.max_over_ranks(widened['ms_per_step'])
         if widened is not None:
             widened['value'] = args.batch * world / (widened['ms_per_step'] * 1e-3)
+    inflight = head['inflight']
+    for k in ('pipe', 'host', 'd'):
+        head.pop(k)
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, each with its own roofline (same process, fewer steps) ----
+    configs = None
+    if not args.no_configs and args.precision == 'bf16' and not args.hires and shape.L == 1:
+        configs = run_baseline_configs(env, args, seed)
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        base = CpuBaseline(shape, args.cpu_sample, seed=19260817)
-        reps = 8 if shape.L == 1 and not args.hires else 3      # a few seconds of CPU work on the box's cores
-        v, sec = base.run(reps, 1)
-        cpu = {'value': v, 'unit': UNIT, 'cores': base.cores, 'kind': 'port',
-               'sample': f'{args.cpu_sample} sentences x {reps} passes (fusion fwd fp32 + Viterbi), oracle port on host CPU, '
-                         f'{sec * 1e3:.0f} ms per pass'}
+        cpu = cpu_baseline_block(args, shape)
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
             'config': {'workload': workload_name(args, shape), 'batch_per_gpu': args.batch, 'global_batch': args.batch * world,
                        'layers': shape.L, 'parallelism': f'batch-sharded x{world}, no collectives',
@@ -420,14 +494,106 @@ def run_gpu_arm(args, shape):
                        'launch': ('CUDA graph replay of the captured step' + (', two batches in flight on two streams' if inflight == 2 else ''))
                                  if use_graph else 'eager host launches',
                        'l2_policy': f'inputs larger than L2 ({args.batch * 1.199e6 / 1e9:.1f} GB of inputs per step vs 126 MB L2); no flush needed'},
-            'clocks': clk.report(), 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
-            'cpu_baseline': cpu, 'widened': widened, 'kernels': kernel_table,
-            'gemm_shapes': {k: {'launches_per_step': v['launches'] // args.steps, 'ms_per_launch': round(v['ms_per_launch'], 4),
-                                'tflops': round(v['tflops'], 1)} for k, v in gemm_shapes.items()},
+            'clocks': head['clocks'], 'e2e': e2e, 'gpu_launches': head['launches'], 'roofline': roofline,
+            'step_frac_of_tensor_peak': round(head['step_frac_of_tensor_peak'], 4),
+            'cpu_baseline': cpu, 'widened': widened, 'configs': configs, 'kernels': head['kernels'],
+            'gemm_shapes': head['gemm_shapes'],
         }
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
+
+
+def bench_e2e_fusion_viterbi(env, args, pipe, host, shape, seed, use_graph):
+    """Fallback e2e for shapes the emission head's persistent kernel is not built for: FusionViterbiPipeline.infer_host
+    (emission scores are a host input, D2H of tags / lengths / gates)."""
+    n_e2e = max(4, min(args.steps, 10))
+    hosts = [host, pipe.make_host_batch(args.batch, shape, seed + 1000)]
+    seq = [hosts[i & 1] for i in range(n_e2e)]
+    pipe.infer_host(seq[:2], use_graphs=use_graph)
+    env.barrier()
+    results, (s2, e2) = pipe.infer_host(seq, use_graphs=use_graph)
+    env.barrier()
+    ms = env.max_over_ranks(s2.elapsed_time(e2))
+    return {'value': args.batch * env.world * n_e2e / (ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': pipe.h2d_bytes(host),
+            'd2h_bytes_per_step': sum(x.numel() * x.element_size() for x in results[0]), 'steps': n_e2e,
+            'api': 'icka_b200.pipeline.FusionViterbiPipeline.infer_host (pinned host fp32 inputs incl. emission scores; D2H of tags, lengths, gates)'}
+
+
+def cpu_baseline_block(args, shape):
+    """The oracle port timed on this box's host cores: all threads on `--cpu-sample` sentences (the headline CPU number),
+    plus BASELINE.md section 4.3's points: one thread, and all threads at B = 2 and B = 32."""
+    import torch
+    base = CpuBaseline(shape, args.cpu_sample, seed=19260817)
+    reps = 8 if shape.L == 1 and not args.hires else 3      # a few seconds of CPU work on the box's cores
+    v, sec = base.run(reps, 1)
+    cpu = {'value': v, 'unit': UNIT, 'cores': base.cores, 'kind': 'port',
+           'sample': f'{args.cpu_sample} sentences x {reps} passes (fusion fwd fp32 + Viterbi), oracle port on host CPU, '
+                     f'{sec * 1e3:.0f} ms per pass'}
+    if shape.L == 1 and not args.hires:
+        points = {}
+        for b in (2, 32):
+            pb = CpuBaseline(shape, b, seed=19260817)
+            pv, _ = pb.run(5 if b == 2 else 3, 1)
+            points[f'B{b}_all_threads'] = round(pv, 1)
+        one = CpuBaseline(shape, 32, seed=19260817, threads=1)
+        ov, osec = one.run(2, 1)
+        points['B32_one_thread'] = round(ov, 1)
+        torch.set_num_threads(base.cores)
+        cpu['points'] = points
+        cpu['points_note'] = 'sentences/s of the same port at the batch sizes of BASELINE.md 4.3 (B = 2: configs[0]); one_thread = torch.set_num_threads(1)'
+    return cpu
+
+
+def run_baseline_configs(env, args, seed):
+    """BASELINE.json configs[1], [3], [4] and the script-default depth of configs[2], measured in the same run so that the
+    driver's BENCH / SCALE records carry them.  Fewer steps than the headline; each entry has its
+    own roofline."""
+    from icka_b200 import synth
+    torch = env.torch
+    out = {}
+    steps = max(3, min(args.steps, 6))
+
+    def slim(r, batch, shape, extra):
+        e = {'value': r['value'], 'unit': UNIT, 'ms_per_step': r['ms_per_step'], 'steps': steps, 'batch_per_gpu': batch,
+             'global_batch': batch * env.world, 'workload': f'S{shape.S}_R{shape.R}_H{shape.H}_L{shape.L}',
+             'roofline': {k: r['roofline'][k] for k in ('kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic',
+                                                        'launches_per_step', 'gemm_ms_per_step')},
+             'step_frac_of_tensor_peak': round(r['step_frac_of_tensor_peak'], 4), 'gpu_launches': r['launches']}
+        e.update(extra)
+        hbm_rows = {k: v for k, v in r['kernels'].items() if k in ('cross_attn_core', 'i2t_pool', 'layernorm', 'ln_gate_blend',
+                                                                     'region_rows', 'viterbi', 'cast_bf16')}
+        e['hbm_kernels'] = {k: {'ms_per_step': v['ms_per_step'], 'frac_hbm': v['frac_hbm']} for k, v in hbm_rows.items()}
+        return e
+
+    def infer(name, shape, batch, extra):
+        try:
+            r = bench_inference(env, args, shape, batch, steps, seed, precision='bf16', inflight=args.inflight,
+                                use_graph=not args.no_graph)
+            for k in ('pipe', 'host', 'd'):
+                r.pop(k)
+            out[name] = slim(r, batch, shape, extra)
+        except RuntimeError as e:
+            out[name] = {'error': str(e)[:300]}
+        torch.cuda.empty_cache()
+
+    infer('configs[2]_inference_L5', synth.Shape(L=5), args.batch,
+          {'baseline_config': 'configs[2] at the training script\'s default depth layer_num1 = 5 (My_cross_attention.py:603)'})
+    infer('configs[3]_hires_S256_R196', synth.Shape(S=256, R=196), 512,
+          {'baseline_config': 'configs[3]: seq 256 x 196 regions fusion + Viterbi, batch-sharded over the N GPUs of this run (8 in the SCALE record)'})
+    infer('configs[2]_inference_B256', synth.Shape(), 256,
+          {'baseline_config': 'configs[2] at the low end of the 256-4096 sweep (north_star: >= 50 % of roofline per kernel at batch >= 256)'})
+    for name, batch, real_head, note in (
+            ('configs[1]_train_B32', 32, False, 'configs[1]: training step batch 32 bf16 on 1 B200 (per GPU when N > 1)'),
+            ('configs[1]_train_B32_bilstm_head', 32, True, 'configs[1] with the reference\'s BiLSTM + classifier emission head (BPTT on per-step kernels)'),
+            ('configs[4]_train_dp_B128_per_gpu', 128, False, 'configs[4]: data-parallel training, 128 sentences per GPU = global batch 1024 at N = 8, NCCL gradient all-reduce')):
+        try:
+            r = bench_training(env, args, synth.Shape(), batch, steps, real_head)
+            r['baseline_config'] = note
+            out[name] = r
+        except RuntimeError as e:
+            out[name] = {'error': str(e)[:300]}
+        torch.cuda.empty_cache()
+    return out
 
 
 def run_widened(args, shape, dev, seed, d, barrier):
@@ -515,32 +681,23 @@ def run_widened(args, shape, dev, seed, d, barrier):
             'note': 'extra measurement (SURVEY 8f rows), not included in `value`'}
 
 
-def run_train_arm(args, shape):
-    """Extra (non-headline) mode for BASELINE configs[1] / [4]: one data-parallel training step of the hot path.
+def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
+    """One data-parallel training step of the hot path (BASELINE configs[1] / [4]), `steps` times:
 
-    step = fusion forward (recording) -> emission head -> CRF negative log-likelihood (token_mean, CMIM:1047-1048)
-           -> backward through the kernel-backed autograd nodes -> bucketed gradient all-reduce (NCCL, overlapped
-           with backward) -> AdamW.  The emission head is a torch nn.Linear(H, T) standing in for the reference's
-           BiLSTM + classifier (CMIM:1042-1043, SURVEY 8f "next" row) and AdamW is torch's (the reference uses
-           transformers.AdamW): both are outside the hot path and are named in `config`."""
-    import torch
-    import torch.distributed as dist
-    from icka_b200 import CRF, CrossModalFusion, FusionConfig, _lib, set_precision, shard, synth
-
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dev = f'cuda:{local_rank}'
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device(dev))
-    set_precision(args.precision)
+    fusion forward (recording) -> emission head -> CRF negative log-likelihood (token_mean, CMIM:1047-1048) -> backward
+    through the kernel-backed autograd nodes -> bucketed gradient all-reduce (NCCL, overlapped with backward) -> AdamW.
+    The emission head is a torch nn.Linear(H, T) standing in for the reference's BiLSTM + classifier unless `real_head`
+    (CMIM:1042-1043, SURVEY 8f "next" row) and AdamW is torch's (the reference uses transformers.AdamW): both are outside
+    the hot path and are named in the result."""
+    torch, dist = env.torch, env.dist
+    from icka_b200 import CRF, CrossModalFusion, FusionConfig, _lib, precision as precision_ctx, shard, synth
+    from icka_b200.profiler import KernelTimer
+    rank, world, dev, local_rank = env.rank, env.world, env.dev, env.local_rank
     torch.manual_seed(19260817)
     cfg = FusionConfig(hidden_size=shape.H, num_attention_heads=shape.heads, intermediate_size=shape.inter,
                        layer_norm_eps=shape.eps)
-    fusion = CrossModalFusion(cfg, layer_num1=shape.L).to(dev).train()      # dropout p = 0.1 on all three sites
-    if args.real_head:
+    fusion = CrossModalFusion(cfg, layer_num1=shape.L, precision=precision).to(dev).train()      # dropout p = 0.1 on all three sites
+    if real_head:
         from icka_b200 import EmissionHead
         head = EmissionHead(cfg, num_labels=shape.T).to(dev).train()
     else:
@@ -551,79 +708,103 @@ def run_train_arm(args, shape):
         shard.broadcast_parameters(m)
     reducer = shard.GradientAllReducer(params)
     opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
-    f = synth.fusion_inputs(args.batch, shape, seed=19260817 + rank)
-    c = synth.crf_batch(args.batch, shape, seed=19260817 + rank)
+    f = synth.fusion_inputs(batch, shape, seed=19260817 + rank)
+    c = synth.crf_batch(batch, shape, seed=19260817 + rank)
     d = {k: f[k].to(dev) for k in ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask',
                                    'text_mask')}
     tags, mask = c['tags'].to(dev), c['mask'].to(dev)
 
     def step():
-        opt.zero_grad(set_to_none=True)
-        result, clip = fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
-                              d['img_mask'], d['text_mask'])
-        loss = -crf(head(result), tags, mask, reduction='token_mean') + 1e-3 * clip.mean()
-        loss.backward()
-        reducer.finish()
-        opt.step()
+        with precision_ctx(precision):
+            opt.zero_grad(set_to_none=True)
+            result, clip = fusion(d['text_states'], d['visual_embeds_att'], d['clip_features'], d['token_embedding'],
+                                  d['img_mask'], d['text_mask'])
+            loss = -crf(head(result), tags, mask, reduction='token_mean') + 1e-3 * clip.mean()
+            loss.backward()
+            reducer.finish()
+            opt.step()
         return loss
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
-    barrier()
+    env.barrier()
     l0 = _lib.launch_count(local_rank)
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         s_ev.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             loss = step()
         e_ev.record()
-        barrier()
-    ms = shard.max_over_ranks(s_ev.elapsed_time(e_ev), device=dev)
+        env.barrier()
+    ms = env.max_over_ranks(s_ev.elapsed_time(e_ev))
     launches = _lib.launch_count(local_rank) - l0
-    from icka_b200.profiler import KernelTimer
-    n_prof = min(args.steps, 5)
+    n_prof = min(steps, 5)
     with KernelTimer() as kt:                 # per-kernel CUDA-event pass of the same step
         for _ in range(n_prof):
             step()
         ksum = kt.summary()
-    hbm = load_peaks().get('hbm_gbs', FALLBACK_PEAKS['hbm_gbs'])
     kernel_table = {name: {'launches_per_step': k['launches'] // n_prof, 'ms_per_step': round(k['ms_total'] / n_prof, 4),
                            'tflops': round(k['tflops'], 1), 'gbs': round(k['gbs'], 1)} for name, k in ksum.items()}
+    # the one collective: time every bucket's all-reduce on its own (NCCL over NVLink), after the timed region
+    allreduce = None
+    if world > 1:
+        per_bucket = []
+        for b in reducer.buckets:
+            env.barrier()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                dist.all_reduce(b.flat, op=dist.ReduceOp.AVG)
+            z.record()
+            torch.cuda.synchronize()
+            t = env.max_over_ranks(a.elapsed_time(z) / 3)
+            per_bucket.append({'mb': round(b.numel * 4 / 1e6, 1), 'ms': round(t, 4),
+                               'bus_gbs': round(2 * (world - 1) / world * b.numel * 4 / (t * 1e-3) / 1e9, 1)})
+        allreduce = {'buckets': per_bucket, 'ms_total_if_serial': round(sum(x['ms'] for x in per_bucket), 4),
+                     'launched_inside_backward_per_step': reducer.launched_early // (steps + warm + n_prof)}
+    reducer.remove_hooks()
     n_param = sum(p.numel() for p in params)
     # dense-GEMM FLOPs per sentence: forward (unfolded single-query encoders) x3 for forward + dgrad + wgrad
     S, R, H, I, L = shape.S, shape.R, shape.H, shape.inter, shape.L
     layer = lambda sq, skv: 2.0 * (sq * H * H + 2 * skv * H * H + sq * H * H + 2 * sq * H * I)
     fwd = 2.0 * R * shape.region_dim * H + L * layer(S, R) + 2 * L * layer(1, S)
-    peaks = load_peaks()
-    peak_tf = peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
-    tf = 3.0 * fwd * args.batch * args.steps / (ms * 1e-3) / 1e12
-    if rank == 0:
-        emit({
-            'metric': 'sentences/sec fusion+CRF training step', 'value': args.batch * world * args.steps / (ms * 1e-3),
-            'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32',
-            'data': 'synthetic', 'mode': 'train',
-            'config': {'workload': f'twitter2015_training_B{args.batch}_per_gpu_S{S}_R{R}_H{H}_I{I}_T{shape.T}_L{L}',
-                       'global_batch': args.batch * world, 'parallelism': f'data-parallel x{world}, bucketed NCCL gradient all-reduce',
-                       'params_allreduced': n_param, 'buckets': len(reducer.buckets),
-                       'buckets_launched_inside_backward_per_step': reducer.launched_early // (args.steps + max(args.warmup, 3)),
-                       'outside_hot_path': ('emission head = icka_b200.EmissionHead (BiLSTM + classifier, BPTT on per-step kernels)' if args.real_head
-                                            else 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier') + '; optimizer = torch AdamW(fused)',
-                       'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)'},
-            'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
-            'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor', 'achieved': tf,
-                         'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf / peak_tf, 'traffic': None,
-                         'note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, '
-                                 'the all-reduce and the optimizer'},
-            'kernels': kernel_table,
-        })
-    if world > 1:
-        dist.destroy_process_group()
+    peak_tf = env.peaks.get('bf16_tflops_sustained', FALLBACK_PEAKS['bf16_tflops_sustained'])
+    tf = 3.0 * fwd * batch * steps / (ms * 1e-3) / 1e12
+    gemm_ms = sum(v['ms_per_step'] for k, v in kernel_table.items() if 'tcgen05' in k)
+    gemm_fl = sum(ksum[k]['flops_per_launch'] * ksum[k]['launches'] for k in ksum if 'tcgen05' in k) / n_prof
+    return {
+        'metric': 'sentences/sec fusion+CRF training step', 'value': batch * world * steps / (ms * 1e-3),
+        'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': ms / steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if precision == 'bf16' else 'f32',
+        'data': 'synthetic', 'mode': 'train',
+        'config': {'workload': f'twitter2015_training_B{batch}_per_gpu_S{S}_R{R}_H{H}_I{I}_T{shape.T}_L{L}',
+                   'batch_per_gpu': batch, 'global_batch': batch * world,
+                   'parallelism': f'data-parallel x{world}, bucketed NCCL gradient all-reduce',
+                   'params_allreduced': n_param, 'buckets': len(reducer.buckets),
+                   'outside_hot_path': ('emission head = icka_b200.EmissionHead (BiLSTM + classifier, BPTT on per-step kernels)' if real_head
+                                        else 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier') + '; optimizer = torch AdamW(fused)',
+                   'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)'},
+        'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
+        'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor',
+                     'achieved': (gemm_fl / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else 0.0, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peak_tf) if gemm_ms > 0 else 0.0, 'traffic': None,
+                     'gemm_ms_per_step': round(gemm_ms, 4),
+                     'note': 'tcgen05 GEMM launches of one step (forward, dgrad, wgrad): executed FLOPs / their CUDA-event time'},
+        'step_frac_of_tensor_peak': round(tf / peak_tf, 4),
+        'step_frac_note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, the all-reduce and the optimizer',
+        'allreduce': allreduce, 'kernels': kernel_table,
+    }
+
+
+def run_train_arm(args, shape):
+    """`--mode train`: BASELINE configs[1] / [4] as the headline of the line (extra mode; the default line carries the same
+    measurement inside `configs`)."""
+    env = Env(args)
+    line = bench_training(env, args, shape, args.batch, args.steps, args.real_head, precision=args.precision)
+    if env.rank == 0:
+        emit(line)
+    env.close()
 
 
 def main():

@@ -26,6 +26,7 @@ SIGNATURES = {
     'icka_launch_count': (c_int64, [c_void_p]),
     'icka_cast_f32_to_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'icka_cast_bf16_to_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'icka_split_bf16x3': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p]),
     'icka_region_rows': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_mask_additive': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p]),
     'icka_linear_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,

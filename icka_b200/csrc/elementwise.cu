@@ -28,6 +28,32 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split-precision operand ("bf16 x 3"): x fp32 [M, K] -> [M, 3K] bf16 with hi = bf16(x), lo = bf16(x - hi), laid out
+//   as_weight = 0:  [hi | lo | hi]        as_weight = 1:  [hi | hi | lo]
+// so that ONE bf16 tensor-core GEMM over K' = 3K forms a_hi.w_hi + a_lo.w_hi + a_hi.w_lo: the fp32 product to ~2^-16
+// relative (the dropped a_lo.w_lo term).  Used for the single-query image->text chain (CMIM:981-989), whose GEMMs have
+// M = batch rows only: one token per sentence walks 2 L layers, and at L = 5 plain bf16 operands bring it to the 2e-2 gate.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ x, int64_t ldx,
+                                                           __nv_bfloat16* __restrict__ y, int M, int K, int as_weight) {
+  const int kv = K / 4;
+  const int64_t total = (int64_t)M * kv;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int m = (int)(i / kv), c = (int)(i % kv) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + c);
+    const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+    const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+    const uint2 hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    const uint2 lo = make_uint2(pack_bf16x2(v.x - h0, v.y - h1), pack_bf16x2(v.z - h2, v.w - h3));
+    __nv_bfloat16* row = y + (size_t)m * 3 * K + c;
+    *reinterpret_cast<uint2*>(row) = hi;
+    *reinterpret_cast<uint2*>(row + K) = as_weight ? hi : lo;
+    *reinterpret_cast<uint2*>(row + 2 * K) = as_weight ? lo : hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // bf16 -> fp32 widening (exact): a caller that already holds bf16 text states / token embeddings (the
 // encoders ran in bf16) hands them over as the GEMM operand directly; this builds the fp32 residual stream.
 // ------------------------------------------------------------------------------------------------
@@ -475,6 +501,22 @@ extern "C" int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y, in
   if (blocks < 1) blocks = 1;
   cast_f32_bf16_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<__nv_bfloat16*>(y), n);
+  ICKA_LAUNCHED(h);
+  return ICKA_OK;
+}
+
+extern "C" int icka_split_bf16x3(icka_handle* h, const float* x, int64_t ldx, void* y_bf16, int M, int K, int as_weight,
+                                 void* stream) {
+  ICKA_CHECK_HANDLE(h);
+  ICKA_REQUIRE(x && y_bf16 && M >= 0 && K >= 4 && K % 4 == 0 && ldx >= K && ldx % 4 == 0,
+               "split_bf16x3: bad arguments (K and the pitch must be multiples of 4)");
+  ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(y_bf16, 8), "split_bf16x3: pointers must be 16 / 8-byte aligned");
+  if (M == 0) return ICKA_OK;
+  int64_t blocks = ((int64_t)M * (K / 4) + 255) / 256;
+  const int64_t cap = (int64_t)h->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  split_bf16x3_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, static_cast<__nv_bfloat16*>(y_bf16), M, K, as_weight ? 1 : 0);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

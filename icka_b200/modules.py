@@ -43,6 +43,10 @@ from .autograd import (AddFn, AttnCoreFn, CastFn, CrossLayerFn, DenseActFn, Dens
                        LayerNormFn)
 from .precision import compute_dtype, get_precision, precision, set_precision  # noqa: F401  (re-exported)
 
+_X3_SINGLE_QUERY = True   # bf16 inference: vismapping and the FFN of the single-query (image->text) layers run on split-precision
+                          # ("bf16 x 3", ops.split3) operands.  One CLIP token per sentence walks 2 x layer_num1 layers; measured
+                          # at 256 sentences, L = 5 (tools/i2t_precision_probe2.py): plain bf16 operands end at 2.5e-2 of the fp32
+                          # reference (gate 2e-2; z0 alone is 6e-3 off and LayerNorm amplifies it), split FFN + exact z0 at 9e-3
 _FUSE_LN = False     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
                      # B200 the second (normalising) pass re-reads rows that have left L2 and is latency-bound:
                      # 511 us fused vs 227 + 152 us unfused at B=1024, so it stays off
@@ -180,6 +184,16 @@ class _DenseResidualNorm(nn.Module):
         return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
                              self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=get_precision() == 'bf16')
 
+    def _run_x3(self, h32: torch.Tensor, res32: torch.Tensor, defer_ln: bool = False):
+        """Same as ``_run`` with split-precision operands (fp32 product accuracy on the tensor cores): the single-query rows."""
+        w3 = self._cache.get('w3', (self.dense.weight,), lambda: ops.split3(self.dense.weight.detach().contiguous(), True))
+        pre = ops.linear(ops.split3(h32), w3, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32,
+                         alg_k=h32.shape[1])
+        if defer_ln:
+            return pre, None
+        return ops.layernorm(pre, self.LayerNorm.weight.detach(), self.LayerNorm.bias.detach(),
+                             self.LayerNorm.variance_epsilon, want_f32=True, want_bf16=True)
+
     def forward(self, hidden_states, input_tensor):
         _check_inference(self, self.dropout.p)
         shape = input_tensor.shape
@@ -227,6 +241,12 @@ class BertIntermediate(nn.Module):
     def _run(self, x_lp: torch.Tensor) -> torch.Tensor:
         w = _operand(self._cache, 'w', self.dense.weight)
         return ops.linear(x_lp, w, self.dense.bias.detach(), act=self.act, out_dtype=_cdt())
+
+    def _run_x3(self, x32: torch.Tensor) -> torch.Tensor:
+        """fp32 in, fp32 out, split-precision operands (see ``_DenseResidualNorm._run_x3``)."""
+        w3 = self._cache.get('w3', (self.dense.weight,), lambda: ops.split3(self.dense.weight.detach().contiguous(), True))
+        return ops.linear(ops.split3(x32), w3, self.dense.bias.detach(), act=self.act, out_dtype=torch.float32,
+                          alg_k=x32.shape[1])
 
     def forward(self, hidden_states):
         shape = hidden_states.shape[:-1]
@@ -379,6 +399,9 @@ class BertCrossAttentionLayer(nn.Module):
         if _recording(x32, y32, module=self):
             return self._run_recorded(x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv)
         a32, a_lp = self.attention._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
+        if Sq == 1 and _X3_SINGLE_QUERY and get_precision() == 'bf16' and a32.shape[1] % 4 == 0:
+            o32, o_lp = self.output._run_x3(self.intermediate._run_x3(a32), a32, defer_ln=defer_ln)
+            return o32, (o_lp if o_lp is not None else o32)
         f = self.intermediate._run(a_lp if a_lp is not None else a32)
         o32, o_lp = self.output._run(f, a32, defer_ln=defer_ln)      # deferred: o32 is the PRE-LayerNorm tensor
         return o32, (o_lp if o_lp is not None else o32)
@@ -527,12 +550,20 @@ class CrossModalFusion(nn.Module):
     def _image_to_text(self, clip_features, fused32, fused_lp, txt_mask, B, S, rec):
         """CMIM:954, 981-989: the single CLIP token queries the fused text states through every encoder of
         ``cls_layer_Y`` -> z32 [B, H]."""
-        clip_in = _to_lp(clip_features.detach().float().reshape(B, -1).contiguous())
-        w_vmap = _operand(self._cache, 'vmap', self.vismapping.weight)
-        if rec:
-            z32 = DenseFn.apply(clip_in, self.vismapping.weight, self.vismapping.bias, w_vmap)
+        clip32 = clip_features.detach().float().reshape(B, -1).contiguous()
+        if not rec and _X3_SINGLE_QUERY and get_precision() == 'bf16' and clip32.shape[1] % 4 == 0:
+            # z0 feeds a LayerNorm that amplifies its error by 1 / std(z0) ~ 1.7: split-precision operands (fp32 accuracy)
+            w3 = self._cache.get('vmap3', (self.vismapping.weight,),
+                                 lambda: ops.split3(self.vismapping.weight.detach().contiguous(), True))
+            z32 = ops.linear(ops.split3(clip32), w3, self.vismapping.bias.detach(), out_dtype=torch.float32,
+                             alg_k=clip32.shape[1])
         else:
-            z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
+            clip_in = _to_lp(clip32)
+            w_vmap = _operand(self._cache, 'vmap', self.vismapping.weight)
+            if rec:
+                z32 = DenseFn.apply(clip_in, self.vismapping.weight, self.vismapping.bias, w_vmap)
+            else:
+                z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
         z_lp = _to_lp(z32.detach())
         for enc in self.cls_layer_Y:
             zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None)

@@ -57,6 +57,18 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def split3(x: torch.Tensor, as_weight: bool = False) -> torch.Tensor:
+    """fp32 [M, K] (unit stride along K) -> bf16 [M, 3K] split-precision operand: [hi | lo | hi] (activations) or
+    [hi | hi | lo] (``as_weight``); see icka_split_bf16x3."""
+    if x.dim() != 2 or x.dtype != torch.float32 or x.stride(1) != 1:
+        raise RuntimeError('split3: need a 2-D fp32 tensor with unit stride along K')
+    M, K = x.shape
+    lib, h, st = _ctx(x)
+    y = torch.empty(M, 3 * K, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.icka_split_bf16x3(h, x.data_ptr(), _ld(x, K), y.data_ptr(), M, K, int(as_weight), st), 'icka_split_bf16x3')
+    return y
+
+
 def region_rows(grid: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     """[B, C, g, g] (or [B, C, R]) fp32 ResNet grid -> [B*R, C] rows (CMIM:956)."""
     _need(grid, torch.float32, 'region_rows(grid)')
@@ -86,11 +98,12 @@ def mask_additive(mask01: torch.Tensor, n: int) -> torch.Tensor:
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, residual: Optional[torch.Tensor] = None,
            act: int = ACT_NONE, out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
-           pre_act_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           pre_act_out: Optional[torch.Tensor] = None, alg_k: Optional[int] = None) -> torch.Tensor:
     """out[M,N] = act(a[M,K] . w[N,K]^T + bias) (+ residual).  a/w fp32 -> FFMA path, bf16 -> tcgen05 path.
 
     ``a`` and ``w`` may be row-pitched 2-D views (stride(1) == 1).  ``pre_act_out`` (contiguous [M,N] in the
-    operand dtype, GELU layers only) receives a . w^T + bias for the backward pass."""
+    operand dtype, GELU layers only) receives a . w^T + bias for the backward pass.  ``alg_k``: the contraction length of
+    the ALGORITHM when the operands are split-precision (``split3``: K' = 3K) -- bookkeeping for the profiler only."""
     if a.dim() != 2 or w.dim() != 2 or a.shape[1] != w.shape[1]:
         raise RuntimeError(f'linear: bad shapes {tuple(a.shape)} x {tuple(w.shape)}')
     if a.dtype != w.dtype or a.dtype not in _DT:

@@ -71,8 +71,8 @@ class FusionViterbiPipeline:
         return out['result'], out['clip'], tags, lens, out['gate']
 
     # ---- CUDA graph of the device-resident step -----------------------------------------------------
-    def capture(self, d: Dict[str, torch.Tensor], slot: int = 0):
-        """``slot``: library handle slot (own split-K workspace) -- captures that will be replayed CONCURRENTLY on
+    def capture(self, d: Dict[str, torch.Tensor], slot: int = 0, step=None):
+        """``step``: the bound step method to capture (default ``step_device``).  ``slot``: library handle slot (own split-K workspace) -- captures that will be replayed CONCURRENTLY on
         different streams must use different slots.
 
         Capture one ``step_device(d)`` -- ~40 kernel launches on two streams -- into a CUDA graph bound to the
@@ -80,15 +80,15 @@ class FusionViterbiPipeline:
         contents of ``d`` and refreshes ``outputs`` in place.  The step is launch-bound on a slow host (each
         launch goes Python -> ctypes -> cudaLaunchKernelEx); a replay is one driver call."""
         with _lib.use_slot(slot):
-            return self._capture(d)
+            return self._capture(d, step or self.step_device)
 
-    def _capture(self, d: Dict[str, torch.Tensor]):
+    def _capture(self, d: Dict[str, torch.Tensor], step):
         cur = torch.cuda.current_stream(self.device)
         warm = torch.cuda.Stream(self.device)
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):          # operand / fold caches and kernel attributes settle before capture
             for _ in range(2):
-                self.step_device(d)
+                step(d)
         cur.wait_stream(warm)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
@@ -97,7 +97,7 @@ class FusionViterbiPipeline:
         n0 = _lib.launch_count(idx)
         try:
             with torch.cuda.graph(graph):
-                outputs = self.step_device(d)
+                outputs = step(d)
         finally:
             self._capturing = False
         self.graph_kernels = _lib.launch_count(idx) - n0      # kernels one replay launches
@@ -131,12 +131,20 @@ class FusionViterbiPipeline:
     def h2d_bytes(host: Dict[str, torch.Tensor]) -> int:
         return sum(v.numel() * v.element_size() for v in host.values())
 
+    # what one host step hands back (device tensors to copy to pinned host memory), from the step's outputs
+    def _host_step(self, d: Dict[str, torch.Tensor]):
+        return self.step_device(d)
+
+    def _host_results(self, outs):
+        _, _, tags, lens, gate = outs
+        return tags, lens, gate
+
     @torch.no_grad()
     def infer_host(self, batches: List[Dict[str, torch.Tensor]], use_graphs: bool = True):
-        """End-to-end over pinned host batches: H2D copy of every input, fusion + Viterbi, D2H of tags,
-        lengths and gate values.  Copies of batch i+1 overlap the kernels of batch i (two device buffer
-        sets).  Returns per-batch (tags [B,S] int32, lens [B] int32, gate [B] fp32) pinned host tensors
-        and the (start, end) CUDA events that bracket all the work."""
+        """End-to-end over pinned host batches: H2D copy of every input, the device step, D2H of its results (fusion +
+        Viterbi pipeline: tags, lengths, gate values).  Copies of batch i+1 overlap the kernels of batch i (two device
+        buffer sets).  Returns per-batch tuples of pinned host tensors and the (start, end) CUDA events that bracket all
+        the work."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         cs = self._copy_stream
@@ -171,18 +179,14 @@ class FusionViterbiPipeline:
             if use_graphs:
                 if slots['graphs'][slot] is None:      # first use of this buffer set: capture its step once
                     main.synchronize()
-                    slots['graphs'][slot] = self.capture(dev_bufs[slot])
+                    slots['graphs'][slot] = self.capture(dev_bufs[slot], step=self._host_step)
                 graph, outs = slots['graphs'][slot]
                 graph.replay()
-                _, _, tags, lens, gate = outs
             else:
-                _, _, tags, lens, gate = self.step_device(dev_bufs[slot])
-            out = (torch.empty(tags.shape, dtype=tags.dtype, pin_memory=True),
-                   torch.empty(lens.shape, dtype=lens.dtype, pin_memory=True),
-                   torch.empty(gate.shape, dtype=gate.dtype, pin_memory=True))
-            out[0].copy_(tags, non_blocking=True)
-            out[1].copy_(lens, non_blocking=True)
-            out[2].copy_(gate, non_blocking=True)
+                outs = self._host_step(dev_bufs[slot])
+            out = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in self._host_results(outs))
+            for h, t in zip(out, self._host_results(outs)):
+                h.copy_(t, non_blocking=True)
             compute_done[slot] = torch.cuda.Event()
             compute_done[slot].record(main)
             results.append(out)
@@ -217,3 +221,26 @@ class TaggingPipeline(FusionViterbiPipeline):
         if label_ids is not None and self.f1 is not None:
             self.f1.update(tags, label_ids, d['crf_mask'])
         return emissions, tags, lens
+
+    # ---- end to end from host buffers: the tags DEPEND on the fusion result, emissions never cross PCIe ----------------
+    @staticmethod
+    def make_host_batch(B: int, shape: synth.Shape, seed: int, pin: bool = True,
+                        bf16_states: bool = False) -> Dict[str, torch.Tensor]:
+        """The fusion inputs + the CRF mask + the gold label ids (for the chunk-F1 counters); no emissions -- the emission
+        head produces them on the device from the fusion result (CMIM:1042-1043)."""
+        host = FusionViterbiPipeline.make_host_batch(B, shape, seed, pin=False, bf16_states=bf16_states)
+        del host['emissions']
+        host['label_ids'] = synth.crf_batch(B, shape, seed=seed)['tags']
+        if pin:
+            host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+        return host
+
+    def _host_step(self, d: Dict[str, torch.Tensor]):
+        """fusion -> BiLSTM + classifier -> Viterbi of those emissions -> chunk-F1 counters of THIS batch."""
+        if self.f1 is not None:
+            self.f1.reset()
+        _, tags, lens = self.step_tagging(d, d.get('label_ids'))
+        return tags, lens, (self.f1.totals if self.f1 is not None else lens)
+
+    def _host_results(self, outs):
+        return outs                      # tags [B,S] int32, lens [B] int32, chunk-F1 counters [6] int64

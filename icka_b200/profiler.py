@@ -16,12 +16,13 @@ from . import ops
 _ESZ = {torch.float32: 4, torch.bfloat16: 2, torch.uint8: 1, torch.int32: 4, torch.int64: 8}
 
 
-def _work_linear(a, w, bias, residual=None, act=0, out_dtype=None, out=None, pre_act_out=None):
+def _work_linear(a, w, bias, residual=None, act=0, out_dtype=None, out=None, pre_act_out=None, alg_k=None):
     M, K = a.shape
     N = w.shape[0]
     od = out_dtype or (out.dtype if out is not None else a.dtype)
     nbytes = M * K * _ESZ[a.dtype] + N * K * _ESZ[w.dtype] + M * N * _ESZ[od] + (M * N * 4 if residual is not None else 0)
-    return 'linear_bf16_tcgen05' if a.dtype == torch.bfloat16 else 'linear_fp32_ffma', 2.0 * M * N * K, nbytes
+    # split-precision operands (ops.split3): the algorithm's FLOPs are 2 M N K, the kernel executes 3x that
+    return 'linear_bf16_tcgen05' if a.dtype == torch.bfloat16 else 'linear_fp32_ffma', 2.0 * M * N * (alg_k or K), nbytes
 
 
 def _work(name, args, kwargs):

@@ -63,6 +63,14 @@ int icka_cast_f32_to_bf16(icka_handle* h, const float* x, void* y_bf16, int64_t 
  * (`+ input_tensor` of CMIM:564) / the fp32 `token_embedding` operand of the gate + blend (CMIM:1036). */
 int icka_cast_bf16_to_f32(icka_handle* h, const void* x_bf16, float* y, int64_t n, void* stream);
 
+/* Split-precision GEMM operand ("bf16 x 3"): x fp32 [M, K] (row pitch ldx) -> y bf16 [M, 3K] holding hi = bf16(x) and
+ * lo = bf16(x - hi) as [hi | lo | hi] (as_weight = 0, the activation side) or [hi | hi | lo] (as_weight = 1, the nn.Linear
+ * weight side).  icka_linear_fwd over K' = 3K of two such operands accumulates a_hi.w_hi + a_lo.w_hi + a_hi.w_lo in fp32:
+ * the fp32 product to ~2^-16 relative on the tensor cores.  The single-query image->text encoders (CMIM:981-989; M = batch
+ * rows) use it for vismapping (CMIM:954) and their FFN so that the CLIP token stays inside the bf16 gate (2e-2) after the
+ * 2 x layer_num1 layers it walks (10 at the script default, My_cross_attention.py:603).  K % 4 == 0. */
+int icka_split_bf16x3(icka_handle* h, const float* x, int64_t ldx, void* y_bf16, int M, int K, int as_weight, void* stream);
+
 /* CMIM:956  `visual_embeds_att.view(-1, 2048, 49).permute(0, 2, 1)`:
  * grid [B, C, R] fp32 (R contiguous) -> rows [B*R, C] in `out_dtype` (C contiguous, the K-major GEMM
  * operand the region projection wants). */
