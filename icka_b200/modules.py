@@ -43,10 +43,14 @@ from .autograd import (AddFn, AttnCoreFn, CastFn, CrossLayerFn, DenseActFn, Dens
                        LayerNormFn)
 from .precision import compute_dtype, get_precision, precision, set_precision  # noqa: F401  (re-exported)
 
-_X3_SINGLE_QUERY = True   # bf16 inference: vismapping and the FFN of the single-query (image->text) layers run on split-precision
-                          # ("bf16 x 3", ops.split3) operands.  One CLIP token per sentence walks 2 x layer_num1 layers; measured
-                          # at 256 sentences, L = 5 (tools/i2t_precision_probe2.py): plain bf16 operands end at 2.5e-2 of the fp32
-                          # reference (gate 2e-2; z0 alone is 6e-3 off and LayerNorm amplifies it), split FFN + exact z0 at 9e-3
+_X3_SINGLE_QUERY = True   # bf16 inference: split-precision ("bf16 x 3", ops.split3) operands on the single-query (image->text) chain.
+                          # One CLIP token per sentence walks 2 x layer_num1 layers; measured at 256 sentences, L = 5
+                          # (tools/i2t_precision_probe*.py): plain bf16 operands end 2.5e-2 off the fp32 reference (gate 2e-2) --
+                          # z0 = vismapping(clip) alone is 6e-3 off and the first LayerNorm amplifies it by 1 / std(z0) = 1.7.
+                          # vismapping always runs split (1.5e-2 -> 7e-3 after 2 layers, +7 us per 1024 sentences); the FFN of
+                          # the chain's layers does when the chain is >= _X3_FFN_MIN_LAYERS deep (10 layers: 1.9e-2 -> 1.5e-2,
+                          # +3 % step time), below that the error budget does not need it
+_X3_FFN_MIN_LAYERS = 4
 _FUSE_LN = False     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
                      # B200 the second (normalising) pass re-reads rows that have left L2 and is latency-bound:
                      # 511 us fused vs 227 + 152 us unfused at B=1024, so it stays off
@@ -395,11 +399,11 @@ class BertCrossAttentionLayer(nn.Module):
         self.intermediate = BertIntermediate(config)
         self.output = BertOutput(config)
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=None, defer_ln=False):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=None, defer_ln=False, x3_ffn=False):
         if _recording(x32, y32, module=self):
             return self._run_recorded(x32, y32, x_lp, y_lp, mask2d, B, Sq, Skv)
         a32, a_lp = self.attention._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv)
-        if Sq == 1 and _X3_SINGLE_QUERY and get_precision() == 'bf16' and a32.shape[1] % 4 == 0:
+        if x3_ffn and Sq == 1 and _X3_SINGLE_QUERY and get_precision() == 'bf16' and a32.shape[1] % 4 == 0:
             o32, o_lp = self.output._run_x3(self.intermediate._run_x3(a32), a32, defer_ln=defer_ln)
             return o32, (o_lp if o_lp is not None else o32)
         f = self.intermediate._run(a_lp if a_lp is not None else a32)
@@ -453,12 +457,15 @@ class BertCrossEncoder(nn.Module):
         layer = BertCrossAttentionLayer(config)
         self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(layer_num)])
 
-    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True, y32=None, defer_last_ln=False):
+    def _run(self, x32, x_lp, y_lp, mask2d, B, Sq, Skv, keep_all=True, y32=None, defer_last_ln=False, x3_ffn=None):
         """``defer_last_ln`` (inference only): the last layer returns its PRE-LayerNorm tensor; the caller applies
-        ``self.layer[-1].output.LayerNorm`` fused into the next kernel."""
+        ``self.layer[-1].output.LayerNorm`` fused into the next kernel.  ``x3_ffn``: split-precision FFN for single-query
+        rows (None: decide from this encoder's own depth)."""
+        if x3_ffn is None:
+            x3_ffn = len(self.layer) >= _X3_FFN_MIN_LAYERS
         outs = []
         for i, layer_module in enumerate(self.layer):
-            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=y32,
+            x32, x_lp = layer_module._run(x32, x_lp, y_lp, mask2d, B, Sq, Skv, y32=y32, x3_ffn=x3_ffn,
                                           defer_ln=defer_last_ln and i == len(self.layer) - 1)
             if keep_all:
                 outs.append(x32)
@@ -565,8 +572,10 @@ class CrossModalFusion(nn.Module):
             else:
                 z32 = ops.linear(clip_in, w_vmap, self.vismapping.bias.detach(), out_dtype=torch.float32)
         z_lp = _to_lp(z32.detach())
+        x3_ffn = sum(len(enc.layer) for enc in self.cls_layer_Y) >= _X3_FFN_MIN_LAYERS
         for enc in self.cls_layer_Y:
-            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None)
+            zs, z_lp = enc._run(z32, z_lp, fused_lp, txt_mask, B, 1, S, keep_all=False, y32=fused32 if rec else None,
+                                x3_ffn=x3_ffn)
             z32 = zs[-1]
         return z32
 
