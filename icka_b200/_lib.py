@@ -54,6 +54,7 @@ SIGNATURES = {
     'icka_crf_llh_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'icka_set_gemm_mode': (c_int, [c_int]),
+    'icka_set_ln_mode': (c_int, [c_int]),
     'icka_set_attn_mode': (c_int, [c_int]),
     'icka_layernorm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
                                    c_int, c_void_p]),

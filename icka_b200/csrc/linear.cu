@@ -21,6 +21,19 @@ int icka_gemm_bf16_ln_launch(icka_handle* h, const void* A, int64_t lda, const v
                              const float* residual, const float* gamma, const float* beta, float eps, float* out32,
                              void* out16, int M, int N, int K, cudaStream_t st);
 
+bool icka_gemm_ln_cluster_supported(int N, int K, const void* residual);
+int icka_gemm_bf16_ln_cluster_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                     const float* bias, const float* residual, const float* gamma, const float* beta,
+                                     float eps, float* out32, void* out16, int M, int N, int K, cudaStream_t st);
+
+// icka_set_ln_mode: 0 = choose per shape (default), 1 = single-CTA kernel (rows re-read from L2), 2 = cluster kernel
+static int g_ln_mode = 0;
+extern "C" int icka_set_ln_mode(int mode) {
+  ICKA_REQUIRE(mode >= 0 && mode <= 2, "ln mode %d not in 0..2", mode);
+  g_ln_mode = mode;
+  return ICKA_OK;
+}
+
 extern "C" int icka_linear_ln_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
                                   const float* bias, const float* residual, const float* gamma, const float* beta,
                                   float eps, float* out_f32, void* out_bf16, int in_dtype, int M, int N, int K,
@@ -32,8 +45,16 @@ extern "C" int icka_linear_ln_fwd(icka_handle* h, const void* A, int64_t lda, co
   ICKA_REQUIRE(in_dtype == ICKA_F32 || in_dtype == ICKA_BF16, "linear_ln: bad in_dtype %d", in_dtype);
   if (M == 0) return ICKA_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (in_dtype == ICKA_BF16)
+  if (in_dtype == ICKA_BF16) {
+    // N = 768 / 1024 (and 512): a cluster of N / 256 CTAs shares each 128-row block and exchanges the row statistics
+    // over distributed shared memory (csrc/gemm_ln_sm100.cu); other widths: one CTA walks the n-tiles of its rows
+    const bool cluster_ok = icka_gemm_ln_cluster_supported(N, K, residual);
+    if (g_ln_mode == 2 && !cluster_ok) ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "linear_ln: cluster kernel does not serve N=%d K=%d", N, K);
+    if (cluster_ok && g_ln_mode != 1)
+      return icka_gemm_bf16_ln_cluster_launch(h, A, lda, W, ldw, bias, residual, gamma, beta, eps, out_f32, out_bf16, M,
+                                              N, K, st);
     return icka_gemm_bf16_ln_launch(h, A, lda, W, ldw, bias, residual, gamma, beta, eps, out_f32, out_bf16, M, N, K, st);
+  }
   // fp32 parity path: the FFMA GEMM writes the pre-LayerNorm rows, the row kernel normalises them in place
   int rc = icka_sgemm_launch(h, static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, bias, residual,
                              out_f32, N, ICKA_F32, M, N, K, ICKA_ACT_NONE, nullptr, st);

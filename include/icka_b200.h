@@ -98,12 +98,19 @@ int icka_linear_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, i
 /* Dense layer + residual + BertLayerNorm in one call (BertSelfOutput CMIM:561-565, BertOutput CMIM:532-536):
  *   out = LayerNorm_{gamma,beta,eps}(A[M,K] . W[N,K]^T + bias + residual[M,N])
  * out_f32 [M,N] (pitch N) and optionally out_bf16 [M,N] (the next GEMM's operand; may be NULL).  bf16 operands:
- * the normalisation runs in the epilogue of the tcgen05 GEMM -- a CTA owns whole 128-row blocks, keeps row sums
- * while it walks the n-tiles, and re-reads its own (L2-resident) fp32 stores once to normalise them in place.
+ * the normalisation runs in the epilogue of the tcgen05 GEMM.  N = 768 / 1024 (the model widths): a thread-block cluster
+ * of N / 256 CTAs owns each 128-row block, CTA r holds columns [256 r, 256 r + 256) in TMEM, pre-LayerNorm values are
+ * parked in TMEM, the row sums travel over distributed shared memory and the normalised rows leave through TMA stores
+ * (csrc/gemm_ln_sm100.cu).  Other widths: one CTA owns whole 128-row blocks, keeps row sums while it walks the n-tiles
+ * and re-reads its own (L2-resident) fp32 stores once to normalise them in place.
  * fp32 operands: FFMA GEMM followed by the row kernel. */
 int icka_linear_ln_fwd(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
                        const float* bias, const float* residual, const float* gamma, const float* beta, float eps,
                        float* out_f32, void* out_bf16, int in_dtype, int M, int N, int K, void* stream);
+
+/* Developer / test switch for icka_linear_ln_fwd with bf16 operands: 0 = choose per shape (default), 1 = the single-CTA
+ * kernel, 2 = the cluster kernel (N = 512 / 768 / 1024: N / 256 CTAs per 128-row block, statistics over DSMEM). */
+int icka_set_ln_mode(int mode);
 
 /* Training-time forward: icka_linear_fwd that can also keep the pre-activation (A.W^T + bias, in the
  * operand dtype, pitch N) of a GELU layer for the backward pass.  pre_act_out may be NULL. */

@@ -68,12 +68,25 @@ def test_linear_bf16_pitched_kv_views(gemm_mode):
     assert float((got.double() - want).abs().max()) <= 2e-5
 
 
+@pytest.fixture(params=[0, 1, 2], ids=['ln_auto', 'ln_single_cta', 'ln_cluster'])
+def ln_mode(request):
+    from icka_b200 import _lib
+    _lib.check(_lib.load().icka_set_ln_mode(request.param), 'icka_set_ln_mode')
+    yield request.param
+    _lib.load().icka_set_ln_mode(0)
+
+
 @pytest.mark.parametrize('M,N,K', [(128, 768, 768), (1000, 768, 3072), (300, 256, 64), (77, 1024, 512), (128 * 160, 768, 768),
-                                    (5, 136, 40)])
+                                    (5, 136, 40), (128 * 300 + 9, 768, 768), (1, 1024, 1024), (4100, 512, 128)])
 @pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
-def test_linear_ln_fused_epilogue(M, N, K, dtype):
-    """Dense + bias + residual + BertLayerNorm in one call (LayerNorm in the tcgen05 epilogue for bf16 operands)."""
+def test_linear_ln_fused_epilogue(M, N, K, dtype, ln_mode):
+    """Dense + bias + residual + BertLayerNorm in one call (LayerNorm in the tcgen05 epilogue for bf16 operands: the
+    cluster kernel for N = 512 / 768 / 1024, the single-CTA kernel otherwise)."""
     from oracle import fusion_ref
+    if ln_mode == 2 and (dtype != torch.bfloat16 or N not in (512, 768, 1024)):
+        pytest.skip('the cluster kernel serves bf16 operands with N = 512 / 768 / 1024')
+    if ln_mode != 0 and dtype != torch.bfloat16:
+        pytest.skip('fp32 operands take the FFMA path in every mode')
     a = rnd(M, K, seed=11).to(dtype)
     w = (rnd(N, K, seed=12) / math.sqrt(K)).to(dtype)
     bias, res = rnd(N, seed=13), rnd(M, N, seed=14)
