@@ -369,11 +369,12 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st);
 
-// 0 = pick per shape (tcgen05 kernel when Skv <= 64, else mma.sync), 1 = always the mma.sync kernel,
-// 2 = like 0 plus the wide tcgen05 variant for 64 < Skv <= 224
+// 0 = pick per shape (tcgen05 kernels for Skv <= 224, mma.sync beyond), 1 = always the mma.sync kernel,
+// 2 = the first wide tcgen05 variant for 64 < Skv <= 224 (one softmax group, P through shared memory),
+// 3 = same as 0 (the second wide variant -- two softmax groups, P in tensor memory -- is the default)
 int g_attn_mode = 0;   // shared with i2t_pool.cu and attention_sm100.cu
 extern "C" int icka_set_attn_mode(int mode) {
-  if (mode < 0 || mode > 2) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..2", mode);
+  if (mode < 0 || mode > 3) ICKA_FAIL(ICKA_ERR_INVALID, "attention mode %d not in 0..3", mode);
   g_attn_mode = mode;
   return ICKA_OK;
 }

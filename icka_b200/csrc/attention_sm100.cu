@@ -22,6 +22,8 @@
 #include "sm100_ptx.cuh"
 #include "philox.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace sm100;
@@ -45,6 +47,7 @@ struct AttnArgs {
   uint32_t drop_thresh;   // attention-probability dropout (CMIM:616), training only; 0 = off
   float drop_scale;
   uint64_t seed;
+  int debug;              // developer probe (ICKA_ATTN_DEBUG=1): CTA 0 prints the cycle stamps of its first items (wide2 kernel)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
@@ -524,6 +527,401 @@ cross_attn_tcgen05_wide_kernel(const __grid_constant__ CUtensorMap tmap_q, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Wide variant 2 (the default for 64 < Skv <= 224): TWO softmax groups alternate items, and the probabilities never
+// touch shared memory: a thread overwrites its fp32 score row in TMEM with the bf16 probabilities (tcgen05.st, two
+// per 32-bit column) and O = P V takes its A operand straight from tensor memory (tcgen05.mma with [a_tmem]).
+//   TMEM  S/P slot g at columns [g * KEYS, (g + 1) * KEYS)  (P = the first KEYS / 2 columns of the slot), O at [2 KEYS, +64)
+//   smem  two rings with different lifetimes: {Q 128 x 64, K KEYS x 64} x 2 -- dead as soon as QK^T has run, so the next
+//         items' Q and K are always in place early -- and V KEYS x 64 x 3, held until P V has run; one 16 KB output
+//         staging tile per group (row -> coalesced 16-byte stores).  (With one ring of whole {Q, K, V} stages, 72 KB each,
+//         only three fit and the loads sat on the critical path: 2200 of the 9500 cycles of an item were spent waiting
+//         for the scores, tools/attn_one.py with ICKA_ATTN_DEBUG=1.)
+// The single O slot serialises only the short P V + read-out of consecutive items; QK^T of item n + 1 and the softmax
+// of item n overlap, as do one group's softmax and the other's epilogue.
+// ------------------------------------------------------------------------------------------------------------
+template <int KEYS>
+struct Wide2Cfg {
+  static constexpr int kKVBytes = KEYS * 128;
+  static constexpr int kQKBytes = kQBytes + kKVBytes;
+  static constexpr int kQKStages = 2, kVStages = 3;
+  static constexpr int kOutBytes = kRows * 128;             // 128 rows x 64 bf16
+  static constexpr int kThreads = 320;
+  static constexpr uint32_t kOCol = 2 * KEYS;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr size_t kSmemBytes = (size_t)kQKStages * kQKBytes + (size_t)kVStages * kKVBytes + 2 * kOutBytes +
+                                       4 * KEYS * sizeof(float) + 1024 + 256;
+  static_assert(2 * KEYS + 64 <= 512, "two score slots and one output slot must fit the 512 TMEM columns");
+  static_assert(KEYS % 32 == 0, "score rows are swept in 32-column pieces");
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem: lane = row, two bf16 per 32-bit column] . B[smem], issued by ONE thread
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// developer timeline (ICKA_ATTN_DEBUG=1): cycle stamps of CTA 0, items [kTraceFrom, kTraceFrom + kTraceItems), read back and
+// printed by the launcher after the kernel: [item][0..1] = QK issued, PV issued (MMA thread); [2..7] = group thread: start,
+// S ready, max known, P written, O ready, done
+constexpr int kTraceFrom = 8, kTraceItems = 16;
+__device__ long long g_wide2_trace[kTraceItems][8];
+
+template <int KEYS>
+__global__ void __launch_bounds__(Wide2Cfg<KEYS>::kThreads, 1)
+cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                                const __grid_constant__ CUtensorMap tmap_v, const AttnArgs args) {
+  using Cfg = Wide2Cfg<KEYS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* qk_base = smem;                                                       // [kQKStages] {Q, K}
+  uint8_t* v_base = smem + (size_t)Cfg::kQKStages * Cfg::kQKBytes;              // [kVStages] V
+  uint8_t* out_buf = v_base + (size_t)Cfg::kVStages * Cfg::kKVBytes;            // [group] 16 KB
+  float* mask_s = reinterpret_cast<float*>(out_buf + 2 * Cfg::kOutBytes);       // [group][2 buffers][KEYS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 4 * KEYS);
+  uint64_t* qk_full = bars;
+  uint64_t* qk_empty = qk_full + Cfg::kQKStages;
+  uint64_t* v_full = qk_empty + Cfg::kQKStages;
+  uint64_t* v_empty = v_full + Cfg::kVStages;
+  uint64_t* s_full = v_empty + Cfg::kVStages;   // [2] S = QK^T of the group's item is in its slot
+  uint64_t* p_full = s_full + 2;                // [2] the group has replaced S by P
+  uint64_t* o_full = p_full + 2;                // [2] O = P V of the group's item is complete
+  uint64_t* o_free = o_full + 2;                // [2] the group has read O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int items = args.B * args.nh * args.q_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < Cfg::kQKStages; ++s) {
+      mbar_init(&qk_full[s], 1);
+      mbar_init(&qk_empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::kVStages; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_free[g], 4);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sq = 0, sv = 0;
+      uint32_t pq = 0, pv = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+        const int h = bh % args.nh, b = bh / args.nh;
+        uint8_t* qk = qk_base + (size_t)sq * Cfg::kQKBytes;
+        mbar_wait(&qk_empty[sq], pq ^ 1);
+        mbar_arrive_expect_tx(&qk_full[sq], Cfg::kQKBytes);
+        tma_load_2d(qk, &tmap_q, &qk_full[sq], h * kD, b * args.Sq + qt * kRows);
+        tma_load_2d(qk + kQBytes, &tmap_k, &qk_full[sq], h * kD, b * args.Skv);
+        if (++sq == Cfg::kQKStages) { sq = 0; pq ^= 1; }
+        mbar_wait(&v_empty[sv], pv ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], Cfg::kKVBytes);
+        tma_load_2d(v_base + (size_t)sv * Cfg::kKVBytes, &tmap_v, &v_full[sv], h * kD, b * args.Skv);
+        if (++sv == Cfg::kVStages) { sv = 0; pv ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16_f32(kRows, KEYS);
+      constexpr uint32_t idesc_o = make_idesc_bf16_f32(kRows, kD, false, true);
+      int sq = 0;
+      uint32_t pq = 0;
+      int n = 0;
+      auto issue_pv = [&](int m) {
+        const int g = m & 1;
+        const int sv = m % Cfg::kVStages;
+        mbar_wait(&v_full[sv], (uint32_t)((m / Cfg::kVStages) & 1));
+        mbar_wait(&p_full[g], (m >> 1) & 1);
+        if (m >= 1) mbar_wait(&o_free[(m - 1) & 1], ((m - 1) >> 1) & 1);     // the previous item's O has been read
+        tc_fence_after();
+        const uint32_t p_tmem = tmem_base + (uint32_t)(g * KEYS);
+        const uint32_t v_addr = smem_u32(v_base + (size_t)sv * Cfg::kKVBytes);
+#pragma unroll
+        for (int k = 0; k < KEYS / 16; ++k)      // 16 keys = 8 packed TMEM columns of P, 16 rows of the in-place V tile
+          umma_bf16_ts(tmem_base + Cfg::kOCol, p_tmem + (uint32_t)(k * 8),
+                       make_mnmajor_sw128_desc(v_addr + k * (16 * 128), Cfg::kKVBytes), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&v_empty[sv]);
+        umma_commit(&o_full[g]);
+      };
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        mbar_wait(&qk_full[sq], pq);
+        tc_fence_after();
+        // slot n & 1 is free: P V of item n - 2 was issued before this point and the tensor pipe runs in order
+        const uint32_t q_addr = smem_u32(qk_base + (size_t)sq * Cfg::kQKBytes);
+        const uint32_t k_addr = q_addr + kQBytes;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem_base + (uint32_t)((n & 1) * KEYS), make_kmajor_sw128_desc(q_addr + k * 32),
+                    make_kmajor_sw128_desc(k_addr + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&qk_empty[sq]);            // Q and K of this item are dead once the scores exist
+        umma_commit(&s_full[n & 1]);
+        const bool tr = args.debug && blockIdx.x == 0;
+        if (tr && n >= kTraceFrom && n < kTraceFrom + kTraceItems) g_wide2_trace[n - kTraceFrom][0] = clock64();
+        if (n >= 1) issue_pv(n - 1);
+        if (tr && n - 1 >= kTraceFrom && n - 1 < kTraceFrom + kTraceItems) g_wide2_trace[n - 1 - kTraceFrom][1] = clock64();
+        if (++sq == Cfg::kQKStages) { sq = 0; pq ^= 1; }
+      }
+      if (n >= 1) issue_pv(n - 1);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int g = (warp - 2) >> 2;                     // softmax group == score slot
+    const int row = quad * 32 + lane;
+    const int gtid = ((warp - 2) & 3) * 32 + lane;
+    const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * KEYS);
+    const uint32_t tmem_o = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kOCol;
+    float* gmask = mask_s + g * 2 * KEYS;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;
+    // additive key mask of an item, two keys per thread: loaded into registers at the start of the PREVIOUS item of the
+    // group, written to the other shared-memory buffer at its end (the global latency is off the critical path)
+    constexpr int kMaskRegs = (KEYS + 127) / 128;
+    auto load_mask = [&](int item, float (&mreg)[kMaskRegs]) {
+#pragma unroll
+      for (int i = 0; i < kMaskRegs; ++i) {
+        const int j = gtid + i * 128;
+        mreg[i] = -INFINITY;
+        if (item < items && j < args.Skv) {
+          const int b = item / (args.q_tiles * args.nh);
+          mreg[i] = args.mask_add ? __ldg(args.mask_add + (size_t)b * args.Skv + j) * kLog2e : 0.0f;
+        }
+      }
+    };
+    auto store_mask = [&](const float (&mreg)[kMaskRegs], float* dst) {
+#pragma unroll
+      for (int i = 0; i < kMaskRegs; ++i)
+        if (gtid + i * 128 < KEYS) dst[gtid + i * 128] = mreg[i];
+    };
+    const int stride = 2 * (int)gridDim.x;
+    float mreg[kMaskRegs];
+    load_mask((int)blockIdx.x + g * (int)gridDim.x, mreg);
+    store_mask(mreg, gmask);
+    int m = 0;                                         // this group's item counter
+    for (int it = blockIdx.x + g * gridDim.x; it < items; it += stride, ++m) {
+      const uint32_t par = m & 1;
+      const int qt = it % args.q_tiles, bh = it / args.q_tiles;
+      const int h = bh % args.nh, b = bh / args.nh;
+      uint8_t* obuf = out_buf + g * Cfg::kOutBytes;
+      const float* mk = gmask + (m & 1) * KEYS;
+      const bool trace = args.debug && blockIdx.x == 0 && quad == 0 && lane == 0 && 2 * m + g >= kTraceFrom &&
+                         2 * m + g < kTraceFrom + kTraceItems;
+      long long tk[6];
+      if (trace) tk[0] = clock64();
+      named_bar_sync(1 + g, 128);            // the mask of this item is in place (and the other buffer is free)
+      load_mask(it + stride, mreg);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      if (trace) tk[1] = clock64();
+      // ---- sweep 1: row maximum.  Scores are scaled and masked two at a time on the packed fp32x2 pipe (FFMA2), the
+      //      maximum runs in four independent chains of 3-input FMNMX; the next 32-column piece is in flight meanwhile ----
+      const uint64_t scale2 = f2_splat(kScale);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      {
+        uint32_t sa[32], sb[32];
+        tmem_ld_32x32b_x32(tmem_s, sa);
+#pragma unroll 1
+        for (int c0 = 0; c0 < KEYS; c0 += 64) {
+          tmem_ld_wait();
+          if (c0 + 32 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 32), sb);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + j);
+            float t0, t1, t2, t3;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sa[j]), __uint_as_float(sa[j + 1])), scale2, f2_pack(mq.x, mq.y)), t0, t1);
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sa[j + 2]), __uint_as_float(sa[j + 3])), scale2, f2_pack(mq.z, mq.w)), t2, t3);
+            mx4[(j >> 2) & 3] = fmaxf(fmaxf(mx4[(j >> 2) & 3], fmaxf(t0, t1)), fmaxf(t2, t3));
+          }
+          if (c0 + 32 < KEYS) {
+            tmem_ld_wait();
+            if (c0 + 64 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 64), sa);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + 32 + j);
+              float t0, t1, t2, t3;
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(sb[j]), __uint_as_float(sb[j + 1])), scale2, f2_pack(mq.x, mq.y)), t0, t1);
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(sb[j + 2]), __uint_as_float(sb[j + 3])), scale2, f2_pack(mq.z, mq.w)), t2, t3);
+              mx4[(j >> 2) & 3] = fmaxf(fmaxf(mx4[(j >> 2) & 3], fmaxf(t0, t1)), fmaxf(t2, t3));
+            }
+          }
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      if (trace) tk[2] = clock64();
+      // ---- sweep 2: P = exp2(s - max) as bf16 pairs over the consumed part of the score row; l = undropped row sum ----
+      const uint64_t nmx2 = f2_splat(-mx);
+      uint64_t l2[2] = {f2_splat(0.0f), f2_splat(0.0f)};
+      const uint64_t drow = ((uint64_t)b * args.nh + h) * (uint64_t)args.Sq + (uint64_t)(qt * kRows + row);
+      uint32_t sr[32];
+      tmem_ld_32x32b_x32(tmem_s, sr);
+#pragma unroll 1
+      for (int c0 = 0; c0 < KEYS; c0 += 32) {
+        tmem_ld_wait();
+        float sc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + j);
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), scale2, f2_pack(mq.x, mq.y)), nmx2),
+                    sc[j], sc[j + 1]);
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[j + 2]), __uint_as_float(sr[j + 3])), scale2, f2_pack(mq.z, mq.w)), nmx2),
+                    sc[j + 2], sc[j + 3]);
+        }
+        if (c0 + 32 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 32), sr);     // in flight during the exponentials
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {      // 8 keys at a time
+          float p[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) p[j] = ex2(sc[8 * c + j]);
+          l2[0] = f2_add(l2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[2], p[3])));
+          l2[1] = f2_add(l2[1], f2_add(f2_pack(p[4], p[5]), f2_pack(p[6], p[7])));
+          if (args.drop_thresh) {
+#pragma unroll
+            for (int g4 = 0; g4 < 2; ++g4) {
+              const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+                                                         icka_rng::attn_group(drow, args.Skv, c0 + 8 * c + 4 * g4), args.drop_thresh);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
+            }
+          }
+          pk[4 * c] = pack_bf16x2(p[0], p[1]);
+          pk[4 * c + 1] = pack_bf16x2(p[2], p[3]);
+          pk[4 * c + 2] = pack_bf16x2(p[4], p[5]);
+          pk[4 * c + 3] = pack_bf16x2(p[6], p[7]);
+        }
+        // columns [c0/2, c0/2 + 16) end at or below c0 + 32: their scores are in registers already, and the piece in flight
+        // starts at c0 + 32
+        tmem_st_32x32b_x16(tmem_s + (uint32_t)(c0 >> 1), pk);
+      }
+      float la, lb, lc, ld;
+      f2_unpack(l2[0], la, lb);
+      f2_unpack(l2[1], lc, ld);
+      const float l = (la + lb) + (lc + ld);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (trace) tk[3] = clock64();
+
+      // ---- epilogue ----
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+      if (trace) tk[4] = clock64();
+      uint32_t orr[64];
+      tmem_ld_32x32b_x32(tmem_o, *reinterpret_cast<uint32_t(*)[32]>(&orr[0]));
+      tmem_ld_32x32b_x32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&orr[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      const float inv = 1.0f / l;
+      uint8_t* prow0 = obuf + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
+        *reinterpret_cast<uint4*>(prow0 + ((c ^ (row & 7)) << 4)) = u;
+      }
+      __syncwarp();
+      {
+        const int cch = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = quad * 32 + i * 4 + (lane >> 3);
+          const int q_row = qt * kRows + r;
+          if (q_row < args.Sq) {
+            const uint4 u = *reinterpret_cast<const uint4*>(obuf + r * 128 + ((cch ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(args.ctx + ((size_t)b * args.Sq + q_row) * args.ldc + (size_t)h * kD + cch * 8) = u;
+          }
+        }
+      }
+      __syncwarp();
+      store_mask(mreg, gmask + ((m & 1) ^ 1) * KEYS);
+      if (trace) {
+        tk[5] = clock64();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g_wide2_trace[2 * m + g - kTraceFrom][2 + i] = tk[i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int KEYS>
+int launch_wide2(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const AttnArgs& args,
+                 cudaStream_t st) {
+  using Cfg = Wide2Cfg<KEYS>;
+  if (h->smem_optin < Cfg::kSmemBytes) return 1;
+  CUtensorMap tq, tk, tv;
+  int rc = icka_make_tmap_bf16(h, &tq, q, (int64_t)args.B * args.Sq, (int64_t)args.nh * kD, ldq, kRows);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tk, k, (int64_t)args.B * args.Skv, (int64_t)args.nh * kD, ldkv, KEYS);
+  if (rc) return rc;
+  rc = icka_make_tmap_bf16(h, &tv, v, (int64_t)args.B * args.Skv, (int64_t)args.nh * kD, ldkv, KEYS);
+  if (rc) return rc;
+  const int items = args.B * args.nh * args.q_tiles;
+  ICKA_CUDA(cudaFuncSetAttribute(cross_attn_tcgen05_wide2_kernel<KEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg::kSmemBytes));
+  const int grid = items < h->sm_count ? items : h->sm_count;
+  cross_attn_tcgen05_wide2_kernel<KEYS><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tq, tk, tv, args);
+  ICKA_LAUNCHED(h);
+  if (args.debug) {      // developer timeline: synchronises, prints cycles relative to the first traced stamp
+    long long tr[kTraceItems][8];
+    ICKA_CUDA(cudaStreamSynchronize(st));
+    ICKA_CUDA(cudaMemcpyFromSymbol(tr, g_wide2_trace, sizeof(tr)));
+    const long long t0 = tr[0][2];
+    fprintf(stderr, "wide2 timeline (cycles, CTA 0): item grp | QK issued  PV issued | start  S ready  max  P written  O ready  done\n");
+    for (int i = 0; i < kTraceItems; ++i)
+      fprintf(stderr, "  %3d  g%d | %8lld %8lld | %8lld %8lld %8lld %8lld %8lld %8lld\n", i + kTraceFrom, (i + kTraceFrom) & 1,
+              tr[i][0] - t0, tr[i][1] - t0, tr[i][2] - t0, tr[i][3] - t0, tr[i][4] - t0, tr[i][5] - t0, tr[i][6] - t0, tr[i][7] - t0);
+  }
+  return ICKA_OK;
+}
+
 template <int KEYS>
 int launch_wide(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, const AttnArgs& args,
                 cudaStream_t st) {
@@ -554,12 +952,17 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st) {
   extern int g_attn_mode;
   if (Skv > kKeys) {
-    // The wide variant is correct but, with one TMEM slot and one softmax group, no faster than the mma.sync kernel
-    // on the 196-region shape (0.47 ms vs 0.46 ms at B=512): it runs only when asked for (icka_set_attn_mode(2)).
-    if (Skv > 224 || g_attn_mode != 2) return 1;
+    // 64 < Skv <= 224 (the 196-region grid): two softmax groups with the probabilities in tensor memory (wide2) by
+    // default; icka_set_attn_mode(2) selects the first wide variant (one group, P through shared memory: no faster than
+    // the mma.sync kernel, 0.46 vs 0.48 ms at 512 hi-res sentences; wide2: 0.28 ms)
+    // (a single query row per sentence -- the image->text encoders in fp32 / training mode -- would fill 1 of the 128 rows
+    // of an item: the mma.sync kernel is faster there, 122 vs 160 us at 1024 sentences)
+    if (Skv > 224 || (Sq < 32 && g_attn_mode == 0)) return 1;
     AttnArgs wargs{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows,
-                   drop_thresh, drop_scale, seed};
-    return Skv <= 128 ? launch_wide<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide<224>(h, q, ldq, k, v, ldkv, wargs, st);
+                   drop_thresh, drop_scale, seed, getenv("ICKA_ATTN_DEBUG") ? 1 : 0};
+    if (g_attn_mode == 2)
+      return Skv <= 128 ? launch_wide<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide<224>(h, q, ldq, k, v, ldkv, wargs, st);
+    return Skv <= 128 ? launch_wide2<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide2<224>(h, q, ldq, k, v, ldkv, wargs, st);
   }
   if (h->smem_optin < kSmemBytes) return 1;
   CUtensorMap tq, tk, tv;

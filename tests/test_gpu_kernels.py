@@ -94,7 +94,7 @@ def test_cross_attn_core_fp32_and_bf16():
 @pytest.mark.parametrize('B,Sq,Skv,nh', [(3, 128, 49, 12), (2, 16, 9, 2), (5, 128, 64, 1), (2, 300, 49, 3), (40, 128, 49, 12),
                                           (1, 1, 1, 1), (2, 256, 196, 12), (30, 256, 196, 12), (3, 128, 128, 4), (3, 100, 100, 2),
                                           (2, 128, 224, 1), (2, 64, 225, 2), (4, 1, 128, 12)])
-@pytest.mark.parametrize('attn_mode', [0, 1, 2], ids=['tcgen05', 'mma_sync', 'tcgen05_wide'])
+@pytest.mark.parametrize('attn_mode', [0, 1, 2, 3], ids=['tcgen05', 'mma_sync', 'tcgen05_wide', 'tcgen05_wide2'])
 def test_cross_attn_core_bf16_kernels(B, Sq, Skv, nh, attn_mode):
     """Both bf16 attention kernels (tcgen05/TMEM for Skv <= 64, mma.sync) against the fp64 formula on the same
     bf16-rounded operands; ragged Sq (rows of the next sentence / zero fill inside the Q box) and key masks."""
