@@ -528,8 +528,10 @@ cross_attn_tcgen05_wide_kernel(const __grid_constant__ CUtensorMap tmap_q, const
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Wide variant 2 (the default for 64 < Skv <= 224): TWO softmax groups alternate items, and the probabilities never
-// touch shared memory: a thread overwrites its fp32 score row in TMEM with the bf16 probabilities (tcgen05.st, two
+// Wide variant 2 (the default for 64 < Skv <= 224): TWO softmax groups of EIGHT warps alternate items (two warps per
+// TMEM lane quadrant: a row's keys are split between two threads, which exchange the partial row maximum and sum through
+// shared memory -- the row softmax is a chain of TMEM loads, exponentials and packs that four warps per scheduler hide
+// far better than two), and the probabilities never touch shared memory: a thread overwrites its fp32 score row in TMEM with the bf16 probabilities (tcgen05.st, two
 // per 32-bit column) and O = P V takes its A operand straight from tensor memory (tcgen05.mma with [a_tmem]).
 //   TMEM  S/P slot g at columns [g * KEYS, (g + 1) * KEYS)  (P = the first KEYS / 2 columns of the slot), O at [2 KEYS, +64)
 //   smem  two rings with different lifetimes: {Q 128 x 64, K KEYS x 64} x 2 -- dead as soon as QK^T has run, so the next
@@ -546,11 +548,13 @@ struct Wide2Cfg {
   static constexpr int kQKBytes = kQBytes + kKVBytes;
   static constexpr int kQKStages = 2, kVStages = 3;
   static constexpr int kOutBytes = kRows * 128;             // 128 rows x 64 bf16
-  static constexpr int kThreads = 320;
+  static constexpr int kThreads = 64 + 512;                  // TMA warp, MMA warp, 2 groups x 8 softmax warps
+  static constexpr int kSplit = ((KEYS / 32 + 1) / 2) * 32; // keys [0, kSplit) belong to the first warp of a quadrant pair
   static constexpr uint32_t kOCol = 2 * KEYS;
   static constexpr uint32_t kTmemCols = 512;
+  static constexpr int kXchBytes = 2 * 2 * 4 * 2 * 32 * 4;   // {max, sum} x group x quadrant x half x lane
   static constexpr size_t kSmemBytes = (size_t)kQKStages * kQKBytes + (size_t)kVStages * kKVBytes + 2 * kOutBytes +
-                                       4 * KEYS * sizeof(float) + 1024 + 256;
+                                       4 * KEYS * sizeof(float) + kXchBytes + 1024 + 256;
   static_assert(2 * KEYS + 64 <= 512, "two score slots and one output slot must fit the 512 TMEM columns");
   static_assert(KEYS % 32 == 0, "score rows are swept in 32-column pieces");
 };
@@ -593,7 +597,8 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
   uint8_t* v_base = smem + (size_t)Cfg::kQKStages * Cfg::kQKBytes;              // [kVStages] V
   uint8_t* out_buf = v_base + (size_t)Cfg::kVStages * Cfg::kKVBytes;            // [group] 16 KB
   float* mask_s = reinterpret_cast<float*>(out_buf + 2 * Cfg::kOutBytes);       // [group][2 buffers][KEYS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_s + 4 * KEYS);
+  float* xch = mask_s + 4 * KEYS;                                               // [max | sum][group][quadrant][half][lane]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + Cfg::kXchBytes / 4);
   uint64_t* qk_full = bars;
   uint64_t* qk_empty = qk_full + Cfg::kQKStages;
   uint64_t* v_full = qk_empty + Cfg::kQKStages;
@@ -621,9 +626,9 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&s_full[g], 1);
-      mbar_init(&p_full[g], 4);
+      mbar_init(&p_full[g], 8);
       mbar_init(&o_full[g], 1);
-      mbar_init(&o_free[g], 4);
+      mbar_init(&o_free[g], 8);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -673,9 +678,12 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
         const uint32_t p_tmem = tmem_base + (uint32_t)(g * KEYS);
         const uint32_t v_addr = smem_u32(v_base + (size_t)sv * Cfg::kKVBytes);
 #pragma unroll
-        for (int k = 0; k < KEYS / 16; ++k)      // 16 keys = 8 packed TMEM columns of P, 16 rows of the in-place V tile
-          umma_bf16_ts(tmem_base + Cfg::kOCol, p_tmem + (uint32_t)(k * 8),
-                       make_mnmajor_sw128_desc(v_addr + k * (16 * 128), Cfg::kKVBytes), idesc_o, k > 0 ? 1u : 0u);
+        for (int k = 0; k < KEYS / 16; ++k) {    // 16 keys = 8 packed TMEM columns of P, 16 rows of the in-place V tile
+          // each half of a row's keys keeps its probabilities at the start of ITS OWN score columns
+          const uint32_t pcol = (16 * k < Cfg::kSplit) ? (uint32_t)(8 * k) : (uint32_t)(Cfg::kSplit + 8 * k - Cfg::kSplit / 2);
+          umma_bf16_ts(tmem_base + Cfg::kOCol, p_tmem + pcol, make_mnmajor_sw128_desc(v_addr + k * (16 * 128), Cfg::kKVBytes),
+                       idesc_o, k > 0 ? 1u : 0u);
+        }
         umma_commit(&v_empty[sv]);
         umma_commit(&o_full[g]);
       };
@@ -700,121 +708,100 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
       if (n >= 1) issue_pv(n - 1);
     }
   } else {
-    const int quad = warp & 3;
-    const int g = (warp - 2) >> 2;                     // softmax group == score slot
+    const int sw = warp - 2;                           // 0..15
+    const int g = sw >> 3;                             // softmax group == score slot
+    const int half = (sw >> 2) & 1;                    // which part of the row's keys / of the output columns
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
-    const int gtid = ((warp - 2) & 3) * 32 + lane;
-    const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * KEYS);
-    const uint32_t tmem_o = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kOCol;
+    const int gtid = (sw & 7) * 32 + lane;             // 0..255 inside the group
+    const int key0 = half ? Cfg::kSplit : 0, key1 = half ? KEYS : Cfg::kSplit;
+    const uint32_t tmem_s = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * KEYS + key0);
+    const uint32_t tmem_o = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::kOCol + (uint32_t)(32 * half);
+    uint8_t* obuf = out_buf + g * Cfg::kOutBytes;
     float* gmask = mask_s + g * 2 * KEYS;
+    float* xmax = xch + ((g * 4 + quad) * 2) * 32;                    // [half][lane]
+    float* xsum = xch + 2 * 4 * 2 * 32 + ((g * 4 + quad) * 2) * 32;
+    const int pair_bar = 3 + g * 4 + quad;             // named barrier of the two warps that share this quadrant's rows
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kScale = 0.125f * kLog2e;
-    // additive key mask of an item, two keys per thread: loaded into registers at the start of the PREVIOUS item of the
-    // group, written to the other shared-memory buffer at its end (the global latency is off the critical path)
-    constexpr int kMaskRegs = (KEYS + 127) / 128;
-    auto load_mask = [&](int item, float (&mreg)[kMaskRegs]) {
-#pragma unroll
-      for (int i = 0; i < kMaskRegs; ++i) {
-        const int j = gtid + i * 128;
-        mreg[i] = -INFINITY;
-        if (item < items && j < args.Skv) {
-          const int b = item / (args.q_tiles * args.nh);
-          mreg[i] = args.mask_add ? __ldg(args.mask_add + (size_t)b * args.Skv + j) * kLog2e : 0.0f;
-        }
+    static_assert(KEYS <= 256, "one mask value per thread of a group");
+    // additive key mask of an item: loaded into a register at the start of the PREVIOUS item of the group, written to the
+    // other shared-memory buffer at its end (the global latency is off the critical path)
+    auto load_mask = [&](int item) -> float {
+      float v = -INFINITY;
+      if (item < items && gtid < args.Skv) {
+        const int b = item / (args.q_tiles * args.nh);
+        v = args.mask_add ? __ldg(args.mask_add + (size_t)b * args.Skv + gtid) * kLog2e : 0.0f;
       }
-    };
-    auto store_mask = [&](const float (&mreg)[kMaskRegs], float* dst) {
-#pragma unroll
-      for (int i = 0; i < kMaskRegs; ++i)
-        if (gtid + i * 128 < KEYS) dst[gtid + i * 128] = mreg[i];
+      return v;
     };
     const int stride = 2 * (int)gridDim.x;
-    float mreg[kMaskRegs];
-    load_mask((int)blockIdx.x + g * (int)gridDim.x, mreg);
-    store_mask(mreg, gmask);
+    float mreg = load_mask((int)blockIdx.x + g * (int)gridDim.x);
+    if (gtid < KEYS) gmask[gtid] = mreg;
+    const uint64_t scale2 = f2_splat(kScale);
     int m = 0;                                         // this group's item counter
     for (int it = blockIdx.x + g * gridDim.x; it < items; it += stride, ++m) {
       const uint32_t par = m & 1;
       const int qt = it % args.q_tiles, bh = it / args.q_tiles;
       const int h = bh % args.nh, b = bh / args.nh;
-      uint8_t* obuf = out_buf + g * Cfg::kOutBytes;
-      const float* mk = gmask + (m & 1) * KEYS;
-      const bool trace = args.debug && blockIdx.x == 0 && quad == 0 && lane == 0 && 2 * m + g >= kTraceFrom &&
+      const float* mk = gmask + (m & 1) * KEYS + key0;
+      const bool trace = args.debug && blockIdx.x == 0 && quad == 0 && half == 0 && lane == 0 && 2 * m + g >= kTraceFrom &&
                          2 * m + g < kTraceFrom + kTraceItems;
       long long tk[6];
       if (trace) tk[0] = clock64();
-      named_bar_sync(1 + g, 128);            // the mask of this item is in place (and the other buffer is free)
-      load_mask(it + stride, mreg);
+      named_bar_sync(1 + g, 256);            // the mask of this item is in place (and the other buffer is free)
+      mreg = load_mask(it + stride);
       mbar_wait(&s_full[g], par);
       tc_fence_after();
       if (trace) tk[1] = clock64();
-      // ---- sweep 1: row maximum.  Scores are scaled and masked two at a time on the packed fp32x2 pipe (FFMA2), the
-      //      maximum runs in four independent chains of 3-input FMNMX; the next 32-column piece is in flight meanwhile ----
-      const uint64_t scale2 = f2_splat(kScale);
+      // ---- sweep 1: maximum over this thread's part of the row (scores scaled and masked two at a time, FFMA2) ----
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      {
-        uint32_t sa[32], sb[32];
-        tmem_ld_32x32b_x32(tmem_s, sa);
 #pragma unroll 1
-        for (int c0 = 0; c0 < KEYS; c0 += 64) {
-          tmem_ld_wait();
-          if (c0 + 32 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 32), sb);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + j);
-            float t0, t1, t2, t3;
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(sa[j]), __uint_as_float(sa[j + 1])), scale2, f2_pack(mq.x, mq.y)), t0, t1);
-            f2_unpack(f2_fma(f2_pack(__uint_as_float(sa[j + 2]), __uint_as_float(sa[j + 3])), scale2, f2_pack(mq.z, mq.w)), t2, t3);
-            mx4[(j >> 2) & 3] = fmaxf(fmaxf(mx4[(j >> 2) & 3], fmaxf(t0, t1)), fmaxf(t2, t3));
-          }
-          if (c0 + 32 < KEYS) {
-            tmem_ld_wait();
-            if (c0 + 64 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 64), sa);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + 32 + j);
-              float t0, t1, t2, t3;
-              f2_unpack(f2_fma(f2_pack(__uint_as_float(sb[j]), __uint_as_float(sb[j + 1])), scale2, f2_pack(mq.x, mq.y)), t0, t1);
-              f2_unpack(f2_fma(f2_pack(__uint_as_float(sb[j + 2]), __uint_as_float(sb[j + 3])), scale2, f2_pack(mq.z, mq.w)), t2, t3);
-              mx4[(j >> 2) & 3] = fmaxf(fmaxf(mx4[(j >> 2) & 3], fmaxf(t0, t1)), fmaxf(t2, t3));
-            }
-          }
-        }
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      if (trace) tk[2] = clock64();
-      // ---- sweep 2: P = exp2(s - max) as bf16 pairs over the consumed part of the score row; l = undropped row sum ----
-      const uint64_t nmx2 = f2_splat(-mx);
-      uint64_t l2[2] = {f2_splat(0.0f), f2_splat(0.0f)};
-      const uint64_t drow = ((uint64_t)b * args.nh + h) * (uint64_t)args.Sq + (uint64_t)(qt * kRows + row);
-      uint32_t sr[32];
-      tmem_ld_32x32b_x32(tmem_s, sr);
-#pragma unroll 1
-      for (int c0 = 0; c0 < KEYS; c0 += 32) {
+      for (int c0 = 0; c0 < key1 - key0; c0 += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tmem_s + (uint32_t)c0, sr);
         tmem_ld_wait();
-        float sc[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const float4 mq = *reinterpret_cast<const float4*>(mk + c0 + j);
-          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), scale2, f2_pack(mq.x, mq.y)), nmx2),
-                    sc[j], sc[j + 1]);
-          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[j + 2]), __uint_as_float(sr[j + 3])), scale2, f2_pack(mq.z, mq.w)), nmx2),
-                    sc[j + 2], sc[j + 3]);
+          float t0, t1, t2, t3;
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[j]), __uint_as_float(sr[j + 1])), scale2, f2_pack(mq.x, mq.y)), t0, t1);
+          f2_unpack(f2_fma(f2_pack(__uint_as_float(sr[j + 2]), __uint_as_float(sr[j + 3])), scale2, f2_pack(mq.z, mq.w)), t2, t3);
+          mx4[(j >> 2) & 3] = fmaxf(fmaxf(mx4[(j >> 2) & 3], fmaxf(t0, t1)), fmaxf(t2, t3));
         }
-        if (c0 + 32 < KEYS) tmem_ld_32x32b_x32(tmem_s + (uint32_t)(c0 + 32), sr);     // in flight during the exponentials
+      }
+      xmax[half * 32 + lane] = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      named_bar_sync(pair_bar, 64);
+      const float mx = fmaxf(xmax[lane], xmax[32 + lane]);
+      if (trace) tk[2] = clock64();
+      // ---- sweep 2: P = exp2(s - max) as bf16 pairs over the consumed part of this thread's score columns ----
+      const uint64_t nmx2 = f2_splat(-mx);
+      uint64_t l2[2] = {f2_splat(0.0f), f2_splat(0.0f)};
+      const uint64_t drow = ((uint64_t)b * args.nh + h) * (uint64_t)args.Sq + (uint64_t)(qt * kRows + row);
+#pragma unroll 1
+      for (int c0 = 0; c0 < key1 - key0; c0 += 32) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(tmem_s + (uint32_t)c0, sr);
+        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {      // 8 keys at a time
+          const float4 ma = *reinterpret_cast<const float4*>(mk + c0 + 8 * c);
+          const float4 mb = *reinterpret_cast<const float4*>(mk + c0 + 8 * c + 4);
           float p[8];
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[8 * c]), __uint_as_float(sr[8 * c + 1])), scale2, f2_pack(ma.x, ma.y)), nmx2), p[0], p[1]);
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[8 * c + 2]), __uint_as_float(sr[8 * c + 3])), scale2, f2_pack(ma.z, ma.w)), nmx2), p[2], p[3]);
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[8 * c + 4]), __uint_as_float(sr[8 * c + 5])), scale2, f2_pack(mb.x, mb.y)), nmx2), p[4], p[5]);
+          f2_unpack(f2_add(f2_fma(f2_pack(__uint_as_float(sr[8 * c + 6]), __uint_as_float(sr[8 * c + 7])), scale2, f2_pack(mb.z, mb.w)), nmx2), p[6], p[7]);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) p[j] = ex2(sc[8 * c + j]);
+          for (int j = 0; j < 8; ++j) p[j] = ex2(p[j]);
           l2[0] = f2_add(l2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[2], p[3])));
           l2[1] = f2_add(l2[1], f2_add(f2_pack(p[4], p[5]), f2_pack(p[6], p[7])));
           if (args.drop_thresh) {
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
               const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
-                                                         icka_rng::attn_group(drow, args.Skv, c0 + 8 * c + 4 * g4), args.drop_thresh);
+                                                         icka_rng::attn_group(drow, args.Skv, key0 + c0 + 8 * c + 4 * g4), args.drop_thresh);
 #pragma unroll
               for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
             }
@@ -824,48 +811,49 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
           pk[4 * c + 2] = pack_bf16x2(p[4], p[5]);
           pk[4 * c + 3] = pack_bf16x2(p[6], p[7]);
         }
-        // columns [c0/2, c0/2 + 16) end at or below c0 + 32: their scores are in registers already, and the piece in flight
-        // starts at c0 + 32
+        // packed columns [c0/2, c0/2 + 16) of this thread's part end at or below c0 + 32: those scores are consumed
         tmem_st_32x32b_x16(tmem_s + (uint32_t)(c0 >> 1), pk);
       }
-      float la, lb, lc, ld;
-      f2_unpack(l2[0], la, lb);
-      f2_unpack(l2[1], lc, ld);
-      const float l = (la + lb) + (lc + ld);
+      {
+        float la, lb, lc, ld;
+        f2_unpack(l2[0], la, lb);
+        f2_unpack(l2[1], lc, ld);
+        xsum[half * 32 + lane] = (la + lb) + (lc + ld);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
       if (trace) tk[3] = clock64();
 
-      // ---- epilogue ----
+      // ---- epilogue: this warp's 32 of the 64 output columns ----
       mbar_wait(&o_full[g], par);
       tc_fence_after();
       if (trace) tk[4] = clock64();
-      uint32_t orr[64];
-      tmem_ld_32x32b_x32(tmem_o, *reinterpret_cast<uint32_t(*)[32]>(&orr[0]));
-      tmem_ld_32x32b_x32(tmem_o + 32, *reinterpret_cast<uint32_t(*)[32]>(&orr[32]));
+      uint32_t orr[32];
+      tmem_ld_32x32b_x32(tmem_o, orr);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[g]);
-      const float inv = 1.0f / l;
+      named_bar_sync(pair_bar, 64);                    // both partial row sums are visible; the staging rows are free
+      const float inv = 1.0f / (xsum[lane] + xsum[32 + lane]);
       uint8_t* prow0 = obuf + row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint4 u;
         u.x = pack_bf16x2(__uint_as_float(orr[8 * c]) * inv, __uint_as_float(orr[8 * c + 1]) * inv);
         u.y = pack_bf16x2(__uint_as_float(orr[8 * c + 2]) * inv, __uint_as_float(orr[8 * c + 3]) * inv);
         u.z = pack_bf16x2(__uint_as_float(orr[8 * c + 4]) * inv, __uint_as_float(orr[8 * c + 5]) * inv);
         u.w = pack_bf16x2(__uint_as_float(orr[8 * c + 6]) * inv, __uint_as_float(orr[8 * c + 7]) * inv);
-        *reinterpret_cast<uint4*>(prow0 + ((c ^ (row & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow0 + (((4 * half + c) ^ (row & 7)) << 4)) = u;
       }
-      __syncwarp();
+      named_bar_sync(pair_bar, 64);                    // the quadrant's 32 rows are complete: each warp copies 16 of them out
       {
         const int cch = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = quad * 32 + i * 4 + (lane >> 3);
+        for (int i = 0; i < 4; ++i) {
+          const int r = quad * 32 + (4 * half + i) * 4 + (lane >> 3);
           const int q_row = qt * kRows + r;
           if (q_row < args.Sq) {
             const uint4 u = *reinterpret_cast<const uint4*>(obuf + r * 128 + ((cch ^ (r & 7)) << 4));
@@ -873,8 +861,7 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
           }
         }
       }
-      __syncwarp();
-      store_mask(mreg, gmask + ((m & 1) ^ 1) * KEYS);
+      if (gtid < KEYS) gmask[((m & 1) ^ 1) * KEYS + gtid] = mreg;
       if (trace) {
         tk[5] = clock64();
 #pragma unroll

@@ -98,6 +98,22 @@ __global__ void __launch_bounds__(256) region_rows_kernel(const float* __restric
     const int nv = total >> 2;
 #pragma unroll 4
     for (int i = threadIdx.x; i < nv; i += 256) t4[i] = __ldcs(s4 + i);
+  } else if ((R & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+    // padded pitch (even R, e.g. the 14 x 14 grid): a warp copies whole channel rows, 16 bytes per lane from global
+    // memory, four scalar stores into the odd-pitch tile (no per-element division, coalesced on the global side)
+    const int warp_l = threadIdx.x >> 5, lane_l = threadIdx.x & 31;
+    const int r4 = R >> 2;
+    for (int c = warp_l; c < nc; c += 8) {
+      const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)c * R);
+      float* trow = tile + c * Rp;
+      for (int i = lane_l; i < r4; i += 32) {
+        const float4 v = __ldcs(s4 + i);
+        trow[4 * i] = v.x;
+        trow[4 * i + 1] = v.y;
+        trow[4 * i + 2] = v.z;
+        trow[4 * i + 3] = v.w;
+      }
+    }
   } else {
     for (int i = threadIdx.x; i < total; i += 256) {
       const int c = i / R, r = i - c * R;

