@@ -707,7 +707,8 @@ def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
     for m in (fusion, head, crf):
         shard.broadcast_parameters(m)
     reducer = shard.GradientAllReducer(params)
-    opt = torch.optim.AdamW(params, lr=1e-5, fused=True)
+    use_graph = not args.no_graph
+    opt = torch.optim.AdamW(params, lr=1e-5, fused=True, capturable=use_graph)
     f = synth.fusion_inputs(batch, shape, seed=19260817 + rank)
     c = synth.crf_batch(batch, shape, seed=19260817 + rank)
     d = {k: f[k].to(dev) for k in ('text_states', 'visual_embeds_att', 'clip_features', 'token_embedding', 'img_mask',
@@ -726,21 +727,35 @@ def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
         return loss
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step()
+    if not use_graph:
+        for _ in range(warm):
+            step()
+    # the whole step (forward, backward, all-reduce, AdamW) as ONE CUDA graph: ~130 launches from Python make the eager
+    # step host-bound at these batch sizes (icka_b200/graphs.py)
+    captured = None
+    run = step
+    if use_graph:
+        from icka_b200.graphs import CapturedStep
+        captured = CapturedStep(step, dev, warmup=warm)          # (eager warm-up steps run on the capture stream)
+        run = captured.replay
+        for _ in range(2):
+            run()
     env.barrier()
     l0 = _lib.launch_count(local_rank)
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         s_ev.record()
         for _ in range(steps):
-            loss = step()
+            loss = run()
         e_ev.record()
         env.barrier()
     ms = env.max_over_ranks(s_ev.elapsed_time(e_ev))
-    launches = _lib.launch_count(local_rank) - l0
+    launches = captured.kernels * steps if captured is not None else _lib.launch_count(local_rank) - l0
+    if captured is not None:
+        captured.close()
     n_prof = min(steps, 5)
-    with KernelTimer() as kt:                 # per-kernel CUDA-event pass of the same step
+    early0 = reducer.launched_early
+    with KernelTimer() as kt:                 # per-kernel CUDA-event pass of the same step (eager launches)
         for _ in range(n_prof):
             step()
         ksum = kt.summary()
@@ -762,7 +777,7 @@ def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
             per_bucket.append({'mb': round(b.numel * 4 / 1e6, 1), 'ms': round(t, 4),
                                'bus_gbs': round(2 * (world - 1) / world * b.numel * 4 / (t * 1e-3) / 1e9, 1)})
         allreduce = {'buckets': per_bucket, 'ms_total_if_serial': round(sum(x['ms'] for x in per_bucket), 4),
-                     'launched_inside_backward_per_step': reducer.launched_early // (steps + warm + n_prof)}
+                     'launched_inside_backward_per_step': (reducer.launched_early - early0) // n_prof}
     reducer.remove_hooks()
     n_param = sum(p.numel() for p in params)
     # dense-GEMM FLOPs per sentence: forward (unfolded single-query encoders) x3 for forward + dgrad + wgrad
@@ -784,7 +799,9 @@ def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
                    'params_allreduced': n_param, 'buckets': len(reducer.buckets),
                    'outside_hot_path': ('emission head = icka_b200.EmissionHead (BiLSTM + classifier, BPTT on per-step kernels)' if real_head
                                         else 'emission head = torch nn.Linear(H,T) stand-in for BiLSTM+classifier') + '; optimizer = torch AdamW(fused)',
-                   'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)'},
+                   'dropout': 'hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (Philox masks regenerated in backward)',
+                   'launch': ('CUDA graph replay of the whole step (forward + backward + all-reduce + AdamW); dropout seed base advanced on the device'
+                              if use_graph else 'eager host launches')},
         'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
         'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor',
                      'achieved': (gemm_fl / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else 0.0, 'peak': peak_tf, 'unit': 'TFLOP/s',

@@ -23,6 +23,7 @@ SIGNATURES = {
     'icka_last_error': (c_char_p, []),
     'icka_create': (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     'icka_destroy': (c_int, [c_void_p]),
+    'icka_set_seed_base': (c_int, [c_void_p, c_void_p]),
     'icka_launch_count': (c_int64, [c_void_p]),
     'icka_cast_f32_to_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'icka_cast_bf16_to_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
@@ -108,6 +109,7 @@ SIGNATURES = {
 
 _lib = None
 _handles = {}
+_seed_base = {}          # device index -> (pointer, keep-alive object): applied to every handle (slot) of the device
 _lock = threading.Lock()
 
 
@@ -168,7 +170,23 @@ def handle(device_index: int) -> c_void_p:
             out = c_void_p()
             check(lib.icka_create(int(device_index), ctypes.byref(out)), 'icka_create')
             h = _handles[key] = out
+            base = _seed_base.get(device_index)
+            if base is not None:
+                check(lib.icka_set_seed_base(h, base[0]), 'icka_set_seed_base')
         return h
+
+
+def set_seed_base(device_index: int, ptr, keep_alive=None) -> None:
+    """Device-resident dropout seed base for every handle (slot) of ``device_index``; ``ptr`` None clears it."""
+    lib = load()
+    with _lock:
+        if ptr is None:
+            _seed_base.pop(device_index, None)
+        else:
+            _seed_base[device_index] = (int(ptr), keep_alive)
+        for (d, _), h in _handles.items():
+            if d == device_index:
+                check(lib.icka_set_seed_base(h, None if ptr is None else int(ptr)), 'icka_set_seed_base')
 
 
 def launch_count(device_index: int = 0) -> int:

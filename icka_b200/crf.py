@@ -45,6 +45,7 @@ class CRF(nn.Module):
 
     # -- validation: same conditions and ValueError as pytorch-crf's _validate ---------------------
     def _validate(self, emissions, tags=None, mask=None) -> None:
+        capturing = emissions.is_cuda and torch.cuda.is_current_stream_capturing()
         if emissions.dim() != 3:
             raise ValueError(f'emissions must have dimension of 3, got {emissions.dim()}')
         if emissions.size(2) != self.num_tags:
@@ -61,9 +62,11 @@ class CRF(nn.Module):
                     'the first two dimensions of emissions and mask must match, '
                     f'got {tuple(emissions.shape[:2])} and {tuple(mask.shape)}')
             first = mask[:, 0] if self.batch_first else mask[0]
-            if not bool(first.all()):
+            # (the two value checks read device memory back: not possible while a CUDA graph is being captured -- the
+            # warm-up passes of icka_b200.graphs.CapturedStep have run them on the same tensors)
+            if not capturing and not bool(first.all()):
                 raise ValueError('mask of the first timestep must all be on')
-        if tags is not None and tags.numel() and bool(((tags < 0) | (tags >= self.num_tags)).any()):
+        if tags is not None and tags.numel() and not capturing and bool(((tags < 0) | (tags >= self.num_tags)).any()):
             # pytorch-crf indexes start_transitions / transitions / emissions with every tag id (masked positions too):
             # an id outside [0, num_tags) -- e.g. an ignore-index of -100 on padding -- is an IndexError there
             raise IndexError(f'tags must lie in [0, {self.num_tags}); got values in '

@@ -45,6 +45,7 @@ extern "C" int icka_create(int device, icka_handle** out) {
   }
   h->encode_tiled = fn;
   h->workspace = nullptr;
+  h->seed_base = nullptr;
   int prev = 0;
   cudaGetDevice(&prev);
   cudaError_t ea = cudaSetDevice(device);
@@ -61,6 +62,13 @@ extern "C" int icka_create(int device, icka_handle** out) {
 extern "C" int icka_destroy(icka_handle* h) {
   if (h && h->workspace) cudaFree(h->workspace);
   delete h;
+  return ICKA_OK;
+}
+
+extern "C" int icka_set_seed_base(icka_handle* h, const uint64_t* seed_base_dev) {
+  ICKA_REQUIRE(h != nullptr, "null handle");
+  ICKA_REQUIRE(icka_aligned(seed_base_dev, 8), "seed base must be 8-byte aligned");
+  h->seed_base = reinterpret_cast<const unsigned long long*>(seed_base_dev);
   return ICKA_OK;
 }
 

@@ -24,6 +24,7 @@ struct DropArgs {
   uint32_t thresh;
   float scale;
   uint64_t seed;
+  const unsigned long long* base;   // device-resident seed base (icka_set_seed_base) or null
 };
 
 template <typename T>
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kRows) cross_attn_kernel(
 
   for (int r = 0; r < Skv; ++r) {
     if (drop.thresh && (r & 3) == 0)
-      keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, r), drop.thresh);
+      keep = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, r), drop.thresh);
     const float4* kr = reinterpret_cast<const float4*>(Ks + r * kD);
     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
@@ -306,8 +307,8 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
       ps1 += p2 + p3;
       if (drop.thresh) {   // this thread's two keys of the tile share one Philox group of four
         const int key = key0 + j * 8 + 2 * t;
-        const uint32_t k0 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow0, Skv, key), drop.thresh) >> (key & 3);
-        const uint32_t k1 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow0 + 8, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t k0 = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow0, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t k1 = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow0 + 8, Skv, key), drop.thresh) >> (key & 3);
         p0 = (k0 & 1u) ? p0 * drop.scale : 0.0f;
         p1 = (k0 & 2u) ? p1 * drop.scale : 0.0f;
         p2 = (k1 & 1u) ? p2 * drop.scale : 0.0f;
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
 
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
-                             uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st);
+                             uint32_t drop_thresh, float drop_scale, uint64_t seed, const unsigned long long* seed_base,
+                             cudaStream_t st);
 
 // 0 = pick per shape (tcgen05 kernels for Skv <= 224, mma.sync beyond), 1 = always the mma.sync kernel,
 // 2 = the first wide tcgen05 variant for 64 < Skv <= 224 (one softmax group, P through shared memory),
@@ -391,7 +393,7 @@ extern "C" int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int6
                                              void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "cross_attn: dropout p=%f outside [0, 1)", (double)p_drop);
-  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed};
+  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed, h->seed_base};
   ICKA_REQUIRE(q && k && v && ctx, "cross_attn: null pointer");
   ICKA_REQUIRE(B >= 0 && Sq >= 1 && Skv >= 1 && nh >= 1, "cross_attn: bad shape");
   ICKA_REQUIRE(d == kD, "cross_attn: head dim %d != 64 (ICKA uses 768/12 and 1024/16)", d);
@@ -408,7 +410,7 @@ extern "C" int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int6
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == ICKA_BF16 && g_attn_mode != 1) {
     const int rc = icka_attn_tcgen05_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, B, Sq, Skv, nh, drop.thresh,
-                                            drop.scale, drop.seed, st);
+                                            drop.scale, drop.seed, drop.base, st);
     if (rc <= 0) return rc;      // launched (0) or failed (< 0); > 0: shape outside that kernel's envelope
   }
   if (dtype == ICKA_BF16) {

@@ -47,6 +47,7 @@ struct AttnArgs {
   uint32_t drop_thresh;   // attention-probability dropout (CMIM:616), training only; 0 = off
   float drop_scale;
   uint64_t seed;
+  const unsigned long long* seed_base;   // device-resident seed base (icka_set_seed_base) or null
   int debug;              // developer probe (ICKA_ATTN_DEBUG=1): CTA 0 prints the cycle stamps of its first items (wide2 kernel)
 };
 
@@ -224,7 +225,7 @@ cross_attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
         if (args.drop_thresh) {              // the normaliser keeps the undropped sum; P' = P keep / (1 - p) feeds P.V
 #pragma unroll
           for (int g4 = 0; g4 < 2; ++g4) {
-            const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+            const uint32_t keep = icka_rng::keep_bits4(icka_rng::effective_seed(args.seed, args.seed_base), icka_rng::kSiteAttention,
                                                        icka_rng::attn_group(drow, args.Skv, 8 * c + 4 * g4), args.drop_thresh);
 #pragma unroll
             for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
@@ -461,7 +462,7 @@ cross_attn_tcgen05_wide_kernel(const __grid_constant__ CUtensorMap tmap_q, const
           if (args.drop_thresh) {
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
-              const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+              const uint32_t keep = icka_rng::keep_bits4(icka_rng::effective_seed(args.seed, args.seed_base), icka_rng::kSiteAttention,
                                                          icka_rng::attn_group(drow, args.Skv, c0 + 8 * c + 4 * g4), args.drop_thresh);
 #pragma unroll
               for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
@@ -800,7 +801,7 @@ cross_attn_tcgen05_wide2_kernel(const __grid_constant__ CUtensorMap tmap_q, cons
           if (args.drop_thresh) {
 #pragma unroll
             for (int g4 = 0; g4 < 2; ++g4) {
-              const uint32_t keep = icka_rng::keep_bits4(args.seed, icka_rng::kSiteAttention,
+              const uint32_t keep = icka_rng::keep_bits4(icka_rng::effective_seed(args.seed, args.seed_base), icka_rng::kSiteAttention,
                                                          icka_rng::attn_group(drow, args.Skv, key0 + c0 + 8 * c + 4 * g4), args.drop_thresh);
 #pragma unroll
               for (int j = 0; j < 4; ++j) p[4 * g4 + j] = (keep >> j & 1u) ? p[4 * g4 + j] * args.drop_scale : 0.0f;
@@ -936,7 +937,8 @@ int launch_wide(icka_handle* h, const void* q, int64_t ldq, const void* k, const
 // (the caller then uses the mma.sync kernel).
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
-                             uint32_t drop_thresh, float drop_scale, uint64_t seed, cudaStream_t st) {
+                             uint32_t drop_thresh, float drop_scale, uint64_t seed, const unsigned long long* seed_base,
+                             cudaStream_t st) {
   extern int g_attn_mode;
   if (Skv > kKeys) {
     // 64 < Skv <= 224 (the 196-region grid): two softmax groups with the probabilities in tensor memory (wide2) by
@@ -946,7 +948,7 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
     // of an item: the mma.sync kernel is faster there, 122 vs 160 us at 1024 sentences)
     if (Skv > 224 || (Sq < 32 && g_attn_mode == 0)) return 1;
     AttnArgs wargs{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows,
-                   drop_thresh, drop_scale, seed, getenv("ICKA_ATTN_DEBUG") ? 1 : 0};
+                   drop_thresh, drop_scale, seed, seed_base, getenv("ICKA_ATTN_DEBUG") ? 1 : 0};
     if (g_attn_mode == 2)
       return Skv <= 128 ? launch_wide<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide<224>(h, q, ldq, k, v, ldkv, wargs, st);
     return Skv <= 128 ? launch_wide2<128>(h, q, ldq, k, v, ldkv, wargs, st) : launch_wide2<224>(h, q, ldq, k, v, ldkv, wargs, st);
@@ -960,7 +962,7 @@ int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const v
   rc = icka_make_tmap_bf16(h, &tv, v, (int64_t)B * Skv, (int64_t)nh * kD, ldkv, kKeys);
   if (rc) return rc;
   AttnArgs args{mask_add, static_cast<__nv_bfloat16*>(ctx), ldc, B, Sq, Skv, nh, (Sq + kRows - 1) / kRows,
-                drop_thresh, drop_scale, seed};
+                drop_thresh, drop_scale, seed, seed_base, 0};
   const int items = B * nh * args.q_tiles;
   ICKA_CUDA(cudaFuncSetAttribute(cross_attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
   const int grid = items < h->sm_count ? items : h->sm_count;

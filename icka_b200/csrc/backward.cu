@@ -15,6 +15,7 @@ struct DropArgs {   // attention-probability dropout (CMIM:616); thresh == 0: of
   uint32_t thresh;
   float scale;
   uint64_t seed;
+  const unsigned long long* base;   // device-resident seed base (icka_set_seed_base) or null
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
       uint32_t keep = 0xfu;
       for (int j = 0; j < Skv; ++j) {
         if (drop.thresh && (j & 3) == 0)
-          keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
+          keep = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
         const float4* vr = reinterpret_cast<const float4*>(Vs + j * kD);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kAttnBwdThreads) cross_attn_bwd_kernel(
         dsrow[j] = ds;
         if (drop.thresh) {   // phase 2 forms dV from the DROPPED probabilities
           if ((j & 3) == 0)
-            keep = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
+            keep = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, j), drop.thresh);
           prow[j] = (keep >> (j & 3) & 1u) ? prow[j] * drop.scale : 0.0f;
         }
         const float4* kr = reinterpret_cast<const float4*>(Ks + j * kD);
@@ -618,8 +619,8 @@ __global__ void __launch_bounds__(kMmaThreads) cross_attn_bwd_mma_kernel(
       if (drop.thresh) {
         const int key = key0 + j * 8 + 2 * t;
         const uint64_t drow = ((uint64_t)b * gridDim.x + h) * (uint64_t)Sq + (uint64_t)(warp * 16 + g);
-        const uint32_t b0 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, key), drop.thresh) >> (key & 3);
-        const uint32_t b1 = icka_rng::keep_bits4(drop.seed, icka_rng::kSiteAttention, icka_rng::attn_group(drow + 8, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t b0 = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow, Skv, key), drop.thresh) >> (key & 3);
+        const uint32_t b1 = icka_rng::keep_bits4(icka_rng::effective_seed(drop.seed, drop.base), icka_rng::kSiteAttention, icka_rng::attn_group(drow + 8, Skv, key), drop.thresh) >> (key & 3);
         k0 = (b0 & 1u) ? drop.scale : 0.0f;
         k1 = (b0 & 2u) ? drop.scale : 0.0f;
         k2 = (b1 & 1u) ? drop.scale : 0.0f;
@@ -869,7 +870,7 @@ extern "C" int icka_cross_attn_core_bwd_drop(icka_handle* h, const void* q, int6
                                              float p_drop, uint64_t seed, void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "cross_attn_bwd: dropout p=%f outside [0, 1)", (double)p_drop);
-  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed};
+  const DropArgs drop{p_drop > 0.0f ? icka_rng::keep_threshold(p_drop) : 0u, 1.0f / (1.0f - p_drop), seed, h->seed_base};
   ICKA_REQUIRE(q && k && v && dctx && dq && dk && dv, "cross_attn_bwd: null pointer");
   ICKA_REQUIRE(B >= 0 && Sq >= 1 && Skv >= 1 && nh >= 1, "cross_attn_bwd: bad shape");
   ICKA_REQUIRE(d == kD, "cross_attn_bwd: head dim %d != 64", d);

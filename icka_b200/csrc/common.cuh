@@ -19,6 +19,7 @@ struct icka_handle {
   std::atomic<long long> launches;
   void* encode_tiled;   // PFN cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
   void* workspace;      // device scratch [ICKA_WORKSPACE_BYTES]: split-K partial tiles of skinny forward GEMMs
+  const unsigned long long* seed_base;   // device-resident dropout seed base (icka_set_seed_base) or null
 };
 
 #define ICKA_WORKSPACE_BYTES ((size_t)32 << 20)

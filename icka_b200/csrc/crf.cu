@@ -234,50 +234,68 @@ __global__ void __launch_bounds__(kV16Threads) viterbi16_kernel(
   const float* e_g = emissions + (size_t)b * S * T;
   const uint8_t* mrow = mask ? mask + (size_t)b * S : nullptr;
 
-  // mask row -> smem, len = sum(mask), prefix = (mask is len ones followed by zeros)
+  // The sentence is a chain of dependent global round trips (mask -> length -> emissions) in front of a 127-step chain:
+  // at 1024 sentences there are ~4 warps per SM and nothing hides them.  So: the first 16 steps of the emission slab are
+  // requested before anything else (they do not depend on the length), the mask row is fetched with all its loads in
+  // flight at once, and the transition column / start / end loads are issued before the mask is reduced.
+  const int head_steps = min(S, 16);
+  const int head_floats = head_steps * T;
+  const bool vec_ok = ((((size_t)S * T) % 4) == 0) && ((reinterpret_cast<uintptr_t>(emissions) % 16) == 0);
+  const int hvec = (head_floats + 3) / 4;                  // <= 3 floats of slack stay inside S*T
+  if (vec_ok) {
+    for (int v = gl; v < hvec; v += 16) cp_async16(sm.em + 4 * v, e_g + 4 * v);
+  } else {
+    for (int i = gl; i < head_floats; i += 16) sm.em[i] = e_g[i];
+  }
+  cp_async_commit();
+
+  const bool active = gl < T;
+  float tr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tr[i] = (i < T) ? (active ? __ldg(trans + i * T + gl) : 0.0f) : -INFINITY;
+  const float st = active ? __ldg(start + gl) : 0.0f;
+  const float en = active ? __ldg(end + gl) : 0.0f;
+
+  // mask row -> smem, len = sum(mask), prefix = (mask is len ones followed by zeros); eight 16-position pieces per batch
   int len = 0;
   bool prefix = true, seen_zero = false;
-  for (int t0 = 0; t0 < S; t0 += 16) {
-    const int t = t0 + gl;
-    uint8_t m = 0;
-    if (t < S) {
-      m = mrow ? (mrow[t] != 0) : 1;
-      sm.mask[t] = m;
+  for (int tb = 0; tb < S; tb += 128) {
+    uint8_t mv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = tb + 16 * i + gl;
+      mv[i] = (t < S) ? (mrow ? (uint8_t)(__ldg(mrow + t) != 0) : (uint8_t)1) : (uint8_t)0;
     }
-    const unsigned bits = (__ballot_sync(kFull, m != 0) >> gshift) & 0xffffu;
-    const int c = __popc(bits);
-    if (bits != 0 && seen_zero) prefix = false;
-    if (bits != ((1u << c) - 1u)) prefix = false;
-    if (c < min(16, S - t0)) seen_zero = true;
-    len += c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t0 = tb + 16 * i;
+      if (t0 < S) {                                       // uniform across the warp
+        const int t = t0 + gl;
+        if (t < S) sm.mask[t] = mv[i];
+        const unsigned bits = (__ballot_sync(kFull, mv[i] != 0) >> gshift) & 0xffffu;
+        const int c = __popc(bits);
+        if (bits != 0 && seen_zero) prefix = false;
+        if (bits != ((1u << c) - 1u)) prefix = false;
+        if (c < min(16, S - t0)) seen_zero = true;
+        len += c;
+      }
+    }
   }
   const bool fast = prefix && len >= 1;
   const int n_steps = fast ? len : S;                                      // this sentence runs t = 0 .. n_steps-1
   const int n_warp = max(n_steps, __shfl_xor_sync(kFull, n_steps, 16));    // the warp's trip count
   const bool all_fast = __all_sync(kFull, fast);
 
-  // emission slab -> smem: the first 16 steps as one cp.async group, the rest as a second one
+  // the rest of the emission slab (steps 16 .. n_steps-1) as a second cp.async group
   const int n_floats = n_steps * T;
-  const int head_floats = min(n_floats, 16 * T);
-  const bool vec_ok = ((((size_t)S * T) % 4) == 0) && ((reinterpret_cast<uintptr_t>(emissions) % 16) == 0);
   if (vec_ok) {
-    const int nvec = (n_floats + 3) / 4, hvec = (head_floats + 3) / 4;   // <= 3 floats of slack stay inside S*T
-    for (int v = gl; v < hvec; v += 16) cp_async16(sm.em + 4 * v, e_g + 4 * v);
-    cp_async_commit();
+    const int nvec = (n_floats + 3) / 4;
     for (int v = hvec + gl; v < nvec; v += 16) cp_async16(sm.em + 4 * v, e_g + 4 * v);
-    cp_async_commit();
   } else {
-    for (int i = gl; i < n_floats; i += 16) sm.em[i] = e_g[i];
-    cp_async_commit();
-    cp_async_commit();
+    for (int i = head_floats + gl; i < n_floats; i += 16) sm.em[i] = e_g[i];
   }
+  cp_async_commit();
 
-  const bool active = gl < T;
-  float tr[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) tr[i] = (i < T) ? (active ? trans[i * T + gl] : 0.0f) : -INFINITY;
-  const float st = active ? start[gl] : 0.0f;
-  const float en = active ? end[gl] : 0.0f;
 
   cp_async_wait<1>();
   __syncwarp();

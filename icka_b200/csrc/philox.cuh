@@ -29,6 +29,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint64_t seed, uint32_t site, uin
   return c;
 }
 
+// Seed of a launch = the by-value seed of the call + an optional device-resident base (icka_set_seed_base): a training step
+// captured into a CUDA graph replays with frozen kernel arguments, so the part of the seed that must change from step to
+// step lives in device memory, advanced by a kernel of the graph itself.
+__device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const unsigned long long* base) {
+  return base ? seed + (uint64_t)__ldg(base) : seed;
+}
+
 // Keep bits (bit j = element 4*group + j kept) of one group of four consecutive elements.
 __device__ __forceinline__ uint32_t keep_bits4(uint64_t seed, uint32_t site, uint64_t group, uint32_t thresh) {
   const uint4 r = philox4x32_10(seed, site, group);

@@ -60,6 +60,14 @@ def _cdt() -> torch.dtype:
     return compute_dtype()
 
 
+_CACHE_EPOCH = [0]      # bumped by graphs.CapturedStep.replay(): a replayed optimizer step changes parameters without
+                        # touching their Python-side version counters, so operand copies made before it are stale
+
+
+def invalidate_operand_caches() -> None:
+    _CACHE_EPOCH[0] += 1
+
+
 class _OperandCache:
     """Compute-dtype copies of fp32 parameters, refreshed when the parameter is modified in place."""
 
@@ -67,7 +75,7 @@ class _OperandCache:
         self._store = {}
 
     def get(self, key: str, params, build):
-        sig = (get_precision(),) + tuple((p.data_ptr(), p._version, p.device) for p in params)
+        sig = (get_precision(), _CACHE_EPOCH[0]) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         hit = self._store.get(key)
         if hit is None or hit[0] != sig:
             with torch.no_grad():

@@ -50,6 +50,13 @@ int icka_version(void);
 const char* icka_last_error(void);
 int icka_create(int device, icka_handle** out);
 int icka_destroy(icka_handle* h);
+/* Device-resident dropout seed base.  Every dropout site (icka_dropout_fwd, the *_drop attention entry points,
+ * icka_dropout_mask) draws its Philox masks from  seed_argument + *seed_base_dev  when a base is set (NULL clears it).  A
+ * training step captured into a CUDA graph replays with frozen kernel arguments: the caller advances the 8-byte counter
+ * with a kernel of the graph itself, so every replay drops different elements while backward still regenerates the
+ * masks of its own forward.  The pointer must stay valid while the handle uses it. */
+int icka_set_seed_base(icka_handle* h, const uint64_t* seed_base_dev);
+
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t icka_launch_count(const icka_handle* h);
 
