@@ -14,6 +14,8 @@
 // steps cannot change `score` and their back-pointers are never read.  Masks with holes run all S steps.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -865,6 +867,11 @@ extern "C" int icka_viterbi_decode(icka_handle* h, const float* emissions, const
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "viterbi: S=%d T=%d needs %zu B shared memory per block (max %zu)", S, T,
               smem, h->smem_optin);
   const int grid = (B + spb - 1) / spb;
+  // (A one-sentence-per-warp variant -- 32 lanes share the 16 x 16 candidates of a step, half the instructions, one
+  // shuffle pair to join the halves -- was built and measured: 31.7 vs 29.8 us at 1024 full-length sentences, 72 vs 65 us
+  // at 4096.  The step is a ~250-cycle chain of shared-memory round trip + two adds + four FMNMX levels + ~140 issue
+  // slots of one warp per scheduler; halving the arithmetic does not shorten it.  tools/viterbi_steps.py: 0.19 us per
+  // step, 2.5 us fixed.)
   if (LPS == 16) {
     ICKA_CUDA(cudaFuncSetAttribute(viterbi16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     viterbi16_kernel<<<grid, spb * 16, smem, st>>>(emissions, mask, start, end, trans, tags_out, lens_out, B, S,

@@ -102,6 +102,20 @@ def test_viterbi_full_batch_property():
     assert np.array_equal(tags.cpu().numpy(), t_ref)
 
 
+@pytest.mark.parametrize('kind', ['ties', 'near_ties'])
+def test_viterbi_large_batch_two_sentences_per_warp(kind):
+    """Above 32 sentences per SM the decode switches from one sentence per warp to two (odd tail included)."""
+    sh = synth.STD
+    B = 32 * 148 + 1265
+    batch = synth.crf_batch(B, sh, seed=77, kind=kind)
+    crf, cp = make_crf(sh.T, 78, 'normal')
+    tags, lens = crf.decode_tensors(batch['emissions'].to(DEV), batch['mask'].to(DEV))
+    t_ref, l_ref = viterbi_c.viterbi(batch['emissions'].numpy(), batch['mask'].numpy(), cp['start_transitions'].numpy(),
+                                     cp['end_transitions'].numpy(), cp['transitions'].numpy())
+    assert np.array_equal(lens.cpu().numpy(), l_ref)
+    assert np.array_equal(tags.cpu().numpy(), t_ref)
+
+
 @pytest.mark.parametrize('reduction', ['none', 'sum', 'mean', 'token_mean'])
 def test_crf_llh(reduction):
     sh = synth.STD
