@@ -41,6 +41,9 @@ class CapturedStep:
                 step()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # (the warm-up passes ran on a side stream, the capture runs on torch's capture stream: autograd's note about
+        # AccumulateGrad nodes seeing a different stream than the one they were created on is expected here)
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count(idx)
         with torch.cuda.graph(self.graph):
