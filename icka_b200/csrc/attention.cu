@@ -366,6 +366,9 @@ __global__ void __launch_bounds__(WARPS * 32) cross_attn_mma_kernel(
 
 }  // namespace
 
+int icka_attn_sq1_fwd_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const float* mask_add, void* ctx, int64_t ldc, int dtype, int B, int Skv, int nh,
+                             uint32_t thresh, float scale, uint64_t seed, const unsigned long long* base, cudaStream_t st);
 int icka_attn_tcgen05_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                              const float* mask_add, void* ctx, int64_t ldc, int B, int Sq, int Skv, int nh,
                              uint32_t drop_thresh, float drop_scale, uint64_t seed, const unsigned long long* seed_base,
@@ -403,6 +406,11 @@ extern "C" int icka_cross_attn_core_fwd_drop(icka_handle* h, const void* q, int6
                "cross_attn: pointers must be 16-byte aligned");
   ICKA_REQUIRE(B <= 65535 && nh <= 65535, "cross_attn: B or nh exceeds grid limits; shard the batch");
   if (B == 0) return ICKA_OK;
+  if (Sq == 1 && g_attn_mode != 1) {   // image->text encoders: one query per sentence (attention_sq1.cu)
+    const int rc = icka_attn_sq1_fwd_launch(h, q, ldq, k, v, ldkv, mask_add, ctx, ldc, dtype, B, Skv, nh, drop.thresh,
+                                            drop.scale, drop.seed, drop.base, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   const size_t smem = ((size_t)2 * Skv * kD + Skv) * sizeof(float);
   if (smem > h->smem_optin)
     ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "cross_attn: Skv=%d needs %zu B shared memory (max %zu)", Skv, smem, h->smem_optin);

@@ -855,6 +855,11 @@ extern "C" int icka_layernorm_bwd(icka_handle* h, const float* dy, const float* 
   return ICKA_OK;
 }
 
+int icka_attn_sq1_bwd_launch(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                             const float* mask_add, const void* dctx, int64_t lddc, void* dq, int64_t lddq, void* dk,
+                             void* dv, int64_t lddkv, int dtype, int B, int Skv, int nh, uint32_t thresh, float scale,
+                             uint64_t seed, const unsigned long long* base, cudaStream_t st);
+
 extern "C" int icka_cross_attn_core_bwd(icka_handle* h, const void* q, int64_t ldq, const void* k, const void* v,
                                         int64_t ldkv, const float* mask_add, const void* ctx, int64_t ldctx,
                                         const void* dctx, int64_t ldc, void* dq, int64_t lddq, void* dk, void* dv,
@@ -882,6 +887,12 @@ extern "C" int icka_cross_attn_core_bwd_drop(icka_handle* h, const void* q, int6
                "cross_attn_bwd: pointers must be 16-byte aligned");
   ICKA_REQUIRE(B <= 65535, "cross_attn_bwd: B exceeds grid limits; shard the batch");
   if (B == 0) return ICKA_OK;
+  if (Sq == 1) {   // image->text encoders: one query per sentence (attention_sq1.cu)
+    const int rc = icka_attn_sq1_bwd_launch(h, q, ldq, k, v, ldkv, mask_add, dctx, ldc, dq, lddq, dk, dv, lddkv, dtype, B,
+                                            Skv, nh, drop.thresh, drop.scale, drop.seed, drop.base,
+                                            static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
   if (dtype == ICKA_BF16 && ctx != nullptr && Sq <= kRowsQ && ldctx % 8 == 0 && icka_aligned(ctx, 16)) {
     // tensor-core path
     const size_t smem_mma = (size_t)(4 * kRowsQ + 2 * kKeyBlk) * kPitch * sizeof(__nv_bfloat16) + kKeyBlk * sizeof(float);

@@ -51,7 +51,8 @@ _X3_SINGLE_QUERY = True   # bf16 inference: split-precision ("bf16 x 3", ops.spl
                           # the chain's layers does when the chain is >= _X3_FFN_MIN_LAYERS deep (10 layers: 1.9e-2 -> 1.5e-2,
                           # +3 % step time), below that the error budget does not need it
 _X3_FFN_MIN_LAYERS = 4
-_FUSE_LN = False     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
+import os as _os
+_FUSE_LN = _os.environ.get('ICKA_FUSE_LN', '0') == '1'     # LayerNorm inside the out-proj / FFN-down GEMM epilogue (icka_linear_ln_fwd): correct, but on
                      # B200 the second (normalising) pass re-reads rows that have left L2 and is latency-bound:
                      # 511 us fused vs 227 + 152 us unfused at B=1024, so it stays off
 
@@ -186,7 +187,7 @@ class _DenseResidualNorm(nn.Module):
         w = _operand(self._cache, 'w', self.dense.weight)
         if defer_ln:          # the caller fuses this LayerNorm into its consumer (icka_ln_gate_blend_fwd)
             return ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32), None
-        if _FUSE_LN and h_lp.shape[0] >= 2048:
+        if _FUSE_LN and h_lp.shape[0] >= 2048 and h_lp.shape[1] <= 1024:
             # dense + residual + LayerNorm in one launch (normalisation in the GEMM epilogue); below ~2k rows a CTA
             # per 128-row block leaves most SMs idle, so skinny problems keep the split-K GEMM + row kernel
             return ops.linear_ln(h_lp, w, self.dense.bias.detach(), res32, self.LayerNorm.weight.detach(),

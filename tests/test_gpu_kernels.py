@@ -74,7 +74,8 @@ def test_linear_fp32_pitched_views():
 
 
 def test_cross_attn_core_fp32_and_bf16():
-    for (B, Sq, Skv, nh) in [(3, 128, 49, 12), (2, 1, 128, 12), (1, 256, 196, 12), (2, 16, 9, 2)]:
+    for (B, Sq, Skv, nh) in [(3, 128, 49, 12), (2, 1, 128, 12), (1, 256, 196, 12), (2, 16, 9, 2),
+                             (70, 1, 37, 12), (3, 1, 1, 2), (2, 1, 300, 16)]:      # single query: attention_sq1.cu
         H = nh * 64
         q, kv = rnd(B * Sq, H, seed=1), rnd(B * Skv, 2 * H, seed=2)
         mask = torch.zeros(B, Skv); mask[:, Skv // 2:] = -10000.0; mask[0] = 0
