@@ -66,6 +66,57 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
   }
 }
 
+// Wide form for 16-byte-aligned rows: a thread owns 16 bytes of columns (8 bf16 / 4 fp32), a warp 512 contiguous bytes of a
+// row, and four rows are in flight per thread -- the 4-byte form above is latency-bound (54 us for the 100 MB intermediate
+// gradient of a B=128 training step; this one runs at HBM speed).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const T* __restrict__ x, int64_t ld, float* __restrict__ out,
+                                                          int M, int N, int rows_per_block) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  __shared__ float red[8][32 * VE + 4];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * VE;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc[VE];
+#pragma unroll
+  for (int j = 0; j < VE; ++j) acc[j] = 0.0f;
+  auto add = [&](const uint4& u) {
+    if constexpr (sizeof(T) == 2) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += __uint_as_float(w[j] << 16);
+        acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+      }
+    } else {
+      acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y);
+      acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
+    }
+  };
+  if (c < N) {
+    const T* base = x + c;
+    int m = m0 + ty;
+    for (; m + 24 < m1; m += 32) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)m * ld));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(m + 8) * ld));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(m + 16) * ld));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(m + 24) * ld));
+      add(u0); add(u1); add(u2); add(u3);
+    }
+    for (; m < m1; m += 8) add(__ldg(reinterpret_cast<const uint4*>(base + (size_t)m * ld)));
+  }
+#pragma unroll
+  for (int j = 0; j < VE; ++j) red[ty][tx * VE + j] = acc[j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VE; i += 256) {
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][i];
+    const int col = blockIdx.x * 32 * VE + i;
+    if (col < N) atomicAdd(out + col, t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  y = w * xhat + b with xhat = (x - mean) * rstd:
 //   g = dy * w;  dx = rstd * (g - mean(g) - xhat * mean(g * xhat));  dw += dy * xhat;  db += dy
@@ -822,6 +873,20 @@ extern "C" int icka_colsum(icka_handle* h, const void* x, int64_t ld, int dtype,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!accumulate) ICKA_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
   if (M == 0) return ICKA_OK;
+  const int ve = dtype == ICKA_BF16 ? 8 : 4;
+  if (N % ve == 0 && ld % ve == 0 && icka_aligned(x, 16) && M >= 256) {
+    const int cb = (N + 32 * ve - 1) / (32 * ve);
+    int rb = (8 * h->sm_count + cb - 1) / cb;
+    if (rb > (M + 31) / 32) rb = (M + 31) / 32;
+    const int rows = (M + rb - 1) / rb;
+    dim3 grid_w(cb, (M + rows - 1) / rows);
+    if (dtype == ICKA_BF16)
+      colsum_wide_kernel<__nv_bfloat16><<<grid_w, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ld, out, M, N, rows);
+    else
+      colsum_wide_kernel<float><<<grid_w, 256, 0, st>>>(static_cast<const float*>(x), ld, out, M, N, rows);
+    ICKA_LAUNCHED(h);
+    return ICKA_OK;
+  }
   const int col_blocks = (N + 63) / 64;
   int row_blocks = (4 * h->sm_count + col_blocks - 1) / col_blocks;
   if (row_blocks > (M + 63) / 64) row_blocks = (M + 63) / 64;
