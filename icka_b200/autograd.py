@@ -344,6 +344,25 @@ class LinearFn(torch.autograd.Function):
         return ops.linear_dgrad(dout, w, out_dtype=F32), ops.linear_wgrad(dout, x32), db
 
 
+class ClassifierFn(torch.autograd.Function):
+    """emissions[M,T] = y[M,2H] . W^T + b for the 2H -> num_labels classifier (CMIM:910, 1043), T <= 16: the skinny
+    streaming kernels (``icka_emission_head_fwd`` / ``_bwd``: one pass over the states each) instead of GEMM tiles."""
+
+    @staticmethod
+    def forward(ctx, y32, weight, bias):
+        y32 = y32.contiguous()
+        w = weight.detach().float().contiguous()
+        ctx.save_for_backward(y32, w)
+        return ops.emission_head(y32, w, bias.detach().float().contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        y32, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        dy, dw = ops.emission_head_bwd(dout, y32, w, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1])
+        return dy, dw, (_colsum_any(dout) if ctx.needs_input_grad[2] else None)
+
+
 _side_streams = {}
 
 

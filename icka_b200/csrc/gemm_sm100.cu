@@ -544,6 +544,73 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// The same reduction followed by the row LayerNorm (two-pass statistics, as layernorm_kernel): one warp per row, the row
+// in registers.  The single-query encoders end every block with  LN(split-K GEMM + bias + residual)  on a few hundred to a few
+// thousand rows; as two launches the fp32 pre-LayerNorm rows made a round trip and the second launch cost more than its work.
+constexpr int kRedLnMaxVec = 8;   // N <= 1024
+__global__ void __launch_bounds__(256) splitk_reduce_ln_kernel(const float* __restrict__ part, int64_t split_stride, int splits,
+                                                               const float* __restrict__ bias,
+                                                               const float* __restrict__ residual,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, float* __restrict__ y32,
+                                                               __nv_bfloat16* __restrict__ y16, int M, int N) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nvec = N / 4;
+  float4 v[kRedLnMaxVec];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kRedLnMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const size_t off = (size_t)row * N + 4 * c;
+      float4 a = __ldcg(reinterpret_cast<const float4*>(part + off));
+      for (int sp = 1; sp < splits; ++sp) {
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(part + (size_t)sp * split_stride + off));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      if (residual) {
+        const float4 r = *reinterpret_cast<const float4*>(residual + off);
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+      }
+      v[i] = a;
+      sum += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)N;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < kRedLnMaxVec; ++i)
+    if (lane + 32 * i < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = 1.0f / sqrtf(sq / (float)N + eps);
+#pragma unroll
+  for (int i = 0; i < kRedLnMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 o;
+      o.x = g.x * ((v[i].x - mean) * rstd) + bt.x;
+      o.y = g.y * ((v[i].y - mean) * rstd) + bt.y;
+      o.z = g.z * ((v[i].z - mean) * rstd) + bt.z;
+      o.w = g.w * ((v[i].w - mean) * rstd) + bt.w;
+      reinterpret_cast<float4*>(y32 + (size_t)row * N)[c] = o;
+      if (y16) reinterpret_cast<uint2*>(y16 + (size_t)row * N)[c] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -625,6 +692,62 @@ extern "C" int icka_set_gemm_mode(int mode) {
   return ICKA_OK;
 }
 
+namespace {
+// split count for a skinny fp32-out problem (0 / 1: do not split)
+int plan_splits(const icka_handle* h, int M, int N, int K, int BN) {
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  const int num_kb = (K + kBK - 1) / kBK;
+  int splits = h->sm_count / tiles;
+  if (splits > num_kb / 8) splits = num_kb / 8;
+  if (splits < 2 || (size_t)splits * M * N * sizeof(float) > ICKA_WORKSPACE_BYTES || h->workspace == nullptr || N % 4 != 0)
+    return 0;
+  return splits;
+}
+// per-split partial products into the handle's workspace; args.splits / split_stride describe the slabs afterwards
+int launch_split_partials(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& args, int M, int N, int K,
+                          int BN, int splits, cudaStream_t st) {
+  const int num_kb = (K + kBK - 1) / kBK;
+  const int kbps = (num_kb + splits - 1) / splits;
+  args.splits = (num_kb + kbps - 1) / kbps;
+  args.kb_per_split = kbps;
+  args.split_stride = (int64_t)M * N;
+  args.out = h->workspace;
+  args.ldo = N;
+  args.bias = nullptr;
+  args.residual = nullptr;
+  return (BN == 256) ? launch_gemm<256, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st)
+                     : launch_gemm<128, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st);
+}
+}  // namespace
+
+// LayerNorm(A . W^T + bias + residual) for skinny problems: split-K partials, then ONE reduce + LayerNorm pass.
+// Returns 0 = launched, < 0 = error, > 0 = the shape does not split (the caller picks another route).
+int icka_gemm_bf16_splitk_ln_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                    const float* residual, const float* gamma, const float* beta, float eps, float* out32,
+                                    void* out16, int M, int N, int K, cudaStream_t st) {
+  if (lda % 8 != 0 || ldw % 8 != 0 || N % 8 != 0 || N > 128 * kRedLnMaxVec || !icka_aligned(A, 16) || !icka_aligned(W, 16) ||
+      !icka_aligned(out32, 16) || !icka_aligned(out16, 8) || !icka_aligned(residual, 16) || !icka_aligned(bias, 16) ||
+      !icka_aligned(gamma, 16) || !icka_aligned(beta, 16))
+    return 1;
+  const int BN = (N > 128) ? 256 : 128;
+  const int splits = plan_splits(h, M, N, K, BN);
+  if (splits < 2) return 1;
+  CUtensorMap ta, tb;
+  int rc = icka_make_tmap_bf16(h, &ta, A, M, K, lda, kBM);
+  if (rc) return rc < 0 ? rc : -1;
+  rc = icka_make_tmap_bf16(h, &tb, W, N, K, ldw, BN);
+  if (rc) return rc < 0 ? rc : -1;
+  GemmArgs args{nullptr, nullptr, h->workspace, N, M, N, K, g_gemm_debug, nullptr, nullptr, (int64_t)N, 1, (K + kBK - 1) / kBK, 0};
+  args.act_rt = ICKA_ACT_NONE;
+  rc = launch_split_partials(h, ta, tb, args, M, N, K, BN, splits, st);
+  if (rc) return rc < 0 ? rc : -1;
+  splitk_reduce_ln_kernel<<<(M + 7) / 8, 256, 0, st>>>(static_cast<const float*>(h->workspace), args.split_stride, args.splits,
+                                                       bias, residual, gamma, beta, eps, out32,
+                                                       static_cast<__nv_bfloat16*>(out16), M, N);
+  ICKA_LAUNCHED(h);
+  return 0;
+}
+
 // Forward GEMM  out[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual); aux_out (optional, with ACT_GELU_ERF)
 // receives the bf16 pre-activation for the backward pass.
 int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
@@ -668,19 +791,9 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   // tiles for 148 SMs: split the contraction over CTAs into per-split slabs of the handle's workspace, then add the
   // slabs in split order (+ bias, residual) with a small reduce pass -- bit-reproducible, unlike atomics.
   if (!bf && !gelu && !rt && !pair && ldo == N) {
-    const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
-    const int num_kb = (K + kBK - 1) / kBK;
-    int splits = h->sm_count / tiles;
-    if (splits > num_kb / 8) splits = num_kb / 8;
-    if (splits >= 2 && (size_t)splits * M * N * sizeof(float) <= ICKA_WORKSPACE_BYTES && h->workspace != nullptr &&
-        N % 4 == 0) {
-      const int kbps = (num_kb + splits - 1) / splits;
-      args.splits = (num_kb + kbps - 1) / kbps;
-      args.kb_per_split = kbps;
-      args.split_stride = (int64_t)M * N;
-      args.out = h->workspace;
-      int rc2 = (BN == 256) ? launch_gemm<256, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st)
-                            : launch_gemm<128, ICKA_ACT_NONE, false, 1, 0>(h, ta, tb, args, st);
+    const int splits = plan_splits(h, M, N, K, BN);
+    if (splits >= 2) {
+      int rc2 = launch_split_partials(h, ta, tb, args, M, N, K, BN, splits, st);
       if (rc2) return rc2;
       const int64_t total = (int64_t)M * N;
       int blocks = (int)((total / 4 + 255) / 256);

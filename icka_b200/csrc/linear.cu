@@ -21,6 +21,9 @@ int icka_gemm_bf16_ln_launch(icka_handle* h, const void* A, int64_t lda, const v
                              const float* residual, const float* gamma, const float* beta, float eps, float* out32,
                              void* out16, int M, int N, int K, cudaStream_t st);
 
+int icka_gemm_bf16_splitk_ln_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                                    const float* residual, const float* gamma, const float* beta, float eps, float* out32,
+                                    void* out16, int M, int N, int K, cudaStream_t st);
 bool icka_gemm_ln_cluster_supported(int N, int K, const void* residual);
 int icka_gemm_bf16_ln_cluster_launch(icka_handle* h, const void* A, int64_t lda, const void* W, int64_t ldw,
                                      const float* bias, const float* residual, const float* gamma, const float* beta,
@@ -48,6 +51,18 @@ extern "C" int icka_linear_ln_fwd(icka_handle* h, const void* A, int64_t lda, co
   if (in_dtype == ICKA_BF16) {
     // N = 768 / 1024 (and 512): a cluster of N / 256 CTAs shares each 128-row block and exchanges the row statistics
     // over distributed shared memory (csrc/gemm_ln_sm100.cu); other widths: one CTA walks the n-tiles of its rows
+    if (g_ln_mode == 0) {
+      // skinny problems (the single-query encoders): split-K partials + one reduce-and-normalise pass
+      int rc = icka_gemm_bf16_splitk_ln_launch(h, A, lda, W, ldw, bias, residual, gamma, beta, eps, out_f32, out_bf16, M, N, K,
+                                               st);
+      if (rc <= 0) return rc;
+      if (M < 2048) {   // too few row blocks for a CTA (cluster) per block: plain GEMM, then the row kernel in place
+        rc = icka_gemm_bf16_launch(h, A, lda, W, ldw, bias, residual, out_f32, N, ICKA_F32, M, N, K, ICKA_ACT_NONE, nullptr,
+                                   st);
+        if (rc) return rc;
+        return icka_layernorm_fwd(h, out_f32, gamma, beta, eps, out_f32, out_bf16, M, N, stream);
+      }
+    }
     const bool cluster_ok = icka_gemm_ln_cluster_supported(N, K, residual);
     if (g_ln_mode == 2 && !cluster_ok) ICKA_FAIL(ICKA_ERR_UNSUPPORTED, "linear_ln: cluster kernel does not serve N=%d K=%d", N, K);
     if (cluster_ok && g_ln_mode != 1)

@@ -8,7 +8,7 @@
 (``weight_ih_l0`` ... ``bias_hh_l0_reverse`` -> the same state_dict keys) and return value
 ``(output, (h_n, c_n))``; ``EmissionHead`` owns ``lstm`` + ``classifier`` under the reference's attribute names.
 Inference runs on the persistent kernel (parameters detached); when autograd is recording, ``autograd.BiLstmFn`` /
-``LinearFn`` take over (per-step kernels with backpropagation through time).
+``ClassifierFn`` take over (per-step kernels with backpropagation through time).
 
 bf16 mode, H = 768:  x -> [icka_linear_fwd: Gx = x . W_ih^T + b for both directions, slice-ordered columns, bf16]
                        -> [icka_lstm_rec_fwd: ONE persistent weight-stationary tcgen05 kernel, all S steps]
@@ -24,7 +24,7 @@ import torch
 from torch import nn
 
 from . import modules, ops
-from .autograd import BiLstmFn, LinearFn
+from .autograd import BiLstmFn, ClassifierFn, LinearFn
 from .modules import _OperandCache
 
 REC_H = 768          # hidden size the persistent kernel is built for (csrc/lstm_sm100.cu)
@@ -186,7 +186,8 @@ class EmissionHead(nn.Module):
         B, S, _ = result.shape
         if self.lstm._recording(result) or (torch.is_grad_enabled() and self.classifier.weight.requires_grad):
             y = self.lstm._train_forward(result.float())                     # [B,S,2H] fp32, autograd node (BPTT)
-            return LinearFn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
+            fn = ClassifierFn if self.classifier.out_features <= 16 and y.shape[-1] % 8 == 0 else LinearFn
+            return fn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
         if B > REC_CHUNK and self.lstm.uses_persistent_kernel():
             out = torch.empty(B, S, self.classifier.out_features, dtype=torch.float32, device=result.device)
             for b0 in range(0, B, REC_CHUNK):

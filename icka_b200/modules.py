@@ -187,9 +187,9 @@ class _DenseResidualNorm(nn.Module):
         w = _operand(self._cache, 'w', self.dense.weight)
         if defer_ln:          # the caller fuses this LayerNorm into its consumer (icka_ln_gate_blend_fwd)
             return ops.linear(h_lp, w, self.dense.bias.detach(), residual=res32, out_dtype=torch.float32), None
-        if _FUSE_LN and h_lp.shape[0] >= 2048 and h_lp.shape[1] <= 1024:
-            # dense + residual + LayerNorm in one launch (normalisation in the GEMM epilogue); below ~2k rows a CTA
-            # per 128-row block leaves most SMs idle, so skinny problems keep the split-K GEMM + row kernel
+        if h_lp.shape[0] < 2048 or (_FUSE_LN and h_lp.shape[1] <= 1024):
+            # skinny problems (the single-query encoders): split-K partials + ONE reduce-and-normalise pass.  Large ones
+            # (opt-in, ICKA_FUSE_LN=1): dense + residual + LayerNorm in one launch, normalisation in the GEMM epilogue
             return ops.linear_ln(h_lp, w, self.dense.bias.detach(), res32, self.LayerNorm.weight.detach(),
                                  self.LayerNorm.bias.detach(), self.LayerNorm.variance_epsilon,
                                  want_bf16=get_precision() == 'bf16')
@@ -383,9 +383,8 @@ class BertCrossAttention(nn.Module):
         wqk, u0, wov, bo2 = self._folded_operands()
         u = ops.linear(z_lp, wqk, u0, out_dtype=torch.bfloat16)                       # [B, nh*H]
         xbar = ops.i2t_pool(u, y_lp, mask2d, B, Skv, H, nh)                           # [B, nh*H]
-        pre = ops.linear(xbar, wov, bo2, residual=z32, out_dtype=torch.float32)       # dense(ctx) + input
-        return ops.layernorm(pre, out.LayerNorm.weight.detach(), out.LayerNorm.bias.detach(),
-                             out.LayerNorm.variance_epsilon, want_f32=True, want_bf16=True)
+        return ops.linear_ln(xbar, wov, bo2, z32, out.LayerNorm.weight.detach(), out.LayerNorm.bias.detach(),
+                             out.LayerNorm.variance_epsilon, want_bf16=True)        # LN(dense(ctx) + input)
 
     def forward(self, s1_input_tensor, s2_input_tensor, s2_attention_mask):
         _check_inference(self, self.self.dropout.p, self.output.dropout.p)

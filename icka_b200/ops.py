@@ -586,6 +586,24 @@ def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, time_maj
     return out
 
 
+def emission_head_bwd(dout: torch.Tensor, x: torch.Tensor, w: torch.Tensor, want_dx: bool = True, want_dw: bool = True):
+    """Classifier backward: dout [M,T] fp32, x [M,K] fp32 / bf16, w [T,K] fp32 -> (dx [M,K] fp32 | None, dw [T,K] fp32 | None)."""
+    _need(dout, torch.float32, 'emission_head_bwd(dout)')
+    _need(w, torch.float32, 'emission_head_bwd(w)')
+    if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:
+        raise RuntimeError('emission_head_bwd: bad x')
+    M, K = x.shape
+    T = w.shape[0]
+    if dout.shape != (M, T) or w.shape != (T, K):
+        raise RuntimeError('emission_head_bwd: shape mismatch')
+    lib, h, st = _ctx(x)
+    dx = torch.empty(M, K, dtype=torch.float32, device=x.device) if want_dx else None
+    dw = torch.empty(T, K, dtype=torch.float32, device=x.device) if want_dw else None
+    _lib.check(lib.icka_emission_head_bwd(h, dout.data_ptr(), x.data_ptr(), _ld(x, K), w.data_ptr(), _p(dx), _p(dw),
+                                          _DT[x.dtype], M, K, T, 0, st), 'icka_emission_head_bwd')
+    return dx, dw
+
+
 def region_tail(x: torch.Tensor, att_size: int, *, want_fc: bool = True, want_att: bool = True,
                 rows_dtype: Optional[torch.dtype] = None):
     """layer4 output x [B,C,g,g] fp32 -> (fc [B,C] | None, att [B,C,a,a] fp32 | None, rows [B, a*a, C] | None)."""

@@ -33,7 +33,8 @@ def _work(name, args, kwargs):
         M, K = a.shape
         N = w.shape[0]
         nb = M * K * _ESZ[a.dtype] + N * K * _ESZ[w.dtype] + M * N * 8 + (M * N * 2 if kwargs.get('want_bf16') else 0)
-        return ('linear_bf16_tcgen05' if a.dtype == torch.bfloat16 else 'linear_fp32_ffma'), 2.0 * M * N * K, nb
+        # GEMM + (split-K reduce +) LayerNorm in one op: its own row, so that the GEMM roofline row holds GEMM launches only
+        return ('linear_ln_bf16_tcgen05' if a.dtype == torch.bfloat16 else 'linear_ln_fp32_ffma'), 2.0 * M * N * K, nb
     if name == 'cast_bf16':
         return name, 0.0, args[0].numel() * 6
     if name == 'region_rows':

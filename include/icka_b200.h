@@ -365,6 +365,12 @@ int icka_lstm_dir_bwd(icka_handle* h, const float* dy_dir, int64_t ld_dy_row, in
 int icka_emission_head_fwd(icka_handle* h, const void* x, int64_t ldx, const float* W, const float* bias, float* out,
                            int dtype, int64_t M, int K, int T, int time_major_S, void* stream);
 
+/* Backward of the classifier (CMIM:910, 1043; autograd of torch.nn.Linear(2H, num_labels)) in one pass over the states:
+ * dx [M,K] fp32 = dout [M,T] . W [T,K]  (dx may be NULL) and dW [T,K] fp32 (+)= dout^T . x  (dW may be NULL; zeroed
+ * first unless accumulate != 0).  x [M,K] fp32 or bf16 with row pitch ldx, T <= 16, K % 4 == 0. */
+int icka_emission_head_bwd(icka_handle* h, const float* dout, const void* x, int64_t ldx, const float* W, float* dx,
+                           float* dW, int dtype, int64_t M, int K, int T, int accumulate, void* stream);
+
 /* x [B,S,H] (fp32 or bf16) -> y [S,B,H] bf16: the time-major operand of the input projection of icka_lstm_rec_fwd. */
 int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_bf16, int in_dtype, int B, int S, int H,
                               void* stream);

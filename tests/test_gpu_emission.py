@@ -109,6 +109,24 @@ def test_emission_head_kernel(dtype, M, K, T):
     assert got.shape == (M, T) and rel(got, want) <= (1e-5 if dtype == torch.float32 else 1e-4)
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,K,T', [(1, 8, 1), (37, 1536, 15), (5000, 1536, 16), (9, 264, 7), (130, 2048, 3)])
+def test_emission_head_bwd_kernel(dtype, M, K, T):
+    """Classifier backward (autograd of nn.Linear(2H, T), CMIM:910): dx = dout . W and dW = dout^T . x against fp64."""
+    torch.manual_seed(M + K + T)
+    x = torch.randn(M, K).to(dtype)
+    w = torch.randn(T, K) / K ** 0.5
+    dout = torch.randn(M, T)
+    dx, dw = ops.emission_head_bwd(dout.cuda(), x.cuda(), w.cuda())
+    assert dx.shape == (M, K) and dw.shape == (T, K)
+    assert rel(dx, dout.double() @ w.double()) <= 1e-5
+    want_dw = dout.double().t() @ x.double()
+    scale = want_dw.abs().max().item()                   # sums of M products: fp32 rounding scales with the largest entries
+    assert (dw.double().cpu() - want_dw).abs().max().item() <= 1e-5 * max(scale, 1.0)
+    only_dw = ops.emission_head_bwd(dout.cuda(), x.cuda(), w.cuda(), want_dx=False)
+    assert only_dw[0] is None and (only_dw[1].double().cpu() - want_dw).abs().max().item() <= 1e-5 * max(scale, 1.0)
+
+
 @pytest.mark.parametrize('precision,tol', [('fp32', 1e-5), ('bf16', 2e-2)])
 def test_emission_head_module(precision, tol):
     icka_b200.set_precision(precision)
