@@ -18,6 +18,8 @@ backward regenerates from a per-call seed, so no mask tensor is stored.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, ops
@@ -380,6 +382,11 @@ def _two_streams(dev, run_direction):
     main.wait_stream(side)
 
 
+_FUSED_STEP_H = 768                                   # hidden size csrc/lstm_train.cu is built for
+_FUSED_STEPS = os.environ.get('ICKA_LSTM_FUSED_STEPS', '1') != '0'
+_FUSED_STEP_MAX_B = int(os.environ.get('ICKA_LSTM_FUSED_STEPS_MAX_B', '64'))
+
+
 class BiLstmFn(torch.autograd.Function):
     """Bidirectional single-layer LSTM (CMIM:905-908, 1042) with backpropagation through time, per-step kernels.
 
@@ -412,6 +419,20 @@ class BiLstmFn(torch.autograd.Function):
         lib = _lib.load()
         esz_dt = _lib.BF16 if bf16 else _lib.F32
 
+        # above 64 sentences the fused step kernel walks its 32-row blocks one after the other and loses to the GEMM launches
+        # (measured on a B200, whole training step: B=32 3.75 vs 6.30 ms, B=64 5.85 vs 7.03, B=128 9.85 vs 8.33)
+        ctx.fused_steps = bool(bf16 and H == _FUSED_STEP_H and _FUSED_STEPS and B <= _FUSED_STEP_MAX_B)
+        if ctx.fused_steps:
+            # one launch per step for both directions: recurrent product + cell update (csrc/lstm_train.cu)
+            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            _lib.check(lib.icka_lstm_bidir_fwd_save(h_dev, gx.data_ptr(), wh_ops[0].data_ptr(), wh_ops[1].data_ptr(),
+                                                    y_op.data_ptr(), y32.data_ptr(), acts.data_ptr(), c_all.data_ptr(),
+                                                    B, S, H, torch.cuda.current_stream(dev).cuda_stream),
+                       'icka_lstm_bidir_fwd_save')
+            ctx.save_for_backward(x_op, wi_op, wh_ops[0], wh_ops[1], y_op, acts, c_all)
+            ctx.dims = (B, S, I, H, bf16)
+            return y32
+
         def run_direction(d):
             h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
             gates = torch.empty(B, 4 * H, dtype=F32, device=dev)
@@ -440,6 +461,15 @@ class BiLstmFn(torch.autograd.Function):
         lib = _lib.load()
         esz_dt = _lib.BF16 if bf16 else _lib.F32
 
+        if ctx.fused_steps:
+            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+            dc = torch.empty(2, B, H, dtype=F32, device=dev)
+            wt0, wt1 = wh0.t().contiguous(), wh1.t().contiguous()          # W_hh^T [H, 4H]: rows = the units a CTA owns
+            _lib.check(lib.icka_lstm_bidir_bwd(h_dev, dy.data_ptr(), wt0.data_ptr(), wt1.data_ptr(), acts.data_ptr(),
+                                               c_all.data_ptr(), dg.data_ptr(), dc.data_ptr(), B, S, H,
+                                               torch.cuda.current_stream(dev).cuda_stream), 'icka_lstm_bidir_bwd')
+            return BiLstmFn._weight_grads(ctx, dg, x_op, wi_op, y_op, B, S, I, H, cdt, dev)
+
         def run_direction(d):
             wh = wh1 if d else wh0
             h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
@@ -454,6 +484,11 @@ class BiLstmFn(torch.autograd.Function):
             dh.record_stream(torch.cuda.current_stream(dev))
 
         _two_streams(dev, run_direction)
+        return BiLstmFn._weight_grads(ctx, dg, x_op, wi_op, y_op, B, S, I, H, cdt, dev)
+
+    @staticmethod
+    def _weight_grads(ctx, dg, x_op, wi_op, y_op, B, S, I, H, cdt, dev):
+        """Weight, bias and input gradients from the gate pre-activation gradients of all steps: four big GEMMs."""
         dg2 = dg.view(B * S, 8 * H)
         # h_{t-1} of every step = the output sequence shifted by one position (zeros at the sequence ends)
         hprev = torch.zeros(B, S, 2 * H, dtype=cdt, device=dev)

@@ -201,7 +201,7 @@ def _grad_case(precision, B, S, H, T, seed):
 
 
 @pytest.mark.parametrize('precision,B,S,H,tol', [('fp32', 3, 7, 32, 2e-4), ('fp32', 2, 5, 768, 2e-4), ('bf16', 4, 12, 64, 4e-2),
-                                                 ('bf16', 3, 6, 768, 4e-2)])
+                                                 ('bf16', 3, 6, 768, 4e-2), ('bf16', 40, 9, 768, 4e-2), ('bf16', 32, 1, 768, 4e-2)])
 def test_training_gradients_match_oracle_autograd(precision, B, S, H, tol):
     """BiLstmFn / LinearFn (BPTT on per-step kernels) against autograd through the oracle: every gradient within `tol`
     of its own scale (max |g|), as in tests/test_gpu_training.py."""
@@ -218,3 +218,20 @@ def test_training_gradients_match_oracle_autograd(precision, B, S, H, tol):
         close(k, v.grad, po[k].grad)
     close('classifier.weight', head.classifier.weight.grad, wc.grad)
     close('classifier.bias', head.classifier.bias.grad, bc.grad)
+
+
+def test_fused_step_kernels_agree_with_the_per_step_path(monkeypatch):
+    """bf16, H = 768: one launch per step for both directions (csrc/lstm_train.cu) against the GEMM + cell kernels per
+    direction and step it replaces -- same operands and rounding points, so outputs and gradients agree to bf16 rounding."""
+    from icka_b200 import autograd
+    outs = []
+    for fused in (True, False):
+        monkeypatch.setattr(autograd, '_FUSED_STEPS', fused)
+        monkeypatch.setattr(autograd, '_FUSED_STEP_MAX_B', 1 << 30)       # 70 sentences: three 32-row blocks, the last ragged
+        head, xg, got, *_ = _grad_case('bf16', 70, 11, 768, 15, seed=5)
+        outs.append((got.detach(), xg.grad.clone(), {k: v.grad.clone() for k, v in head.named_parameters()}))
+    (ea, xa, pa), (eb, xb, pb) = outs
+    assert (ea - eb).abs().max().item() <= 2e-2
+    assert (xa - xb).abs().max().item() <= 3e-2 * xb.abs().max().item()
+    for k in pa:
+        assert (pa[k] - pb[k]).abs().max().item() <= 3e-2 * pb[k].abs().max().item() + 1e-6, k
