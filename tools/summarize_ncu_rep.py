@@ -10,7 +10,7 @@ import os
 import subprocess
 import sys
 
-from summarize_profiles import G, P, short
+from summarize_profiles import G, P, read_raw, short
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
@@ -26,8 +26,7 @@ SCALE = {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9, 'ns': 1e-3, 'us': 
 
 
 def main(rep_name, out_name, note):
-    rep = os.path.join(G, rep_name + '.ncu-rep')
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = read_raw(rep_name)
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}

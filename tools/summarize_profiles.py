@@ -55,9 +55,21 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'launch__grid_size', 'launch__registers_per_thread', 'smsp__inst_executed.sum']
 
 
+LN_FUSED = (8, 10, 12, 14)
+
+
+def read_raw(name):
+    """`ncu --page raw --csv` of gpurun_out/<name>: exported on the GPU box (<name>.raw.csv; reports with sources exceed
+    what gpurun brings back) or from the report itself when it is here."""
+    pre = os.path.join(G, name + '.raw.csv')
+    if os.path.isfile(pre):
+        return open(pre).read()
+    rep = os.path.join(G, name + '.ncu-rep')
+    return subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+
+
 def gemm(R):
-    rep = os.path.join(G, f'gemm_{R}.ncu-rep')
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = read_raw(f'gemm_{R}')
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -79,6 +91,12 @@ def gemm(R):
         rec['duration_us'] = val('gpu__time_duration.sum', 1)
         out_rows.append(rec)
         traffic.append(rec['dram_bytes'])
+    # bench.py's `linear_bf16_tcgen05` row (roofline.achieved) holds the plain GEMM ops only; the four GEMMs of a step whose
+    # split-K partials go through the fused reduce + LayerNorm kernel (ops.linear_ln: launches 8, 10, 12, 14 of the 15, the
+    # single-query encoders' output projections) are reported in their own row, so they are left out of the traffic mean too
+    for i, rec in enumerate(out_rows):
+        rec['in_gemm_roofline_row'] = int(not (len(out_rows) == 15 and i in LN_FUSED))
+    traffic = [t for t, rec in zip(traffic, out_rows) if rec['in_gemm_roofline_row']]
     keys = list(out_rows[0].keys())
     try:          # the batch of the bench line captured in the same round
         batch = json.load(open(os.path.join(G, f'bench_{R}.json')))['config']['batch_per_gpu']
@@ -86,7 +104,7 @@ def gemm(R):
         batch = 1024
     with open(os.path.join(P, f'ncu_gemm_{R}.csv'), 'w') as f:
         f.write('# ncu --set full --clock-control none -k regex:gemm_bf16_tcgen05 --launch-skip 45 -c 15 '
-                'python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e\n')
+                'python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-widened --no-configs\n')
         f.write(f'# = the 15 tcgen05 GEMM launches of one bench step (B={batch}, L=1), in launch order\n')
         w = csv.DictWriter(f, fieldnames=keys)
         w.writeheader()
@@ -102,7 +120,8 @@ def main():
     os.makedirs(P, exist_ok=True)
     launches(R)
     gemm(R)
-    for name in (f'bench_{R}.json', f'bench_ref_{R}.json', f'bench_{R}_L5.json'):
+    for name in [f'bench_{R}.json', f'bench_ref_{R}.json'] + [f'bench_{R}_{x}.json' for x in (
+            'L5', 'hires', 'B256', 'train128', 'train32', 'train32_bilstm')]:
         src = os.path.join(G, name)
         if os.path.isfile(src):
             lines = [l for l in open(src) if l.startswith('{')]
