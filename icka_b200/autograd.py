@@ -388,7 +388,9 @@ _FUSED_STEP_MAX_B = int(os.environ.get('ICKA_LSTM_FUSED_STEPS_MAX_B', '64'))
 
 
 class BiLstmFn(torch.autograd.Function):
-    """Bidirectional single-layer LSTM (CMIM:905-908, 1042) with backpropagation through time, per-step kernels.
+    """Bidirectional single-layer LSTM (CMIM:905-908, 1042) with backpropagation through time.  bf16, H = 768, up to
+    ``_FUSED_STEP_MAX_B`` sentences: one fused launch per time step for both directions (csrc/lstm_train.cu); otherwise the
+    per-step kernels described below.
 
     forward   Gx = x . [W_ih; W_ih_r]^T + (b_ih + b_hh) in one GEMM; per direction and step: gates = h_{t-1} . W_hh^T
               (GEMM) and ``icka_lstm_cell_fwd_save`` (keeps the gate activations and the cell state, fp32)
@@ -396,7 +398,7 @@ class BiLstmFn(torch.autograd.Function):
               [B, S, 8H] buffer in position order) and dh_{t-1} = dpre_t . W_hh (dgrad GEMM); afterwards the weight,
               bias and input gradients as FOUR big GEMMs over all B*S rows (dW_hh per direction against the shifted
               output sequence, dW_ih, dx) and one column sum.
-    The persistent tcgen05 kernel serves inference; this first training path pays a GEMM launch per step.
+    The persistent tcgen05 kernel serves inference.
     """
 
     @staticmethod
