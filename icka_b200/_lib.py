@@ -104,7 +104,7 @@ SIGNATURES = {
     'icka_emission_head_fwd': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int,
                                        c_int, c_int, c_void_p]),
     'icka_emission_head_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64,
-                                       c_int, c_int, c_int, c_void_p]),
+                                       c_int, c_int, c_int, c_int, c_void_p]),
     'icka_cast_bf16_time_major': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'icka_add_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'icka_region_tail_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

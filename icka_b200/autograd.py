@@ -351,18 +351,22 @@ class ClassifierFn(torch.autograd.Function):
     streaming kernels (``icka_emission_head_fwd`` / ``_bwd``: one pass over the states each) instead of GEMM tiles."""
 
     @staticmethod
-    def forward(ctx, y32, weight, bias):
+    def forward(ctx, y32, weight, bias, time_major_S=0):
+        """``time_major_S`` = S: the rows of y32 are time-major (t*B + b, as the fused BiLSTM training kernels write them);
+        the emissions come out batch-major (b*S + t) either way."""
         y32 = y32.contiguous()
         w = weight.detach().float().contiguous()
         ctx.save_for_backward(y32, w)
-        return ops.emission_head(y32, w, bias.detach().float().contiguous())
+        ctx.tm_S = int(time_major_S)
+        return ops.emission_head(y32, w, bias.detach().float().contiguous(), time_major_S=ctx.tm_S)
 
     @staticmethod
     def backward(ctx, dout):
         y32, w = ctx.saved_tensors
         dout = dout.contiguous()
-        dy, dw = ops.emission_head_bwd(dout, y32, w, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1])
-        return dy, dw, (_colsum_any(dout) if ctx.needs_input_grad[2] else None)
+        dy, dw = ops.emission_head_bwd(dout, y32, w, want_dx=ctx.needs_input_grad[0], want_dw=ctx.needs_input_grad[1],
+                                       time_major_S=ctx.tm_S)
+        return dy, dw, (_colsum_any(dout) if ctx.needs_input_grad[2] else None), None
 
 
 _side_streams = {}
@@ -408,6 +412,11 @@ class BiLstmFn(torch.autograd.Function):
         cdt = torch.bfloat16 if bf16 else F32
         dev = x.device
         op = (lambda t: ops.cast_bf16(t.detach().float().contiguous())) if bf16 else (lambda t: t.detach().float().contiguous())
+        # above 64 sentences the fused step kernel walks its 32-row blocks one after the other and loses to the GEMM launches
+        ctx.fused_steps = bool(bf16 and H == _FUSED_STEP_H and _FUSED_STEPS and B <= _FUSED_STEP_MAX_B)
+        if ctx.fused_steps:
+            return BiLstmFn._forward_fused(ctx, x, op(torch.cat([w_ih, w_ih_r])), (op(w_hh), op(w_hh_r)),
+                                           (b_ih, b_ih_r, b_hh, b_hh_r), B, S, I, H)
         x_op = op(x.reshape(B * S, I))
         wi_op = op(torch.cat([w_ih, w_ih_r]))
         wh_ops = (op(w_hh), op(w_hh_r))
@@ -420,20 +429,6 @@ class BiLstmFn(torch.autograd.Function):
         c_all = torch.empty(2, S, B, H, dtype=F32, device=dev)
         lib = _lib.load()
         esz_dt = _lib.BF16 if bf16 else _lib.F32
-
-        # above 64 sentences the fused step kernel walks its 32-row blocks one after the other and loses to the GEMM launches
-        # (measured on a B200, whole training step: B=32 3.75 vs 6.30 ms, B=64 5.85 vs 7.03, B=128 9.85 vs 8.33)
-        ctx.fused_steps = bool(bf16 and H == _FUSED_STEP_H and _FUSED_STEPS and B <= _FUSED_STEP_MAX_B)
-        if ctx.fused_steps:
-            # one launch per step for both directions: recurrent product + cell update (csrc/lstm_train.cu)
-            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
-            _lib.check(lib.icka_lstm_bidir_fwd_save(h_dev, gx.data_ptr(), wh_ops[0].data_ptr(), wh_ops[1].data_ptr(),
-                                                    y_op.data_ptr(), y32.data_ptr(), acts.data_ptr(), c_all.data_ptr(),
-                                                    B, S, H, torch.cuda.current_stream(dev).cuda_stream),
-                       'icka_lstm_bidir_fwd_save')
-            ctx.save_for_backward(x_op, wi_op, wh_ops[0], wh_ops[1], y_op, acts, c_all)
-            ctx.dims = (B, S, I, H, bf16)
-            return y32
 
         def run_direction(d):
             h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
@@ -453,7 +448,61 @@ class BiLstmFn(torch.autograd.Function):
         return y32
 
     @staticmethod
+    def _forward_fused(ctx, x, wi_op, wh_ops, biases, B, S, I, H):
+        """One launch per time step for both directions (csrc/lstm_train.cu).  Every sequence tensor is TIME-MAJOR
+        ([S, B, .]): a step touches one contiguous block per tensor instead of B rows S x 12 KB apart.  The result is
+        returned as the batch-first VIEW of the time-major tensor."""
+        dev = x.device
+        lib = _lib.load()
+        b_ih, b_ih_r, b_hh, b_hh_r = biases
+        x_tm = ops.cast_bf16_time_major(x.detach().float().contiguous())             # [S, B, I] bf16
+        bsum = ops.add_f32(torch.cat([b_ih, b_ih_r]).detach().float().contiguous(),
+                           torch.cat([b_hh, b_hh_r]).detach().float().contiguous())
+        gx = ops.linear(x_tm.view(S * B, I), wi_op, bsum, out_dtype=torch.bfloat16)  # [S*B, 8H]
+        y32 = torch.empty(S, B, 2 * H, dtype=F32, device=dev)
+        y_op = torch.empty(S, B, 2 * H, dtype=torch.bfloat16, device=dev)
+        acts = torch.empty(2, S, B, 4 * H, dtype=F32, device=dev)
+        c_all = torch.empty(2, S, B, H, dtype=F32, device=dev)
+        h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        _lib.check(lib.icka_lstm_bidir_fwd_save(h_dev, gx.data_ptr(), wh_ops[0].data_ptr(), wh_ops[1].data_ptr(),
+                                                y_op.data_ptr(), y32.data_ptr(), acts.data_ptr(), c_all.data_ptr(),
+                                                B, S, H, torch.cuda.current_stream(dev).cuda_stream),
+                   'icka_lstm_bidir_fwd_save')
+        ctx.save_for_backward(x_tm.view(S * B, I), wi_op, wh_ops[0], wh_ops[1], y_op, acts, c_all)
+        ctx.dims = (B, S, I, H, True)
+        return y32.transpose(0, 1)
+
+    @staticmethod
+    def _backward_fused(ctx, dy):
+        x_op, wi_op, wh0, wh1, y_op, acts, c_all = ctx.saved_tensors
+        B, S, I, H, _ = ctx.dims
+        dev = dy.device
+        lib = _lib.load()
+        dy_tm = dy.transpose(0, 1).contiguous()                      # no copy when dy is the view of a time-major gradient
+        dg = torch.empty(S, B, 8 * H, dtype=torch.bfloat16, device=dev)
+        dc = torch.empty(2, B, H, dtype=F32, device=dev)
+        wt0, wt1 = wh0.t().contiguous(), wh1.t().contiguous()        # W_hh^T [H, 4H]: rows = the units a CTA owns
+        h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
+        _lib.check(lib.icka_lstm_bidir_bwd(h_dev, dy_tm.data_ptr(), wt0.data_ptr(), wt1.data_ptr(), acts.data_ptr(),
+                                           c_all.data_ptr(), dg.data_ptr(), dc.data_ptr(), B, S, H,
+                                           torch.cuda.current_stream(dev).cuda_stream), 'icka_lstm_bidir_bwd')
+        dg2 = dg.view(S * B, 8 * H)
+        # h_{t-1} of every step = the output sequence shifted by one position (zeros at the sequence ends)
+        hprev = torch.zeros(S, B, 2 * H, dtype=torch.bfloat16, device=dev)
+        hprev[1:, :, :H] = y_op[:-1, :, :H]
+        hprev[:-1, :, H:] = y_op[1:, :, H:]
+        hp2 = hprev.view(S * B, 2 * H)
+        d_whh = ops.linear_wgrad(dg2[:, :4 * H], hp2[:, :H])
+        d_whh_r = ops.linear_wgrad(dg2[:, 4 * H:], hp2[:, H:])
+        d_wih = ops.linear_wgrad(dg2, x_op)
+        db = ops.colsum(dg2)
+        dx = ops.linear_dgrad(dg2, wi_op, out_dtype=F32).view(S, B, I).transpose(0, 1)
+        return (dx, d_wih[:4 * H], d_whh, db[:4 * H], db[:4 * H], d_wih[4 * H:], d_whh_r, db[4 * H:], db[4 * H:], None)
+
+    @staticmethod
     def backward(ctx, dy):
+        if ctx.fused_steps:
+            return BiLstmFn._backward_fused(ctx, dy)
         x_op, wi_op, wh0, wh1, y_op, acts, c_all = ctx.saved_tensors
         B, S, I, H, bf16 = ctx.dims
         cdt = torch.bfloat16 if bf16 else F32
@@ -462,15 +511,6 @@ class BiLstmFn(torch.autograd.Function):
         dg = torch.empty(B, S, 8 * H, dtype=cdt, device=dev)           # gate pre-activation gradients, position order
         lib = _lib.load()
         esz_dt = _lib.BF16 if bf16 else _lib.F32
-
-        if ctx.fused_steps:
-            h_dev = _lib.handle(dev.index if dev.index is not None else torch.cuda.current_device())
-            dc = torch.empty(2, B, H, dtype=F32, device=dev)
-            wt0, wt1 = wh0.t().contiguous(), wh1.t().contiguous()          # W_hh^T [H, 4H]: rows = the units a CTA owns
-            _lib.check(lib.icka_lstm_bidir_bwd(h_dev, dy.data_ptr(), wt0.data_ptr(), wt1.data_ptr(), acts.data_ptr(),
-                                               c_all.data_ptr(), dg.data_ptr(), dc.data_ptr(), B, S, H,
-                                               torch.cuda.current_stream(dev).cuda_stream), 'icka_lstm_bidir_bwd')
-            return BiLstmFn._weight_grads(ctx, dg, x_op, wi_op, y_op, B, S, I, H, cdt, dev)
 
         def run_direction(d):
             wh = wh1 if d else wh0

@@ -293,7 +293,7 @@ constexpr int kHeadBwdRows = 32;     // dout rows staged per slab
 template <typename T>
 __global__ void __launch_bounds__(384)
 emission_head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x, int64_t ldx, const float* __restrict__ W,
-                         float* __restrict__ dx, float* __restrict__ dW, int64_t M, int K, int NT) {
+                         float* __restrict__ dx, float* __restrict__ dW, int64_t M, int K, int NT, int tm_S) {
   __shared__ __align__(16) float d_s[kHeadBwdRows][kHeadMaxT];
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   const bool live = c < K;
@@ -309,7 +309,7 @@ emission_head_bwd_kernel(const float* __restrict__ dout, const T* __restrict__ x
     __syncthreads();
     for (int i = threadIdx.x; i < kHeadBwdRows * kHeadMaxT; i += blockDim.x) {
       const int r = i / kHeadMaxT, t = i % kHeadMaxT;
-      d_s[r][t] = (r0 + r < M && t < NT) ? __ldg(dout + (r0 + r) * NT + t) : 0.0f;
+      d_s[r][t] = (r0 + r < M && t < NT) ? __ldg(dout + out_row(r0 + r, M, tm_S) * NT + t) : 0.0f;
     }
     __syncthreads();
     if (!live) continue;
@@ -591,7 +591,8 @@ extern "C" int icka_lstm_dir_bwd(icka_handle* h, const float* dy_dir, int64_t ld
 }
 
 extern "C" int icka_emission_head_bwd(icka_handle* h, const float* dout, const void* x, int64_t ldx, const float* W, float* dx,
-                                      float* dW, int dtype, int64_t M, int K, int T, int accumulate, void* stream) {
+                                      float* dW, int dtype, int64_t M, int K, int T, int accumulate, int time_major_S,
+                                      void* stream) {
   ICKA_CHECK_HANDLE(h);
   ICKA_REQUIRE(M >= 0 && K >= 4 && T >= 1 && T <= kHeadMaxT, "emission_head_bwd: bad shape M=%lld K=%d T=%d (T <= %d)",
                (long long)M, K, T, kHeadMaxT);
@@ -599,6 +600,8 @@ extern "C" int icka_emission_head_bwd(icka_handle* h, const float* dout, const v
   ICKA_REQUIRE(dout && x && W && (dx || dW), "emission_head_bwd: null pointer");
   ICKA_REQUIRE(icka_aligned(x, 16) && icka_aligned(W, 16) && icka_aligned(dx, 16), "emission_head_bwd: 16-byte alignment");
   ICKA_REQUIRE(dtype == ICKA_F32 || dtype == ICKA_BF16, "emission_head_bwd: bad dtype %d", dtype);
+  ICKA_REQUIRE(time_major_S >= 0 && (time_major_S == 0 || M % time_major_S == 0),
+               "emission_head_bwd: M=%lld is not a multiple of the time-major S=%d", (long long)M, time_major_S);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dW && !accumulate) ICKA_CUDA(cudaMemsetAsync(dW, 0, (size_t)T * K * sizeof(float), st));
   if (M == 0) return ICKA_OK;
@@ -611,10 +614,11 @@ extern "C" int icka_emission_head_bwd(icka_handle* h, const float* dout, const v
   if (row_blocks > cap) row_blocks = cap;
   dim3 grid((unsigned)row_blocks, (unsigned)col_blocks);
   if (dtype == ICKA_F32)
-    emission_head_bwd_kernel<float><<<grid, threads, 0, st>>>(dout, static_cast<const float*>(x), ldx, W, dx, dW, M, K, T);
+    emission_head_bwd_kernel<float><<<grid, threads, 0, st>>>(dout, static_cast<const float*>(x), ldx, W, dx, dW, M, K, T,
+                                                              time_major_S);
   else
     emission_head_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(dout, static_cast<const __nv_bfloat16*>(x), ldx, W,
-                                                                      dx, dW, M, K, T);
+                                                                      dx, dW, M, K, T, time_major_S);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

@@ -11,7 +11,7 @@
 //             output sequence, which is also the next step's A operand), and the saved gate activations.
 //   backward  the same kernel shape on the transposed weights: dh_rec[:, slice] = dpre_{t+1} . W_hh[:, slice]
 //             (K = 3072; the A operand streams through a 6-stage ring of 256-wide chunks), then the cell backward of the slice:
-//             dpre_t goes into the position-ordered [B, S, 8H] gradient buffer that the next launch reads as its A operand
+//             dpre_t goes into the time-major [S, B, 8H] gradient buffer that the next launch reads as its A operand
 //             and that the big weight / input gradient GEMMs consume afterwards.
 // Dependencies between steps are kernel boundaries; 2 x 128 launches replace ~1000, and a CUDA graph replays them.
 // (The persistent tcgen05 kernel of lstm_sm100.cu serves inference, where thousands of sentences give each CTA four
@@ -65,15 +65,15 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_
 
 struct StepArgs {
   // forward
-  const __nv_bfloat16* gx;     // [B, S, 8H] bf16, position order: x . W_ih^T + b for both directions
+  const __nv_bfloat16* gx;     // [S, B, 8H] bf16, TIME-MAJOR (position order): x . W_ih^T + b for both directions
   const __nv_bfloat16* w[2];   // forward: W_hh [4H, H] per direction; backward: W_hh^T [H, 4H] per direction
-  __nv_bfloat16* y_op;         // [B, S, 2H] bf16: the output sequence = h of every step (A operand of the next step)
-  float* y32;                  // [B, S, 2H] fp32 copy (the autograd output)
+  __nv_bfloat16* y_op;         // [S, B, 2H] bf16: the output sequence = h of every step (A operand of the next step)
+  float* y32;                  // [S, B, 2H] fp32 copy (the autograd output)
   float* acts;                 // [2, S, B, 4H] fp32: i, f, g, o after their nonlinearities, indexed by STEP
   float* c_all;                // [2, S, B, H] fp32 cell states, indexed by step
   // backward
-  const float* dy;             // [B, S, 2H] fp32
-  __nv_bfloat16* dg;           // [B, S, 8H] bf16 gate pre-activation gradients, position order
+  const float* dy;             // [S, B, 2H] fp32
+  __nv_bfloat16* dg;           // [S, B, 8H] bf16 gate pre-activation gradients, time-major
   float* dc;                   // [2, B, H] fp32 running cell gradient (zero before the first launch)
   int B, S, t;
 };
@@ -115,9 +115,12 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_kernel(const StepArgs 
   const int nrb = (B + kRows - 1) / kRows;
   const int nchunks = has_rec ? nrb * NKC : 0;
 
-  const __nv_bfloat16* a_base = BWD ? args.dg + (size_t)pos_src * 8 * kTH + (size_t)dir * 4 * kTH
-                                    : args.y_op + (size_t)pos_src * 2 * kTH + (size_t)dir * kTH;
-  const int64_t a_ld = BWD ? (int64_t)S * 8 * kTH : (int64_t)S * 2 * kTH;
+  // every sequence tensor is TIME-MAJOR ([S, B, .]): a step touches one contiguous block per tensor.  (Batch-major rows are
+  // S x 12 KB apart -- one DRAM page and one TLB entry per sentence and tensor: the first version of this kernel spent
+  // ~4 us per 32 sentences and step on exactly that.)
+  const __nv_bfloat16* a_base = BWD ? args.dg + (size_t)pos_src * B * 8 * kTH + (size_t)dir * 4 * kTH
+                                    : args.y_op + (size_t)pos_src * B * 2 * kTH + (size_t)dir * kTH;
+  const int64_t a_ld = BWD ? (int64_t)8 * kTH : (int64_t)2 * kTH;
   auto issue_chunk = [&](int c) {
     const int rb = c / NKC, kc = c % NKC;
     const int rows_valid = min(kRows, B - rb * kRows);
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_kernel(const StepArgs 
     for (int i = 0; i < 8; ++i) pf[i] = make_float2(0.0f, 0.0f);
     if (live) {
       if constexpr (!BWD) {
-        const __nv_bfloat16* gxp = args.gx + ((size_t)row * S + pos) * 8 * kTH + (size_t)dir * 4 * kTH + unit;
+        const __nv_bfloat16* gxp = args.gx + ((size_t)pos * B + row) * 8 * kTH + (size_t)dir * 4 * kTH + unit;
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) gxw[gate] = __ldg(reinterpret_cast<const uint32_t*>(gxp + gate * kTH));
         if (t > 0) pf[0] = *reinterpret_cast<const float2*>(args.c_all + (st_row - B) * kTH + unit);
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_kernel(const StepArgs 
         for (int gate = 0; gate < 4; ++gate) pf[gate] = *reinterpret_cast<const float2*>(ap + gate * kTH);
         pf[4] = *reinterpret_cast<const float2*>(args.c_all + st_row * kTH + unit);
         if (t > 0) pf[5] = *reinterpret_cast<const float2*>(args.c_all + (st_row - B) * kTH + unit);
-        pf[6] = *reinterpret_cast<const float2*>(args.dy + ((size_t)row * S + pos) * 2 * kTH + (size_t)dir * kTH + unit);
+        pf[6] = *reinterpret_cast<const float2*>(args.dy + ((size_t)pos * B + row) * 2 * kTH + (size_t)dir * kTH + unit);
         pf[7] = *reinterpret_cast<const float2*>(args.dc + ((size_t)dir * B + row) * kTH + unit);
       }
     }
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_kernel(const StepArgs 
       *reinterpret_cast<float2*>(ap + kTH) = make_float2(fg[0], fg[1]);
       *reinterpret_cast<float2*>(ap + 2 * kTH) = make_float2(gg[0], gg[1]);
       *reinterpret_cast<float2*>(ap + 3 * kTH) = make_float2(og[0], og[1]);
-      const size_t yo = ((size_t)row * S + pos) * 2 * kTH + (size_t)dir * kTH + unit;
+      const size_t yo = ((size_t)pos * B + row) * 2 * kTH + (size_t)dir * kTH + unit;
       *reinterpret_cast<uint32_t*>(args.y_op + yo) = pack_bf16x2(hn[0], hn[1]);
       *reinterpret_cast<float2*>(args.y32 + yo) = make_float2(hn[0], hn[1]);
     } else {
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_kernel(const StepArgs 
         dcn[e] = dct * fgv[e];
       }
       *reinterpret_cast<float2*>(args.dc + ((size_t)dir * B + row) * kTH + unit) = make_float2(dcn[0], dcn[1]);
-      __nv_bfloat16* dp = args.dg + ((size_t)row * S + pos) * 8 * kTH + (size_t)dir * 4 * kTH + unit;
+      __nv_bfloat16* dp = args.dg + ((size_t)pos * B + row) * 8 * kTH + (size_t)dir * 4 * kTH + unit;
       *reinterpret_cast<uint32_t*>(dp) = pack_bf16x2(d_i[0], d_i[1]);
       *reinterpret_cast<uint32_t*>(dp + kTH) = pack_bf16x2(d_f[0], d_f[1]);
       *reinterpret_cast<uint32_t*>(dp + 2 * kTH) = pack_bf16x2(d_g[0], d_g[1]);

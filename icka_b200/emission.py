@@ -186,8 +186,13 @@ class EmissionHead(nn.Module):
         B, S, _ = result.shape
         if self.lstm._recording(result) or (torch.is_grad_enabled() and self.classifier.weight.requires_grad):
             y = self.lstm._train_forward(result.float())                     # [B,S,2H] fp32, autograd node (BPTT)
-            fn = ClassifierFn if self.classifier.out_features <= 16 and y.shape[-1] % 8 == 0 else LinearFn
-            return fn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
+            if self.classifier.out_features > 16 or y.shape[-1] % 8:
+                return LinearFn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
+            y_tm = y.transpose(0, 1)
+            if y_tm.is_contiguous():          # the fused step kernels write the sequence time-major: classify it in place
+                return ClassifierFn.apply(y_tm.reshape(S * B, -1), self.classifier.weight, self.classifier.bias,
+                                          S).view(B, S, -1)
+            return ClassifierFn.apply(y.reshape(B * S, -1), self.classifier.weight, self.classifier.bias).view(B, S, -1)
         if B > REC_CHUNK and self.lstm.uses_persistent_kernel():
             out = torch.empty(B, S, self.classifier.out_features, dtype=torch.float32, device=result.device)
             for b0 in range(0, B, REC_CHUNK):

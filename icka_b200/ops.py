@@ -586,8 +586,10 @@ def emission_head(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, time_maj
     return out
 
 
-def emission_head_bwd(dout: torch.Tensor, x: torch.Tensor, w: torch.Tensor, want_dx: bool = True, want_dw: bool = True):
-    """Classifier backward: dout [M,T] fp32, x [M,K] fp32 / bf16, w [T,K] fp32 -> (dx [M,K] fp32 | None, dw [T,K] fp32 | None)."""
+def emission_head_bwd(dout: torch.Tensor, x: torch.Tensor, w: torch.Tensor, want_dx: bool = True, want_dw: bool = True,
+                      time_major_S: int = 0):
+    """Classifier backward: dout [M,T] fp32, x [M,K] fp32 / bf16, w [T,K] fp32 -> (dx [M,K] fp32 | None, dw [T,K] fp32 | None).
+    ``time_major_S`` = S: the rows of x / dx are t*B + b while those of dout are b*S + t (as ``emission_head`` pairs them)."""
     _need(dout, torch.float32, 'emission_head_bwd(dout)')
     _need(w, torch.float32, 'emission_head_bwd(w)')
     if x.dim() != 2 or x.dtype not in _DT or x.stride(1) != 1:
@@ -600,7 +602,7 @@ def emission_head_bwd(dout: torch.Tensor, x: torch.Tensor, w: torch.Tensor, want
     dx = torch.empty(M, K, dtype=torch.float32, device=x.device) if want_dx else None
     dw = torch.empty(T, K, dtype=torch.float32, device=x.device) if want_dw else None
     _lib.check(lib.icka_emission_head_bwd(h, dout.data_ptr(), x.data_ptr(), _ld(x, K), w.data_ptr(), _p(dx), _p(dw),
-                                          _DT[x.dtype], M, K, T, 0, st), 'icka_emission_head_bwd')
+                                          _DT[x.dtype], M, K, T, 0, int(time_major_S), st), 'icka_emission_head_bwd')
     return dx, dw
 
 

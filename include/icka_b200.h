@@ -368,11 +368,12 @@ int icka_emission_head_fwd(icka_handle* h, const void* x, int64_t ldx, const flo
 /* Training (backpropagation through time) of the bidirectional LSTM (CMIM:905-908, 1042; autograd of nn.LSTM) with bf16
  * operands, H = 768: one launch per time step computes the recurrent product and the cell arithmetic of both directions
  * (csrc/lstm_train.cu).
- *   fwd_save: gx [B,S,8H] bf16 = x . [W_ih; W_ih_reverse]^T + biases (position order, gate order i,f,g,o per direction),
- *             w_hh_* [4H,H] bf16 -> y_op [B,S,2H] bf16 and y32 [B,S,2H] fp32 (the output sequence), acts [2,S,B,4H] fp32
+ * Every sequence tensor is TIME-MAJOR ([S,B,.], row = position * B + sentence): a step touches one contiguous block.
+ *   fwd_save: gx [S,B,8H] bf16 = x . [W_ih; W_ih_reverse]^T + biases (gate order i,f,g,o per direction),
+ *             w_hh_* [4H,H] bf16 -> y_op [S,B,2H] bf16 and y32 [S,B,2H] fp32 (the output sequence), acts [2,S,B,4H] fp32
  *             (gate activations per STEP) and c_all [2,S,B,H] fp32 (cell states per step) for the backward pass.
- *   bwd:      dy [B,S,2H] fp32, w_hh_t_* [H,4H] bf16 (W_hh transposed), the saved acts / c_all -> dg [B,S,8H] bf16 = the
- *             gradients of the gate pre-activations (position order); dc_scratch [2,B,H] fp32 is working storage.
+ *   bwd:      dy [S,B,2H] fp32, w_hh_t_* [H,4H] bf16 (W_hh transposed), the saved acts / c_all -> dg [S,B,8H] bf16 = the
+ *             gradients of the gate pre-activations; dc_scratch [2,B,H] fp32 is working storage.
  *             The weight / bias / input gradients follow from dg as plain GEMMs (icka_linear_wgrad / _dgrad, icka_colsum). */
 int icka_lstm_bidir_fwd_save(icka_handle* h, const void* gx, const void* w_hh_fwd, const void* w_hh_bwd, void* y_op,
                              float* y32, float* acts, float* c_all, int B, int S, int H, void* stream);
@@ -381,9 +382,10 @@ int icka_lstm_bidir_bwd(icka_handle* h, const float* dy, const void* w_hh_t_fwd,
 
 /* Backward of the classifier (CMIM:910, 1043; autograd of torch.nn.Linear(2H, num_labels)) in one pass over the states:
  * dx [M,K] fp32 = dout [M,T] . W [T,K]  (dx may be NULL) and dW [T,K] fp32 (+)= dout^T . x  (dW may be NULL; zeroed
- * first unless accumulate != 0).  x [M,K] fp32 or bf16 with row pitch ldx, T <= 16, K % 4 == 0. */
+ * first unless accumulate != 0).  x [M,K] fp32 or bf16 with row pitch ldx, T <= 16, K % 4 == 0.  time_major_S = S > 0:
+ * the rows of x / dx are time-major (t*B + b) while dout is batch-major (b*S + t), as icka_emission_head_fwd pairs them. */
 int icka_emission_head_bwd(icka_handle* h, const float* dout, const void* x, int64_t ldx, const float* W, float* dx,
-                           float* dW, int dtype, int64_t M, int K, int T, int accumulate, void* stream);
+                           float* dW, int dtype, int64_t M, int K, int T, int accumulate, int time_major_S, void* stream);
 
 /* x [B,S,H] (fp32 or bf16) -> y [S,B,H] bf16: the time-major operand of the input projection of icka_lstm_rec_fwd. */
 int icka_cast_bf16_time_major(icka_handle* h, const void* x, void* y_bf16, int in_dtype, int B, int S, int H,

@@ -123,6 +123,12 @@ def test_emission_head_bwd_kernel(dtype, M, K, T):
     want_dw = dout.double().t() @ x.double()
     scale = want_dw.abs().max().item()                   # sums of M products: fp32 rounding scales with the largest entries
     assert (dw.double().cpu() - want_dw).abs().max().item() <= 1e-5 * max(scale, 1.0)
+    if M % 5 == 0:                                       # time-major states (row t*B + b) against batch-major dout (row b*S + t)
+        S_, B_ = 5, M // 5
+        x_tm = x.view(B_, S_, K).transpose(0, 1).reshape(M, K).contiguous()
+        dx_tm, dw_tm = ops.emission_head_bwd(dout.cuda(), x_tm.cuda(), w.cuda(), time_major_S=S_)
+        assert rel(dx_tm.view(S_, B_, K).transpose(0, 1).reshape(M, K), dout.double() @ w.double()) <= 1e-5
+        assert (dw_tm.double().cpu() - want_dw).abs().max().item() <= 1e-5 * max(scale, 1.0)
     only_dw = ops.emission_head_bwd(dout.cuda(), x.cuda(), w.cuda(), want_dx=False)
     assert only_dw[0] is None and (only_dw[1].double().cpu() - want_dw).abs().max().item() <= 1e-5 * max(scale, 1.0)
 
