@@ -121,11 +121,15 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      auto x_chunks = [&](int b) {   // the H/64 chunk tiles of sentence b, in order
+      // The first pass asks L2 to KEEP the lines (evict_last), the second releases them (evict_first): between the two reads
+      // of a chunk every SM streams another sentence (58 MB in flight machine-wide, against two 63 MB L2 partitions), and
+      // with the default policy 18 % of the second pass came from DRAM again (ncu: 281 MB per launch vs 239 MB algorithmic).
+      const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
+      auto x_chunks = [&](int b, uint64_t pol) {   // the H/64 chunk tiles of sentence b, in order
         for (int c = 0; c < Cfg::kChunks; ++c) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kChunkBytes);
-          tma_load_2d(x_ring + (size_t)stage * kChunkBytes, &tmap_x, &full_bar[stage], c * 64, b * args.S);
+          tma_load_2d_hint(x_ring + (size_t)stage * kChunkBytes, &tmap_x, &full_bar[stage], c * 64, b * args.S, pol);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       };
@@ -140,9 +144,9 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           mbar_arrive_expect_tx(&u_full[slot], Cfg::kUBytes);
           for (int c = 0; c < Cfg::kChunks; ++c)
             tma_load_2d(u_base + slot * Cfg::kUBytes + c * (kHeads * 128), &tmap_u, &u_full[slot], c * 64, b * args.nh);
-          x_chunks(b);            // pass 1 of sentence n
+          x_chunks(b, pol_keep);            // pass 1 of sentence n
         }
-        if (prev_b >= 0) x_chunks(prev_b);   // pass 2 of sentence n-1
+        if (prev_b >= 0) x_chunks(prev_b, pol_done);   // pass 2 of sentence n-1
         if (!live) break;
         prev_b = b;
       }
