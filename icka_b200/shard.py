@@ -6,6 +6,7 @@ the only distributed logic: shard bounds, and gathering ragged per-rank tag list
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List, Sequence, Tuple
 
 import torch
@@ -76,8 +77,8 @@ class _Bucket:
 class GradientAllReducer:
     """Bucketed, backward-overlapped gradient all-reduce for one process per GPU.
 
-    Parameters are grouped into buckets of about ``bucket_bytes`` in REVERSE registration order (roughly the
-    order backward produces their gradients: the kernel-backed autograd nodes of ``icka_b200.autograd`` emit
+    Parameters are grouped into buckets of about ``bucket_bytes`` (the last one to complete: ``last_bucket_bytes``) in
+    REVERSE registration order (roughly the order backward produces their gradients: the kernel-backed autograd nodes of ``icka_b200.autograd`` emit
     all 16 parameter gradients of a cross layer at once, so buckets fill layer by layer).  A
     post-accumulate-grad hook counts a bucket's gradients in; when the last one lands, the bucket is packed
     into one flat fp32 buffer and all-reduced asynchronously (NCCL over NVLink 5 / NVSwitch on GPU ranks --
@@ -94,7 +95,8 @@ class GradientAllReducer:
     asynchronous all-reduce is still reading: it raises instead.
     """
 
-    def __init__(self, params, bucket_bytes: int = 25 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 25 << 20, group=None, last_bucket_bytes: int = 4 << 20,
+                 overlap: bool = True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         plist = [p for p in params if p.requires_grad]
@@ -104,8 +106,21 @@ class GradientAllReducer:
                 seen.add(id(p))
                 uniq.append(p)
         self.buckets: List[_Bucket] = []
+        # The bucket that completes LAST (the first-registered parameters: their gradients are the last ones backward
+        # produces) cannot overlap anything -- the optimizer waits for it -- so it is kept small: just enough of the first
+        # parameters to reach ``last_bucket_bytes``.
+        tail, tail_bytes = [], 0
+        if last_bucket_bytes and len(uniq) > 1:
+            for p in uniq:
+                if tail_bytes >= last_bucket_bytes or len(tail) == len(uniq) - 1:
+                    break
+                tail.append(p)
+                tail_bytes += p.numel() * 4
+            if tail_bytes > bucket_bytes:
+                tail = []
+        head = uniq[len(tail):]
         cur, cur_bytes = [], 0
-        for p in reversed(uniq):
+        for p in reversed(head):
             nbytes = p.numel() * 4
             if cur and cur_bytes + nbytes > bucket_bytes:
                 self.buckets.append(_Bucket(cur))
@@ -114,6 +129,8 @@ class GradientAllReducer:
             cur_bytes += nbytes
         if cur:
             self.buckets.append(_Bucket(cur))
+        if tail:
+            self.buckets.append(_Bucket(list(reversed(tail))))
         self._where = {}
         self._handles = []
         for b in self.buckets:
@@ -121,6 +138,8 @@ class GradientAllReducer:
                 self._where[id(p)] = b
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.launched_early = 0      # buckets whose all-reduce started from inside backward (diagnostics)
+        # overlap = False: every bucket is sent from finish(), after backward (developer knob ICKA_ALLREDUCE_OVERLAP=0)
+        self.overlap = overlap and os.environ.get('ICKA_ALLREDUCE_OVERLAP', '1') != '0'
         self._sync = True
 
     @contextlib.contextmanager
@@ -147,7 +166,7 @@ class GradientAllReducer:
                                'all-reduce -- a second backward() before finish(); wrap all micro-batches but the last '
                                'in `with reducer.no_sync():`')
         b.pending -= 1
-        if b.pending == 0 and self.world > 1:
+        if b.pending == 0 and self.world > 1 and self.overlap:
             self._launch(b)
             self.launched_early += 1
 

@@ -187,3 +187,20 @@ def test_two_rank_gradient_accumulation_matches_full_batch():
         for got, p in zip(grads[step], model.parameters()):
             assert torch.allclose(torch.from_numpy(got), p.grad, rtol=1e-5, atol=1e-6)
     assert raised
+
+
+def test_last_bucket_is_small():
+    """The bucket that completes last (first-registered parameters) cannot overlap backward: it is kept small."""
+    import torch
+    from icka_b200 import shard
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (300_000, 300_000, 200_000, 5_000_000, 4_000_000, 10)]
+    r = shard.GradientAllReducer(ps, bucket_bytes=25 << 20, last_bucket_bytes=2 << 20)
+    sizes = [sum(p.numel() for p in b.params) for b in r.buckets]
+    assert sum(sizes) == sum(p.numel() for p in ps)
+    assert [id(p) for p in r.buckets[-1].params] == [id(ps[1]), id(ps[0])]          # 2.4 MB >= 2 MB: the first two parameters
+    assert [id(p) for b in r.buckets[:-1] for p in b.params] == [id(p) for p in reversed(ps[2:])]   # reverse registration order
+    assert len(r.buckets) == 3                                                       # 16 MB + 20 MB do not share a 25 MB bucket
+    r.remove_hooks()
+    r1 = shard.GradientAllReducer(ps, last_bucket_bytes=0)
+    assert [id(p) for b in r1.buckets for p in b.params] == [id(p) for p in reversed(ps)]
+    r1.remove_hooks()
