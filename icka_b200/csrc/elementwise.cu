@@ -130,7 +130,39 @@ __global__ void __launch_bounds__(256) region_rows_kernel(const float* __restric
   // conflict bound at 60 % of HBM); lane = channel (and channel + 32) with the odd pitch is conflict-free, and two
   // shuffles hand each lane the neighbouring channel it stores next to its own.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (nc == kRegC) {
+  if (nc == kRegC && Rp == R && (R & 31) == 4) {
+    // Unpadded even pitch with R = 4 (mod 32) -- the 14 x 14 grid of the 448-px configuration, R = 196: lane = channel
+    // reads column r with a 4-way bank conflict (bank = 4 lane + r), but if the lanes of octet o read column r0 + (o + i) % 4
+    // instead, the 32 lanes hit 32 banks; after four rounds every lane has its channel at regions r0 .. r0 + 3.  The two
+    // source lanes of a destination lane share an octet, so the shuffles of round i deliver region r0 + (o_src + i) % 4;
+    // the destination keeps its four packed results and picks, for each output row, the round that produced it.  This is
+    // what lets the slab arrive as one contiguous 16-byte copy (the padded-pitch path stores scalars: 59 % of HBM).
+    const int src = 2 * (lane & 15);
+    const bool upper = lane >= 16;
+    const int oct = lane >> 3, oct_src = src >> 3;
+    const int c = (upper ? 32 : 0) + src;
+    for (int r0 = 4 * warp; r0 < R; r0 += 32) {
+      float2 res[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = r0 + ((oct + i) & 3);
+        const float lo = tile[lane * R + rr], hi = tile[(lane + 32) * R + rr];
+        const float a0 = __shfl_sync(0xffffffffu, lo, src), a1 = __shfl_sync(0xffffffffu, lo, src + 1);
+        const float b0 = __shfl_sync(0xffffffffu, hi, src), b1 = __shfl_sync(0xffffffffu, hi, src + 1);
+        res[i] = make_float2(upper ? b0 : a0, upper ? b1 : a1);       // region r0 + (oct_src + i) % 4
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = (q - oct_src) & 3;
+        const float2 v = i == 0 ? res[0] : i == 1 ? res[1] : i == 2 ? res[2] : res[3];
+        if constexpr (sizeof(OutT) == 2) {
+          *reinterpret_cast<uint32_t*>(dst + (size_t)(r0 + q) * C + c) = pack_bf16x2(v.x, v.y);
+        } else {
+          *reinterpret_cast<float2*>(dst + (size_t)(r0 + q) * C + c) = v;
+        }
+      }
+    }
+  } else if (nc == kRegC) {
     const int src = 2 * (lane & 15);                 // lanes 0-15 store channels 0-31, lanes 16-31 channels 32-63
     const bool upper = lane >= 16;
 #pragma unroll 2
@@ -586,7 +618,7 @@ extern "C" int icka_region_rows(icka_handle* h, const float* grid, void* rows, i
   ICKA_REQUIRE(B <= 65535, "region_rows: B=%d exceeds the grid.y limit; shard the batch", B);
   ICKA_REQUIRE(out_dtype == ICKA_F32 || out_dtype == ICKA_BF16, "region_rows: bad dtype %d", out_dtype);
   if (B == 0) return ICKA_OK;
-  const int Rp = R | 1;
+  const int Rp = ((R & 31) == 4 && C % kRegC == 0) ? R : (R | 1);   // R = 4 (mod 32): unpadded, rotated reads (see the kernel)
   const size_t smem = (size_t)kRegC * Rp * sizeof(float);
   ICKA_REQUIRE(smem <= h->smem_optin, "region_rows: R=%d too large", R);
   dim3 g((C + kRegC - 1) / kRegC, B);

@@ -31,7 +31,7 @@ def test_cast_bf16():
         assert torch.equal(y, x.bfloat16())
 
 
-@pytest.mark.parametrize('B,C,R', [(2, 2048, 49), (1, 2048, 196), (3, 64, 9), (2, 100, 7), (3, 512, 50), (2, 256, 1), (1, 2048, 8),
+@pytest.mark.parametrize('B,C,R', [(2, 2048, 49), (1, 2048, 196), (3, 64, 9), (2, 100, 7), (3, 512, 50), (2, 256, 1), (1, 2048, 8), (2, 128, 36), (3, 64, 4), (2, 192, 100), (5, 2048, 196),
                                    (70, 2048, 49)])
 @pytest.mark.parametrize('dt', [torch.float32, torch.bfloat16])
 def test_region_rows(B, C, R, dt):
