@@ -36,6 +36,8 @@
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
+#include <stdlib.h>
+
 namespace {
 
 using namespace sm100;
@@ -45,6 +47,16 @@ constexpr int kBK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kEpiWarps = 8;           // two per TMEM lane quadrant; they split the column blocks
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+__device__ __forceinline__ void tma_store_2d_out(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 constexpr int kActRuntime = 100;   // template ACT value: relu / swish (config.hidden_act, CMIM:43) chosen by GemmArgs::act_rt
 
 // CTAS == 1: one CTA computes a 128 x BN tile.  CTAS == 2: a CTA pair (cluster of 2, tcgen05 cta_group::2)
@@ -82,6 +94,10 @@ struct GemmArgs {
   float ln_eps;
   __nv_bfloat16* out16;          // [M, N] bf16 copy of the normalised rows (pitch N) or null
   int act_rt;                    // ACT == kActRuntime: ICKA_ACT_RELU or ICKA_ACT_SWISH
+  // bf16 outputs without residual / aux copy (Q, K||V, FFN-up): the epilogue packs rows straight out of TMEM and a TMA store
+  // per 32 x 32 block writes them (tmap_out: box {32 columns, 32 rows}, SWIZZLE_64B); 0 = the transposing epilogue
+  int tma_epi;
+  alignas(64) CUtensorMap tmap_out;
 };
 
 constexpr int kChunkBytes = kBK * 128;   // one 64-element-wide MN-major chunk of a stage: 64 contraction rows x 128 B
@@ -107,12 +123,13 @@ __device__ __forceinline__ bool tile_at(int i, int group_id, int num_groups, int
   return true;
 }
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false>
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false, bool TMAE = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmArgs args) {
+                         const __grid_constant__ GemmArgs args) {
   static_assert(!LNF || (MAJOR == 0 && CTAS == 1 && !OUT_BF16 && ACT == ICKA_ACT_NONE), "LNF: plain fp32 forward only");
   static_assert(ACT != kActRuntime || MAJOR == 0, "runtime activations are forward-only");
+  static_assert(!TMAE || (OUT_BF16 && MAJOR == 0 && !LNF), "TMA-store epilogue: bf16 forward outputs only");
   static_assert(MAJOR == 0 || CTAS == 1, "MN-major operands are built for single-CTA tiles only");
   static_assert(MAJOR != 2 || (!OUT_BF16 && ACT == ICKA_ACT_NONE), "wgrad accumulates plain fp32");
   using Cfg = GemmCfg<BN, CTAS>;
@@ -268,6 +285,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int it = 0;
     const uint32_t empty_leader[2] = {CTAS == 2 ? map_to_cta(&tmem_empty_bar[0], 0) : 0u,
                                       CTAS == 2 ? map_to_cta(&tmem_empty_bar[1], 0) : 0u};
+    int tma_blocks = 0;     // TMA-store epilogue: blocks this warp has issued (staging half = parity)
     float rs[16], rq[16];   // LNF: per-thread partial row sums / sums of squares of rows 2i+sub over this warp's columns
     // LNF keeps its pre-LayerNorm rows in L2 between the two passes: they are written and re-read with evict_last,
     // everything that streams (residual reads, final fp32 / bf16 stores) goes through with evict_first
@@ -295,6 +313,74 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool slabs = (MAJOR != 2) && args.splits > 1;
       uint32_t r[32];
       bool released = false;
+      if constexpr (TMAE) {
+        {
+          // ---- bf16 rows straight out of TMEM (thread = row, 32 consecutive columns): bias (+ activation), pack, four
+          //      16-byte shared-memory stores into a 32 x 64 B tile (SWIZZLE_64B: chunk ^= (row >> 1) & 3, conflict-free
+          //      for lane = row) and ONE TMA store per block -- no transpose through shared memory, no per-thread global
+          //      stores; the two 2 KB halves of the warp's staging tile alternate, so a store drains while the next
+          //      block is computed.  TMA clips rows >= M.  (host: N % 32 == 0, no residual / aux copy / split-K)
+          for (int c = half; c < nchunks; c += 2) {
+            tmem_ld_32x32b_x32(taddr0 + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+            if (c + 2 >= nchunks) {   // this warp's last TMEM read of the tile: hand the accumulator back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+              released = true;
+            }
+            const int col0 = n_tile0 + c * 32;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 bb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              if (args.bias) bb = __ldg(reinterpret_cast<const float4*>(args.bias + col0) + j4);   // warp-uniform address
+              float x0 = __uint_as_float(r[4 * j4]) + bb.x, x1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+              float x2 = __uint_as_float(r[4 * j4 + 2]) + bb.z, x3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+              if (ACT == ICKA_ACT_GELU_ERF) {
+                const float2 g0 = gelu_erf_tanh2(x0, x1), g1 = gelu_erf_tanh2(x2, x3);
+                x0 = g0.x; x1 = g0.y; x2 = g1.x; x3 = g1.y;
+              }
+              if (ACT == kActRuntime) {
+                if (args.act_rt == ICKA_ACT_RELU) {
+                  x0 = act_relu(x0); x1 = act_relu(x1); x2 = act_relu(x2); x3 = act_relu(x3);
+                } else {
+                  x0 = act_swish_fast(x0); x1 = act_swish_fast(x1); x2 = act_swish_fast(x2); x3 = act_swish_fast(x3);
+                }
+              }
+              if (ACT == ICKA_ACT_TANH) {
+                asm("tanh.approx.f32 %0, %1;" : "=f"(x0) : "f"(x0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(x1) : "f"(x1));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(x2) : "f"(x2));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(x3) : "f"(x3));
+              }
+              pk[2 * j4] = pack_bf16x2(x0, x1);
+              pk[2 * j4 + 1] = pack_bf16x2(x2, x3);
+            }
+            uint8_t* buf = stage_tile + (tma_blocks & 1) * 2048;
+            if (lane == 0 && tma_blocks >= 2) bulk_wait_group_read1();   // the store that used this half has read it
+            __syncwarp();
+            uint8_t* rowp = buf + lane * 64;
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+              *reinterpret_cast<uint4*>(rowp + ((sl ^ sw) << 4)) = make_uint4(pk[4 * sl], pk[4 * sl + 1], pk[4 * sl + 2], pk[4 * sl + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d_out(&args.tmap_out, buf, col0, row_base);
+              bulk_commit_group();
+            }
+            ++tma_blocks;
+          }
+          if (!released) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(empty_leader[acc]); else mbar_arrive(&tmem_empty_bar[acc]); }
+          }
+          continue;
+        }
+      }
       if (args.debug == 1) {
         tc_fence_before();
         __syncwarp();
@@ -509,6 +595,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
     }
+    if (tma_blocks > 0 && lane == 0) bulk_wait_group_all();   // TMA-store epilogue: writes performed before the CTA retires
   }
 
   // ---- teardown ----
@@ -654,10 +741,10 @@ int icka_make_tmap_bf16_mn(icka_handle* h, CUtensorMap* tm, const void* ptr, int
 
 namespace {
 
-template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false>
+template <int BN, int ACT, bool OUT_BF16, int CTAS, int MAJOR, bool LNF = false, bool TMAE = false>
 int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTAS>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS, MAJOR, LNF>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_BF16, CTAS, MAJOR, LNF, TMAE>;
   ICKA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
   const int m_tiles = (args.M + kBM * CTAS - 1) / (kBM * CTAS), n_tiles = (args.N + BN - 1) / BN;
   const int tiles = LNF ? m_tiles : m_tiles * n_tiles * args.splits;   // LNF: a CTA owns whole row-blocks
@@ -681,6 +768,26 @@ int launch_gemm(icka_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, co
 }
 
 }  // namespace
+
+// Output tensor map of the TMA-store epilogue: [rows, cols] bf16, box {32 columns, 32 rows}, 64-byte swizzle.
+static int icka_make_tmap_bf16_out(icka_handle* h, CUtensorMap* tm, void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {32u, 32u};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    ICKA_FAIL(ICKA_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+  return ICKA_OK;
+}
+// developer knob ICKA_GEMM_TMA_EPI=0: bf16 outputs through the transposing epilogue as well
+static const bool g_gemm_tma_epi = [] {
+  const char* e = getenv("ICKA_GEMM_TMA_EPI");
+  return !(e && e[0] == '0');
+}();
 
 // icka_gemm_mode: 0 = choose per shape (default), 1 = force single-CTA tiles, 2 = force CTA pairs.
 static int g_gemm_mode = 0;
@@ -779,6 +886,12 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
   args.act_rt = act;
   const bool bf = out_dtype == ICKA_BF16;
   const bool gelu = act == ICKA_ACT_GELU_ERF;
+  if (bf && !residual && !aux_out && (act == ICKA_ACT_NONE || gelu) && N % 32 == 0 && ldo % 8 == 0 && g_gemm_tma_epi &&
+      (!bias || icka_aligned(bias, 16))) {
+    rc = icka_make_tmap_bf16_out(h, &args.tmap_out, out, M, N, ldo);
+    if (rc) return rc;
+    args.tma_epi = 1;
+  }
   if (act == ICKA_ACT_TANH) {   // prompt mapping networks (CMIM:914-930): M = batch, single-CTA tiles
     if (BN == 256) {
       if (bf) return launch_gemm<256, ICKA_ACT_TANH, true, 1, 0>(h, ta, tb, args, st);
@@ -803,6 +916,13 @@ int icka_gemm_bf16_launch(icka_handle* h, const void* A, int64_t lda, const void
       ICKA_LAUNCHED(h);
       return ICKA_OK;
     }
+  }
+  if (args.tma_epi && !rt) {   // bf16 output, no residual / aux copy: TMA-store epilogue (own instantiations)
+#define ICKA_GEMM_T(BN_, ACT_, C_) return launch_gemm<BN_, ACT_, true, C_, 0, false, true>(h, ta, tb, args, st)
+    if (pair)           { if (gelu) ICKA_GEMM_T(256, ICKA_ACT_GELU_ERF, 2); else ICKA_GEMM_T(256, ICKA_ACT_NONE, 2); }
+    else if (BN == 256) { if (gelu) ICKA_GEMM_T(256, ICKA_ACT_GELU_ERF, 1); else ICKA_GEMM_T(256, ICKA_ACT_NONE, 1); }
+    else                { if (gelu) ICKA_GEMM_T(128, ICKA_ACT_GELU_ERF, 1); else ICKA_GEMM_T(128, ICKA_ACT_NONE, 1); }
+#undef ICKA_GEMM_T
   }
 #define ICKA_GEMM(BN_, ACT_, BF_, C_) return launch_gemm<BN_, ACT_, BF_, C_, 0>(h, ta, tb, args, st)
   if (rt) {   // non-default config.hidden_act
