@@ -812,10 +812,14 @@ def bench_training(env, args, shape, batch, steps, real_head, precision='bf16'):
                               if use_graph else 'eager host launches')},
         'clocks': clk.report(), 'gpu_launches': int(launches), 'loss': float(loss.detach()),
         'roofline': {'kernel': 'gemm_bf16_tcgen05_kernel (fwd + dgrad + wgrad)', 'bound': 'tensor',
-                     'achieved': (gemm_fl / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else 0.0, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                     'frac': (gemm_fl / (gemm_ms * 1e-3) / 1e12 / peak_tf) if gemm_ms > 0 else 0.0, 'traffic': None,
-                     'gemm_ms_per_step': round(gemm_ms, 4),
-                     'note': 'tcgen05 GEMM launches of one step (forward, dgrad, wgrad): executed FLOPs / their CUDA-event time'},
+                     'achieved': gemm_fl / (ms / steps * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                     'frac': gemm_fl / (ms / steps * 1e-3) / 1e12 / peak_tf, 'traffic': None,
+                     'note': 'EXECUTED tcgen05 GEMM FLOPs of one step (forward, dgrad, wgrad) / WHOLE-step time of the timed '
+                             'replays: a lower bound for the GEMM launches (the step also holds every non-GEMM kernel, the '
+                             'all-reduce and the optimizer).  The per-kernel CUDA-event times in `kernels` come from an EAGER pass; '
+                             'at 32-128 sentences the host cannot keep the GPU busy there, so they include launch gaps '
+                             '(device-only durations: profiles/launches_*_train128.csv)',
+                     'gemm_event_ms_per_step_eager': round(gemm_ms, 4)},
         'step_frac_of_tensor_peak': round(tf / peak_tf, 4),
         'step_frac_note': 'whole-step dense-GEMM FLOPs (3 x forward) / whole-step time: includes every non-GEMM kernel, the all-reduce and the optimizer',
         'allreduce': allreduce, 'kernels': kernel_table,
