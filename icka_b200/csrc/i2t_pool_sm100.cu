@@ -1,4 +1,5 @@
-// Single-query (image -> text) attention pool in folded form on tcgen05 / TMEM (sm_100a), S <= 128 keys.
+// Single-query (image -> text) attention pool in folded form on tcgen05 / TMEM (sm_100a), S <= 128 keys (KB = 1) or
+// S <= 256 keys as two 128-key blocks per sentence (KB = 2; the description below is for one block).
 //
 // Same contract as i2t_pool_kernel (i2t_pool.cu): per sentence, U [nh x H] (the folded queries) against the text
 // states X [S x H]:  scores[h][s] = U_h . x_s / 8 + mask[s],  p = softmax_s,  xbar_h = sum_s p[h][s] x_s.
@@ -28,14 +29,15 @@ constexpr int kHeads = 16;
 constexpr int kChunkBytes = kKeys * 128;   // [128 keys][64 dims] bf16
 constexpr int kThreads = 320;
 
-template <int H>
+template <int H, int KB = 1>     // KB: 128-key blocks per sentence (1: S <= 128; 2: S <= 256, the 448-px configuration)
 struct PoolCfg {
   static constexpr int kChunks = H / 64;
   static constexpr int kPairs = H / 128;
   static constexpr int kUBytes = kChunks * kHeads * 128;           // [chunk][16 heads][64 dims]
-  static constexpr int kPTBytes = 2 * kHeads * 128;                // [2 key chunks][16 heads][64 keys]
-  static constexpr int kStages = (H <= 768) ? 10 : 8;              // even: pass 2 consumes stages in pairs
-  static constexpr int kSlotCols = 32 + ((kPairs * 16 + 31) / 32) * 32;   // S^T at +0 (16 cols), O^T at +32
+  static constexpr int kPTBytes = KB * 2 * kHeads * 128;           // [2 KB key chunks][16 heads][64 keys]
+  static constexpr int kStages = (H <= 768 && KB == 1) ? 10 : 8;   // even: pass 2 consumes stages in pairs
+  static constexpr int kSlotCols = 32 + ((kPairs * 16 + 31) / 32) * 32;   // S^T at +0 (16 cols per key block), O^T at +32
+  static_assert(KB >= 1 && KB <= 2, "the score slot holds two key blocks");
   static constexpr int kTmemCols = (2 * kSlotCols <= 256) ? 256 : 512;
   static constexpr size_t kSmemBytes = (size_t)kStages * kChunkBytes + 2 * kUBytes + 2 * kPTBytes + 2 * 2 * 4 * kHeads * 4 +
                                        1024 /*align*/ + 512 /*barriers*/;
@@ -65,11 +67,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-template <int H>
+template <int H, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_u,
                         const PoolArgs args) {
-  using Cfg = PoolCfg<H>;
+  using Cfg = PoolCfg<H, KB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* x_ring = smem;                                           // kStages x 16 KB
@@ -125,12 +127,24 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       // of a chunk every SM streams another sentence (58 MB in flight machine-wide, against two 63 MB L2 partitions), and
       // with the default policy 18 % of the second pass came from DRAM again (ncu: 281 MB per launch vs 239 MB algorithmic).
       const uint64_t pol_keep = l2_policy_evict_last(), pol_done = l2_policy_evict_first();
-      auto x_chunks = [&](int b, uint64_t pol) {   // the H/64 chunk tiles of sentence b, in order
-        for (int c = 0; c < Cfg::kChunks; ++c) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kChunkBytes);
-          tma_load_2d_hint(x_ring + (size_t)stage * kChunkBytes, &tmap_x, &full_bar[stage], c * 64, b * args.S, pol);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      auto x_tile = [&](int b, int kb, int c, uint64_t pol) {   // chunk c (64 dims) of key block kb of sentence b
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], kChunkBytes);
+        tma_load_2d_hint(x_ring + (size_t)stage * kChunkBytes, &tmap_x, &full_bar[stage], c * 64, b * args.S + kb * kKeys, pol);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      };
+      // pass 1 walks (key block, chunk); pass 2 walks (pair, key block, the pair's two chunks): the MMA warp consumes in
+      // exactly this order
+      auto x_chunks = [&](int b, uint64_t pol, bool second) {
+        if (!second) {
+          for (int kb = 0; kb < KB; ++kb)
+            for (int c = 0; c < Cfg::kChunks; ++c) x_tile(b, kb, c, pol);
+        } else {
+          for (int pr = 0; pr < Cfg::kPairs; ++pr)
+            for (int kb = 0; kb < KB; ++kb) {
+              x_tile(b, kb, 2 * pr, pol);
+              x_tile(b, kb, 2 * pr + 1, pol);
+            }
         }
       };
       // Software-pipelined by one sentence: pass 1 of sentence n+1 is streamed (from HBM) BEFORE pass 2 of
@@ -144,9 +158,9 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           mbar_arrive_expect_tx(&u_full[slot], Cfg::kUBytes);
           for (int c = 0; c < Cfg::kChunks; ++c)
             tma_load_2d(u_base + slot * Cfg::kUBytes + c * (kHeads * 128), &tmap_u, &u_full[slot], c * 64, b * args.nh);
-          x_chunks(b, pol_keep);            // pass 1 of sentence n
+          x_chunks(b, pol_keep, false);            // pass 1 of sentence n
         }
-        if (prev_b >= 0) x_chunks(prev_b, pol_done);   // pass 2 of sentence n-1
+        if (prev_b >= 0) x_chunks(prev_b, pol_done, true);   // pass 2 of sentence n-1
         if (!live) break;
         prev_b = b;
       }
@@ -163,17 +177,18 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const uint32_t tmem_s = tmem_base + (uint32_t)(slot * Cfg::kSlotCols);
         mbar_wait(&u_full[slot], (n >> 1) & 1);
         const uint32_t u_addr = smem_u32(u_base + slot * Cfg::kUBytes);
-        for (int c = 0; c < Cfg::kChunks; ++c) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t x_addr = smem_u32(x_ring + (size_t)stage * kChunkBytes);
+        for (int kb = 0; kb < KB; ++kb)
+          for (int c = 0; c < Cfg::kChunks; ++c) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(x_ring + (size_t)stage * kChunkBytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_s, make_kmajor_sw128_desc(x_addr + k * 32),
-                      make_kmajor_sw128_desc(u_addr + c * (kHeads * 128) + k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-        }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_s + (uint32_t)(kb * kHeads), make_kmajor_sw128_desc(x_addr + k * 32),
+                        make_kmajor_sw128_desc(u_addr + c * (kHeads * 128) + k * 32), idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
         umma_commit(&u_empty[slot]);
         umma_commit(&s_full[slot]);
       };
@@ -183,20 +198,22 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         mbar_wait(&p_full[slot], (n >> 1) & 1);
         if (n >= 2) mbar_wait(&o_free[slot], ((n >> 1) - 1) & 1);
         const uint32_t pt_addr = smem_u32(pt_base + slot * Cfg::kPTBytes);
-        for (int pr = 0; pr < Cfg::kPairs; ++pr) {
-          mbar_wait(&full_bar[stage], phase);
-          mbar_wait(&full_bar[stage + 1], phase);      // kStages is even and pairs start on even stages
-          tc_fence_after();
-          const uint32_t x_addr = smem_u32(x_ring + (size_t)stage * kChunkBytes);
+        for (int pr = 0; pr < Cfg::kPairs; ++pr)
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(&full_bar[stage + 1], phase);      // kStages is even and pairs start on even stages
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(x_ring + (size_t)stage * kChunkBytes);
 #pragma unroll
-          for (int k = 0; k < kKeys / 16; ++k)
-            umma_bf16(tmem_o + (uint32_t)(pr * 16), make_mnmajor_sw128_desc(x_addr + k * (16 * 128), kChunkBytes),
-                      make_kmajor_sw128_desc(pt_addr + (k >> 2) * (kHeads * 128) + (k & 3) * 32), idesc_o, k > 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
-          umma_commit(&empty_bar[stage + 1]);
-          stage += 2;
-          if (stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-        }
+            for (int k = 0; k < kKeys / 16; ++k)
+              umma_bf16(tmem_o + (uint32_t)(pr * 16), make_mnmajor_sw128_desc(x_addr + k * (16 * 128), kChunkBytes),
+                        make_kmajor_sw128_desc(pt_addr + (kb * 2 + (k >> 2)) * (kHeads * 128) + (k & 3) * 32), idesc_o,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            umma_commit(&empty_bar[stage + 1]);
+            stage += 2;
+            if (stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
         umma_commit(&o_full[slot]);
       };
       // same order as the producer: P1(0), P1(1), P2(0), P1(2), P2(1), ...  (S^T of slot (n+1)&1 is free: its last
@@ -226,17 +243,25 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     for (int b = blockIdx.x; b < args.B; b += gridDim.x, ++n) {
       if ((n & 1) != group) continue;
       const uint32_t par = (n >> 1) & 1;
-      const float mk = (key < args.S) ? (args.mask_add ? args.mask_add[(size_t)b * args.S + key] * kLog2e : 0.0f) : -INFINITY;
+      float mk[KB];
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const int gk = kb * kKeys + key;
+        mk[kb] = (gk < args.S) ? (args.mask_add ? args.mask_add[(size_t)b * args.S + gk] * kLog2e : 0.0f) : -INFINITY;
+      }
       mbar_wait(&s_full[group], par);
       tc_fence_after();
-      uint32_t sr[16];
-      tmem_ld_32x32b_x16(tmem_s, sr);
-      tmem_ld_wait();
-      float v[16], m[16];
+      float v[KB][16], m[16];
 #pragma unroll
-      for (int h = 0; h < 16; ++h) {
-        v[h] = fmaf(__uint_as_float(sr[h]), kScale, mk);
-        m[h] = v[h];
+      for (int kb = 0; kb < KB; ++kb) {
+        uint32_t sr[16];
+        tmem_ld_32x32b_x16(tmem_s + (uint32_t)(kb * kHeads), sr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+          v[kb][h] = fmaf(__uint_as_float(sr[h]), kScale, mk[kb]);
+          m[h] = kb == 0 ? v[kb][h] : fmaxf(m[h], v[kb][h]);
+        }
       }
       // per-head max over the 128 keys: butterflies inside the warp, then one hop through shared memory
 #pragma unroll
@@ -252,8 +277,12 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
       for (int h = 0; h < 16; ++h) {
         const float mh = fmaxf(fmaxf(red_max[h], red_max[kHeads + h]), fmaxf(red_max[2 * kHeads + h], red_max[3 * kHeads + h]));
-        v[h] = ex2(v[h] - mh);
-        l[h] = v[h];
+        l[h] = 0.0f;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+          v[kb][h] = ex2(v[kb][h] - mh);
+          l[h] += v[kb][h];
+        }
       }
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1)
@@ -266,12 +295,15 @@ i2t_pool_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       named_bar_sync(1 + group, 128);
       // P^T[h][key] (bf16) into the K-major 128-B-swizzled [16 heads][64 keys] x 2 tile
       {
-        uint8_t* col = pt_buf + (key >> 6) * (kHeads * 128) + (key & 7) * 2;
         const int c16 = (key & 63) >> 3;
 #pragma unroll
         for (int h = 0; h < 16; ++h) {
           const float lh = (red_sum[h] + red_sum[kHeads + h]) + (red_sum[2 * kHeads + h] + red_sum[3 * kHeads + h]);
-          *reinterpret_cast<__nv_bfloat16*>(col + h * 128 + ((c16 ^ (h & 7)) << 4)) = __float2bfloat16_rn(v[h] / lh);
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {     // key chunk (64 keys) index: 2 kb + (key >> 6)
+            uint8_t* col = pt_buf + (kb * 2 + (key >> 6)) * (kHeads * 128) + (key & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(col + h * 128 + ((c16 ^ (h & 7)) << 4)) = __float2bfloat16_rn(v[kb][h] / lh);
+          }
         }
       }
       fence_proxy_async();
@@ -310,10 +342,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int H>
+template <int H, int KB>
 int launch_pool(icka_handle* h, const void* U, const void* X, const float* mask_add, void* xbar, int B, int S, int nh,
                 cudaStream_t st) {
-  using Cfg = PoolCfg<H>;
+  using Cfg = PoolCfg<H, KB>;
   if (h->smem_optin < Cfg::kSmemBytes) return 1;
   CUtensorMap tx, tu;
   int rc = icka_make_tmap_bf16(h, &tx, X, (int64_t)B * S, H, H, kKeys);          // box {64 dims, 128 keys}
@@ -321,9 +353,9 @@ int launch_pool(icka_handle* h, const void* U, const void* X, const float* mask_
   rc = icka_make_tmap_bf16(h, &tu, U, (int64_t)B * nh, H, H, kHeads);            // box {64 dims, 16 heads}
   if (rc) return rc;
   PoolArgs args{mask_add, static_cast<__nv_bfloat16*>(xbar), B, S, nh};
-  ICKA_CUDA(cudaFuncSetAttribute(i2t_pool_tcgen05_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+  ICKA_CUDA(cudaFuncSetAttribute(i2t_pool_tcgen05_kernel<H, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
   const int grid = B < h->sm_count ? B : h->sm_count;
-  i2t_pool_tcgen05_kernel<H><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tx, tu, args);
+  i2t_pool_tcgen05_kernel<H, KB><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tx, tu, args);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }
@@ -333,8 +365,13 @@ int launch_pool(icka_handle* h, const void* U, const void* X, const float* mask_
 // ICKA_OK after launching; > 0 when the shape is outside this kernel's envelope (caller uses the mma.sync kernel).
 int icka_i2t_pool_tcgen05_launch(icka_handle* h, const void* U, const void* X, const float* mask_add, void* xbar, int B,
                                  int S, int H, int nh, cudaStream_t st) {
-  if (S > kKeys || nh > kHeads) return 1;
-  if (H == 768) return launch_pool<768>(h, U, X, mask_add, xbar, B, S, nh, st);
-  if (H == 1024) return launch_pool<1024>(h, U, X, mask_add, xbar, B, S, nh, st);
+  if (S > 2 * kKeys || nh > kHeads) return 1;
+  if (S <= kKeys) {
+    if (H == 768) return launch_pool<768, 1>(h, U, X, mask_add, xbar, B, S, nh, st);
+    if (H == 1024) return launch_pool<1024, 1>(h, U, X, mask_add, xbar, B, S, nh, st);
+  } else {   // two 128-key blocks per sentence (S = 256: the 448-px configuration)
+    if (H == 768) return launch_pool<768, 2>(h, U, X, mask_add, xbar, B, S, nh, st);
+    if (H == 1024) return launch_pool<1024, 2>(h, U, X, mask_add, xbar, B, S, nh, st);
+  }
   return 1;
 }

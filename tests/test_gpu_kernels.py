@@ -138,7 +138,7 @@ def test_gate_fold_and_blend():
 
 
 @pytest.mark.parametrize('B,S,H,nh', [(3, 128, 768, 12), (2, 256, 768, 12), (2, 40, 1024, 16), (1, 7, 768, 12), (300, 128, 768, 12),
-                                      (5, 100, 768, 16)])
+                                      (5, 100, 768, 16), (300, 256, 768, 12), (7, 200, 768, 12), (3, 129, 1024, 16), (2, 300, 768, 12)])
 @pytest.mark.parametrize('attn_mode', [0, 1], ids=['tcgen05', 'mma_sync'])
 def test_i2t_pool(B, S, H, nh, attn_mode):
     from icka_b200 import _lib
