@@ -82,16 +82,17 @@ __device__ __forceinline__ float wsum(float v) {
   return v;
 }
 
-// stage one [Skv, 64] head tile (global row pitch ld elements) into the padded shared-memory tile
+// stage one [Skv, 64] head tile (global row pitch ld elements) into the padded shared-memory tile: cp.async, so that the
+// whole tile is in flight at once (a warp is alone with its 32 KB of K and V, five warps per SM: with loads staged through
+// registers, four per lane in flight, the kernel ran at 1.5 TB/s -- 45 us per forward launch at 128 sentences)
 template <typename T>
 __device__ __forceinline__ void stage_tile(const T* __restrict__ g, int64_t ld, int Skv, uint8_t* s, int lane) {
   constexpr int kVecPerRow = kD / Tile<T>::kVec;                // 8 (bf16) or 16 (fp32) pieces per row
   const int n = Skv * kVecPerRow;
-#pragma unroll 4
   for (int i = lane; i < n; i += 32) {
     const int r = i / kVecPerRow, c = i % kVecPerRow;
-    *reinterpret_cast<uint4*>(s + (size_t)r * Tile<T>::kPitch + c * 16) =
-        __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * ld) + c);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s + (size_t)r * Tile<T>::kPitch + c * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(reinterpret_cast<const uint4*>(g + (size_t)r * ld) + c));
   }
 }
 
@@ -139,6 +140,7 @@ attn_sq1_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, c
       dos[2 * lane + 1] = u.y;
     }
   }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncwarp();
 
   // ---- lane = key: score = q . K[s] / 8 + mask,  dP'[s] = dO . V[s] ----
