@@ -306,11 +306,15 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return warp_sum(t);
 }
 
+constexpr int kGateRowsFwd = 16;
 __global__ void __launch_bounds__(kGateThreads) gate_blend_kernel(
     const float* __restrict__ fused, const float* __restrict__ tok, const float* __restrict__ ln_w,
     const float* __restrict__ ln_b, float ln_eps, const float* __restrict__ w_fold, const float* __restrict__ c_fold,
-    float* __restrict__ out, float* __restrict__ gate_out, int S, int H) {
+    float* __restrict__ out, float* __restrict__ gate_out, int S, int H, int rpb) {
   __shared__ float red[kGateThreads / 32];
+  // block = (sentence, chunk of rpb rows): every block recomputes the sentence's gate from the [CLS] rows (3 KB,
+  // L2-resident) and streams its own rows -- with one block per sentence a training batch of 32-128 sentences left most
+  // SMs idle
   const int b = blockIdx.x;
   const float* f = fused + (size_t)b * S * H;
   const float* t = tok + (size_t)b * S * H;
@@ -333,13 +337,14 @@ __global__ void __launch_bounds__(kGateThreads) gate_blend_kernel(
   const float logit = block_sum(dot, red) + c_fold[0];
   const float g = 1.0f / (1.0f + expf(-logit));
   const float og = 1.0f - g;
-  if (threadIdx.x == 0 && gate_out) gate_out[b] = g;
+  if (threadIdx.x == 0 && blockIdx.y == 0 && gate_out) gate_out[b] = g;
 
-  const int nvec = S * H / 4;
+  const int r0 = blockIdx.y * rpb, r1 = min(S, r0 + rpb);
+  const int v0 = (int)((size_t)r0 * H / 4), nvec = (int)((size_t)r1 * H / 4);   // H % 4 != 0: rpb == S (one chunk)
   const float4* f4 = reinterpret_cast<const float4*>(f);
   const float4* t4 = reinterpret_cast<const float4*>(t);
   float4* o4 = reinterpret_cast<float4*>(o);
-  for (int v = threadIdx.x; v < nvec; v += kGateThreads) {
+  for (int v = v0 + threadIdx.x; v < nvec; v += kGateThreads) {
     const float4 a = __ldcs(t4 + v), c = __ldcs(f4 + v);
     float4 r;
     r.x = g * a.x + og * c.x;
@@ -670,8 +675,9 @@ extern "C" int icka_gate_blend_fwd(icka_handle* h, const float* fused, const flo
   ICKA_REQUIRE(icka_aligned(fused, 16) && icka_aligned(tok, 16) && icka_aligned(out, 16),
                "gate_blend: pointers must be 16-byte aligned");
   if (B == 0) return ICKA_OK;
-  gate_blend_kernel<<<B, kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(fused, tok, ln_w, ln_b, ln_eps, w_fold,
-                                                                            c_fold, out, gate_out, S, H);
+  const int rpb = (H % 4 == 0 && S <= 65535 * kGateRowsFwd) ? kGateRowsFwd : S;   // H % 4 != 0: chunks would start unaligned
+  gate_blend_kernel<<<dim3(B, (S + rpb - 1) / rpb), kGateThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      fused, tok, ln_w, ln_b, ln_eps, w_fold, c_fold, out, gate_out, S, H, rpb);
   ICKA_LAUNCHED(h);
   return ICKA_OK;
 }

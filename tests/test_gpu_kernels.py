@@ -123,8 +123,8 @@ def test_cross_attn_core_bf16_kernels(B, Sq, Skv, nh, attn_mode):
     assert err <= 2e-2, err     # P rounded to bf16 for the second GEMM + bf16 output
 
 
-def test_gate_fold_and_blend():
-    B, S, H = 5, 128, 768
+@pytest.mark.parametrize('B,S,H', [(5, 128, 768), (3, 37, 64), (2, 4, 6), (40, 256, 1024)])
+def test_gate_fold_and_blend(B, S, H):
     fused, tok = rnd(B, S, H, seed=1), rnd(B, S, H, seed=2)
     lw, lb = rnd(H, seed=3) * 0.1 + 1, rnd(H, seed=4) * 0.1
     wp, bp, wa, ba = rnd(H, H, seed=5) / math.sqrt(H), rnd(H, seed=6), rnd(H, seed=7) / math.sqrt(H), rnd(1, seed=8)
